@@ -1,0 +1,241 @@
+"""numpy/ctypes front end of the CPU oracle (oracle/pyl_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Mirrors the reference's Python surface for the hot path so parity tests read like reference
+usage (`MA(pos, delta, BoxSize, MAS, W)`, `Pk(delta, BoxSize, axis, MAS, threads)`,
+`XPk([d1, d2], BoxSize, axis, MAS=[..], threads)`), citing /root/reference/library files.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package (pylians_b200) never does.
+
+Third-party arithmetic on the path: the reference's FFT is pyfftw -> FFTW3 (Pk_library.pyx:3,
+:120-133), un-vendored and un-pinned in the reference tree.  The oracle restates it with
+scipy.fft.rfftn (pocketfft) in float32 -> complex64, the same precision as FFT3Dr_f.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(HERE, "pyl_oracle.c")
+_SO = os.path.join(HERE, "_build", "libpyl_oracle.so")
+_LIB = None
+
+MAS_ID = {"NGP": 0, "CIC": 1, "TSC": 2, "PCS": 3}
+
+
+def build(force=False):
+    """gcc -O2 build of the C restatement (no -ffast-math: the oracle keeps IEEE semantics)."""
+    os.makedirs(os.path.dirname(_SO), exist_ok=True)
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.check_call([cc, "-O2", "-fPIC", "-shared", "-std=gnu99", "-o", _SO, _SRC, "-lm"])
+    return _SO
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        build()
+        L = ctypes.CDLL(_SO)
+        fp, dp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+        L.orc_ma_f32.argtypes = [fp, ctypes.c_long, ctypes.c_int, ctypes.c_long, ctypes.c_long, fp,
+                                 ctypes.c_int, ctypes.c_float, ctypes.c_int, fp]
+        L.orc_ma_f64.argtypes = [fp, ctypes.c_long, ctypes.c_int, ctypes.c_long, ctypes.c_long, dp,
+                                 ctypes.c_int, ctypes.c_float, ctypes.c_int, fp]
+        L.orc_pos_redshift_space.argtypes = [fp, fp, ctypes.c_long, ctypes.c_float, ctypes.c_float,
+                                             ctypes.c_float, ctypes.c_int]
+        L.orc_pk_loop.argtypes = [ctypes.POINTER(fp), ctypes.c_int, ctypes.c_int, ctypes.c_int, ip,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_int] + [dp] * 12
+        for f in (L.orc_ma_f32, L.orc_ma_f64, L.orc_pos_redshift_space, L.orc_pk_loop):
+            f.restype = None
+        _LIB = L
+    return _LIB
+
+
+def _fp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+# ------------------------------------------------------------------------------------------------
+# MAS_library.pyx:57-112
+# ------------------------------------------------------------------------------------------------
+def MA(pos, number, BoxSize, MAS="CIC", W=None, verbose=False, renormalize_2D=True):
+    coord, coord_aux = pos.shape[1], number.ndim
+    if coord != coord_aux:                       # :64-66
+        print("pos have %d dimensions and the density %d!!!" % (coord, coord_aux))
+        sys.exit()
+    if MAS not in MAS_ID:                        # :81-82
+        print("option not valid!!!")
+        sys.exit()
+    if pos.dtype != np.float32 or (W is not None and W.dtype != np.float32):
+        raise ValueError("Buffer dtype mismatch, expected 'float32_t'")
+    if number.dtype not in (np.float32, np.float64) or not number.flags["C_CONTIGUOUS"]:
+        raise ValueError("number must be a C-contiguous float32 (or float64) array")
+    dims = number.shape[0]
+    es = pos.itemsize
+    ps0, ps1 = pos.strides[0] // es, pos.strides[1] // es
+    Wp = None
+    if W is not None:
+        W = np.ascontiguousarray(W)
+        Wp = _fp(W)
+    L = lib()
+    if number.dtype == np.float32:
+        L.orc_ma_f32(_fp(pos), pos.shape[0], coord, ps0, ps1, _fp(number), dims, float(BoxSize), MAS_ID[MAS], Wp)
+    else:
+        L.orc_ma_f64(_fp(pos), pos.shape[0], coord, ps0, ps1, _dp(number), dims, float(BoxSize), MAS_ID[MAS], Wp)
+    if coord == 2 and renormalize_2D and MAS != "NGP":   # :90-107: the WHOLE array is divided
+        number /= {"CIC": 2.0, "TSC": 3.0, "PCS": 4.0}[MAS]
+
+
+def pos_redshift_space(pos, vel, BoxSize, Hubble, redshift, axis):
+    """redshift_space_library.pyx:29-43 (in place on pos)."""
+    assert pos.dtype == np.float32 and vel.dtype == np.float32 and pos.flags["C_CONTIGUOUS"] and vel.flags["C_CONTIGUOUS"]
+    lib().orc_pos_redshift_space(_fp(pos), _fp(vel), pos.shape[0], float(BoxSize), float(Hubble), float(redshift), int(axis))
+
+
+# ------------------------------------------------------------------------------------------------
+# Pk_library.pyx:59-87
+# ------------------------------------------------------------------------------------------------
+def frequencies(BoxSize, dims):
+    kF = 2.0 * np.pi / BoxSize
+    middle = dims // 2                            # python-2 integer division in the reference :60
+    kN = middle * kF
+    kmax_par = middle
+    kmax_per = int(np.sqrt(middle ** 2 + middle ** 2))
+    kmax = int(np.sqrt(middle ** 2 + middle ** 2 + middle ** 2))
+    return kF, kN, kmax_par, kmax_per, kmax
+
+
+def MAS_function(MAS):
+    return {"NGP": 1, "CIC": 2, "TSC": 3, "PCS": 4}.get(MAS, 0)
+
+
+def FFT3Dr_f(a, threads=1):
+    """Pk_library.pyx:120-133 -- unnormalised forward R2C, float32 -> complex64, half-spectrum on z."""
+    import scipy.fft as sf
+    assert a.dtype == np.float32 and a.ndim == 3
+    return np.ascontiguousarray(sf.rfftn(a, axes=(0, 1, 2), workers=threads).astype(np.complex64, copy=False))
+
+
+def check_number_modes(Nmodes, dims):            # :90-102
+    own = 1 if dims % 2 == 1 else 8
+    indep = (dims ** 3 - own) // 2 + own
+    if int(np.sum(Nmodes)) != indep:
+        print("WARNING: Not all modes counted")
+        sys.exit()
+
+
+def _mode_loop(delta_k_list, dims, axis, mas_index, BoxSize, want_phase):
+    F = len(delta_k_list)
+    X = F * (F - 1) // 2
+    kF, kN, kmax_par, kmax_per, kmax = frequencies(BoxSize, dims)
+    B2 = (kmax_par + 1) * (kmax_per + 1)
+    z = lambda *s: np.zeros(s, dtype=np.float64)
+    out = dict(k3d=z(kmax + 1), n3d=z(kmax + 1), p3d=z(kmax + 1, 3, F), x3d=z(kmax + 1, 3, max(X, 1)),
+               phase=z(kmax + 1), k1d=z(kmax_par + 1), n1d=z(kmax_par + 1), p1d=z(kmax_par + 1, F),
+               x1d=z(kmax_par + 1, max(X, 1)), n2d=z(B2), p2d=z(B2, F), x2d=z(B2, max(X, 1)))
+    fpp = ctypes.POINTER(ctypes.c_float)
+    ptrs = (fpp * F)(*[dk.ctypes.data_as(fpp) for dk in delta_k_list])
+    mi = np.asarray(mas_index, dtype=np.int32)
+    # x-arrays are allocated with max(X,1) columns but addressed with stride X inside C; for X==0
+    # they are never touched.
+    lib().orc_pk_loop(ptrs, F, dims, int(axis), mi.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                      kmax_par, kmax_per, kmax, _dp(out["k3d"]), _dp(out["n3d"]), _dp(out["p3d"]),
+                      _dp(out["x3d"]), _dp(out["phase"]) if want_phase else None, _dp(out["k1d"]),
+                      _dp(out["n1d"]), _dp(out["p1d"]), _dp(out["x1d"]), _dp(out["n2d"]),
+                      _dp(out["p2d"]), _dp(out["x2d"]))
+    if X == 0:
+        out["x3d"] = out["x3d"][:, :, :0]; out["x1d"] = out["x1d"][:, :0]; out["x2d"] = out["x2d"][:, :0]
+    out.update(kF=kF, kN=kN, kmax_par=kmax_par, kmax_per=kmax_per, kmax=kmax, X=X, F=F)
+    return out
+
+
+def _kpar_kper(kmax_par, kmax_per, kF):          # :397-403
+    kpar = np.zeros((kmax_par + 1) * (kmax_per + 1)); kper = np.zeros_like(kpar)
+    for k_per in range(kmax_per + 1):
+        sl = slice((kmax_par + 1) * k_per, (kmax_par + 1) * (k_per + 1))
+        kpar[sl] = 0.5 * (2 * np.arange(kmax_par + 1) + 1) * kF
+        kper[sl] = 0.5 * (k_per + k_per + 1) * kF
+    return kpar, kper
+
+
+class Pk(object):
+    """Pk_library.pyx:266-425."""
+
+    def __init__(self, delta, BoxSize, axis=2, MAS="CIC", threads=1, keep_deltak=False):
+        if delta.dtype != np.float32:
+            raise ValueError("Buffer dtype mismatch, expected 'float32_t'")
+        dims = len(delta)
+        delta_k = FFT3Dr_f(delta, threads)
+        o = _mode_loop([delta_k.view(np.float32)], dims, axis, [MAS_function(MAS)], BoxSize, True)
+        kF, kN = o["kF"], o["kN"]
+        fact = (BoxSize / dims ** 2) ** 3
+        # 1-D  :387-394
+        k1D, N1, P1 = o["k1d"][1:].copy(), o["n1d"][1:].copy(), o["p1d"][1:, 0].copy()
+        P1 = P1 * fact
+        k1D = (k1D / N1) * kF
+        kmaxper = np.sqrt(kN ** 2 - k1D ** 2)
+        P1 = P1 * (np.pi * kmaxper ** 2 / N1) / (2.0 * np.pi) ** 2
+        self.k1D, self.Pk1D, self.Nmodes1D = k1D, P1, N1
+        # 2-D  :397-407 (DC bin kept; an empty bin divides by zero like the reference)
+        self.kpar, self.kper = _kpar_kper(o["kmax_par"], o["kmax_per"], kF)
+        if np.any(o["n2d"] == 0):
+            raise ZeroDivisionError("float division")
+        self.Pk2D = o["p2d"][:, 0] * fact / o["n2d"]
+        self.Nmodes2D = o["n2d"]
+        # 3-D  :411-421
+        check_number_modes(o["n3d"], dims)
+        N3 = o["n3d"][1:].copy()
+        self.k3D = (o["k3d"][1:] / N3) * kF
+        P3 = o["p3d"][1:, :, 0].copy()
+        P3[:, 0] = (P3[:, 0] / N3) * fact
+        P3[:, 1] = (P3[:, 1] * 5.0 / N3) * fact
+        P3[:, 2] = (P3[:, 2] * 9.0 / N3) * fact
+        self.Pk, self.Nmodes3D = P3, N3
+        self.Pkphase = (o["phase"][1:] / N3) * fact
+        if keep_deltak:
+            self.delta_k = delta_k
+
+
+class XPk(object):
+    """Pk_library.pyx:534-798."""
+
+    def __init__(self, delta, BoxSize, axis=2, MAS=None, threads=1):
+        dims = len(delta[0])
+        for d in delta[1:]:
+            if len(d) != dims:                   # :563-565
+                print("Fields have different grid sizes!!!")
+                sys.exit()
+        dks = [FFT3Dr_f(d, threads) for d in delta]
+        o = _mode_loop([dk.view(np.float32) for dk in dks], dims, axis, [MAS_function(m) for m in MAS], BoxSize, False)
+        kF, kN = o["kF"], o["kN"]
+        fact = (BoxSize / dims ** 2) ** 3
+        # 1-D  :745-758
+        N1 = o["n1d"][1:].copy()
+        k1D = (o["k1d"][1:] / N1) * kF
+        kmaxper = np.sqrt(kN ** 2 - k1D ** 2)
+        s1 = (np.pi * kmaxper ** 2 / N1) / (2.0 * np.pi) ** 2
+        self.k1D, self.Nmodes1D = k1D, N1
+        self.Pk1D = o["p1d"][1:] * fact * s1[:, None]
+        self.PkX1D = o["x1d"][1:] * fact * s1[:, None]
+        # 2-D  :761-775
+        self.kpar, self.kper = _kpar_kper(o["kmax_par"], o["kmax_per"], kF)
+        if np.any(o["n2d"] == 0):
+            raise ZeroDivisionError("float division")
+        self.Nmodes2D = o["n2d"]
+        self.Pk2D = o["p2d"] * fact / o["n2d"][:, None]
+        self.PkX2D = o["x2d"] * fact / o["n2d"][:, None]
+        # 3-D  :779-796
+        check_number_modes(o["n3d"], dims)
+        N3 = o["n3d"][1:].copy()
+        self.k3D, self.Nmodes3D = (o["k3d"][1:] / N3) * kF, N3
+        ell = np.array([1.0, 5.0, 9.0])[None, :, None]
+        self.Pk = (o["p3d"][1:] * ell / N3[:, None, None]) * fact
+        self.XPk = (o["x3d"][1:] * ell / N3[:, None, None]) * fact

@@ -1,0 +1,151 @@
+"""Generate golden vectors from the UNMODIFIED reference (oracle/_ref, built by oracle/build_ref.py
+from /root/reference).  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz (inputs + reference outputs).  The reference cannot travel to the GPU
+box, these files can.  Sizes are tiny on purpose (whole directory < 3 MB).
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MASL, PKL = ref_loader.load()
+RSL = ref_loader.load_rsl()
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def particles(seed, n, box, ndim=3):
+    rng = np.random.default_rng(seed)
+    pos = (rng.random((n, ndim)) * box).astype(np.float32)
+    # edge cases the reference accepts: exactly 0, exactly BoxSize (wraps to cell 0), just below
+    # BoxSize, exactly on grid points and on cell mid-points.
+    pos[0] = 0.0
+    pos[1] = box
+    pos[2] = np.nextafter(np.float32(box), np.float32(0))
+    pos[3] = box / 4.0
+    pos[4] = box / 4.0 + box / 48.0
+    W = (rng.random(n) * 2.0 + 0.1).astype(np.float32)
+    return pos, W
+
+
+def gold_ma():
+    out = {}
+    box, dims, n = 1000.0, 24, 6000
+    pos, W = particles(1, n, box)
+    out["box"], out["dims"], out["pos"], out["W"] = box, dims, pos, W
+    for mas in ("NGP", "CIC", "TSC", "PCS"):
+        for wname, w in (("", None), ("W", W)):
+            g = np.zeros((dims,) * 3, np.float32)
+            MASL.MA(pos, g, box, mas, W=w)
+            out["grid_%s%s" % (mas, wname)] = g
+    # accumulate-in-place contract: second call adds on top of a non-zero grid
+    g = np.full((dims,) * 3, 0.5, np.float32)
+    MASL.MA(pos[:1000], g, box, "CIC")
+    MASL.MA(pos[1000:2000], g, box, "TSC", W=W[1000:2000])
+    out["grid_accum"] = g
+    # 2-D
+    dims2 = 32
+    pos2 = np.ascontiguousarray(pos[:, :2])
+    out["dims2"] = dims2
+    for mas in ("NGP", "CIC", "TSC", "PCS"):
+        for wname, w in (("", None), ("W", W)):
+            g = np.zeros((dims2,) * 2, np.float32)
+            MASL.MA(pos2, g, box, mas, W=w)
+            out["grid2d_%s%s" % (mas, wname)] = g
+    g = np.zeros((dims2,) * 2, np.float32)
+    MASL.MA(pos2, g, box, "TSC", renormalize_2D=False)
+    out["grid2d_TSC_norenorm"] = g
+    # fp64 grids (NGPW_d / CICW_d)
+    g = np.zeros((dims,) * 3, np.float64); MASL.NGPW_d(pos, g, box, W); out["grid_NGPW_d"] = g
+    g = np.zeros((dims,) * 3, np.float64); MASL.CICW_d(pos, g, box, W); out["grid_CICW_d"] = g
+    # OpenMP C entry points (MAS_c.c) -- same numbers up to summation order
+    g = np.zeros((dims,) * 3, np.float32); MASL.PCSWc3D(pos, g, W, box, 2); out["grid_PCSWc3D"] = g
+    np.savez_compressed(os.path.join(HERE, "ma.npz"), **out)
+
+
+def pk_attrs(p, names):
+    return {n: np.asarray(getattr(p, n)) for n in names}
+
+
+PK_NAMES = ["k3D", "Pk", "Nmodes3D", "Pkphase", "k1D", "Pk1D", "Nmodes1D", "kpar", "kper", "Pk2D", "Nmodes2D"]
+XPK_NAMES = ["k3D", "Pk", "XPk", "Nmodes3D", "k1D", "Pk1D", "PkX1D", "Nmodes1D", "kpar", "kper", "Pk2D", "PkX2D", "Nmodes2D"]
+
+
+def fields(dims, box, seeds_mas):
+    fs = []
+    for seed, mas, weighted in seeds_mas:
+        pos, W = particles(seed, 4 * dims ** 3, box)
+        g = np.zeros((dims,) * 3, np.float32)
+        MASL.MA(pos, g, box, mas, W=W if weighted else None)
+        g /= np.mean(g, dtype=np.float64)
+        g -= 1.0
+        fs.append(g)
+    return fs
+
+
+def gold_pk():
+    out = {}
+    box = 1000.0
+    for dims in (16, 20):
+        (d,) = fields(dims, box, [(7, "TSC", False)])
+        out["delta_%d" % dims] = d
+        for axis in (0, 1, 2):
+            for mas in ("TSC", "None"):
+                p = quiet(PKL.Pk, d, box, axis, mas, 1)
+                for n, v in pk_attrs(p, PK_NAMES).items():
+                    out["pk_%d_a%d_%s_%s" % (dims, axis, mas, n)] = v
+    p = quiet(PKL.Pk, out["delta_16"], box, 2, "TSC", 1, True)
+    out["pk_16_deltak"] = np.asarray(p.delta_k)
+    out["box"] = box
+    np.savez_compressed(os.path.join(HERE, "pk.npz"), **out)
+
+
+def gold_xpk():
+    out = {}
+    box, dims = 750.0, 16
+    fs = fields(dims, box, [(11, "CIC", False), (12, "PCS", True), (13, "NGP", False)])
+    out["box"], out["dims"] = box, dims
+    for i, f in enumerate(fs):
+        out["delta%d" % i] = f
+    x = quiet(PKL.XPk, fs[:2], box, 2, ["CIC", "PCS"], 1)
+    for n, v in pk_attrs(x, XPK_NAMES).items():
+        out["x2_a2_%s" % n] = v
+    x = quiet(PKL.XPk, fs, box, 0, ["CIC", "PCS", "None"], 1)
+    for n, v in pk_attrs(x, XPK_NAMES).items():
+        out["x3_a0_%s" % n] = v
+    np.savez_compressed(os.path.join(HERE, "xpk.npz"), **out)
+
+
+def gold_rsd():
+    if RSL is None:
+        return
+    rng = np.random.default_rng(5)
+    box = 100.0
+    pos = (rng.random((4000, 3)) * box).astype(np.float32)
+    vel = (rng.standard_normal((4000, 3)) * 2500).astype(np.float32)
+    out = {"pos": pos, "vel": vel, "box": box, "hubble": 100.0, "redshift": 0.5}
+    for axis in (0, 1, 2):
+        a = pos.copy()
+        RSL.pos_redshift_space(a, vel, box, 100.0, 0.5, axis)
+        out["rsd_a%d" % axis] = a
+    np.savez_compressed(os.path.join(HERE, "rsd.npz"), **out)
+
+
+if __name__ == "__main__":
+    gold_ma(); gold_pk(); gold_xpk(); gold_rsd()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,94 @@
+"""Parity metrics shared by the CPU (oracle) and GPU (CUDA vs oracle) tests.
+
+Tolerances follow BASELINE.json's north_star and SURVEY.md section 8c:
+  * density grids: |a-b| <= 1e-5*|b| + 1e-5*mean(|b|)   (atomic order is not fixed)
+  * spectra:       |a-b| <= 1e-5*|b| + 1e-5*scale, scale = median(|P0|) (or the matching auto
+                   spectrum for multipoles / cross terms, which can cancel to ~0)
+  * Nmodes*, kpar, kper: bit-exact;  k3D, k1D: 1e-12 relative.
+"""
+import numpy as np
+
+GRID_RTOL = 1e-5
+PK_RTOL = 1e-5
+K_RTOL = 1e-12
+
+
+def assert_grid_close(a, b, what="grid", rtol=GRID_RTOL):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    tol = rtol * np.abs(b) + rtol * np.mean(np.abs(b))
+    err = np.abs(a - b)
+    bad = err > tol
+    assert not bad.any(), "%s: %d cells off, worst err %.3e (tol %.3e)" % (
+        what, int(bad.sum()), float(err.max()), float(tol.flat[np.argmax(err)]))
+
+
+def assert_exact(a, b, what):
+    a = np.asarray(a); b = np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    assert np.array_equal(a, b), "%s not bit-exact: %d differ" % (what, int((a != b).sum()))
+
+
+def assert_k_close(a, b, what):
+    a = np.asarray(a); b = np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    np.testing.assert_allclose(a, b, rtol=K_RTOL, atol=0, err_msg=what)
+
+
+def assert_spec_close(a, b, scale, what, rtol=PK_RTOL):
+    """scale: array broadcastable to b giving the absolute floor (per-bin auto-power level)."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    tol = rtol * np.abs(b) + rtol * np.abs(scale)
+    err = np.abs(a - b)
+    bad = err > tol
+    assert not bad.any(), "%s: %d bins off, worst err/tol %.3f" % (what, int(bad.sum()), float((err / tol).max()))
+
+
+def _get(o, n):
+    return np.asarray(o[n] if isinstance(o, dict) else getattr(o, n))
+
+
+def check_pk(test, ref, phase=True):
+    """test/ref: objects or dicts with the reference's Pk attribute names."""
+    for n in ("Nmodes3D", "Nmodes1D", "Nmodes2D", "kpar", "kper"):
+        assert_exact(_get(test, n), _get(ref, n), n)
+    assert_k_close(_get(test, "k3D"), _get(ref, "k3D"), "k3D")
+    assert_k_close(_get(test, "k1D"), _get(ref, "k1D"), "k1D")
+    P = _get(ref, "Pk")
+    p0 = np.abs(P[:, 0])
+    floor3 = p0 + np.median(p0)               # multipoles may cancel; floor at the monopole level
+    assert_spec_close(_get(test, "Pk"), P, floor3[:, None] * np.array([1.0, 5.0, 9.0])[None, :], "Pk3D")
+    if phase:
+        ph = _get(ref, "Pkphase")
+        assert_spec_close(_get(test, "Pkphase"), ph, np.median(np.abs(ph)), "Pkphase", rtol=2e-5)
+    p1 = _get(ref, "Pk1D")
+    assert_spec_close(_get(test, "Pk1D"), p1, np.median(np.abs(p1)), "Pk1D")
+    p2 = _get(ref, "Pk2D")
+    # bins holding a single (or few) modes carry the FFT's own 1e-7..1e-6 noise; floor at the median
+    assert_spec_close(_get(test, "Pk2D"), p2, np.median(np.abs(p2)), "Pk2D")
+
+
+def check_xpk(test, ref):
+    for n in ("Nmodes3D", "Nmodes1D", "Nmodes2D", "kpar", "kper"):
+        assert_exact(_get(test, n), _get(ref, n), n)
+    assert_k_close(_get(test, "k3D"), _get(ref, "k3D"), "k3D")
+    assert_k_close(_get(test, "k1D"), _get(ref, "k1D"), "k1D")
+    P = _get(ref, "Pk")                        # (k, 3, F)
+    F = P.shape[2]
+    p0 = np.abs(P[:, 0, :])
+    floor = p0 + np.median(p0, axis=0)[None, :]
+    ell = np.array([1.0, 5.0, 9.0])[None, :, None]
+    assert_spec_close(_get(test, "Pk"), P, floor[:, None, :] * ell, "XPk.Pk")
+    XP = _get(ref, "XPk")
+    pairs = [(i, j) for i in range(F) for j in range(i + 1, F)]
+    if pairs:
+        xfloor = np.stack([np.sqrt(floor[:, i] * floor[:, j]) for i, j in pairs], axis=1)
+        assert_spec_close(_get(test, "XPk"), XP, xfloor[:, None, :] * ell, "XPk.XPk")
+    for n, xn in (("Pk1D", "PkX1D"), ("Pk2D", "PkX2D")):
+        p = _get(ref, n)
+        med = np.median(np.abs(p), axis=0)
+        assert_spec_close(_get(test, n), p, med[None, :], n)
+        if pairs:
+            xmed = np.array([np.sqrt(med[i] * med[j]) for i, j in pairs])
+            assert_spec_close(_get(test, xn), _get(ref, xn), xmed[None, :], xn)
