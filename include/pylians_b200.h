@@ -1,0 +1,176 @@
+/*
+ * pylians_b200.h -- C ABI of the B200-native density-field -> power-spectrum path.
+ *
+ * Boundary contract
+ * -----------------
+ *  * plain C linkage, plain pointers and sizes, no torch / C++ types;
+ *  * every `pylb_*` function returns 0 on success, non-zero on failure; the message is available
+ *    from pylb_last_error() (thread-local);
+ *  * unless a function name ends in `_host`, every data pointer is a DEVICE pointer and every call
+ *    is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *  * the library never falls back to the CPU: without a CUDA device every compute entry fails.
+ *
+ * What each entry point replaces in the reference (paths relative to the Pylians tree):
+ *  * NGP/CIC/TSC/PCS (host pointers)   = library/MAS_library/MAS_c.h:3-10, the reference's own C ABI,
+ *                                        bound by MAS_c.pxd:1-10 and called from MAS_library.pyx:1136-1220;
+ *  * pylb_ma                           = the Cython kernels behind MASL.MA, MAS_library.pyx:57-112
+ *                                        (NGP :273, CIC :123, TSC :369, PCS :463 and their W variants,
+ *                                        NGPW_d :338 / CICW_d :229 for the float64 grid);
+ *  * pylb_fft_r2c                      = FFT3Dr_f, library/Pk_library/Pk_library.pyx:120-133 (pyfftw/FFTW);
+ *  * pylb_pk_bin                       = the mode loops of class Pk :314-381 and class XPk :628-737;
+ *  * pylb_pk_get_layout                = frequencies() :59-64 (bin counts);
+ *  * pylb_overdensity                  = `delta /= mean; delta -= 1` done by every caller,
+ *                                        e.g. library/Pk_library/Pk_snapshot.py:88,194;
+ *  * pylb_pos_redshift_space           = library/redshift_space_library.pyx:29-43;
+ *  * pylb_slab_pack / pylb_fft_*slab*  = new (the reference is single-process): the slab-decomposed FFT.
+ */
+#ifndef PYLIANS_B200_H
+#define PYLIANS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYLB_VERSION 100
+
+/* mass-assignment scheme ids (deposit).  The Pk-side deconvolution exponent is MAS_function()'s
+ * index (Pk_library.pyx:75-81): 0 none, 1 NGP, 2 CIC, 3 TSC, 4 PCS, i.e. id+1. */
+enum { PYLB_NGP = 0, PYLB_CIC = 1, PYLB_TSC = 2, PYLB_PCS = 3 };
+
+/* deposit algorithm selector for pylb_ma */
+enum { PYLB_MA_AUTO = 0, PYLB_MA_DIRECT = 1, PYLB_MA_TILED = 2 };
+
+/* binning algorithm selector for pylb_pk_bin */
+enum { PYLB_BIN_AUTO = 0, PYLB_BIN_GENERIC = 1, PYLB_BIN_RING = 2 };
+
+int pylb_version(void);
+const char *pylb_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (bench accounting) */
+int64_t pylb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mass assignment
+ * ------------------------------------------------------------------------------------------- */
+
+/* Reference-compatible host entry points: identical signatures to MAS_c.h:3-10.
+ * pos: (particles, axes) row-major host floats; number: dims^axes row-major host floats, accumulated
+ * in place; W may be NULL; `threads` is accepted and ignored.  No return value and no error channel,
+ * exactly like the reference; on failure the message is left in pylb_last_error() and `number`
+ * is untouched.  2-D calls reproduce MAS_c.c's single update per cell (n_max = 1). */
+void NGP(float *pos, float *number, float *W, long particles, int dims, int axes, float BoxSize, int threads);
+void CIC(float *pos, float *number, float *W, long particles, int dims, int axes, float BoxSize, int threads);
+void TSC(float *pos, float *number, float *W, long particles, int dims, int axes, float BoxSize, int threads);
+void PCS(float *pos, float *number, float *W, long particles, int dims, int axes, float BoxSize, int threads);
+
+/* Device entry point behind MASL.MA.
+ *   pos          device float32, element (i, a) at pos[i*pos_stride0 + a*pos_stride1]
+ *   ndim         2 or 3 (= pos.shape[1] = number.ndim)
+ *   grid         device, dims^ndim, C-contiguous, float32 (grid_f64 = 0) or float64 (grid_f64 = 1);
+ *                ACCUMULATED INTO (+=), never cleared
+ *   mas          PYLB_NGP..PYLB_PCS
+ *   w            device float32 weights or NULL
+ *   z_repeat     2-D only: multiply each update by this factor (the Cython 2-D path adds every
+ *                contribution 2/3/4 times before MA() divides the array, MAS_library.pyx:84-110);
+ *                pass 1 for the MAS_c.c behaviour
+ *   algo         PYLB_MA_AUTO | PYLB_MA_DIRECT | PYLB_MA_TILED
+ *   workspace    device scratch of at least pylb_ma_workspace_bytes(...) bytes (may be NULL when
+ *                that function returns 0) */
+size_t pylb_ma_workspace_bytes(int64_t np, int ndim, int dims, int mas, int has_w, int grid_f64, int algo);
+int pylb_ma(const float *pos, int64_t np, int ndim, int64_t pos_stride0, int64_t pos_stride1,
+            void *grid, int grid_f64, int dims, float box, int mas, const float *w, int z_repeat,
+            int algo, void *workspace, size_t workspace_bytes, void *stream);
+
+/* grid[i] /= divisor  (the `number2 /= 2|3|4` of MAS_library.pyx:90-107; applies to the WHOLE array) */
+int pylb_divide(float *grid, int64_t n, float divisor, void *stream);
+
+/* Host (dims,dims,dims) float32 -> device padded in-place-FFT layout (dims,dims,2*(dims/2+1)), one
+ * strided copy (cudaMemcpy2DAsync).  Lets Pk() transform a host field with a single device buffer. */
+int pylb_h2d_padded(const float *host, float *dev, int dims, void *stream);
+
+/* delta = grid/mean(grid) - 1 in place.  mean is accumulated in float64 (np.mean(dtype=float64) in
+ * the callers); `scratch` is a device double[2]; if mean_out != NULL the mean is stored there (device). */
+int pylb_overdensity(float *grid, int64_t n, double *scratch, void *stream);
+
+/* pos[:,axis] += vel[:,axis]*(1+z)/H with the reference's wrap rule; pos/vel (np,3) C-contiguous */
+int pylb_pos_redshift_space(float *pos, const float *vel, int64_t np, float box, float hubble,
+                            float redshift, int axis, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * FFT (cuFFT, plans cached inside the library per shape)
+ * ------------------------------------------------------------------------------------------- */
+
+/* 3-D real-to-complex, unnormalised, float32 (dims,dims,dims) -> complex64 (dims,dims,dims/2+1).
+ * in == out is allowed when `in` uses the padded in-place layout (row length 2*(dims/2+1) floats).
+ * work: device scratch of pylb_fft_r2c_work_bytes(dims) bytes. */
+size_t pylb_fft_r2c_work_bytes(int dims, int inplace);
+int pylb_fft_r2c(const float *in, void *out, int dims, int inplace, void *work, size_t work_bytes, void *stream);
+
+/* Slab-decomposed pieces (multi-GPU).  Real slab [nx_local][dims][dims] -> batched 2-D R2C over
+ * (y,z) -> complex [nx_local][dims][dims/2+1]; then, after the all-to-all, 1-D C2C along x on the
+ * transposed layout [dims][ny_local][dims/2+1] (in place). */
+size_t pylb_fft_slab_yz_work_bytes(int dims, int nx_local);
+int pylb_fft_slab_yz(const float *in, void *out, int dims, int nx_local, void *work, size_t work_bytes, void *stream);
+size_t pylb_fft_slab_x_work_bytes(int dims, int ny_local);
+int pylb_fft_slab_x(void *data, int dims, int ny_local, void *work, size_t work_bytes, void *stream);
+
+/* Slab transpose pack: src complex [nx_local][dims][nz] -> dst [G][nx_local][dims/G][nz], i.e. the
+ * send buffer of the all-to-all, block g going to rank g.  nz = dims/2+1. */
+int pylb_slab_pack(const void *src, void *dst, int dims, int nx_local, int G, void *stream);
+/* Same transpose, but written straight into each peer's receive buffer over NVLink (peer-mapped
+ * pointers): block g goes to peer_recv[g] + my_rank*nx_local*(dims/G)*nz complex elements. */
+int pylb_slab_pack_push(const void *src, void *const *peer_recv, int dims, int nx_local, int G,
+                        int my_rank, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Power-spectrum binning
+ * ------------------------------------------------------------------------------------------- */
+
+/* Bin geometry for a dims^3 grid and F fields (X = F(F-1)/2 cross pairs in the reference's order
+ * (0,1),(0,2),..,(1,2),..).  All accumulators live in two device buffers the caller allocates and
+ * the library zeroes: `sums` (double[n_doubles]) and `counts` (uint64[n_counts]).
+ * Raw sums only -- units, (2l+1), /Nmodes and the DC-bin handling of Pk_library.pyx:387-421 are
+ * host bookkeeping on a few KB done by the caller.
+ *   k3d   [kmax+1]            sum of |k| (in units of kF)
+ *   p3d   [kmax+1][3][F]      sum of |delta_k|^2 * {1, L2(mu), L4(mu)}
+ *   x3d   [kmax+1][3][X]
+ *   phase [kmax+1]            sum of atan2(re, |delta_k|)^2, field 0 (Pk only)
+ *   p1d   [kmax_par+1][F]     x1d [kmax_par+1][X]       (modes with |k| <= dims/2)
+ *   p2d   [B2][F]             x2d [B2][X]               index (kmax_par+1)*k_per + |k_par|
+ *   n3d [kmax+1], n1d [kmax_par+1], n2d [B2]   integer mode counts (bit-exact contract) */
+typedef struct {
+    int dims, F, X, middle, kmax_par, kmax_per, kmax;
+    int64_t B2;
+    int64_t o_k3d, o_p3d, o_x3d, o_phase, o_p1d, o_x1d, o_p2d, o_x2d, n_doubles;
+    int64_t o_n3d, o_n1d, o_n2d, n_counts;
+} pylb_pk_layout;
+int pylb_pk_get_layout(int dims, int F, pylb_pk_layout *out);
+
+/* Which part of k-space a device buffer holds.  Element (kxx, kyy, kzz) of field f lives at
+ * dk[f][(kxx-x0)*stride_x + (kyy-y0)*stride_y + kzz] (complex64 elements), kzz in [0, dims/2].
+ * Single GPU: x0=y0=0, nx=ny=dims, stride_y=dims/2+1, stride_x=dims*stride_y.
+ * Slab FFT output on rank r of G: x0=0, nx=dims, y0=r*dims/G, ny=dims/G,
+ * stride_y=dims/2+1, stride_x=ny*stride_y. */
+typedef struct {
+    int dims, x0, nx, y0, ny;
+    int64_t stride_x, stride_y;
+} pylb_kspace;
+
+/* Deconvolve (MAS window), square, bin.  dk: HOST array of F device pointers.
+ *   mas_index[f]  deconvolution exponent of field f (0..4)
+ *   axis          line of sight (0,1,2)
+ *   want_phase    accumulate `phase` (class Pk does; XPk does not)
+ *   write_back    store the deconvolved modes back into dk (keep_deltak; the reference always
+ *                 overwrites its private copy, Pk_library.pyx:355)
+ *   algo          PYLB_BIN_AUTO | PYLB_BIN_GENERIC | PYLB_BIN_RING
+ * sums/counts are zeroed by this call unless accumulate != 0. */
+int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int axis, const int *mas_index,
+                int want_phase, int write_back, int algo, int accumulate, double *sums,
+                uint64_t *counts, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYLIANS_B200_H */

@@ -1,0 +1,278 @@
+"""Drop-in mirror of the reference's `Pk_library` for the FFT power-spectrum hot path.
+
+    import Pk_library as PKL               # repo-root shim re-exports this module
+    Pk  = PKL.Pk(delta, BoxSize, axis=2, MAS='CIC', threads=1)
+    XPk = PKL.XPk([d1, d2], BoxSize, axis=2, MAS=['CIC', 'PCS'], threads=1)
+
+Same constructor signatures, attribute names, dtypes, shapes and error behaviour as
+library/Pk_library/Pk_library.pyx (class Pk :266-425, class XPk :534-798, frequencies :59-64,
+MAS_function :75-81, check_number_modes :90-102, FFT3Dr_f :120-133).  The transform is cuFFT and the
+mode loop is one fused CUDA kernel (pylians_b200/csrc/binning.cu); only the final bookkeeping on a few
+KB of bins (units, (2l+1), /Nmodes, DC-bin handling, :387-421) runs here in numpy float64.
+`threads` is accepted and ignored.  There is no CPU fallback.
+"""
+import ctypes
+import sys
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from .MAS_library import _device, _is_torch, _dtype_name
+
+VERBOSE = True          # the reference prints progress lines unconditionally; set False to silence
+# binning algorithm override for tests / benchmarks: 0 auto, 1 generic (atomics), 2 ring (registers)
+ALGO = _lib.BIN_AUTO
+
+
+def _say(msg):
+    if VERBOSE:
+        print(msg)
+
+
+def frequencies(BoxSize, dims):
+    """Pk_library.pyx:59-64 (python-2 integer division for `middle`)."""
+    kF = 2.0 * np.pi / BoxSize
+    middle = dims // 2
+    kN = middle * kF
+    kmax_par = middle
+    kmax_per = int(np.sqrt(middle ** 2 + middle ** 2))
+    kmax = int(np.sqrt(middle ** 2 + middle ** 2 + middle ** 2))
+    return kF, kN, kmax_par, kmax_per, kmax
+
+
+def MAS_function(MAS):
+    """Pk_library.pyx:75-81: any unknown string (e.g. 'None') means no correction."""
+    MAS_index = 0
+    if MAS == "NGP": MAS_index = 1
+    if MAS == "CIC": MAS_index = 2
+    if MAS == "TSC": MAS_index = 3
+    if MAS == "PCS": MAS_index = 4
+    return MAS_index
+
+
+def MAS_correction(x, MAS_index):
+    """Pk_library.pyx:86-87."""
+    return 1.0 if x == 0.0 else (x / np.sin(x)) ** MAS_index
+
+
+def check_number_modes(Nmodes, dims):
+    """Pk_library.pyx:90-102: abort (SystemExit) unless every independent mode was counted once."""
+    own_modes = 1 if dims % 2 == 1 else 8
+    repeated_modes = (dims ** 3 - own_modes) // 2
+    indep_modes = repeated_modes + own_modes
+    if int(np.sum(Nmodes)) != indep_modes:
+        print("WARNING: Not all modes counted")
+        print("Counted  %d independent modes" % (int(np.sum(Nmodes))))
+        print("Expected %d independent modes" % indep_modes)
+        sys.exit()
+
+
+def _check_field(delta):
+    if _is_torch(delta):
+        ok = delta.dtype == torch.float32
+    else:
+        delta = np.asarray(delta) if not isinstance(delta, np.ndarray) else delta
+        ok = delta.dtype == np.float32
+    if not ok:
+        raise ValueError("Buffer dtype mismatch, expected 'float32_t' but got '%s'" % _dtype_name(delta))
+    if delta.ndim != 3:
+        raise ValueError("Buffer has wrong number of dimensions (expected 3, got %d)" % delta.ndim)
+    if not (delta.shape[0] == delta.shape[1] == delta.shape[2]):
+        raise ValueError("delta must be a (dims,dims,dims) cube")
+    return delta
+
+
+def _work(nbytes, dev):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=dev)
+
+
+def _fft_field(lib, delta, dims, dev, stream):
+    """FFT3Dr_f on the device.  Returns a complex64 tensor (dims,dims,dims/2+1); `delta` is never modified.
+
+    Host input: one strided H2D copy into the padded in-place layout, then an in-place R2C, so the
+    device holds a single copy of the field.  Device input: out-of-place R2C into a fresh buffer."""
+    nz = dims // 2 + 1
+    if _is_torch(delta) and delta.is_cuda:
+        src = delta if delta.is_contiguous() else delta.contiguous()
+        out = torch.empty((dims, dims, nz), dtype=torch.complex64, device=dev)
+        wb = lib.pylb_fft_r2c_work_bytes(dims, 0)
+        if wb == ctypes.c_size_t(-1).value:
+            raise _lib.PylbError("cuFFT plan failed: " + lib.pylb_last_error().decode())
+        work = _work(wb, dev)
+        _lib.check(lib.pylb_fft_r2c(src.data_ptr(), out.data_ptr(), dims, 0, work.data_ptr(), int(wb),
+                                    stream.cuda_stream), "pylb_fft_r2c")
+        return out
+    host = delta.contiguous() if _is_torch(delta) else np.ascontiguousarray(delta)
+    buf = torch.empty((dims, dims, 2 * nz), dtype=torch.float32, device=dev)
+    hptr = host.data_ptr() if _is_torch(host) else host.ctypes.data
+    _lib.check(lib.pylb_h2d_padded(hptr, buf.data_ptr(), dims, stream.cuda_stream), "pylb_h2d_padded")
+    wb = lib.pylb_fft_r2c_work_bytes(dims, 1)
+    if wb == ctypes.c_size_t(-1).value:
+        raise _lib.PylbError("cuFFT plan failed: " + lib.pylb_last_error().decode())
+    work = _work(wb, dev)
+    _lib.check(lib.pylb_fft_r2c(buf.data_ptr(), buf.data_ptr(), dims, 1, work.data_ptr(), int(wb),
+                                stream.cuda_stream), "pylb_fft_r2c")
+    out = torch.view_as_complex(buf.view(dims, dims, nz, 2))
+    out._pylb_keepalive = host
+    return out
+
+
+def get_layout(dims, F):
+    L = _lib.PkLayout()
+    _lib.check(_lib.load().pylb_pk_get_layout(int(dims), int(F), ctypes.byref(L)), "pylb_pk_get_layout")
+    return L
+
+
+def bin_modes(delta_k, dims, axis, mas_index, want_phase, write_back, ks=None, sums=None, counts=None,
+              accumulate=False, algo=None):
+    """Run the fused binning kernel on a list of device complex64 k-space fields.
+
+    Returns (layout, sums, counts): device float64 / int64 tensors of raw bin sums (see
+    include/pylians_b200.h, pylb_pk_layout).  `ks` describes which part of k-space the tensors hold
+    (default: the whole (dims,dims,dims/2+1) cube)."""
+    lib = _lib.load()
+    dev = delta_k[0].device
+    F = len(delta_k)
+    L = get_layout(dims, F)
+    if ks is None:
+        nz = dims // 2 + 1
+        ks = _lib.KSpace(dims, 0, dims, 0, dims, dims * nz, nz)
+    if sums is None:
+        sums = torch.empty(L.n_doubles, dtype=torch.float64, device=dev)
+        counts = torch.empty(L.n_counts, dtype=torch.int64, device=dev)
+    ptrs = (ctypes.c_void_p * F)(*[t.data_ptr() for t in delta_k])
+    mi = (ctypes.c_int * F)(*[int(m) for m in mas_index])
+    stream = torch.cuda.current_stream(dev)
+    _lib.check(lib.pylb_pk_bin(ptrs, F, ctypes.byref(ks), int(axis), mi, int(want_phase), int(write_back),
+                               ALGO if algo is None else algo, int(accumulate), sums.data_ptr(),
+                               counts.data_ptr(), stream.cuda_stream), "pylb_pk_bin")
+    return L, sums, counts
+
+
+class _Bins(object):
+    """Host view (numpy float64) of the raw sums laid out by pylb_pk_layout."""
+
+    def __init__(self, L, sums, counts):
+        s = sums.cpu().numpy()
+        c = counts.cpu().numpy().astype(np.float64)     # counts < 2^53: exact in float64
+        F, X, n3, n1, B2 = L.F, L.X, L.kmax + 1, L.kmax_par + 1, L.B2
+        self.F, self.X = F, X
+        self.k3d = s[L.o_k3d:L.o_k3d + n3]
+        self.p3d = s[L.o_p3d:L.o_p3d + n3 * 3 * F].reshape(n3, 3, F)
+        self.x3d = s[L.o_x3d:L.o_x3d + n3 * 3 * X].reshape(n3, 3, X)
+        self.phase = s[L.o_phase:L.o_phase + n3]
+        self.p1d = s[L.o_p1d:L.o_p1d + n1 * F].reshape(n1, F)
+        self.x1d = s[L.o_x1d:L.o_x1d + n1 * X].reshape(n1, X)
+        self.p2d = s[L.o_p2d:L.o_p2d + B2 * F].reshape(B2, F)
+        self.x2d = s[L.o_x2d:L.o_x2d + B2 * X].reshape(B2, X)
+        self.n3d = c[L.o_n3d:L.o_n3d + n3]
+        self.n1d = c[L.o_n1d:L.o_n1d + n1]
+        self.n2d = c[L.o_n2d:L.o_n2d + B2]
+
+
+def _finish(obj, b, dims, BoxSize, is_x):
+    """Units and normalisation.  Pk: Pk_library.pyx:387-421;  XPk: :740-796."""
+    kF, kN, kmax_par, kmax_per, kmax = frequencies(BoxSize, dims)
+    fact = (BoxSize / dims ** 2) ** 3
+
+    # 1-D: drop the DC bin; k1D accumulates k_par once per mode, i.e. k_par*Nmodes (:365)
+    N1 = b.n1d[1:].copy()
+    k1D = np.arange(1, kmax_par + 1, dtype=np.float64) * kF
+    kmaxper = np.sqrt(kN ** 2 - k1D ** 2)
+    s1 = (np.pi * kmaxper ** 2 / N1) / (2.0 * np.pi) ** 2
+    obj.k1D, obj.Nmodes1D = k1D, N1
+    P1 = b.p1d[1:] * fact * s1[:, None]
+    X1 = b.x1d[1:] * fact * s1[:, None]
+
+    # 2-D: the DC bin is kept; an empty bin is a ZeroDivisionError in the reference (cdivision False)
+    if np.any(b.n2d == 0):
+        raise ZeroDivisionError("float division")
+    i2 = np.arange((kmax_par + 1) * (kmax_per + 1))
+    obj.kpar = 0.5 * (2 * (i2 % (kmax_par + 1)) + 1) * kF
+    obj.kper = 0.5 * (2 * (i2 // (kmax_par + 1)) + 1) * kF
+    obj.Nmodes2D = b.n2d.copy()
+    P2 = b.p2d * fact / b.n2d[:, None]
+    X2 = b.x2d * fact / b.n2d[:, None]
+
+    # 3-D
+    check_number_modes(b.n3d, dims)
+    N3 = b.n3d[1:].copy()
+    obj.k3D, obj.Nmodes3D = (b.k3d[1:] / N3) * kF, N3
+    ell = np.array([1.0, 5.0, 9.0])[None, :, None]
+    P3 = (b.p3d[1:] * ell / N3[:, None, None]) * fact
+    X3 = (b.x3d[1:] * ell / N3[:, None, None]) * fact
+
+    if is_x:
+        obj.Pk1D, obj.PkX1D, obj.Pk2D, obj.PkX2D, obj.Pk, obj.XPk = P1, X1, P2, X2, P3, X3
+    else:
+        obj.Pk1D, obj.Pk2D, obj.Pk = P1[:, 0].copy(), P2[:, 0].copy(), np.ascontiguousarray(P3[:, :, 0])
+        obj.Pkphase = (b.phase[1:] / N3) * fact
+
+
+class Pk(object):
+    """1-D, 2-D and 3-D power spectrum (monopole, quadrupole, hexadecapole) of a density field.
+
+    Attributes (all numpy float64, as in the reference): k3D, Pk[:,0..2], Nmodes3D, Pkphase,
+    k1D, Pk1D, Nmodes1D, kpar, kper, Pk2D, Nmodes2D, and delta_k (complex64) when keep_deltak."""
+
+    def __init__(self, delta, BoxSize, axis=2, MAS="CIC", threads=1, keep_deltak=False):
+        start = time.time()
+        _say("\nComputing power spectrum of the field...")
+        delta = _check_field(delta)
+        lib = _lib.load()
+        dev = _device()
+        dims = len(delta)
+        stream = torch.cuda.current_stream(dev)
+        delta_k = _fft_field(lib, delta, dims, dev, stream)
+        start2 = time.time()
+        L, sums, counts = bin_modes([delta_k], dims, int(axis), [MAS_function(MAS)], True, bool(keep_deltak))
+        bins = _Bins(L, sums, counts)       # D2H of a few KB; synchronises the stream
+        _say("Time to complete loop = %.2f" % (time.time() - start2))
+        _finish(self, bins, dims, BoxSize, False)
+        if keep_deltak:
+            self.delta_k = delta_k if (_is_torch(delta) and delta.is_cuda) else delta_k.cpu().numpy()
+        _say("Time taken = %.2f seconds" % (time.time() - start))
+
+
+class XPk(object):
+    """Auto- and cross-power spectra of several density fields.  Pk_library.pyx:534-798.
+
+    Attributes: k3D, Nmodes3D, Pk[k, ell, field], XPk[k, ell, pair]; k1D, Nmodes1D, Pk1D, PkX1D;
+    kpar, kper, Nmodes2D, Pk2D, PkX2D.  Pairs are ordered (0,1),(0,2),...,(1,2),..."""
+
+    def __init__(self, delta, BoxSize, axis=2, MAS=None, threads=1):
+        start = time.time()
+        _say("\nComputing power spectra of the fields...")
+        dims = len(delta[0])
+        fields = len(delta)
+        for i in range(1, fields):                      # :563-565
+            if len(delta[i]) != dims:
+                print("Fields have different grid sizes!!!")
+                sys.exit()
+        mas_index = [MAS_function(m) for m in list(MAS)]   # MAS=None -> TypeError, as in the reference (:573)
+        if len(mas_index) < fields:
+            raise IndexError("list index out of range")  # MAS[i] for i >= len(MAS), :577
+        delta = [_check_field(d) for d in delta]
+        lib = _lib.load()
+        dev = _device()
+        stream = torch.cuda.current_stream(dev)
+        delta_k = [_fft_field(lib, d, dims, dev, stream) for d in delta]
+        _say("Time FFTS = %.2f" % (time.time() - start))
+        start2 = time.time()
+        L, sums, counts = bin_modes(delta_k, dims, int(axis), mas_index[:fields], False, False)
+        bins = _Bins(L, sums, counts)
+        _say("Time loop = %.2f" % (time.time() - start2))
+        _finish(self, bins, dims, BoxSize, True)
+        _say("Time taken = %.2f seconds" % (time.time() - start))
+
+
+def FFT3Dr_f(a, threads=1):
+    """Pk_library.pyx:120-133: unnormalised forward R2C, float32 -> complex64 (dims,dims,dims/2+1).
+    numpy in -> numpy out; CUDA tensor in -> CUDA tensor out."""
+    a = _check_field(a)
+    lib = _lib.load()
+    dev = _device()
+    out = _fft_field(lib, a, len(a), dev, torch.cuda.current_stream(dev))
+    return out if (_is_torch(a) and a.is_cuda) else out.cpu().numpy()

@@ -1,0 +1,14 @@
+"""pylians_b200 -- B200-native (sm_100a) implementation of Pylians' density-field -> power-spectrum
+hot path: MAS_library.MA (NGP/CIC/TSC/PCS, weights) and Pk_library.Pk / XPk, behind the reference's
+own call signatures.  CUDA kernels + C ABI live in csrc/ (built by `python -m pylians_b200.build`);
+the modules here are the thin host-side mirror of the reference's Python interface.
+"""
+from . import _lib  # noqa: F401
+
+__all__ = ["MAS_library", "Pk_library", "redshift_space_library", "dist", "set_verbose"]
+
+
+def set_verbose(flag):
+    """The reference prints progress lines from Pk/XPk unconditionally; silence them with False."""
+    from . import Pk_library
+    Pk_library.VERBOSE = bool(flag)

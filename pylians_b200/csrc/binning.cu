@@ -1,0 +1,567 @@
+// Fused MAS-deconvolution + |delta_k|^2 + k-shell / (k_par,k_per) / 1-D binning + Legendre weighting.
+//
+// Replaces the serial mode loops of class Pk (library/Pk_library/Pk_library.pyx:314-381) and
+// class XPk (:628-737).  HBM-bound: every complex mode (8 B per field) is read exactly once.
+//
+// Two kernels:
+//
+//  ring_kernel (line of sight = z, the contiguous half-spectrum axis)
+//     Rows (kx,ky) are sorted by r2 = kx^2+ky^2.  A thread owns one kz and walks a contiguous span of
+//     the sorted row list, so that
+//       * all rows with the same r2 share |k|, mu, the Legendre weights and every bin index
+//         -> geometry is evaluated once per r2-group, the per-mode work is load + deconvolve + square;
+//       * inside a ring p <= sqrt(r2) < p+1 a thread can only hit 3-D bins b0 or b0+1 with
+//         b0 = floor(sqrt(p^2+kz^2)), one 2-D bin (p, kz) and one 1-D bin kz
+//         -> all accumulation is in REGISTERS; no shared or global atomic in the inner loop
+//            (shared fp32/fp64 atomics are CAS loops on sm_100a; only red.global is native).
+//     Registers are flushed with red.global.add.f64 when the ring changes (a few times per span).
+//     The self-conjugate columns kz=0 and kz=dims/2 (skip rule :326-330) are left to generic_kernel.
+//
+//  generic_kernel (any axis, any F <= 8, any subset of kz columns)
+//     One thread per mode, red.global for everything.  Used for the two special columns above and
+//     as the any-axis path.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace pylb {
+
+constexpr int MAX_F = 8;
+
+struct FieldPtrs {
+    float2 *p[MAX_F];
+};
+
+struct BinGeom {
+    int dims, middle, even;
+    int x0, nx, y0, ny;
+    long long stride_x, stride_y;
+    int axis;
+    int kmax_par1;  // kmax_par + 1
+    int F, X;
+    long long o_k3d, o_p3d, o_x3d, o_phase, o_p1d, o_x1d, o_p2d, o_x2d;
+    long long o_n3d, o_n1d, o_n2d;
+    double *sums;
+    uint64_t *counts;
+    const double *mas_tab;  // [F][middle+1]: (x/sin x)^p at |k| = 0..middle
+    int mas_idx[MAX_F];
+};
+
+// ------------------------------------------------------------------------------------------------
+// MAS window table, Pk_library.pyx:86-87 and :316,:320,:324:  (x/sin x)^p, x = pi*k/dims, 1 at k=0.
+// x/sin(x) is even, so |k| indexes it.
+// ------------------------------------------------------------------------------------------------
+__global__ void mas_table_kernel(double *tab, int middle, int dims, int F, BinGeom g) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * (middle + 1)) return;
+    const int f = i / (middle + 1), k = i % (middle + 1);
+    const int p = g.mas_idx[f];
+    double v = 1.0;
+    if (k != 0 && p != 0) {
+        const double x = (M_PI / (double)dims) * (double)k;
+        const double q = x / sin(x);
+        v = q;
+        if (p == 2) v = q * q;
+        else if (p == 3) v = q * q * q;
+        else if (p == 4) { const double q2 = q * q; v = q2 * q2; }
+    }
+    tab[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row table for the ring kernel
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) RowEnt {
+    int r2;
+    short kx, ky;
+    long long off;  // element offset of the row start: ix*stride_x + iy*stride_y
+};
+
+__global__ void row_keys_kernel(unsigned *keys, unsigned *vals, int nrows, BinGeom g) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const int ix = r / g.ny, iy = r - ix * g.ny;
+    const int kx = wavenumber(g.x0 + ix, g.dims, g.middle), ky = wavenumber(g.y0 + iy, g.dims, g.middle);
+    keys[r] = (unsigned)(kx * kx + ky * ky);
+    vals[r] = (unsigned)r;
+}
+
+__global__ void row_table_kernel(const unsigned *keys, const unsigned *vals, RowEnt *tab, int nrows, BinGeom g) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const int r = (int)vals[i];
+    const int ix = r / g.ny, iy = r - ix * g.ny;
+    RowEnt e;
+    e.r2 = (int)keys[i];
+    e.kx = (short)wavenumber(g.x0 + ix, g.dims, g.middle);
+    e.ky = (short)wavenumber(g.y0 + iy, g.dims, g.middle);
+    e.off = (long long)ix * g.stride_x + (long long)iy * g.stride_y;
+    tab[i] = e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase = atan2(re, |delta_k|)  (Pk_library.pyx:361 -- sic, the real part against the modulus), so
+// |re/|delta_k|| <= 1 and the angle is in [-pi/4, pi/4].  fp32 evaluation: t = re*rsqrt(d2), then
+// atan(t) with one range reduction (|t| > tan(pi/8) -> pi/4 + atan((|t|-1)/(|t|+1))) and an odd
+// minimax polynomial on [-tan(pi/8), tan(pi/8)] (abs error < 2e-8).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float phase_sq(float re, float d2) {
+    if (!(d2 > 0.0f)) return 0.0f;  // atan2(0, 0) = 0
+    float t = fabsf(re) * rsqrtf(d2);
+    t = fminf(t, 1.0f);
+    const bool hi = t > 0.41421356f;
+    const float u = hi ? __fdividef(t - 1.0f, t + 1.0f) : t;
+    const float s = u * u;
+    // atan(u) = u*(1 + s*(c1 + s*(c2 + s*(c3 + s*c4)))),  |u| <= 0.4143
+    float q = 0.0805374449538e-0f;
+    q = fmaf(q, s, -0.138776856032e-0f);
+    q = fmaf(q, s, 0.199777106478e-0f);
+    q = fmaf(q, s, -0.333329491539e-0f);
+    float a = fmaf(q * s, u, u);
+    if (hi) a += 0.78539816339f;
+    return a * a;
+}
+
+__device__ __forceinline__ float2 ld_stream(const float2 *p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ring kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int RING_T = 256;      // threads per CTA = kz values per CTA
+constexpr int RING_CHUNK = 128;  // rows staged in shared memory at a time
+constexpr int RING_U = 8;        // rows whose loads are in flight per thread
+
+template <int F>
+struct RingSmem {
+    RowEnt ent[RING_CHUNK];
+    double cxy[RING_CHUNK][F];
+};
+
+template <int F, bool PHASE, bool WB>
+__global__ void __launch_bounds__(RING_T)
+ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, int rows_per_span, int kz_hi) {
+    constexpr int X = F * (F - 1) / 2;
+    constexpr int Q = F + X;
+    __shared__ RingSmem<F> sm;
+
+    const int kz = 1 + blockIdx.y * RING_T + threadIdx.x;
+    const bool active = kz <= kz_hi;
+    const int kzc = active ? kz : kz_hi;  // clamp so idle lanes stay in bounds
+    const int kz2 = kzc * kzc;
+    const int i0 = blockIdx.x * rows_per_span;
+    const int i1 = min(nrows, i0 + rows_per_span);
+    if (i0 >= i1) return;
+
+    double cz[F];
+#pragma unroll
+    for (int f = 0; f < F; f++) cz[f] = g.mas_tab[f * (g.middle + 1) + kzc];
+    const int mid2 = g.middle * g.middle;
+
+    // ring state (bins b0 / b0+1, 2-D bin (p, kz)) and span state (1-D bin kz)
+    double lo3[3][Q], hi3[3][Q], lok = 0, hik = 0, loph = 0, hiph = 0, a2[Q], a1[Q];
+    int locn = 0, hicn = 0, c2 = 0, c1 = 0;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        a2[q] = 0; a1[q] = 0;
+#pragma unroll
+        for (int l = 0; l < 3; l++) { lo3[l][q] = 0; hi3[l][q] = 0; }
+    }
+    // group state (rows sharing r2)
+    double gq[Q], gph = 0;
+    int gcnt = 0;
+#pragma unroll
+    for (int q = 0; q < Q; q++) gq[q] = 0;
+    int cur_r2 = -1, ring_p = -1, ring_hi = 0, b0 = 0, thr = 0;
+    bool sel = false, in1d = false;
+    double w2 = 0, w4 = 0, kk = 0;
+
+    auto apply_group = [&]() {
+        if (gcnt == 0) return;
+        if (sel) {
+#pragma unroll
+            for (int q = 0; q < Q; q++) { hi3[0][q] += gq[q]; hi3[1][q] += gq[q] * w2; hi3[2][q] += gq[q] * w4; }
+            hik += (double)gcnt * kk; hicn += gcnt; hiph += gph;
+        } else {
+#pragma unroll
+            for (int q = 0; q < Q; q++) { lo3[0][q] += gq[q]; lo3[1][q] += gq[q] * w2; lo3[2][q] += gq[q] * w4; }
+            lok += (double)gcnt * kk; locn += gcnt; loph += gph;
+        }
+#pragma unroll
+        for (int q = 0; q < Q; q++) { a2[q] += gq[q]; if (in1d) a1[q] += gq[q]; gq[q] = 0; }
+        c2 += gcnt;
+        if (in1d) c1 += gcnt;
+        gcnt = 0; gph = 0;
+    };
+
+    auto flush_bin3 = [&](int b, double (&s3)[3][Q], double ks, double ph, int cn) {
+        if (cn == 0) return;
+        red_add(g.sums + g.o_k3d + b, ks);
+        red_add_u64(g.counts + g.o_n3d + b, (uint64_t)cn);
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+#pragma unroll
+            for (int f = 0; f < F; f++) red_add(g.sums + g.o_p3d + ((long long)b * 3 + l) * F + f, s3[l][f]);
+#pragma unroll
+            for (int x = 0; x < X; x++) red_add(g.sums + g.o_x3d + ((long long)b * 3 + l) * X + x, s3[l][F + x]);
+        }
+        if (PHASE) red_add(g.sums + g.o_phase + b, ph);
+    };
+
+    auto flush_ring = [&]() {
+        if (active && c2 > 0) {
+            flush_bin3(b0, lo3, lok, loph, locn);
+            flush_bin3(b0 + 1, hi3, hik, hiph, hicn);
+            const long long i2 = (long long)g.kmax_par1 * ring_p + kz;  // (kmax_par+1)*k_per + k_par, :371
+            red_add_u64(g.counts + g.o_n2d + i2, (uint64_t)c2);
+#pragma unroll
+            for (int f = 0; f < F; f++) red_add(g.sums + g.o_p2d + i2 * F + f, a2[f]);
+#pragma unroll
+            for (int x = 0; x < X; x++) red_add(g.sums + g.o_x2d + i2 * X + x, a2[F + x]);
+        }
+        lok = hik = loph = hiph = 0; locn = hicn = c2 = 0;
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            a2[q] = 0;
+#pragma unroll
+            for (int l = 0; l < 3; l++) { lo3[l][q] = 0; hi3[l][q] = 0; }
+        }
+    };
+
+    for (int c0 = i0; c0 < i1; c0 += RING_CHUNK) {
+        const int cn = min(RING_CHUNK, i1 - c0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < cn; j += RING_T) {
+            const RowEnt e = tab[c0 + j];
+            sm.ent[j] = e;
+            const int ax = e.kx < 0 ? -e.kx : e.kx, ay = e.ky < 0 ? -e.ky : e.ky;
+#pragma unroll
+            for (int f = 0; f < F; f++)
+                sm.cxy[j][f] = g.mas_tab[f * (g.middle + 1) + ax] * g.mas_tab[f * (g.middle + 1) + ay];
+        }
+        __syncthreads();
+
+        for (int j0 = 0; j0 < cn; j0 += RING_U) {
+            float2 z[RING_U][F];
+#pragma unroll
+            for (int u = 0; u < RING_U; u++) {
+                if (j0 + u < cn) {
+                    const long long off = sm.ent[j0 + u].off + kzc;
+#pragma unroll
+                    for (int f = 0; f < F; f++) z[u][f] = WB ? dk.p[f][off] : ld_stream(dk.p[f] + off);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RING_U; u++) {
+                if (j0 + u < cn) {
+                    const int r2 = sm.ent[j0 + u].r2;
+                    if (r2 != cur_r2) {  // CTA-uniform
+                        apply_group();
+                        cur_r2 = r2;
+                        if (r2 >= ring_hi) {
+                            flush_ring();
+                            ring_p = isqrt_exact(r2);
+                            ring_hi = (ring_p + 1) * (ring_p + 1);
+                            b0 = isqrt_exact(ring_p * ring_p + kz2);
+                            thr = (b0 + 1) * (b0 + 1);
+                        }
+                        const int n = r2 + kz2;
+                        sel = n >= thr;
+                        in1d = n <= mid2;                   // k <= middle, :364
+                        const double dn = (double)n;
+                        kk = sqrt(dn);                      // :334
+                        const double mu = (double)kzc / kk; // :347 (n > 0 because kz >= 1)
+                        const double mu2 = mu * mu;
+                        w2 = (3.0 * mu2 - 1.0) / 2.0;       // :378
+                        w4 = (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0;  // :379
+                    }
+                    float re[F], im[F];
+#pragma unroll
+                    for (int f = 0; f < F; f++) {
+                        const float mf = (float)(sm.cxy[j0 + u][f] * cz[f]);  // double product -> float, :354
+                        re[f] = __fmul_rn(z[u][f].x, mf);                      // complex64 *= float, :355
+                        im[f] = __fmul_rn(z[u][f].y, mf);
+                        if (WB && active) dk.p[f][sm.ent[j0 + u].off + kz] = make_float2(re[f], im[f]);
+                        gq[f] += (double)re[f] * (double)re[f] + (double)im[f] * (double)im[f];  // :358-360
+                    }
+                    if (X > 0) {
+                        int ix = 0;
+#pragma unroll
+                        for (int a = 0; a < F; a++)
+#pragma unroll
+                            for (int b = a + 1; b < F; b++) {
+                                gq[F + ix] += (double)re[a] * (double)re[b] + (double)im[a] * (double)im[b];  // :721-722
+                                ix++;
+                            }
+                    }
+                    if (PHASE) gph += (double)phase_sq(re[0], fmaf(re[0], re[0], im[0] * im[0]));
+                    gcnt++;
+                }
+            }
+        }
+    }
+    apply_group();
+    flush_ring();
+    if (active && c1 > 0) {
+        red_add_u64(g.counts + g.o_n1d + kz, (uint64_t)c1);
+#pragma unroll
+        for (int f = 0; f < F; f++) red_add(g.sums + g.o_p1d + (long long)kz * F + f, a1[f]);
+#pragma unroll
+        for (int x = 0; x < X; x++) red_add(g.sums + g.o_x1d + (long long)kz * X + x, a1[F + x]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic kernel: one thread per mode, kzz = kz_start + j*kz_step for j < kz_num
+// ------------------------------------------------------------------------------------------------
+template <bool WB>
+__global__ void __launch_bounds__(256)
+generic_kernel(BinGeom g, FieldPtrs dk, long long nmodes, int kz_start, int kz_step, int kz_num, int want_phase) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nmodes) return;
+    const int j = (int)(idx % kz_num);
+    const int r = (int)(idx / kz_num);
+    const int kzz = kz_start + j * kz_step;
+    const int ix = r / g.ny, iy = r - ix * g.ny;
+    const int kx = wavenumber(g.x0 + ix, g.dims, g.middle);
+    const int ky = wavenumber(g.y0 + iy, g.dims, g.middle);
+    const int kz = kzz;  // kzz <= middle always
+    // one of each conjugate pair on the self-conjugate planes, :326-330
+    if (kz == 0 || (kz == g.middle && g.even)) {
+        if (kx < 0) return;
+        if (kx == 0 || (kx == g.middle && g.even)) {
+            if (ky < 0) return;
+        }
+    }
+    const int n = kx * kx + ky * ky + kz * kz;
+    const int k_index = isqrt_exact(n);  // <int>sqrt(...), :334-335
+    const double k = sqrt((double)n);
+    int k_par, k_per;  // :338-343
+    if (g.axis == 0) { k_par = kx; k_per = isqrt_exact(ky * ky + kz * kz); }
+    else if (g.axis == 1) { k_par = ky; k_per = isqrt_exact(kx * kx + kz * kz); }
+    else { k_par = kz; k_per = isqrt_exact(kx * kx + ky * ky); }
+    const double mu = (n == 0) ? 0.0 : (double)k_par / k;  // :346-347
+    const double mu2 = mu * mu;
+    const double w2 = (3.0 * mu2 - 1.0) / 2.0;
+    const double w4 = (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0;
+    if (k_par < 0) k_par = -k_par;  // :351
+    const bool in1d = n <= g.middle * g.middle;
+    const long long i2 = (long long)g.kmax_par1 * k_per + k_par;
+    const int F = g.F, X = g.X, m1 = g.middle + 1;
+    const int ax = kx < 0 ? -kx : kx, ay = ky < 0 ? -ky : ky;
+
+    if (in1d) red_add_u64(g.counts + g.o_n1d + k_par, 1);
+    red_add_u64(g.counts + g.o_n2d + i2, 1);
+    red_add_u64(g.counts + g.o_n3d + k_index, 1);
+    red_add(g.sums + g.o_k3d + k_index, k);
+
+    const long long off = (long long)ix * g.stride_x + (long long)iy * g.stride_y + kzz;
+    float re[MAX_F], im[MAX_F];
+    for (int f = 0; f < F; f++) {
+        const double c = g.mas_tab[f * m1 + ax] * g.mas_tab[f * m1 + ay] * g.mas_tab[f * m1 + kz];
+        const float mf = (float)c;
+        const float2 z = dk.p[f][off];
+        re[f] = __fmul_rn(z.x, mf);
+        im[f] = __fmul_rn(z.y, mf);
+        if (WB) dk.p[f][off] = make_float2(re[f], im[f]);
+        const double d2 = (double)re[f] * (double)re[f] + (double)im[f] * (double)im[f];
+        if (f == 0 && want_phase) {
+            const double ph = atan2((double)re[0], sqrt(d2));  // :361
+            red_add(g.sums + g.o_phase + k_index, ph * ph);
+        }
+        if (in1d) red_add(g.sums + g.o_p1d + (long long)k_par * F + f, d2);
+        red_add(g.sums + g.o_p2d + i2 * F + f, d2);
+        red_add(g.sums + g.o_p3d + ((long long)k_index * 3 + 0) * F + f, d2);
+        red_add(g.sums + g.o_p3d + ((long long)k_index * 3 + 1) * F + f, d2 * w2);
+        red_add(g.sums + g.o_p3d + ((long long)k_index * 3 + 2) * F + f, d2 * w4);
+    }
+    int xi = 0;
+    for (int a = 0; a < F; a++)
+        for (int b = a + 1; b < F; b++) {
+            const double dx = (double)re[a] * (double)re[b] + (double)im[a] * (double)im[b];
+            if (in1d) red_add(g.sums + g.o_x1d + (long long)k_par * X + xi, dx);
+            red_add(g.sums + g.o_x2d + i2 * X + xi, dx);
+            red_add(g.sums + g.o_x3d + ((long long)k_index * 3 + 0) * X + xi, dx);
+            red_add(g.sums + g.o_x3d + ((long long)k_index * 3 + 1) * X + xi, dx * w2);
+            red_add(g.sums + g.o_x3d + ((long long)k_index * 3 + 2) * X + xi, dx * w4);
+            xi++;
+        }
+}
+
+static int launch_generic(const BinGeom &g, const FieldPtrs &dk, int kz_start, int kz_step, int kz_num,
+                          int want_phase, int write_back, cudaStream_t st) {
+    const long long nmodes = (long long)g.nx * g.ny * kz_num;
+    if (nmodes == 0) return 0;
+    const unsigned blocks = (unsigned)((nmodes + 255) / 256);
+    if (write_back) generic_kernel<true><<<blocks, 256, 0, st>>>(g, dk, nmodes, kz_start, kz_step, kz_num, want_phase);
+    else generic_kernel<false><<<blocks, 256, 0, st>>>(g, dk, nmodes, kz_start, kz_step, kz_num, want_phase);
+    PYLB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int F>
+static int launch_ring_f(const BinGeom &g, const FieldPtrs &dk, const RowEnt *tab, int nrows, int kz_hi,
+                         int want_phase, int write_back, cudaStream_t st) {
+    const int nseg = (kz_hi + RING_T - 1) / RING_T;
+    // two waves of resident CTAs, but never fewer than 32 rows per span
+    int occ = 1;
+    if (want_phase) {
+        if (write_back) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, true, true>, RING_T, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, true, false>, RING_T, 0);
+    } else {
+        if (write_back) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, false, true>, RING_T, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, false, false>, RING_T, 0);
+    }
+    if (occ < 1) occ = 1;
+    int nspan = (sm_count() * occ * 2 + nseg - 1) / nseg;
+    if (nspan > (nrows + 31) / 32) nspan = (nrows + 31) / 32;
+    if (nspan < 1) nspan = 1;
+    const int rows_per_span = (nrows + nspan - 1) / nspan;
+    nspan = (nrows + rows_per_span - 1) / rows_per_span;
+    dim3 grid(nspan, nseg);
+    if (want_phase) {
+        if (write_back) ring_kernel<F, true, true><<<grid, RING_T, 0, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
+        else ring_kernel<F, true, false><<<grid, RING_T, 0, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
+    } else {
+        if (write_back) ring_kernel<F, false, true><<<grid, RING_T, 0, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
+        else ring_kernel<F, false, false><<<grid, RING_T, 0, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
+    }
+    PYLB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int bits_for(unsigned v) {
+    int b = 1;
+    while (b < 32 && (v >> b)) b++;
+    return b;
+}
+
+static int run_ring(const BinGeom &g, const FieldPtrs &dk, int want_phase, int write_back, cudaStream_t st) {
+    const int nrows = g.nx * g.ny;
+    const int kz_hi = g.even ? g.middle - 1 : g.middle;  // columns 1..kz_hi carry no skip rule
+    // special columns first (kz = 0 and, for even dims, kz = middle)
+    if (launch_generic(g, dk, 0, g.middle > 0 ? g.middle : 1, (g.even && g.middle > 0) ? 2 : 1, want_phase, write_back, st))
+        return 1;
+    if (kz_hi < 1 || nrows == 0) return 0;
+
+    // scratch: keys/vals (double-buffered for the radix sort), row table, cub temp
+    unsigned *buf = nullptr;
+    RowEnt *tab = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    const int kmaxsq = 2 * (g.dims / 2 + 1) * (g.dims / 2 + 1);
+    const int end_bit = bits_for((unsigned)kmaxsq);
+    PYLB_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned *)nullptr, (unsigned *)nullptr,
+                                               (unsigned *)nullptr, (unsigned *)nullptr, nrows, 0, end_bit, st));
+    PYLB_CHECK(cudaMallocAsync(&buf, sizeof(unsigned) * 4 * (size_t)nrows, st));
+    PYLB_CHECK(cudaMallocAsync(&tab, sizeof(RowEnt) * (size_t)nrows, st));
+    PYLB_CHECK(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st));
+    unsigned *k_in = buf, *v_in = buf + nrows, *k_out = buf + 2 * (size_t)nrows, *v_out = buf + 3 * (size_t)nrows;
+    const unsigned blocks = (unsigned)((nrows + 255) / 256);
+    row_keys_kernel<<<blocks, 256, 0, st>>>(k_in, v_in, nrows, g);
+    PYLB_LAUNCH_CHECK();
+    PYLB_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, nrows, 0, end_bit, st));
+    count_launch(3);
+    row_table_kernel<<<blocks, 256, 0, st>>>(k_out, v_out, tab, nrows, g);
+    PYLB_LAUNCH_CHECK();
+
+    int rc = 1;
+    switch (g.F) {
+        case 1: rc = launch_ring_f<1>(g, dk, tab, nrows, kz_hi, want_phase, write_back, st); break;
+        case 2: rc = launch_ring_f<2>(g, dk, tab, nrows, kz_hi, want_phase, write_back, st); break;
+        case 3: rc = launch_ring_f<3>(g, dk, tab, nrows, kz_hi, want_phase, write_back, st); break;
+        default: set_error("ring binning supports 1..3 fields, got %d", g.F);
+    }
+    cudaFreeAsync(buf, st);
+    cudaFreeAsync(tab, st);
+    cudaFreeAsync(tmp, st);
+    return rc;
+}
+
+}  // namespace pylb
+
+using namespace pylb;
+
+extern "C" int pylb_pk_get_layout(int dims, int F, pylb_pk_layout *L) {
+    PYLB_REQUIRE(L != nullptr && dims >= 2 && F >= 1 && F <= MAX_F, "pylb_pk_get_layout: need dims >= 2 and 1 <= F <= %d", MAX_F);
+    const int middle = dims / 2;  // python-2 integer division in frequencies(), Pk_library.pyx:60
+    L->dims = dims; L->F = F; L->X = F * (F - 1) / 2; L->middle = middle;
+    L->kmax_par = middle;
+    L->kmax_per = isqrt_exact(2 * middle * middle);      // int(sqrt(middle^2+middle^2)), :62
+    L->kmax = isqrt_exact(3 * middle * middle);          // :63
+    L->B2 = (int64_t)(L->kmax_par + 1) * (L->kmax_per + 1);
+    int64_t o = 0;
+    const int64_t n3 = L->kmax + 1, n1 = L->kmax_par + 1;
+    L->o_k3d = o; o += n3;
+    L->o_p3d = o; o += n3 * 3 * F;
+    L->o_x3d = o; o += n3 * 3 * L->X;
+    L->o_phase = o; o += n3;
+    L->o_p1d = o; o += n1 * F;
+    L->o_x1d = o; o += n1 * L->X;
+    L->o_p2d = o; o += L->B2 * F;
+    L->o_x2d = o; o += L->B2 * L->X;
+    L->n_doubles = o;
+    o = 0;
+    L->o_n3d = o; o += n3;
+    L->o_n1d = o; o += n1;
+    L->o_n2d = o; o += L->B2;
+    L->n_counts = o;
+    return 0;
+}
+
+extern "C" int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int axis, const int *mas_index,
+                           int want_phase, int write_back, int algo, int accumulate, double *sums,
+                           uint64_t *counts, void *stream) {
+    PYLB_REQUIRE(dk && ks && mas_index && sums && counts, "pylb_pk_bin: NULL argument");
+    PYLB_REQUIRE(F >= 1 && F <= MAX_F, "pylb_pk_bin: 1 <= F <= %d required, got %d", MAX_F, F);
+    PYLB_REQUIRE(axis >= 0 && axis <= 2, "pylb_pk_bin: axis must be 0, 1 or 2");
+    PYLB_REQUIRE(ks->dims >= 2 && ks->dims <= 32768, "pylb_pk_bin: dims out of range");
+    PYLB_REQUIRE(ks->nx >= 0 && ks->ny >= 0 && ks->x0 >= 0 && ks->y0 >= 0 && ks->x0 + ks->nx <= ks->dims &&
+                 ks->y0 + ks->ny <= ks->dims, "pylb_pk_bin: k-space window out of range");
+    PYLB_REQUIRE((long long)ks->nx * ks->ny < (1ll << 31), "pylb_pk_bin: too many rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    pylb_pk_layout L;
+    if (pylb_pk_get_layout(ks->dims, F, &L)) return 1;
+
+    BinGeom g;
+    g.dims = ks->dims; g.middle = L.middle; g.even = (ks->dims % 2 == 0);
+    g.x0 = ks->x0; g.nx = ks->nx; g.y0 = ks->y0; g.ny = ks->ny;
+    g.stride_x = ks->stride_x; g.stride_y = ks->stride_y;
+    g.axis = axis; g.kmax_par1 = L.kmax_par + 1; g.F = F; g.X = L.X;
+    g.o_k3d = L.o_k3d; g.o_p3d = L.o_p3d; g.o_x3d = L.o_x3d; g.o_phase = L.o_phase;
+    g.o_p1d = L.o_p1d; g.o_x1d = L.o_x1d; g.o_p2d = L.o_p2d; g.o_x2d = L.o_x2d;
+    g.o_n3d = L.o_n3d; g.o_n1d = L.o_n1d; g.o_n2d = L.o_n2d;
+    g.sums = sums; g.counts = counts;
+    FieldPtrs fp;
+    for (int f = 0; f < MAX_F; f++) { fp.p[f] = nullptr; g.mas_idx[f] = 0; }
+    for (int f = 0; f < F; f++) {
+        PYLB_REQUIRE(dk[f] != nullptr, "pylb_pk_bin: field %d is NULL", f);
+        PYLB_REQUIRE(mas_index[f] >= 0 && mas_index[f] <= 4, "pylb_pk_bin: MAS index %d out of range", mas_index[f]);
+        fp.p[f] = (float2 *)dk[f];
+        g.mas_idx[f] = mas_index[f];
+    }
+    if (!accumulate) {
+        PYLB_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)L.n_doubles, st));
+        PYLB_CHECK(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * (size_t)L.n_counts, st));
+    }
+    double *tab = nullptr;
+    const int ntab = F * (L.middle + 1);
+    PYLB_CHECK(cudaMallocAsync(&tab, sizeof(double) * (size_t)ntab, st));
+    g.mas_tab = tab;
+    mas_table_kernel<<<(ntab + 127) / 128, 128, 0, st>>>(tab, L.middle, ks->dims, F, g);
+    PYLB_LAUNCH_CHECK();
+
+    if (algo == PYLB_BIN_AUTO) algo = (axis == 2 && F <= 3) ? PYLB_BIN_RING : PYLB_BIN_GENERIC;
+    int rc;
+    if (algo == PYLB_BIN_RING) {
+        if (axis != 2) { set_error("pylb_pk_bin: the ring kernel needs axis=2 (transpose the field for other axes)"); rc = 1; }
+        else rc = run_ring(g, fp, want_phase, write_back, st);
+    } else {
+        rc = launch_generic(g, fp, 0, 1, L.middle + 1, want_phase, write_back, st);
+    }
+    cudaFreeAsync(tab, st);
+    return rc;
+}

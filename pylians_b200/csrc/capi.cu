@@ -1,0 +1,165 @@
+// C-ABI glue: error channel, launch accounting, pylb_ma dispatch, the reference-compatible host
+// entry points (MAS_c.h:3-10) and the slab-transpose pack kernels.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace pylb {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+int ma_direct(const float *pos, int64_t np, int ndim, int64_t ps0, int64_t ps1, void *grid, int f64,
+              int dims, float inv, int mas, const float *w, float zrep, cudaStream_t st);
+int ma_tiled(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv,
+             int mas, const float *w, void *workspace, size_t workspace_bytes, cudaStream_t st);
+size_t ma_tiled_workspace(int64_t np, int dims, int mas, int has_w);
+bool ma_tiled_supported(int ndim, int dims, int grid_f64);
+
+// ------------------------------------------------------------------------------------------------
+// slab transpose: src [nx][dims][nz] -> dst [G][nx][dims/G][nz]; 16-byte vector copies when the
+// row length allows, 8-byte otherwise.  One CTA per (ix, g) block of ny_loc*nz contiguous elements.
+// ------------------------------------------------------------------------------------------------
+template <typename V>
+__global__ void __launch_bounds__(256)
+slab_pack_kernel(const V *__restrict__ src, V *__restrict__ dst, V *const *peer, long long blk,
+                 int nx, int G, int my_rank) {
+    // blk = ny_loc*nz in units of V
+    const int ix = blockIdx.y, gq = blockIdx.z;
+    const V *s = src + ((long long)ix * G + gq) * blk;
+    V *d = peer ? peer[gq] + ((long long)my_rank * nx + ix) * blk : dst + ((long long)gq * nx + ix) * blk;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < blk; i += (long long)gridDim.x * blockDim.x)
+        d[i] = s[i];
+}
+
+static int slab_pack_impl(const void *src, void *dst, void *const *peer, int dims, int nx, int G, int my_rank,
+                          cudaStream_t st) {
+    PYLB_REQUIRE(G >= 1 && dims % G == 0 && nx >= 1, "pylb_slab_pack: dims must be divisible by G");
+    const long long nz = dims / 2 + 1, blk = (long long)(dims / G) * nz;  // complex elements per block
+    int bx = (int)((blk + 256 * 8 - 1) / (256 * 8));
+    if (bx < 1) bx = 1;
+    if (bx > 64) bx = 64;
+    dim3 grid(bx, nx, G);
+    void *const *dpeer = nullptr;
+    void **dtmp = nullptr;
+    if (peer) {
+        PYLB_CHECK(cudaMallocAsync(&dtmp, sizeof(void *) * G, st));
+        PYLB_CHECK(cudaMemcpyAsync(dtmp, peer, sizeof(void *) * G, cudaMemcpyHostToDevice, st));
+        dpeer = dtmp;
+    }
+    bool v16 = (blk % 2 == 0) && (((uintptr_t)src & 15) == 0) && (peer || ((uintptr_t)dst & 15) == 0);
+    if (peer) for (int i = 0; i < G; i++) v16 = v16 && (((uintptr_t)peer[i] & 15) == 0);
+    if (v16)
+        slab_pack_kernel<float4><<<grid, 256, 0, st>>>((const float4 *)src, (float4 *)dst, (float4 *const *)dpeer, blk / 2, nx, G, my_rank);
+    else
+        slab_pack_kernel<float2><<<grid, 256, 0, st>>>((const float2 *)src, (float2 *)dst, (float2 *const *)dpeer, blk, nx, G, my_rank);
+    PYLB_LAUNCH_CHECK();
+    if (dtmp) cudaFreeAsync(dtmp, st);
+    return 0;
+}
+
+}  // namespace pylb
+
+using namespace pylb;
+
+extern "C" int pylb_version(void) { return PYLB_VERSION; }
+extern "C" const char *pylb_last_error(void) { return g_err; }
+extern "C" int64_t pylb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" size_t pylb_ma_workspace_bytes(int64_t np, int ndim, int dims, int mas, int has_w, int grid_f64, int algo) {
+    if (algo == PYLB_MA_DIRECT) return 0;
+    if (!ma_tiled_supported(ndim, dims, grid_f64)) return 0;
+    return ma_tiled_workspace(np, dims, mas, has_w);
+}
+
+extern "C" int pylb_ma(const float *pos, int64_t np, int ndim, int64_t ps0, int64_t ps1, void *grid, int grid_f64,
+                       int dims, float box, int mas, const float *w, int z_repeat, int algo, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+    PYLB_REQUIRE(ndim == 2 || ndim == 3, "pylb_ma: pos must have 2 or 3 coordinates, got %d", ndim);
+    PYLB_REQUIRE(mas >= PYLB_NGP && mas <= PYLB_PCS, "pylb_ma: unknown mass-assignment scheme %d", mas);
+    PYLB_REQUIRE(dims >= 1 && np >= 0, "pylb_ma: bad sizes");
+    PYLB_REQUIRE(np == 0 || (pos != nullptr && grid != nullptr), "pylb_ma: NULL pointer");
+    PYLB_REQUIRE(box > 0.0f, "pylb_ma: BoxSize must be positive");
+    const float inv = (float)dims / box;  // `cdef float inv_cell_size = dims/BoxSize`, MAS_library.pyx:135
+    const float zrep = (ndim == 2 && z_repeat > 1) ? (float)z_repeat : 1.0f;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool tiled = false;
+    if (algo != PYLB_MA_DIRECT && ma_tiled_supported(ndim, dims, grid_f64)) {
+        // AUTO: the tiled path pays a binning pass; it wins once the grid no longer lives in L2
+        const bool big = (size_t)dims * dims * dims * sizeof(float) > (size_t)48 << 20;
+        tiled = (algo == PYLB_MA_TILED) || (big && np >= (int64_t)1 << 20);
+        if (tiled && workspace_bytes < ma_tiled_workspace(np, dims, mas, w != nullptr)) {
+            PYLB_REQUIRE(algo != PYLB_MA_TILED, "pylb_ma: workspace too small for the tiled path (%zu < %zu)",
+                         workspace_bytes, ma_tiled_workspace(np, dims, mas, w != nullptr));
+            tiled = false;
+        }
+    } else {
+        PYLB_REQUIRE(algo != PYLB_MA_TILED, "pylb_ma: tiled path needs a 3-D float32 grid with dims >= 32");
+    }
+    if (tiled) return ma_tiled(pos, np, ps0, ps1, (float *)grid, dims, inv, mas, w, workspace, workspace_bytes, st);
+    return ma_direct(pos, np, ndim, ps0, ps1, grid, grid_f64, dims, inv, mas, w, zrep, st);
+}
+
+// ---- reference-compatible host entry points (MAS_c.h:3-10) -------------------------------------
+static void masc_host(int mas, float *pos, float *number, float *W, long particles, int dims, int axes, float box) {
+    g_err[0] = 0;
+    if (axes != 2 && axes != 3) { set_error("MAS_c entry: axes must be 2 or 3"); return; }
+    size_t cells = (size_t)dims * dims * (axes == 3 ? dims : 1);
+    float *dpos = nullptr, *dgrid = nullptr, *dw = nullptr;
+    void *ws = nullptr;
+    cudaStream_t st = nullptr;
+    bool ok = cudaStreamCreate(&st) == cudaSuccess;
+    ok = ok && cudaMalloc(&dpos, sizeof(float) * (size_t)particles * axes + 16) == cudaSuccess;
+    ok = ok && cudaMalloc(&dgrid, sizeof(float) * cells) == cudaSuccess;
+    if (ok && W) ok = cudaMalloc(&dw, sizeof(float) * (size_t)particles + 16) == cudaSuccess;
+    size_t wsb = pylb_ma_workspace_bytes(particles, axes, dims, mas, W != nullptr, 0, PYLB_MA_AUTO);
+    if (ok && wsb) ok = cudaMalloc(&ws, wsb) == cudaSuccess;
+    if (!ok) set_error("MAS_c entry: CUDA allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (ok) {
+        cudaMemcpyAsync(dpos, pos, sizeof(float) * (size_t)particles * axes, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dgrid, number, sizeof(float) * cells, cudaMemcpyHostToDevice, st);
+        if (W) cudaMemcpyAsync(dw, W, sizeof(float) * (size_t)particles, cudaMemcpyHostToDevice, st);
+        if (pylb_ma(dpos, particles, axes, axes, 1, dgrid, 0, dims, box, mas, dw, 1, PYLB_MA_AUTO, ws, wsb, st) == 0) {
+            cudaMemcpyAsync(number, dgrid, sizeof(float) * cells, cudaMemcpyDeviceToHost, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess)
+                set_error("MAS_c entry: execution failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    cudaFree(dpos); cudaFree(dgrid); cudaFree(dw); cudaFree(ws);
+    if (st) cudaStreamDestroy(st);
+}
+
+extern "C" void NGP(float *pos, float *number, float *W, long particles, int dims, int axes, float BoxSize, int threads) {
+    (void)threads; masc_host(PYLB_NGP, pos, number, W, particles, dims, axes, BoxSize);
+}
+extern "C" void CIC(float *pos, float *number, float *W, long particles, int dims, int axes, float BoxSize, int threads) {
+    (void)threads; masc_host(PYLB_CIC, pos, number, W, particles, dims, axes, BoxSize);
+}
+extern "C" void TSC(float *pos, float *number, float *W, long particles, int dims, int axes, float BoxSize, int threads) {
+    (void)threads; masc_host(PYLB_TSC, pos, number, W, particles, dims, axes, BoxSize);
+}
+extern "C" void PCS(float *pos, float *number, float *W, long particles, int dims, int axes, float BoxSize, int threads) {
+    (void)threads; masc_host(PYLB_PCS, pos, number, W, particles, dims, axes, BoxSize);
+}
+
+extern "C" int pylb_slab_pack(const void *src, void *dst, int dims, int nx_local, int G, void *stream) {
+    PYLB_REQUIRE(src && dst, "pylb_slab_pack: NULL pointer");
+    return slab_pack_impl(src, dst, nullptr, dims, nx_local, G, 0, (cudaStream_t)stream);
+}
+
+extern "C" int pylb_slab_pack_push(const void *src, void *const *peer_recv, int dims, int nx_local, int G,
+                                   int my_rank, void *stream) {
+    PYLB_REQUIRE(src && peer_recv && my_rank >= 0 && my_rank < G, "pylb_slab_pack_push: bad arguments");
+    return slab_pack_impl(src, nullptr, peer_recv, dims, nx_local, G, my_rank, (cudaStream_t)stream);
+}

@@ -1,0 +1,84 @@
+// Shared helpers for the pylians_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pylians_b200.h"
+
+namespace pylb {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define PYLB_CHECK(expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            pylb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return 1;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+#define PYLB_LAUNCH_CHECK()                                                                       \
+    do {                                                                                          \
+        pylb::count_launch();                                                                     \
+        cudaError_t _e = cudaGetLastError();                                                      \
+        if (_e != cudaSuccess) {                                                                  \
+            pylb::set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return 1;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+#define PYLB_REQUIRE(cond, ...)                                                                   \
+    do {                                                                                          \
+        if (!(cond)) {                                                                            \
+            pylb::set_error(__VA_ARGS__);                                                         \
+            return 1;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// floor(sqrt(n)) exactly, n < 2^31.  fp32 sqrt is only the first guess; the integer fix-up makes
+// the result independent of rounding mode / fast-math (Nmodes is a bit-exact contract).
+__host__ __device__ __forceinline__ int isqrt_exact(int n) {
+#ifdef __CUDA_ARCH__
+    int s = (int)__fsqrt_rn((float)n);
+#else
+    int s = (int)sqrtf((float)n);
+#endif
+    while ((long long)s * s > (long long)n) --s;
+    while ((long long)(s + 1) * (s + 1) <= (long long)n) ++s;
+    return s;
+}
+
+// signed wavenumber of FFT index i (Pk_library.pyx:315): i > middle ? i - dims : i
+__host__ __device__ __forceinline__ int wavenumber(int i, int dims, int middle) {
+    return (i > middle) ? i - dims : i;
+}
+
+// non-negative remainder; equals the reference's (i+dims)%dims on its valid domain and stays in
+// range where the reference would read/write out of bounds
+__device__ __forceinline__ int wrap(int i, int dims) {
+    int r = i % dims;
+    return r < 0 ? r + dims : r;
+}
+
+__device__ __forceinline__ void red_add(float *p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void red_add(double *p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void red_add(double *p, float v) { atomicAdd(p, (double)v); }
+__device__ __forceinline__ void red_add_u64(uint64_t *p, uint64_t v) {
+    atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
+}
+
+}  // namespace pylb

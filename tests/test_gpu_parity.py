@@ -1,0 +1,337 @@
+"""GPU: the CUDA path, called through the reference-shaped Python API (which goes through the C ABI),
+against the CPU oracle and the reference-generated golden vectors."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import parity
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import pylians_oracle as O  # noqa: E402  (checker only)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pylians_b200
+    pylians_b200.set_verbose(False)
+
+
+@pytest.fixture(scope="module")
+def MASL():
+    import MAS_library
+    return MAS_library
+
+
+@pytest.fixture(scope="module")
+def PKL():
+    import Pk_library
+    return Pk_library
+
+
+@pytest.fixture(scope="module")
+def gma(golden_dir):
+    return np.load(os.path.join(golden_dir, "ma.npz"))
+
+
+# ------------------------------------------------------------------------------------------------
+# deposit
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_ma3d_golden(MASL, gma, mas, weighted):
+    box, dims = float(gma["box"]), int(gma["dims"])
+    g = np.zeros((dims,) * 3, np.float32)
+    MASL.MA(gma["pos"], g, box, mas, W=gma["W"] if weighted else None)
+    ref = gma["grid_%s%s" % (mas, "W" if weighted else "")]
+    if mas == "NGP" and not weighted:
+        parity.assert_exact(g, ref, "NGP grid")
+    parity.assert_grid_close(g, ref, mas)
+
+
+def test_ma_accumulates_in_place(MASL, gma):
+    box, dims = float(gma["box"]), int(gma["dims"])
+    g = np.full((dims,) * 3, 0.5, np.float32)
+    MASL.MA(gma["pos"][:1000], g, box, "CIC")
+    MASL.MA(gma["pos"][1000:2000], g, box, "TSC", W=gma["W"][1000:2000])
+    parity.assert_grid_close(g, gma["grid_accum"], "accumulate")
+
+
+@pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_ma2d_golden(MASL, gma, mas, weighted):
+    box, dims = float(gma["box"]), int(gma["dims2"])
+    g = np.zeros((dims,) * 2, np.float32)
+    MASL.MA(np.ascontiguousarray(gma["pos"][:, :2]), g, box, mas, W=gma["W"] if weighted else None)
+    parity.assert_grid_close(g, gma["grid2d_%s%s" % (mas, "W" if weighted else "")], "2d " + mas)
+
+
+def test_ma2d_norenorm(MASL, gma):
+    box, dims = float(gma["box"]), int(gma["dims2"])
+    g = np.zeros((dims,) * 2, np.float32)
+    MASL.MA(np.ascontiguousarray(gma["pos"][:, :2]), g, box, "TSC", renormalize_2D=False)
+    parity.assert_grid_close(g, gma["grid2d_TSC_norenorm"], "2d TSC no renorm")
+
+
+def test_ma_fp64_grid(MASL, gma):
+    box, dims = float(gma["box"]), int(gma["dims"])
+    g = np.zeros((dims,) * 3, np.float64); MASL.NGPW_d(gma["pos"], g, box, gma["W"])
+    np.testing.assert_allclose(g, gma["grid_NGPW_d"], rtol=1e-6, atol=1e-6)
+    g = np.zeros((dims,) * 3, np.float64); MASL.CICW_d(gma["pos"], g, box, gma["W"])
+    np.testing.assert_allclose(g, gma["grid_CICW_d"], rtol=1e-6, atol=1e-6)
+
+
+def test_ma_openmp_shims(MASL, gma):
+    box, dims = float(gma["box"]), int(gma["dims"])
+    g = np.zeros((dims,) * 3, np.float32); MASL.PCSWc3D(gma["pos"], g, gma["W"], box, 2)
+    parity.assert_grid_close(g, gma["grid_PCSWc3D"], "PCSWc3D")
+    g = np.zeros((dims,) * 3, np.float32); MASL.CICc3D(gma["pos"], g, box, 3)
+    parity.assert_grid_close(g, gma["grid_CIC"], "CICc3D")
+
+
+def test_ma_fortran_order_and_device_tensors(MASL, gma):
+    box, dims = float(gma["box"]), int(gma["dims"])
+    g = np.zeros((dims,) * 3, np.float32)
+    MASL.MA(np.asfortranarray(gma["pos"]), g, box, "CIC")
+    parity.assert_grid_close(g, gma["grid_CIC"], "F-order pos")
+    gt = torch.zeros((dims,) * 3, dtype=torch.float32, device="cuda")
+    MASL.MA(torch.from_numpy(gma["pos"]).cuda(), gt, box, "PCS", W=torch.from_numpy(gma["W"]).cuda())
+    parity.assert_grid_close(gt.cpu().numpy(), gma["grid_PCSW"], "device tensors")
+
+
+def test_ma_errors(MASL):
+    pos = np.zeros((4, 3), np.float32)
+    with pytest.raises(SystemExit):
+        MASL.MA(pos, np.zeros((8, 8), np.float32), 1.0, "CIC")
+    with pytest.raises(SystemExit):
+        MASL.MA(pos, np.zeros((8, 8, 8), np.float32), 1.0, "XYZ")
+    with pytest.raises(ValueError):
+        MASL.MA(pos.astype(np.float64), np.zeros((8, 8, 8), np.float32), 1.0, "CIC")
+    with pytest.raises(ValueError):
+        MASL.MA(pos, np.zeros((8, 8, 8), np.float64), 1.0, "CIC")
+    MASL.MA(np.zeros((0, 3), np.float32), np.zeros((8, 8, 8), np.float32), 1.0, "CIC")   # empty input is fine
+
+
+# the reference's own unit tests (Test/test_MAS.py:10-84): mass conservation
+@pytest.mark.parametrize("mas,places", [("NGP", 20), ("CIC", 8), ("TSC", 8), ("PCS", 8)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_reference_unit_tests_mass_conservation(MASL, mas, places, weighted):
+    particles, BoxSize, dims, seed = 1000, 1.0, 64, 1
+    np.random.seed(seed)
+    pos = np.random.random((particles, 3)).astype(np.float32)
+    delta = np.zeros((dims, dims, dims), dtype=np.float32)
+    W = np.ones(particles, dtype=np.float32) * 3.0 if weighted else None
+    MASL.MA(pos, delta, BoxSize, mas, W=W)
+    suma = np.sum(delta, dtype=np.float64)
+    assert round(abs(suma / (3.0 * particles if weighted else particles) - 1.0), places) == 0
+
+
+@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
+@pytest.mark.parametrize("dims", [64, 80])
+def test_ma_vs_oracle_both_algorithms(MASL, algo, mas, dims):
+    """Seeded random + clustered particles, direct and tiled kernels against the oracle."""
+    rng = np.random.default_rng(100 + dims)
+    box, n = 1000.0, 300000
+    pos = (rng.random((n, 3)) * box).astype(np.float32)
+    pos[: n // 4] = (np.float32(box) * 0.37 + rng.standard_normal((n // 4, 3)) * 6.0).astype(np.float32) % np.float32(box)
+    pos[0] = 0.0; pos[1] = box; pos[2] = np.nextafter(np.float32(box), np.float32(0))
+    W = (rng.random(n) + 0.5).astype(np.float32)
+    old = MASL.ALGO if hasattr(MASL, "ALGO") else 0
+    import pylians_b200.MAS_library as M
+    M.ALGO = algo
+    try:
+        for w in (None, W):
+            a = np.zeros((dims,) * 3, np.float32); b = np.zeros((dims,) * 3, np.float32)
+            MASL.MA(pos, a, box, mas, W=w); O.MA(pos, b, box, mas, W=w)
+            if mas == "NGP" and w is None:
+                parity.assert_exact(a, b, "NGP")
+            parity.assert_grid_close(a, b, "%s algo %d" % (mas, algo))
+    finally:
+        M.ALGO = old
+
+
+def test_cabi_host_entry_points(gma):
+    """The MAS_c.h-compatible symbols (host pointers), called the way a cgo/ctypes binding would."""
+    from pylians_b200 import _lib
+    lib = _lib.load()
+    box, dims = float(gma["box"]), int(gma["dims"])
+    pos = np.ascontiguousarray(gma["pos"]); W = np.ascontiguousarray(gma["W"])
+    for name, key, w in (("CIC", "grid_CIC", None), ("PCS", "grid_PCSW", W), ("NGP", "grid_NGP", None), ("TSC", "grid_TSCW", W)):
+        g = np.zeros((dims,) * 3, np.float32)
+        getattr(lib, name)(pos.ctypes.data, g.ctypes.data, w.ctypes.data if w is not None else None,
+                           pos.shape[0], dims, 3, ctypes.c_float(box), 4)
+        assert lib.pylb_last_error() == b"", lib.pylb_last_error()
+        parity.assert_grid_close(g, gma[key], "C ABI " + name)
+
+
+# ------------------------------------------------------------------------------------------------
+# power spectra
+# ------------------------------------------------------------------------------------------------
+PK_NAMES = ["k3D", "Pk", "Nmodes3D", "Pkphase", "k1D", "Pk1D", "Nmodes1D", "kpar", "kper", "Pk2D", "Nmodes2D"]
+
+
+@pytest.fixture(scope="module")
+def gpk(golden_dir):
+    return np.load(os.path.join(golden_dir, "pk.npz"))
+
+
+@pytest.mark.parametrize("dims", [16, 20])
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("mas", ["TSC", "None"])
+def test_pk_golden(PKL, gpk, dims, axis, mas):
+    p = PKL.Pk(gpk["delta_%d" % dims], float(gpk["box"]), axis, mas, 1)
+    ref = {n: gpk["pk_%d_a%d_%s_%s" % (dims, axis, mas, n)] for n in PK_NAMES}
+    parity.check_pk(p, ref)
+    for n in PK_NAMES:
+        assert np.asarray(getattr(p, n)).dtype == np.float64
+
+
+def test_pk_keep_deltak(PKL, gpk):
+    p = PKL.Pk(gpk["delta_16"], float(gpk["box"]), 2, "TSC", 1, keep_deltak=True)
+    ref = gpk["pk_16_deltak"]
+    assert p.delta_k.dtype == np.complex64 and p.delta_k.shape == ref.shape
+    np.testing.assert_allclose(p.delta_k, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+
+
+def test_xpk_golden(PKL, golden_dir):
+    g = np.load(os.path.join(golden_dir, "xpk.npz"))
+    names = ["k3D", "Pk", "XPk", "Nmodes3D", "k1D", "Pk1D", "PkX1D", "Nmodes1D", "kpar", "kper", "Pk2D", "PkX2D", "Nmodes2D"]
+    fs = [g["delta%d" % i] for i in range(3)]
+    x = PKL.XPk(fs[:2], float(g["box"]), 2, ["CIC", "PCS"], 1)
+    parity.check_xpk(x, {n: g["x2_a2_" + n] for n in names})
+    x = PKL.XPk(fs, float(g["box"]), 0, ["CIC", "PCS", "None"], 1)
+    parity.check_xpk(x, {n: g["x3_a0_" + n] for n in names})
+
+
+def _field(dims, box, seed, mas="CIC"):
+    rng = np.random.default_rng(seed)
+    pos = (rng.random((2 * dims ** 3, 3)) * box).astype(np.float32)
+    d = np.zeros((dims,) * 3, np.float32)
+    O.MA(pos, d, box, mas)
+    d /= np.mean(d, dtype=np.float64); d -= 1.0
+    return d
+
+
+@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("dims", [48, 64, 33])
+def test_pk_vs_oracle(PKL, algo, dims):
+    import pylians_b200.Pk_library as P
+    box = 750.0
+    d = _field(dims, box, dims)
+    old, P.ALGO = P.ALGO, algo
+    try:
+        for axis in ((2,) if algo == 2 else (0, 1, 2)):
+            parity.check_pk(PKL.Pk(d, box, axis, "CIC", 1), O.Pk(d, box, axis, "CIC", 1))
+    finally:
+        P.ALGO = old
+
+
+@pytest.mark.parametrize("algo", [1, 2])
+def test_xpk_vs_oracle(PKL, algo):
+    import pylians_b200.Pk_library as P
+    box, dims = 500.0, 40
+    fs = [_field(dims, box, 5, "CIC"), _field(dims, box, 6, "TSC"), _field(dims, box, 7, "PCS")]
+    old, P.ALGO = P.ALGO, algo
+    try:
+        parity.check_xpk(PKL.XPk(fs[:2], box, 2, ["CIC", "TSC"], 1), O.XPk(fs[:2], box, 2, ["CIC", "TSC"], 1))
+        parity.check_xpk(PKL.XPk(fs, box, 2, ["CIC", "TSC", "PCS"], 1), O.XPk(fs, box, 2, ["CIC", "TSC", "PCS"], 1))
+    finally:
+        P.ALGO = old
+
+
+def test_pk_device_tensor_input_and_untouched_delta(PKL):
+    box, dims = 300.0, 32
+    d = _field(dims, box, 3)
+    dt = torch.from_numpy(d).cuda()
+    keep = dt.clone()
+    p = PKL.Pk(dt, box, 2, "CIC", 1)
+    assert torch.equal(dt, keep)                       # Pk never mutates delta
+    parity.check_pk(p, O.Pk(d, box, 2, "CIC", 1))
+
+
+def test_pk_errors(PKL):
+    with pytest.raises(ValueError):
+        PKL.Pk(np.zeros((8, 8, 8), np.float64), 1.0, 2, "CIC", 1)
+    with pytest.raises(SystemExit):
+        PKL.XPk([np.zeros((8, 8, 8), np.float32), np.zeros((16, 16, 16), np.float32)], 1.0, 2, ["CIC", "CIC"], 1)
+    with pytest.raises(TypeError):
+        PKL.XPk([np.zeros((8, 8, 8), np.float32)] * 2, 1.0, 2, None, 1)
+
+
+def test_plane_wave_known_answer(PKL):
+    N, L, A = 64, 1000.0, 2.0
+    z = np.arange(N)
+    d = np.broadcast_to(A * np.cos(2 * np.pi * 5 * z / N), (N, N, N)).astype(np.float32).copy()
+    p = PKL.Pk(d, L, 2, "None", 1)
+    b = 4
+    np.testing.assert_allclose(p.Pk[b, 0] * p.Nmodes3D[b], (A * N ** 3 / 2) ** 2 * (L / N ** 2) ** 3, rtol=1e-5)
+    np.testing.assert_allclose(p.Pk[b, 1] / p.Pk[b, 0], 5.0, rtol=1e-5)
+    np.testing.assert_allclose(p.Pk[b, 2] / p.Pk[b, 0], 9.0, rtol=1e-5)
+    p = PKL.Pk(d, L, 0, "None", 1)
+    np.testing.assert_allclose(p.Pk[b, 1] / p.Pk[b, 0], -2.5, rtol=1e-5)
+    np.testing.assert_allclose(p.Pk[b, 2] / p.Pk[b, 0], 3.375, rtol=1e-5)
+
+
+def test_rsd_and_overdensity(golden_dir):
+    import redshift_space_library as RSL
+    from pylians_b200 import _lib
+    g = np.load(os.path.join(golden_dir, "rsd.npz"))
+    for axis in (0, 1, 2):
+        a = g["pos"].copy()
+        RSL.pos_redshift_space(a, g["vel"], float(g["box"]), float(g["hubble"]), float(g["redshift"]), axis)
+        assert np.array_equal(a, g["rsd_a%d" % axis])
+    rng = np.random.default_rng(0)
+    x = (rng.random((40, 40, 40)) * 3 + 0.1).astype(np.float32)
+    want = x.copy(); want /= np.mean(want, dtype=np.float64); want -= 1.0
+    t = torch.from_numpy(x).cuda(); scratch = torch.zeros(2, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().pylb_overdensity(t.data_ptr(), t.numel(), scratch.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), "pylb_overdensity")
+    np.testing.assert_allclose(t.cpu().numpy(), want, rtol=0, atol=3e-7)
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE configs[1]: 512^3 particles, CIC, 512^3 grid)
+# ------------------------------------------------------------------------------------------------
+def test_full_size_properties(MASL, PKL):
+    dims, box = 512, 1000.0
+    gen = torch.Generator(device="cuda"); gen.manual_seed(1)
+    pos = torch.rand((dims ** 3, 3), device="cuda", dtype=torch.float32, generator=gen) * box
+    grid = torch.zeros((dims,) * 3, device="cuda", dtype=torch.float32)
+    MASL.MA(pos, grid, box, "CIC")
+    total = float(grid.sum(dtype=torch.float64))
+    assert abs(total / dims ** 3 - 1.0) < 1e-6                       # mass conservation
+    # linearity / algorithm independence: direct kernel on the same input gives the same grid
+    import pylians_b200.MAS_library as M
+    grid2 = torch.zeros_like(grid)
+    old, M.ALGO = M.ALGO, 1
+    try:
+        MASL.MA(pos, grid2, box, "CIC")
+    finally:
+        M.ALGO = old
+    err = (grid - grid2).abs().max().item()
+    assert err <= 1e-5 * float(grid.max()), err
+    del grid2, pos
+    grid /= grid.mean(dtype=torch.float64).float(); grid -= 1.0
+    p = PKL.Pk(grid, box, 2, "CIC", 1)
+    assert p.Nmodes3D.sum() + 1 == (dims ** 3 - 8) // 2 + 8           # Pk_library.pyx:90-102
+    kF = 2 * np.pi / box
+    i = np.arange(len(p.k3D))
+    assert np.all(p.k3D >= (i + 1) * kF * (1 - 1e-12)) and np.all(p.k3D < (i + 2) * kF)
+    # Poisson shot noise: P0 ~ V/N_particles at all k for uniform random particles
+    w = p.Nmodes3D
+    shot = box ** 3 / dims ** 3
+    assert abs(np.sum(p.Pk[20:250, 0] * w[20:250]) / np.sum(w[20:250]) / shot - 1.0) < 0.01
+    # the generic (atomics) kernel agrees with the ring kernel at full size
+    import pylians_b200.Pk_library as P
+    old, P.ALGO = P.ALGO, 1
+    try:
+        q = PKL.Pk(grid, box, 2, "CIC", 1)
+    finally:
+        P.ALGO = old
+    parity.check_pk(p, q)
