@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the density-field -> power-spectrum hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one snapshot: deposit Np particles (MASL.MA) -> overdensity -> PKL.Pk.
+  N = 1   workload = BASELINE configs[1]: 512^3 uniform particles, CIC, 512^3 grid, real-space Pk.
+  N > 1   weak scaling: 512^3 particles per GPU, sharded; grid side chosen so cells ~ particles
+          (640 / 800 / 1024 for N = 2 / 4 / 8); slab-decomposed FFT, see pylians_b200/dist.py.
+Prints ONE JSON line (rank 0).  `value` = particles/s with inputs resident in HBM; `e2e` = same metric
+through the public API with the particle array in pinned HOST memory (H2D inside the timed region,
+D2H of the spectra).  The reference arm (--impl reference) times the reference's own CPU code
+(oracle/_ref, the unmodified Cython/C compiled from its sources) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (particles per GPU side, MAS, axis, description)
+    "cfg2_512_cic": dict(nside=512, mas="CIC", axis=2),
+    "cfg1_128_cic": dict(nside=128, mas="CIC", axis=2),
+    "cfg3_1024_tsc": dict(nside=1024, mas="TSC", axis=2),
+    "256_pcs": dict(nside=256, mas="PCS", axis=2),
+}
+GRID_FOR_GPUS = {1: 1.0, 2: 1.25, 4: 1.5625, 8: 2.0}     # grid side multiplier: 512 -> 640 / 800 / 1024
+BOX = 1000.0
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill(); out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own CPU implementation (oracle/_ref) or, if that was
+# never built, the oracle port.  Checker code is only ever TIMED here, never used by the product path.
+# --------------------------------------------------------------------------------------------------
+def cpu_snapshot_fn():
+    import contextlib, io
+    import numpy as np
+    from oracle import ref_loader
+    if ref_loader.available():
+        MASL, PKL = ref_loader.load()
+        kind = "reference"
+
+        def run(pos, dims, mas, axis, threads):
+            d = np.zeros((dims,) * 3, np.float32)
+            MASL.MA(pos, d, BOX, mas)                      # serial Cython kernel (the path MA() takes)
+            d /= np.mean(d, dtype=np.float64); d -= 1.0
+            with contextlib.redirect_stdout(io.StringIO()):
+                return PKL.Pk(d, BOX, axis, mas, threads)
+    else:
+        from oracle import pylians_oracle as O
+        kind = "port"
+
+        def run(pos, dims, mas, axis, threads):
+            d = np.zeros((dims,) * 3, np.float32)
+            O.MA(pos, d, BOX, mas)
+            d /= np.mean(d, dtype=np.float64); d -= 1.0
+            return O.Pk(d, BOX, axis, mas, threads)
+    return run, kind
+
+
+def cpu_measure(nside, mas, axis, repeats):
+    import numpy as np
+    run, kind = cpu_snapshot_fn()
+    threads = os.cpu_count() or 1
+    rng = np.random.default_rng(1)
+    pos = (rng.random((nside ** 3, 3), dtype=np.float32) * np.float32(BOX)).astype(np.float32)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        run(pos, nside, mas, axis, threads)
+        times.append(time.perf_counter() - t0)
+    return times, kind, threads
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = args.steps + args.warmup
+    nside = 256 if total > 6 else 384                      # bounded sample of the 512^3 workload
+    nside = min(nside, wl["nside"])
+    times, kind, threads = cpu_measure(nside, wl["mas"], wl["axis"], total)
+    timed = times[args.warmup:] if args.steps > 0 else times
+    sec = sum(timed) / max(len(timed), 1)
+    val = nside ** 3 / sec
+    sample = "%d^3 particles %s onto %d^3 grid + overdensity + Pk (axis=%d): same path, reduced size; particles/s" % (
+        nside, wl["mas"], nside, wl["axis"])
+    line = {"impl": "reference", "metric": "MA+Pk snapshot throughput", "value": val, "unit": "particles/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic uniform random particles, seed 1",
+            "config": workload_config(args, wl),
+            "cpu_baseline": {"value": val, "unit": "particles/s", "cores": threads, "kind": kind, "sample": sample,
+                             "note": "MA is the reference's serial Cython kernel (1 core); threads only feed the FFT"},
+            "e2e": {"value": val, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "s_per_snapshot_sample": sec}
+    print(json.dumps(line))
+
+
+def workload_config(args, wl):
+    n = args.gpus
+    gside = int(round(wl["nside"] * GRID_FOR_GPUS.get(n, 1.0)))
+    return {"workload": "%s: %d^3 particles per GPU x %d GPU(s), %s onto %d^3 grid, BoxSize=%g, Pk axis=%d (l=0,2,4)" % (
+                args.workload, wl["nside"], n, wl["mas"], gside, BOX, wl["axis"]),
+            "particles_total": wl["nside"] ** 3 * n, "grid": gside, "mas": wl["mas"], "axis": wl["axis"],
+            "l2": "inputs exceed L2 (pos %.2f GB, grid %.2f GB per GPU vs 126 MB L2)" % (
+                wl["nside"] ** 3 * 12 / 1e9, gside ** 3 * 4 / 1e9 / n)}
+
+
+# --------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import numpy as np
+    import torch
+    import pylians_b200
+    from pylians_b200 import _lib, MAS_library as MASL, Pk_library as PKL
+    pylians_b200.set_verbose(False)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    nside, mas, axis = wl["nside"], wl["mas"], wl["axis"]
+    npart = nside ** 3
+    gside = int(round(nside * GRID_FOR_GPUS.get(world, 1.0)))
+    peaks, peak_src = read_peaks()
+
+    # synthetic particles, generated on the device (seed 1 + rank), uniform in the box
+    gen = torch.Generator(device=dev); gen.manual_seed(1 + rank)
+    pos = torch.rand((npart, 3), device=dev, dtype=torch.float32, generator=gen) * BOX
+    if world > 1:
+        from pylians_b200 import dist as pdist
+        engine = pdist.SlabPk(gside, BOX, mas, axis)
+
+        def snapshot(p):
+            return engine.run(p)
+    else:
+        grid = torch.empty((gside,) * 3, device=dev, dtype=torch.float32)
+
+        def snapshot(p):
+            grid.zero_()
+            MASL.MA(p, grid, BOX, mas)
+            MASL.overdensity(grid)
+            return PKL.Pk(grid, BOX, axis, mas, 1)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            out = fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    # ---- device-resident arm -----------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        snapshot(pos)
+    _lib.timing_enable(True)
+    for w in range(4):
+        _lib.timing_collect(w)
+    sampler = ClockSampler(local_rank); sampler.start()
+    l0 = _lib.launch_count()
+    ms, pk = timed_loop(lambda: snapshot(pos), args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop()
+    ring_ms, ring_n = _lib.timing_collect(_lib.T_RING)
+    tile_ms, tile_n = _lib.timing_collect(_lib.T_TILE)
+    dir_ms, dir_n = _lib.timing_collect(_lib.T_DIRECT)
+    _lib.timing_enable(False)
+    ms_step = ms / args.steps
+    value = npart * world / (ms_step * 1e-3)
+
+    # ---- per-stage device times (one extra pass, CUDA events on the current stream) ---------------
+    stages = {}
+    if world == 1:
+        def ev():
+            e = torch.cuda.Event(enable_timing=True); e.record(); return e
+        reps = 3
+        acc = {"deposit_ms": 0.0, "overdensity_ms": 0.0, "pk_ms": 0.0}
+        for _ in range(reps):
+            grid.zero_(); e0 = ev(); MASL.MA(pos, grid, BOX, mas); e1 = ev(); MASL.overdensity(grid); e2 = ev()
+            PKL.Pk(grid, BOX, axis, mas, 1); e3 = ev(); torch.cuda.synchronize()
+            acc["deposit_ms"] += e0.elapsed_time(e1) / reps; acc["overdensity_ms"] += e1.elapsed_time(e2) / reps
+            acc["pk_ms"] += e2.elapsed_time(e3) / reps
+        stages = {k: round(v, 4) for k, v in acc.items()}
+        stages["deposit_particles_per_s"] = npart / (acc["deposit_ms"] * 1e-3)
+        stages["pk_modes_per_s"] = gside * gside * (gside // 2 + 1) / (acc["pk_ms"] * 1e-3)
+
+    # ---- end-to-end arm: particles in pinned host memory, spectra read back ------------------------
+    pos_host = torch.empty((npart, 3), dtype=torch.float32, pin_memory=True)
+    pos_host.copy_(pos); torch.cuda.synchronize()
+    d2h_bytes = 0
+
+    def e2e_step():
+        return snapshot(pos_host.to(dev, non_blocking=True)) if world > 1 else snapshot_host()
+
+    def snapshot_host():
+        grid.zero_()
+        MASL.MA(pos_host, grid, BOX, mas)          # H2D of the particle array happens inside MA
+        MASL.overdensity(grid)
+        return PKL.Pk(grid, BOX, axis, mas, 1)     # D2H of the bins happens inside Pk
+
+    for _ in range(2):
+        e2e_step()
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_e2e, pk_e = timed_loop(e2e_step, e2e_steps)
+    L = PKL.get_layout(gside, 1)
+    d2h_bytes = int(L.n_doubles * 8 + L.n_counts * 8)
+    e2e_val = npart * world / (ms_e2e / e2e_steps * 1e-3)
+
+    # ---- roofline of the dominant bandwidth-bound kernel (binning ring kernel) --------------------
+    nmodes_ring = None
+    roof = None
+    if ring_n > 0:
+        middle = gside // 2
+        kz_hi = middle - 1 if gside % 2 == 0 else middle
+        rows_local = gside * gside // world
+        alg_bytes = 8.0 * rows_local * kz_hi                        # 8 B per complex mode, read once
+        achieved = alg_bytes / (ring_ms / ring_n * 1e-3) / 1e9
+        roof = {"kernel": "ring_kernel<1,phase>", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "peak_source": peak_src, "avg_launch_ms": ring_ms / ring_n, "launches": ring_n,
+                "algorithmic_bytes_per_launch": alg_bytes}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cn = min(256, nside)
+            times, kind, threads = cpu_measure(cn, mas, axis, 2)
+            sec = min(times)
+            cpu = {"value": cn ** 3 / sec, "unit": "particles/s", "cores": threads, "kind": kind,
+                   "sample": "%d^3 particles %s onto %d^3 grid + overdensity + Pk, best of 2 (%.1f s each); "
+                             "MA is the reference's serial kernel, threads feed only the FFT" % (cn, mas, cn, sec)}
+        line = {"metric": "MA+Pk snapshot throughput", "value": value, "unit": "particles/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+                "s_per_snapshot": ms_step * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic uniform random particles generated on device, seed 1+rank",
+                "config": workload_config(args, wl), "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_val, "unit": "particles/s", "h2d_bytes_per_step": int(npart * 12),
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / e2e_steps,
+                        "note": "particle array in pinned host memory -> MASL.MA -> overdensity -> PKL.Pk -> bins on host"},
+                "roofline": roof, "cpu_baseline": cpu, "stages": stages,
+                "kernels": {"ring_ms": ring_ms / max(ring_n, 1), "tile_ms": tile_ms / max(tile_n, 1),
+                            "direct_ms": dir_ms / max(dir_n, 1), "ring_launches": ring_n, "tile_launches": tile_n,
+                            "direct_launches": dir_n},
+                "check": {"P0_first_bins": [float(x) for x in pk.Pk[:3, 0]], "shot_noise_expected": BOX ** 3 / (npart * world)}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2_512_cic", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -211,3 +211,20 @@ for _m in ("NGP", "CIC", "TSC", "PCS"):
             _f = _masc(_m, _d, _w)
             globals()[_f.__name__] = _f
 del _m, _d, _w, _f
+
+
+def overdensity(delta):
+    """In-place `delta /= mean(delta); delta -= 1` (what every caller does between MA and Pk, e.g.
+    Pk_snapshot.py:88,194) as two bandwidth-bound kernels; mean in float64.  numpy or CUDA tensor."""
+    _require_f32(delta, "delta", delta.ndim)
+    lib = _lib.load()
+    dev = _device()
+    stream = torch.cuda.current_stream(dev)
+    host = not (_is_torch(delta) and delta.is_cuda)
+    d = _to_device(delta, dev) if host else delta
+    if not d.is_contiguous():
+        raise ValueError("delta must be C-contiguous")
+    scratch = torch.empty(2, dtype=torch.float64, device=dev)
+    _lib.check(lib.pylb_overdensity(d.data_ptr(), d.numel(), scratch.data_ptr(), stream.cuda_stream), "pylb_overdensity")
+    if host:
+        _write_back(d, delta, stream)

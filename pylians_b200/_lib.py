@@ -29,6 +29,8 @@ SIGNATURES = {
     "pylb_version": (c_int, []),
     "pylb_last_error": (ctypes.c_char_p, []),
     "pylb_launch_count": (c_int64, []),
+    "pylb_timing_enable": (None, [c_int]),
+    "pylb_timing_collect": (c_int, [c_int, ctypes.POINTER(c_double), ctypes.POINTER(c_int)]),
     "NGP": (None, [c_void_p, c_void_p, c_void_p, ctypes.c_long, c_int, c_int, c_float, c_int]),
     "CIC": (None, [c_void_p, c_void_p, c_void_p, ctypes.c_long, c_int, c_int, c_float, c_int]),
     "TSC": (None, [c_void_p, c_void_p, c_void_p, ctypes.c_long, c_int, c_int, c_float, c_int]),
@@ -88,3 +90,17 @@ def check(rc, what):
 
 def launch_count():
     return int(load().pylb_launch_count())
+
+
+T_RING, T_TILE, T_DIRECT, T_GENERIC = 0, 1, 2, 3
+
+
+def timing_enable(on):
+    load().pylb_timing_enable(int(bool(on)))
+
+
+def timing_collect(which):
+    """(total_ms, launches) of kernel `which` since the last collect (CUDA events on its stream)."""
+    ms, n = c_double(0), c_int(0)
+    check(load().pylb_timing_collect(int(which), ctypes.byref(ms), ctypes.byref(n)), "pylb_timing_collect")
+    return ms.value, n.value

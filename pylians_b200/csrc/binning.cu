@@ -422,6 +422,7 @@ static int launch_ring_f(const BinGeom &g, const FieldPtrs &dk, const RowEnt *ta
     const int rows_per_span = (nrows + nspan - 1) / nspan;
     nspan = (nrows + rows_per_span - 1) / rows_per_span;
     dim3 grid(nspan, nseg);
+    timing_begin(PYLB_T_RING, st);
     if (want_phase) {
         if (write_back) ring_kernel<F, true, true><<<grid, RING_T, 0, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
         else ring_kernel<F, true, false><<<grid, RING_T, 0, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
@@ -429,6 +430,7 @@ static int launch_ring_f(const BinGeom &g, const FieldPtrs &dk, const RowEnt *ta
         if (write_back) ring_kernel<F, false, true><<<grid, RING_T, 0, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
         else ring_kernel<F, false, false><<<grid, RING_T, 0, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
     }
+    timing_end(PYLB_T_RING, st);
     PYLB_LAUNCH_CHECK();
     return 0;
 }
@@ -560,7 +562,9 @@ extern "C" int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int ax
         if (axis != 2) { set_error("pylb_pk_bin: the ring kernel needs axis=2 (transpose the field for other axes)"); rc = 1; }
         else rc = run_ring(g, fp, want_phase, write_back, st);
     } else {
+        timing_begin(PYLB_T_GENERIC, st);
         rc = launch_generic(g, fp, 0, 1, L.middle + 1, want_phase, write_back, st);
+        timing_end(PYLB_T_GENERIC, st);
     }
     cudaFreeAsync(tab, st);
     return rc;

@@ -4,6 +4,8 @@
 #include <string.h>
 
 #include <atomic>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -19,6 +21,29 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+
+// ---- per-kernel timing ---------------------------------------------------------------------------
+struct TimingSlot {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;
+    cudaEvent_t cur_begin = nullptr;
+};
+static bool g_timing = false;
+static TimingSlot g_slots[PYLB_T_COUNT];
+
+void timing_begin(int which, cudaStream_t st) {
+    if (!g_timing) return;
+    TimingSlot &s = g_slots[which];
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!s.pool.empty()) { ev = s.pool.back(); s.pool.pop_back(); }
+    else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
+    cudaEventRecord(ev.first, st);
+    s.pending.push_back(ev);
+}
+void timing_end(int which, cudaStream_t st) {
+    if (!g_timing) return;
+    TimingSlot &s = g_slots[which];
+    if (!s.pending.empty()) cudaEventRecord(s.pending.back().second, st);
+}
 
 int ma_direct(const float *pos, int64_t np, int ndim, int64_t ps0, int64_t ps1, void *grid, int f64,
               int dims, float inv, int mas, const float *w, float zrep, cudaStream_t st);
@@ -76,6 +101,23 @@ using namespace pylb;
 extern "C" int pylb_version(void) { return PYLB_VERSION; }
 extern "C" const char *pylb_last_error(void) { return g_err; }
 extern "C" int64_t pylb_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" void pylb_timing_enable(int on) { g_timing = on != 0; }
+extern "C" int pylb_timing_collect(int which, double *total_ms, int *launches) {
+    PYLB_REQUIRE(which >= 0 && which < PYLB_T_COUNT && total_ms && launches, "pylb_timing_collect: bad arguments");
+    TimingSlot &s = g_slots[which];
+    double tot = 0;
+    int n = 0;
+    for (auto &ev : s.pending) {
+        PYLB_CHECK(cudaEventSynchronize(ev.second));
+        float ms = 0;
+        PYLB_CHECK(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        tot += ms; n++;
+        s.pool.push_back(ev);
+    }
+    s.pending.clear();
+    *total_ms = tot; *launches = n;
+    return 0;
+}
 
 extern "C" size_t pylb_ma_workspace_bytes(int64_t np, int ndim, int dims, int mas, int has_w, int grid_f64, int algo) {
     if (algo == PYLB_MA_DIRECT) return 0;

@@ -10,6 +10,9 @@ namespace pylb {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+// optional CUDA-event brackets around the dominant kernels (see pylb_timing_enable)
+void timing_begin(int which, cudaStream_t st);
+void timing_end(int which, cudaStream_t st);
 
 #define PYLB_CHECK(expr)                                                                          \
     do {                                                                                          \

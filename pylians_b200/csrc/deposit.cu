@@ -68,8 +68,10 @@ static int launch_direct(const float *pos, int64_t np, int64_t ps0, int64_t ps1,
     int64_t blocks = (np + threads - 1) / threads;
     const int64_t cap = (int64_t)sm_count() * 32;
     if (blocks > cap) blocks = cap;
+    timing_begin(PYLB_T_DIRECT, st);
     deposit_direct_kernel<MAS, HASW, GT, NDIM><<<(unsigned)blocks, threads, 0, st>>>(
         pos, np, ps0, ps1, (GT *)grid, dims, inv, w, zrep);
+    timing_end(PYLB_T_DIRECT, st);
     PYLB_LAUNCH_CHECK();
     return 0;
 }

@@ -3,8 +3,10 @@
 // Restates (does not copy) the arithmetic of the reference kernels so that every particle lands in
 // the same cells: library/MAS_library/MAS_library.pyx NGP :290-291, CIC :152-157, TSC :392-399,
 // PCS :485-492.  What must match exactly is the CELL selection (fp32 product pos*inv without FMA
-// contraction, double-precision floor/trunc); the weight polynomials are evaluated in fp32 and
-// agree with the reference's double-then-rounded values to ~1 ulp (budget: 1e-5 relative).
+// contraction, double-precision floor/trunc).  The TSC/PCS weight polynomials are evaluated in double
+// and rounded once to float, as the reference's C does (its literals are doubles): an fp32 `*(1/6)`
+// biases every PCS weight by +3e-8 and fails the reference's own 8-decimal mass-conservation test
+// (Test/test_MAS.py:52-84).
 #pragma once
 #include "common.cuh"
 
@@ -32,10 +34,13 @@ __device__ __forceinline__ int axis_stencil(float p, float inv, float (&C)[Suppo
         const int m = __double2int_rd((double)dist - 1.5);  // <int>floor(dist-1.5), :393
 #pragma unroll
         for (int j = 0; j < 3; j++) {
+            // `diff` is a float; the literals are doubles, so the polynomial is evaluated in double and
+            // rounded once to float (:396-399).  Keeps sum(weights) == 1 to ~1e-8 like the reference.
             const float diff = fabsf(__fsub_rn((float)(m + j + 1), dist));
+            const double dd = (double)diff;
             float c;
-            if (diff < 0.5f) c = 0.75f - diff * diff;
-            else if (diff < 1.5f) { const float t = 1.5f - diff; c = 0.5f * t * t; }
+            if (diff < 0.5f) c = (float)(0.75 - (double)__fmul_rn(diff, diff));
+            else if (diff < 1.5f) c = (float)(0.5 * (1.5 - dd) * (1.5 - dd));
             else c = 0.0f;
             C[j] = c;
         }
@@ -45,9 +50,10 @@ __device__ __forceinline__ int axis_stencil(float p, float inv, float (&C)[Suppo
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const float diff = fabsf(__fsub_rn((float)(m + j + 1), dist));
+            const double dd = (double)diff;   // double evaluation, one rounding to float (:489-492)
             float c;
-            if (diff < 1.0f) c = (4.0f - 6.0f * diff * diff + 3.0f * diff * diff * diff) * (1.0f / 6.0f);
-            else if (diff < 2.0f) { const float t = 2.0f - diff; c = t * t * t * (1.0f / 6.0f); }
+            if (diff < 1.0f) c = (float)((4.0 - 6.0 * dd * dd + 3.0 * dd * dd * dd) / 6.0);
+            else if (diff < 2.0f) c = (float)((2.0 - dd) * (2.0 - dd) * (2.0 - dd) / 6.0);
             else c = 0.0f;
             C[j] = c;
         }

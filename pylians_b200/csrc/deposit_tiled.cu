@@ -256,8 +256,10 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
         count_launch(2);
         // upper bound on work items: every non-empty tile has at most count/CHUNK + 1 chunks
         const int64_t max_items = (int64_t)n / CHUNK + tg.ntiles;
+        timing_begin(PYLB_T_TILE, st);
         deposit_tile_kernel<MAS, HASW><<<(unsigned)max_items, TILE_THREADS, smem, st>>>(
             pos, first, ps0, ps1, w, inv, tg, ws.v1, ws.tile_begin, ws.chunk_off, grid);
+        timing_end(PYLB_T_TILE, st);
         PYLB_LAUNCH_CHECK();
     }
     return 0;
