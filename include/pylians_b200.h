@@ -43,8 +43,11 @@ enum { PYLB_NGP = 0, PYLB_CIC = 1, PYLB_TSC = 2, PYLB_PCS = 3 };
 /* deposit algorithm selector for pylb_ma */
 enum { PYLB_MA_AUTO = 0, PYLB_MA_DIRECT = 1, PYLB_MA_TILED = 2 };
 
-/* binning algorithm selector for pylb_pk_bin */
-enum { PYLB_BIN_AUTO = 0, PYLB_BIN_GENERIC = 1, PYLB_BIN_RING = 2 };
+/* binning algorithm selector for pylb_pk_bin.  OR in PYLB_BIN_PRECISE for the fp64 option: every
+ * mode is squared and accumulated in float64 exactly like Pk_library.pyx:358-360 (the default forms
+ * |delta_k|^2 in fp32 and accumulates in fp64 from the first group sum on; the generic kernel is
+ * always fp64). */
+enum { PYLB_BIN_AUTO = 0, PYLB_BIN_GENERIC = 1, PYLB_BIN_RING = 2, PYLB_BIN_PRECISE = 16 };
 
 int pylb_version(void);
 const char *pylb_last_error(void);

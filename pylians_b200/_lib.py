@@ -56,7 +56,7 @@ SIGNATURES = {
 }
 
 MA_AUTO, MA_DIRECT, MA_TILED = 0, 1, 2
-BIN_AUTO, BIN_GENERIC, BIN_RING = 0, 1, 2
+BIN_AUTO, BIN_GENERIC, BIN_RING, BIN_PRECISE = 0, 1, 2, 16
 
 _lib = None
 

@@ -74,7 +74,7 @@ __global__ void mas_table_kernel(double *tab, int middle, int dims, int F, BinGe
 struct __align__(16) RowEnt {
     int r2;
     short kx, ky;
-    long long off;  // element offset of the row start: ix*stride_x + iy*stride_y
+    long long off;  // BYTE offset of the row start: 8*(ix*stride_x + iy*stride_y)
 };
 
 __global__ void row_keys_kernel(unsigned *keys, unsigned *vals, int nrows, BinGeom g) {
@@ -95,31 +95,32 @@ __global__ void row_table_kernel(const unsigned *keys, const unsigned *vals, Row
     e.r2 = (int)keys[i];
     e.kx = (short)wavenumber(g.x0 + ix, g.dims, g.middle);
     e.ky = (short)wavenumber(g.y0 + iy, g.dims, g.middle);
-    e.off = (long long)ix * g.stride_x + (long long)iy * g.stride_y;
+    e.off = 8ll * ((long long)ix * g.stride_x + (long long)iy * g.stride_y);
     tab[i] = e;
 }
 
 // ------------------------------------------------------------------------------------------------
-// phase = atan2(re, |delta_k|)  (Pk_library.pyx:361 -- sic, the real part against the modulus), so
-// |re/|delta_k|| <= 1 and the angle is in [-pi/4, pi/4].  fp32 evaluation: t = re*rsqrt(d2), then
-// atan(t) with one range reduction (|t| > tan(pi/8) -> pi/4 + atan((|t|-1)/(|t|+1))) and an odd
-// minimax polynomial on [-tan(pi/8), tan(pi/8)] (abs error < 2e-8).
+// phase^2 with phase = atan2(re, |delta_k|)  (Pk_library.pyx:361 -- sic, the real part against the
+// modulus).  |re|/|delta_k| <= 1 and atan^2 is even, so phase^2 = s*G(s) with s = re^2/|delta_k|^2 in
+// [0,1]; G(s) = atan(sqrt(s))^2/s is analytic on [0,1] (nearest singularity s = -1) and a degree-9
+// near-minimax polynomial reproduces it to 1e-8 (2e-7 with fp32 Horner rounding).  No branches,
+// no range reduction: 1 MUFU.RCP + 11 FMUL/FFMA.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float phase_sq(float re, float d2) {
-    if (!(d2 > 0.0f)) return 0.0f;  // atan2(0, 0) = 0
-    float t = fabsf(re) * rsqrtf(d2);
-    t = fminf(t, 1.0f);
-    const bool hi = t > 0.41421356f;
-    const float u = hi ? __fdividef(t - 1.0f, t + 1.0f) : t;
-    const float s = u * u;
-    // atan(u) = u*(1 + s*(c1 + s*(c2 + s*(c3 + s*c4)))),  |u| <= 0.4143
-    float q = 0.0805374449538e-0f;
-    q = fmaf(q, s, -0.138776856032e-0f);
-    q = fmaf(q, s, 0.199777106478e-0f);
-    q = fmaf(q, s, -0.333329491539e-0f);
-    float a = fmaf(q * s, u, u);
-    if (hi) a += 0.78539816339f;
-    return a * a;
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaxf(d2, 1e-37f)));   // 1 MUFU; 1-ulp error is irrelevant here
+    const float s = fminf((re * re) * rc, 1.0f);
+    float q = -6.465150895e-03f;
+    q = fmaf(q, s, 3.925943169e-02f);
+    q = fmaf(q, s, -1.113286174e-01f);
+    q = fmaf(q, s, 2.034298861e-01f);
+    q = fmaf(q, s, -2.851652190e-01f);
+    q = fmaf(q, s, 3.508593260e-01f);
+    q = fmaf(q, s, -4.181177634e-01f);
+    q = fmaf(q, s, 5.110430921e-01f);
+    q = fmaf(q, s, -6.666647075e-01f);
+    q = fmaf(q, s, 9.999999906e-01f);
+    return q * s;
 }
 
 __device__ __forceinline__ float2 ld_stream(const float2 *p) {
@@ -130,36 +131,86 @@ __device__ __forceinline__ float2 ld_stream(const float2 *p) {
 
 // ------------------------------------------------------------------------------------------------
 // ring kernel
+//
+// PRECISE = false (default): |delta_k|^2, the cross products and phase^2 are formed in fp32 from the
+//   fp32-deconvolved mode and summed in fp32 over the (<= a few dozen) rows sharing r2, then every
+//   further accumulation is fp64.  Per-mode rounding is 6e-8 relative and unbiased -- below the
+//   reference's own FFT-to-FFT differences and 100x inside the 1e-5 contract.
+// PRECISE = true ("fp64 accumulation option"): every mode is squared and summed in fp64 exactly like
+//   Pk_library.pyx:358-360.
 // ------------------------------------------------------------------------------------------------
-constexpr int RING_T = 256;      // threads per CTA = kz values per CTA
-constexpr int RING_CHUNK = 128;  // rows staged in shared memory at a time
-constexpr int RING_U = 8;        // rows whose loads are in flight per thread
+constexpr int RING_T = 256;         // threads per CTA = kz values per CTA
+constexpr int RING_SPAN_MAX = 512;  // rows per CTA (their table entries are staged in shared memory once)
+
+template <int F> struct RingCfg { static constexpr int D = (F == 1) ? 16 : 8; };  // cp.async pipeline depth (rows)
 
 template <int F>
 struct RingSmem {
-    RowEnt ent[RING_CHUNK];
-    double cxy[RING_CHUNK][F];
+    float2 z[RingCfg<F>::D][RING_T][F];   // per-thread prefetch ring: thread t only ever touches z[.][t][.]
+    RowEnt ent[RING_SPAN_MAX];
+    double cxy[RING_SPAN_MAX][F];
 };
 
-template <int F, bool PHASE, bool WB>
-__global__ void __launch_bounds__(RING_T)
+template <bool PRECISE> struct AccT { typedef float type; };
+template <> struct AccT<true> { typedef double type; };
+
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int F, bool PHASE, bool WB, bool PRECISE>
+__global__ void __launch_bounds__(RING_T, PRECISE ? 2 : 3)
 ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, int rows_per_span, int kz_hi) {
     constexpr int X = F * (F - 1) / 2;
     constexpr int Q = F + X;
-    __shared__ RingSmem<F> sm;
+    constexpr int D = RingCfg<F>::D;
+    typedef typename AccT<PRECISE>::type acc_t;
+    extern __shared__ __align__(16) unsigned char ring_smem_raw[];
+    RingSmem<F> &sm = *reinterpret_cast<RingSmem<F> *>(ring_smem_raw);
 
-    const int kz = 1 + blockIdx.y * RING_T + threadIdx.x;
+    const int tid = threadIdx.x;
+    const int kz = 1 + blockIdx.y * RING_T + tid;
     const bool active = kz <= kz_hi;
     const int kzc = active ? kz : kz_hi;  // clamp so idle lanes stay in bounds
     const int kz2 = kzc * kzc;
     const int i0 = blockIdx.x * rows_per_span;
-    const int i1 = min(nrows, i0 + rows_per_span);
-    if (i0 >= i1) return;
+    const int total = min(nrows, i0 + rows_per_span) - i0;
+    if (total <= 0) return;
+
+    // stage this span's row table (and the per-row x*y MAS factors) once
+    for (int j = tid; j < total; j += RING_T) {
+        const RowEnt e = tab[i0 + j];
+        sm.ent[j] = e;
+        const int ax = e.kx < 0 ? -e.kx : e.kx, ay = e.ky < 0 ? -e.ky : e.ky;
+#pragma unroll
+        for (int f = 0; f < F; f++)
+            sm.cxy[j][f] = g.mas_tab[f * (g.middle + 1) + ax] * g.mas_tab[f * (g.middle + 1) + ay];
+    }
+    __syncthreads();
+
+    // per-thread base pointers: element kz of a row starts at base[f] + row byte offset
+    const char *base[F];
+#pragma unroll
+    for (int f = 0; f < F; f++) base[f] = reinterpret_cast<const char *>(dk.p[f] + kzc);
+
+    auto prefetch = [&](int j) {   // this thread's element of row j -> ring slot j % D
+        if (j < total) {
+            const long long off = sm.ent[j].off;
+#pragma unroll
+            for (int f = 0; f < F; f++) cp_async8(&sm.z[j & (D - 1)][tid][f], base[f] + off);
+        }
+        cp_async_commit();         // one group per row, even when empty, so wait_group<N> counts rows
+    };
+    for (int j = 0; j < D; j++) prefetch(j);
 
     double cz[F];
 #pragma unroll
     for (int f = 0; f < F; f++) cz[f] = g.mas_tab[f * (g.middle + 1) + kzc];
     const int mid2 = g.middle * g.middle;
+    const double dkz2 = (double)kz2;
 
     // ring state (bins b0 / b0+1, 2-D bin (p, kz)) and span state (1-D bin kz)
     double lo3[3][Q], hi3[3][Q], lok = 0, hik = 0, loph = 0, hiph = 0, a2[Q], a1[Q];
@@ -171,7 +222,7 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
         for (int l = 0; l < 3; l++) { lo3[l][q] = 0; hi3[l][q] = 0; }
     }
     // group state (rows sharing r2)
-    double gq[Q], gph = 0;
+    acc_t gq[Q], gph = 0;
     int gcnt = 0;
 #pragma unroll
     for (int q = 0; q < Q; q++) gq[q] = 0;
@@ -183,15 +234,15 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
         if (gcnt == 0) return;
         if (sel) {
 #pragma unroll
-            for (int q = 0; q < Q; q++) { hi3[0][q] += gq[q]; hi3[1][q] += gq[q] * w2; hi3[2][q] += gq[q] * w4; }
-            hik += (double)gcnt * kk; hicn += gcnt; hiph += gph;
+            for (int q = 0; q < Q; q++) { const double v = (double)gq[q]; hi3[0][q] += v; hi3[1][q] += v * w2; hi3[2][q] += v * w4; }
+            hik += (double)gcnt * kk; hicn += gcnt; hiph += (double)gph;
         } else {
 #pragma unroll
-            for (int q = 0; q < Q; q++) { lo3[0][q] += gq[q]; lo3[1][q] += gq[q] * w2; lo3[2][q] += gq[q] * w4; }
-            lok += (double)gcnt * kk; locn += gcnt; loph += gph;
+            for (int q = 0; q < Q; q++) { const double v = (double)gq[q]; lo3[0][q] += v; lo3[1][q] += v * w2; lo3[2][q] += v * w4; }
+            lok += (double)gcnt * kk; locn += gcnt; loph += (double)gph;
         }
 #pragma unroll
-        for (int q = 0; q < Q; q++) { a2[q] += gq[q]; if (in1d) a1[q] += gq[q]; gq[q] = 0; }
+        for (int q = 0; q < Q; q++) { const double v = (double)gq[q]; a2[q] += v; if (in1d) a1[q] += v; gq[q] = 0; }
         c2 += gcnt;
         if (in1d) c1 += gcnt;
         gcnt = 0; gph = 0;
@@ -231,78 +282,100 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
         }
     };
 
-    for (int c0 = i0; c0 < i1; c0 += RING_CHUNK) {
-        const int cn = min(RING_CHUNK, i1 - c0);
-        __syncthreads();
-        for (int j = threadIdx.x; j < cn; j += RING_T) {
-            const RowEnt e = tab[c0 + j];
-            sm.ent[j] = e;
-            const int ax = e.kx < 0 ? -e.kx : e.kx, ay = e.ky < 0 ? -e.ky : e.ky;
-#pragma unroll
-            for (int f = 0; f < F; f++)
-                sm.cxy[j][f] = g.mas_tab[f * (g.middle + 1) + ax] * g.mas_tab[f * (g.middle + 1) + ay];
+    // new r2 group (CTA-uniform branch): bins, |k|, mu^2 and the Legendre weights, once per group
+    auto new_group = [&](int r2) {
+        apply_group();
+        cur_r2 = r2;
+        if (r2 >= ring_hi) {
+            flush_ring();
+            ring_p = isqrt_exact(r2);
+            ring_hi = (ring_p + 1) * (ring_p + 1);
+            b0 = isqrt_exact(ring_p * ring_p + kz2);
+            thr = (b0 + 1) * (b0 + 1);
         }
-        __syncthreads();
+        const int n = r2 + kz2;                 // >= 1 because kz >= 1
+        sel = n >= thr;
+        in1d = n <= mid2;                       // k <= middle, :364
+        const double dn = (double)n;
+        double mu2;
+        if (PRECISE) {
+            kk = sqrt(dn);                      // :334
+            const double mu = (double)kzc / kk; // :347
+            mu2 = mu * mu;
+        } else {
+            // fp32 seed + one Newton step in fp64: relative error < 1e-13 on 1/n and 1/sqrt(n)
+            const float nf = (float)n;
+            double r = (double)__frcp_rn(nf);
+            r = r * (2.0 - dn * r);
+            double x = (double)rsqrtf(nf);
+            x = x * (1.5 - 0.5 * dn * x * x);
+            x = x * (1.5 - 0.5 * dn * x * x);
+            kk = dn * x;
+            mu2 = dkz2 * r;
+        }
+        w2 = (3.0 * mu2 - 1.0) / 2.0;                       // :378
+        w4 = (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0;   // :379
+    };
 
-        for (int j0 = 0; j0 < cn; j0 += RING_U) {
-            float2 z[RING_U][F];
+    auto process = [&](int j, const float2 (&z)[F]) {
+        const RowEnt e = sm.ent[j];
+        if (e.r2 != cur_r2) new_group(e.r2);   // CTA-uniform
+        float re[F], im[F];
 #pragma unroll
-            for (int u = 0; u < RING_U; u++) {
-                if (j0 + u < cn) {
-                    const long long off = sm.ent[j0 + u].off + kzc;
+        for (int f = 0; f < F; f++) {
+            const float mf = (float)(sm.cxy[j][f] * cz[f]);  // double product -> float, :354
+            re[f] = __fmul_rn(z[f].x, mf);                    // complex64 *= float, :355
+            im[f] = __fmul_rn(z[f].y, mf);
+            if (WB && active)
+                *reinterpret_cast<float2 *>(const_cast<char *>(base[f]) + e.off) = make_float2(re[f], im[f]);
+        }
+        float d2_0 = 0.f;
 #pragma unroll
-                    for (int f = 0; f < F; f++) z[u][f] = WB ? dk.p[f][off] : ld_stream(dk.p[f] + off);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < RING_U; u++) {
-                if (j0 + u < cn) {
-                    const int r2 = sm.ent[j0 + u].r2;
-                    if (r2 != cur_r2) {  // CTA-uniform
-                        apply_group();
-                        cur_r2 = r2;
-                        if (r2 >= ring_hi) {
-                            flush_ring();
-                            ring_p = isqrt_exact(r2);
-                            ring_hi = (ring_p + 1) * (ring_p + 1);
-                            b0 = isqrt_exact(ring_p * ring_p + kz2);
-                            thr = (b0 + 1) * (b0 + 1);
-                        }
-                        const int n = r2 + kz2;
-                        sel = n >= thr;
-                        in1d = n <= mid2;                   // k <= middle, :364
-                        const double dn = (double)n;
-                        kk = sqrt(dn);                      // :334
-                        const double mu = (double)kzc / kk; // :347 (n > 0 because kz >= 1)
-                        const double mu2 = mu * mu;
-                        w2 = (3.0 * mu2 - 1.0) / 2.0;       // :378
-                        w4 = (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0;  // :379
-                    }
-                    float re[F], im[F];
-#pragma unroll
-                    for (int f = 0; f < F; f++) {
-                        const float mf = (float)(sm.cxy[j0 + u][f] * cz[f]);  // double product -> float, :354
-                        re[f] = __fmul_rn(z[u][f].x, mf);                      // complex64 *= float, :355
-                        im[f] = __fmul_rn(z[u][f].y, mf);
-                        if (WB && active) dk.p[f][sm.ent[j0 + u].off + kz] = make_float2(re[f], im[f]);
-                        gq[f] += (double)re[f] * (double)re[f] + (double)im[f] * (double)im[f];  // :358-360
-                    }
-                    if (X > 0) {
-                        int ix = 0;
-#pragma unroll
-                        for (int a = 0; a < F; a++)
-#pragma unroll
-                            for (int b = a + 1; b < F; b++) {
-                                gq[F + ix] += (double)re[a] * (double)re[b] + (double)im[a] * (double)im[b];  // :721-722
-                                ix++;
-                            }
-                    }
-                    if (PHASE) gph += (double)phase_sq(re[0], fmaf(re[0], re[0], im[0] * im[0]));
-                    gcnt++;
-                }
+        for (int f = 0; f < F; f++) {
+            if (PRECISE) gq[f] += (acc_t)((double)re[f] * (double)re[f] + (double)im[f] * (double)im[f]);  // :358-360
+            else {
+                const float d2 = fmaf(re[f], re[f], im[f] * im[f]);
+                if (f == 0) d2_0 = d2;
+                gq[f] += (acc_t)d2;
             }
         }
+        if (X > 0) {
+            int ix = 0;
+#pragma unroll
+            for (int a = 0; a < F; a++)
+#pragma unroll
+                for (int b = a + 1; b < F; b++) {  // :721-722
+                    if (PRECISE) gq[F + ix] += (acc_t)((double)re[a] * (double)re[b] + (double)im[a] * (double)im[b]);
+                    else gq[F + ix] += (acc_t)fmaf(re[a], re[b], im[a] * im[b]);
+                    ix++;
+                }
+        }
+        if (PHASE) {
+            if (PRECISE) d2_0 = fmaf(re[0], re[0], im[0] * im[0]);
+            gph += (acc_t)phase_sq(re[0], d2_0);
+        }
+        gcnt++;
+    };
+
+    int j = 0;
+    for (; j + 1 < total; j += 2) {   // two rows per iteration: one wait, two refills
+        cp_async_wait<D - 2>();       // rows complete in order: rows j and j+1 have landed
+        float2 z0[F], z1[F];
+#pragma unroll
+        for (int f = 0; f < F; f++) { z0[f] = sm.z[j & (D - 1)][tid][f]; z1[f] = sm.z[(j + 1) & (D - 1)][tid][f]; }
+        prefetch(j + D);
+        prefetch(j + D + 1);
+        process(j, z0);
+        process(j + 1, z1);
     }
+    if (j < total) {
+        cp_async_wait<0>();
+        float2 z0[F];
+#pragma unroll
+        for (int f = 0; f < F; f++) z0[f] = sm.z[j & (D - 1)][tid][f];
+        process(j, z0);
+    }
+    cp_async_wait<0>();
     apply_group();
     flush_ring();
     if (active && c1 > 0) {
@@ -402,37 +475,47 @@ static int launch_generic(const BinGeom &g, const FieldPtrs &dk, int kz_start, i
     return 0;
 }
 
-template <int F>
-static int launch_ring_f(const BinGeom &g, const FieldPtrs &dk, const RowEnt *tab, int nrows, int kz_hi,
-                         int want_phase, int write_back, cudaStream_t st) {
+template <int F, bool PHASE, bool WB, bool PRECISE>
+static int launch_ring_v(const BinGeom &g, const FieldPtrs &dk, const RowEnt *tab, int nrows, int kz_hi, cudaStream_t st) {
     const int nseg = (kz_hi + RING_T - 1) / RING_T;
-    // two waves of resident CTAs, but never fewer than 32 rows per span
-    int occ = 1;
-    if (want_phase) {
-        if (write_back) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, true, true>, RING_T, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, true, false>, RING_T, 0);
-    } else {
-        if (write_back) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, false, true>, RING_T, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, false, false>, RING_T, 0);
+    const size_t smem = sizeof(RingSmem<F>);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PYLB_CHECK(cudaFuncSetAttribute(ring_kernel<F, PHASE, WB, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
     }
+    // two waves of resident CTAs; spans of 32..RING_SPAN_MAX rows
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, PHASE, WB, PRECISE>, RING_T, smem);
     if (occ < 1) occ = 1;
     int nspan = (sm_count() * occ * 2 + nseg - 1) / nseg;
     if (nspan > (nrows + 31) / 32) nspan = (nrows + 31) / 32;
     if (nspan < 1) nspan = 1;
-    const int rows_per_span = (nrows + nspan - 1) / nspan;
+    int rows_per_span = (nrows + nspan - 1) / nspan;
+    if (rows_per_span > RING_SPAN_MAX) rows_per_span = RING_SPAN_MAX;
     nspan = (nrows + rows_per_span - 1) / rows_per_span;
     dim3 grid(nspan, nseg);
     timing_begin(PYLB_T_RING, st);
-    if (want_phase) {
-        if (write_back) ring_kernel<F, true, true><<<grid, RING_T, 0, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
-        else ring_kernel<F, true, false><<<grid, RING_T, 0, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
-    } else {
-        if (write_back) ring_kernel<F, false, true><<<grid, RING_T, 0, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
-        else ring_kernel<F, false, false><<<grid, RING_T, 0, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
-    }
+    ring_kernel<F, PHASE, WB, PRECISE><<<grid, RING_T, smem, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
     timing_end(PYLB_T_RING, st);
     PYLB_LAUNCH_CHECK();
     return 0;
+}
+
+template <int F>
+static int launch_ring_f(const BinGeom &g, const FieldPtrs &dk, const RowEnt *tab, int nrows, int kz_hi,
+                         int want_phase, int write_back, int precise, cudaStream_t st) {
+    const int sel = (want_phase ? 4 : 0) | (write_back ? 2 : 0) | (precise ? 1 : 0);
+    switch (sel) {
+        case 0: return launch_ring_v<F, false, false, false>(g, dk, tab, nrows, kz_hi, st);
+        case 1: return launch_ring_v<F, false, false, true>(g, dk, tab, nrows, kz_hi, st);
+        case 2: return launch_ring_v<F, false, true, false>(g, dk, tab, nrows, kz_hi, st);
+        case 3: return launch_ring_v<F, false, true, true>(g, dk, tab, nrows, kz_hi, st);
+        case 4: return launch_ring_v<F, true, false, false>(g, dk, tab, nrows, kz_hi, st);
+        case 5: return launch_ring_v<F, true, false, true>(g, dk, tab, nrows, kz_hi, st);
+        case 6: return launch_ring_v<F, true, true, false>(g, dk, tab, nrows, kz_hi, st);
+        default: return launch_ring_v<F, true, true, true>(g, dk, tab, nrows, kz_hi, st);
+    }
 }
 
 static int bits_for(unsigned v) {
@@ -441,7 +524,7 @@ static int bits_for(unsigned v) {
     return b;
 }
 
-static int run_ring(const BinGeom &g, const FieldPtrs &dk, int want_phase, int write_back, cudaStream_t st) {
+static int run_ring(const BinGeom &g, const FieldPtrs &dk, int want_phase, int write_back, int precise, cudaStream_t st) {
     const int nrows = g.nx * g.ny;
     const int kz_hi = g.even ? g.middle - 1 : g.middle;  // columns 1..kz_hi carry no skip rule
     // special columns first (kz = 0 and, for even dims, kz = middle)
@@ -472,9 +555,9 @@ static int run_ring(const BinGeom &g, const FieldPtrs &dk, int want_phase, int w
 
     int rc = 1;
     switch (g.F) {
-        case 1: rc = launch_ring_f<1>(g, dk, tab, nrows, kz_hi, want_phase, write_back, st); break;
-        case 2: rc = launch_ring_f<2>(g, dk, tab, nrows, kz_hi, want_phase, write_back, st); break;
-        case 3: rc = launch_ring_f<3>(g, dk, tab, nrows, kz_hi, want_phase, write_back, st); break;
+        case 1: rc = launch_ring_f<1>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st); break;
+        case 2: rc = launch_ring_f<2>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st); break;
+        case 3: rc = launch_ring_f<3>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st); break;
         default: set_error("ring binning supports 1..3 fields, got %d", g.F);
     }
     cudaFreeAsync(buf, st);
@@ -556,11 +639,13 @@ extern "C" int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int ax
     mas_table_kernel<<<(ntab + 127) / 128, 128, 0, st>>>(tab, L.middle, ks->dims, F, g);
     PYLB_LAUNCH_CHECK();
 
+    const int precise = (algo & PYLB_BIN_PRECISE) ? 1 : 0;
+    algo &= ~PYLB_BIN_PRECISE;
     if (algo == PYLB_BIN_AUTO) algo = (axis == 2 && F <= 3) ? PYLB_BIN_RING : PYLB_BIN_GENERIC;
     int rc;
     if (algo == PYLB_BIN_RING) {
         if (axis != 2) { set_error("pylb_pk_bin: the ring kernel needs axis=2 (transpose the field for other axes)"); rc = 1; }
-        else rc = run_ring(g, fp, want_phase, write_back, st);
+        else rc = run_ring(g, fp, want_phase, write_back, precise, st);
     } else {
         timing_begin(PYLB_T_GENERIC, st);
         rc = launch_generic(g, fp, 0, 1, L.middle + 1, want_phase, write_back, st);

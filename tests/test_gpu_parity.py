@@ -218,7 +218,7 @@ def _field(dims, box, seed, mas="CIC"):
     return d
 
 
-@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("algo", [1, 2, 2 | 16])      # generic, ring (fp32 per-mode), ring (fp64 option)
 @pytest.mark.parametrize("dims", [48, 64, 33])
 def test_pk_vs_oracle(PKL, algo, dims):
     import pylians_b200.Pk_library as P
@@ -226,13 +226,13 @@ def test_pk_vs_oracle(PKL, algo, dims):
     d = _field(dims, box, dims)
     old, P.ALGO = P.ALGO, algo
     try:
-        for axis in ((2,) if algo == 2 else (0, 1, 2)):
+        for axis in ((2,) if (algo & 2) else (0, 1, 2)):
             parity.check_pk(PKL.Pk(d, box, axis, "CIC", 1), O.Pk(d, box, axis, "CIC", 1))
     finally:
         P.ALGO = old
 
 
-@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("algo", [1, 2, 2 | 16])
 def test_xpk_vs_oracle(PKL, algo):
     import pylians_b200.Pk_library as P
     box, dims = 500.0, 40
