@@ -95,6 +95,10 @@ int pylb_ma(const float *pos, int64_t np, int ndim, int64_t pos_stride0, int64_t
             void *grid, int grid_f64, int dims, float box, int mas, const float *w, int z_repeat,
             int algo, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Testing hook: force how the tiled deposit brings particles into tile order.
+ * -1 automatic, 0 binsort with 16x16x32 tiles, 1 binsort with 32x32x32 tiles, 2 radix sort + gather. */
+void pylb_ma_debug_path(int path);
+
 /* grid[i] /= divisor  (the `number2 /= 2|3|4` of MAS_library.pyx:90-107; applies to the WHOLE array) */
 int pylb_divide(float *grid, int64_t n, float divisor, void *stream);
 
@@ -102,9 +106,13 @@ int pylb_divide(float *grid, int64_t n, float divisor, void *stream);
  * strided copy (cudaMemcpy2DAsync).  Lets Pk() transform a host field with a single device buffer. */
 int pylb_h2d_padded(const float *host, float *dev, int dims, void *stream);
 
-/* delta = grid/mean(grid) - 1 in place.  mean is accumulated in float64 (np.mean(dtype=float64) in
- * the callers); `scratch` is a device double[2]; if mean_out != NULL the mean is stored there (device). */
+/* delta = grid/mean(grid) - 1 in place, mean accumulated in float64 (np.mean(dtype=float64) in the
+ * callers).  `scratch` is a device double[2].  The two halves are exposed separately for slab-
+ * decomposed grids: pylb_grid_sum adds sum(grid) into *sum (device double, caller zeroes it and may
+ * all-reduce it), pylb_overdensity_apply maps grid -> grid*(n_total/(*sum)) - 1. */
 int pylb_overdensity(float *grid, int64_t n, double *scratch, void *stream);
+int pylb_grid_sum(const float *grid, int64_t n, double *sum, void *stream);
+int pylb_overdensity_apply(float *grid, int64_t n, const double *sum, int64_t n_total, void *stream);
 
 /* pos[:,axis] += vel[:,axis]*(1+z)/H with the reference's wrap rule; pos/vel (np,3) C-contiguous */
 int pylb_pos_redshift_space(float *pos, const float *vel, int64_t np, float box, float hubble,

@@ -38,9 +38,12 @@ SIGNATURES = {
     "pylb_ma_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int, c_int, c_int, c_int]),
     "pylb_ma": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_float, c_int,
                         c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "pylb_ma_debug_path": (None, [c_int]),
     "pylb_divide": (c_int, [c_void_p, c_int64, c_float, c_void_p]),
     "pylb_h2d_padded": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "pylb_overdensity": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "pylb_grid_sum": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "pylb_overdensity_apply": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "pylb_pos_redshift_space": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_int, c_void_p]),
     "pylb_fft_r2c_work_bytes": (c_size_t, [c_int, c_int]),
     "pylb_fft_r2c": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),

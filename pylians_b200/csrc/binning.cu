@@ -162,7 +162,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int F, bool PHASE, bool WB, bool PRECISE>
-__global__ void __launch_bounds__(RING_T, PRECISE ? 2 : 3)
+__global__ void __launch_bounds__(RING_T, F == 1 ? (PRECISE ? 2 : 3) : (F == 2 ? 2 : 1))
 ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, int rows_per_span, int kz_hi) {
     constexpr int X = F * (F - 1) / 2;
     constexpr int Q = F + X;
@@ -317,9 +317,13 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
         w4 = (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0;   // :379
     };
 
-    auto process = [&](int j, const float2 (&z)[F]) {
-        const RowEnt e = sm.ent[j];
-        if (e.r2 != cur_r2) new_group(e.r2);   // CTA-uniform
+    // Per-mode work is split in two so that the arithmetic of several rows can overlap:
+    //   mode_math : deconvolve, square, phase^2 -- depends only on the loaded value and the row's MAS
+    //               factor, never on the binning state, so RING_B rows are evaluated back to back (ILP);
+    //   mode_bin  : the (CTA-uniform) group / ring bookkeeping and the accumulation into the group sums.
+    struct ModeVals { acc_t q[Q]; acc_t ph; };
+
+    auto mode_math = [&](int j, const float2 (&z)[F], ModeVals &v) {
         float re[F], im[F];
 #pragma unroll
         for (int f = 0; f < F; f++) {
@@ -327,16 +331,16 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
             re[f] = __fmul_rn(z[f].x, mf);                    // complex64 *= float, :355
             im[f] = __fmul_rn(z[f].y, mf);
             if (WB && active)
-                *reinterpret_cast<float2 *>(const_cast<char *>(base[f]) + e.off) = make_float2(re[f], im[f]);
+                *reinterpret_cast<float2 *>(const_cast<char *>(base[f]) + sm.ent[j].off) = make_float2(re[f], im[f]);
         }
         float d2_0 = 0.f;
 #pragma unroll
         for (int f = 0; f < F; f++) {
-            if (PRECISE) gq[f] += (acc_t)((double)re[f] * (double)re[f] + (double)im[f] * (double)im[f]);  // :358-360
+            if (PRECISE) v.q[f] = (acc_t)((double)re[f] * (double)re[f] + (double)im[f] * (double)im[f]);  // :358-360
             else {
                 const float d2 = fmaf(re[f], re[f], im[f] * im[f]);
                 if (f == 0) d2_0 = d2;
-                gq[f] += (acc_t)d2;
+                v.q[f] = (acc_t)d2;
             }
         }
         if (X > 0) {
@@ -345,35 +349,53 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
             for (int a = 0; a < F; a++)
 #pragma unroll
                 for (int b = a + 1; b < F; b++) {  // :721-722
-                    if (PRECISE) gq[F + ix] += (acc_t)((double)re[a] * (double)re[b] + (double)im[a] * (double)im[b]);
-                    else gq[F + ix] += (acc_t)fmaf(re[a], re[b], im[a] * im[b]);
+                    if (PRECISE) v.q[F + ix] = (acc_t)((double)re[a] * (double)re[b] + (double)im[a] * (double)im[b]);
+                    else v.q[F + ix] = (acc_t)fmaf(re[a], re[b], im[a] * im[b]);
                     ix++;
                 }
         }
+        v.ph = 0;
         if (PHASE) {
             if (PRECISE) d2_0 = fmaf(re[0], re[0], im[0] * im[0]);
-            gph += (acc_t)phase_sq(re[0], d2_0);
+            v.ph = (acc_t)phase_sq(re[0], d2_0);
         }
+    };
+
+    auto mode_bin = [&](int j, const ModeVals &v) {
+        const int r2 = sm.ent[j].r2;
+        if (r2 != cur_r2) new_group(r2);   // CTA-uniform
+#pragma unroll
+        for (int q = 0; q < Q; q++) gq[q] += v.q[q];
+        if (PHASE) gph += v.ph;
         gcnt++;
     };
 
+    constexpr int RING_B = (F == 1) ? 4 : 2;   // rows per loop iteration
+    static_assert(RING_B < D, "pipeline depth must exceed the batch");
     int j = 0;
-    for (; j + 1 < total; j += 2) {   // two rows per iteration: one wait, two refills
-        cp_async_wait<D - 2>();       // rows complete in order: rows j and j+1 have landed
-        float2 z0[F], z1[F];
+    for (; j + RING_B <= total; j += RING_B) {
+        cp_async_wait<D - RING_B>();   // rows complete in order: rows j .. j+RING_B-1 have landed
+        float2 z[RING_B][F];
 #pragma unroll
-        for (int f = 0; f < F; f++) { z0[f] = sm.z[j & (D - 1)][tid][f]; z1[f] = sm.z[(j + 1) & (D - 1)][tid][f]; }
-        prefetch(j + D);
-        prefetch(j + D + 1);
-        process(j, z0);
-        process(j + 1, z1);
+        for (int u = 0; u < RING_B; u++)
+#pragma unroll
+            for (int f = 0; f < F; f++) z[u][f] = sm.z[(j + u) & (D - 1)][tid][f];
+#pragma unroll
+        for (int u = 0; u < RING_B; u++) prefetch(j + D + u);
+        ModeVals v[RING_B];
+#pragma unroll
+        for (int u = 0; u < RING_B; u++) mode_math(j + u, z[u], v[u]);
+#pragma unroll
+        for (int u = 0; u < RING_B; u++) mode_bin(j + u, v[u]);
     }
-    if (j < total) {
-        cp_async_wait<0>();
+    if (j < total) cp_async_wait<0>();
+    for (; j < total; j++) {
         float2 z0[F];
 #pragma unroll
         for (int f = 0; f < F; f++) z0[f] = sm.z[j & (D - 1)][tid][f];
-        process(j, z0);
+        ModeVals v0;
+        mode_math(j, z0, v0);
+        mode_bin(j, v0);
     }
     cp_async_wait<0>();
     apply_group();

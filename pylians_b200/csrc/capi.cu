@@ -51,6 +51,7 @@ int ma_tiled(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid
              int mas, const float *w, void *workspace, size_t workspace_bytes, cudaStream_t st);
 size_t ma_tiled_workspace(int64_t np, int dims, int mas, int has_w);
 bool ma_tiled_supported(int ndim, int dims, int grid_f64);
+void ma_tiled_force_path(int p);
 
 // ------------------------------------------------------------------------------------------------
 // slab transpose: src [nx][dims][nz] -> dst [G][nx][dims/G][nz]; 16-byte vector copies when the
@@ -118,6 +119,8 @@ extern "C" int pylb_timing_collect(int which, double *total_ms, int *launches) {
     *total_ms = tot; *launches = n;
     return 0;
 }
+
+extern "C" void pylb_ma_debug_path(int path) { ma_tiled_force_path(path); }
 
 extern "C" size_t pylb_ma_workspace_bytes(int64_t np, int ndim, int dims, int mas, int has_w, int grid_f64, int algo) {
     if (algo == PYLB_MA_DIRECT) return 0;

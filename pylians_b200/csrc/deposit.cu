@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(256) sum_kernel(const float *__restrict__ g, i
 // delta = g/mean - 1 as the callers write it (`delta /= np.mean(delta, dtype=np.float64); delta -= 1.0`,
 // Pk_snapshot.py:88): the quotient is formed in float64 (x * (1/mean), <= 1 ulp of double away from the
 // true quotient), rounded to float32, then 1.0f is subtracted in float32.
-__global__ void __launch_bounds__(256) overdensity_kernel(float *g, int64_t n, const double *sum) {
-    const double rinv = (double)n / sum[0];
+__global__ void __launch_bounds__(256) overdensity_kernel(float *g, int64_t n, const double *sum, int64_t n_total) {
+    const double rinv = (double)n_total / sum[0];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n4 = n / 4;
     float4 *g4 = reinterpret_cast<float4 *>(g);
@@ -194,7 +194,23 @@ extern "C" int pylb_overdensity(float *grid, int64_t n, double *scratch, void *s
     PYLB_CHECK(cudaMemsetAsync(scratch, 0, 2 * sizeof(double), st));
     sum_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, st>>>(grid, n, scratch);
     PYLB_LAUNCH_CHECK();
-    overdensity_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, st>>>(grid, n, scratch);
+    overdensity_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, st>>>(grid, n, scratch, n);
+    PYLB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pylb_grid_sum(const float *grid, int64_t n, double *sum, void *stream) {
+    PYLB_REQUIRE(grid && sum && n > 0, "pylb_grid_sum: bad arguments");
+    PYLB_REQUIRE(((uintptr_t)grid & 15) == 0, "pylb_grid_sum: grid must be 16-byte aligned");
+    sum_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(grid, n, sum);
+    PYLB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pylb_overdensity_apply(float *grid, int64_t n, const double *sum, int64_t n_total, void *stream) {
+    PYLB_REQUIRE(grid && sum && n > 0 && n_total > 0, "pylb_overdensity_apply: bad arguments");
+    PYLB_REQUIRE(((uintptr_t)grid & 15) == 0, "pylb_overdensity_apply: grid must be 16-byte aligned");
+    overdensity_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(grid, n, sum, n_total);
     PYLB_LAUNCH_CHECK();
     return 0;
 }

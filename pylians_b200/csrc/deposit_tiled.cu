@@ -1,17 +1,27 @@
 // Tiled particle deposit for 3-D float32 grids.
 //
-//   K1  tile_key_kernel      particle -> key of the 16x16x32-cell tile holding its lowest touched cell
-//       cub radix sort       (key, particle index) pairs, only the key bits that are in use
-//       tile_begin_kernel    first sorted position of every tile (binary search)
-//       tile_chunks_kernel   + cub exclusive scan: work items = (tile, chunk of <= CHUNK particles),
-//                            so heavy (clustered) tiles are split over several CTAs
-//   K2  deposit_tile_kernel  one CTA per work item: zero a (16+S-1)x(16+S-1)x(32+S-1) fp32 tile in
-//                            shared memory, accumulate the item's particles into it, flush the tile
-//                            with red.global.add.v4.f32 (halo cells overlap neighbouring tiles, so
-//                            the flush must add, and `number` is accumulate-in-place anyway).
+// Particles are first brought into cell-tile order, then every tile is accumulated in shared memory
+// and flushed with red.global.add.v4.f32.  Two ways to get tile order:
 //
-// Shared-memory fp32 atomicAdd is an ATOMS.CAST.SPIN loop on sm_100a; the accumulation is bounded by
-// the shared-memory pipe (3 LSU ops per update), not by HBM.
+//  BINSORT (ntiles <= 32768; tiles are 16x16x32 cells, or 32x32x32 when that is needed to stay under
+//           the limit) -- a single-pass counting sort that moves the (x,y,z,w) payload itself:
+//     bin_hist_kernel     one CTA per SM builds a histogram over ALL tiles in shared memory (native int
+//                         ATOMS.ADD, 2.6 T/s) and merges it into the global per-tile counts
+//     cub ExclusiveSum    counts -> first output slot of every tile
+//     bin_scatter_kernel  per 32k-particle sub-chunk: count per tile in shared memory, reserve one
+//                         contiguous range per (sub-chunk, tile) with a single atom.global, rank inside
+//                         it with shared atomics, write the payload as float4.  Streaming reads, ~0.4
+//                         global atomics per particle, no random gather (a random 12-byte gather costs
+//                         3.9 ms per 2^27 particles on B200, a streaming read 0.25 ms: profiles/microbench).
+//  RADIX (any ntiles) -- cub radix sort of (tile key, particle index); the tile kernel then gathers
+//     particles through the sorted index.
+//
+//  deposit_tile_kernel   one CTA per work item (tile, chunk of <= CHUNK particles): zero the tile
+//                         (+ halo) in shared memory, accumulate, flush.  Halo cells overlap neighbouring
+//                         tiles, so the flush must add -- and `number` is accumulate-in-place anyway.
+//
+// Shared-memory fp32 atomicAdd is an ATOMS.CAST.SPIN loop on sm_100a (2.9 updates/clk/SM measured vs
+// 9.2 for native int atomics); that pipe, not HBM, bounds the accumulation.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -19,43 +29,162 @@
 
 namespace pylb {
 
-constexpr int TX = 16, TY = 16, TZ = 32;
-constexpr int CHUNK = 8192;             // particles per work item
-constexpr int64_t BATCH = 1ll << 28;    // particles sorted per pass (bounds the workspace)
+template <int TX_, int TY_, int TZ_>
+struct TileCfg {
+    static constexpr int TX = TX_, TY = TY_, TZ = TZ_;
+};
+typedef TileCfg<16, 16, 32> TileS;   // default: 38-51 KB of shared memory per CTA, 4-5 CTAs/SM
+typedef TileCfg<32, 32, 32> TileL;   // large grids: 144-176 KB, 1 CTA/SM, 8x fewer tiles
+
+constexpr int CHUNK = 8192;              // particles per work item
+constexpr int64_t BATCH = 1ll << 28;     // particles binned per pass (bounds the workspace)
 constexpr int TILE_THREADS = 256;
+constexpr int BIN_THREADS = 1024;        // binsort CTAs: one per SM, 32 warps
+constexpr int BIN_MAX_TILES = 32768;     // per-CTA histogram must fit shared memory (128 KB)
 
 struct TileGeom {
     int dims, ntx, nty, ntz, ntiles;
 };
 
+template <class TC>
 static TileGeom tile_geom(int dims) {
     TileGeom t;
     t.dims = dims;
-    t.ntx = (dims + TX - 1) / TX;
-    t.nty = (dims + TY - 1) / TY;
-    t.ntz = (dims + TZ - 1) / TZ;
+    t.ntx = (dims + TC::TX - 1) / TC::TX;
+    t.nty = (dims + TC::TY - 1) / TC::TY;
+    t.ntz = (dims + TC::TZ - 1) / TC::TZ;
     t.ntiles = t.ntx * t.nty * t.ntz;
     return t;
 }
 
-template <int MAS>
+// key of the tile holding the particle's lowest touched cell
+template <int MAS, class TC>
+__device__ __forceinline__ unsigned tile_key(float x, float y, float z, float inv, const TileGeom &tg) {
+    float C[Support<MAS>::S];
+    const int bx = wrap(axis_stencil<MAS>(x, inv, C), tg.dims);
+    const int by = wrap(axis_stencil<MAS>(y, inv, C), tg.dims);
+    const int bz = wrap(axis_stencil<MAS>(z, inv, C), tg.dims);
+    return (unsigned)(((bx / TC::TX) * tg.nty + (by / TC::TY)) * tg.ntz + (bz / TC::TZ));
+}
+
+// ------------------------------------------------------------------------------------------------
+// BINSORT
+// ------------------------------------------------------------------------------------------------
+constexpr int BIN_PER_THREAD = 32;                            // particles per thread per sub-chunk
+constexpr int BIN_SUB = BIN_THREADS * BIN_PER_THREAD;         // 32768 particles per sub-chunk
+constexpr int BIN_MLP = 8;                                    // particles whose loads are in flight per thread
+
+// per-tile particle counts: per-CTA shared histogram, merged with one red.global per (CTA, tile)
+template <int MAS, class TC>
+__global__ void __launch_bounds__(BIN_THREADS, 1)
+bin_hist_kernel(const float *__restrict__ pos, int64_t first, int n, int64_t ps0, int64_t ps1, float inv,
+                TileGeom tg, int *__restrict__ counts) {
+    extern __shared__ int hist[];
+    for (int t = threadIdx.x; t < tg.ntiles; t += BIN_THREADS) hist[t] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * BIN_THREADS) {
+        const float *p = pos + (first + i) * ps0;
+        atomicAdd(&hist[tile_key<MAS, TC>(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), inv, tg)], 1);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < tg.ntiles; t += BIN_THREADS) {
+        const int c = hist[t];
+        if (c) atomicAdd(&counts[t], c);
+    }
+}
+
+// Scatter the (x,y,z,w) payload into tile order.  cursor[t] starts at tile_begin[t].  Per sub-chunk:
+//   sweep A  key every particle, count per tile in shared memory (native ATOMS.ADD);
+//   claim    one atom.global.add per tile present in the sub-chunk reserves a contiguous output range
+//            (ranges of one tile handed to different CTAs are adjacent, so L2 write-combines them);
+//   sweep B  re-read the particles (L1/L2 hits), rank inside the range with a shared atomic, write float4.
+template <int MAS, class TC, bool HASW>
+__global__ void __launch_bounds__(BIN_THREADS, 1)
+bin_scatter_kernel(const float *__restrict__ pos, const float *__restrict__ W, int64_t first, int n, int64_t ps0,
+                   int64_t ps1, float inv, TileGeom tg, int *__restrict__ cursor, float4 *__restrict__ out) {
+    extern __shared__ int slot[];
+    const int nsub = (n + BIN_SUB - 1) / BIN_SUB;
+    for (int sc = blockIdx.x; sc < nsub; sc += gridDim.x) {
+        const int lo = sc * BIN_SUB;
+        for (int t = threadIdx.x; t < tg.ntiles; t += BIN_THREADS) slot[t] = 0;
+        __syncthreads();
+        // sweep A: BIN_MLP particles' coordinates are loaded before any is used (memory-level parallelism)
+        unsigned short keys[BIN_PER_THREAD];   // ntiles <= 32768, 0xffff = no particle
+#pragma unroll
+        for (int k0 = 0; k0 < BIN_PER_THREAD; k0 += BIN_MLP) {
+            float px[BIN_MLP], py[BIN_MLP], pz[BIN_MLP];
+#pragma unroll
+            for (int u = 0; u < BIN_MLP; u++) {
+                const int i = lo + (k0 + u) * BIN_THREADS + threadIdx.x;
+                if (i < n) {
+                    const float *p = pos + (first + i) * ps0;
+                    px[u] = __ldg(p); py[u] = __ldg(p + ps1); pz[u] = __ldg(p + 2 * ps1);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BIN_MLP; u++) {
+                const int i = lo + (k0 + u) * BIN_THREADS + threadIdx.x;
+                keys[k0 + u] = 0xffffu;
+                if (i < n) {
+                    keys[k0 + u] = (unsigned short)tile_key<MAS, TC>(px[u], py[u], pz[u], inv, tg);
+                    atomicAdd(&slot[keys[k0 + u]], 1);
+                }
+            }
+        }
+        __syncthreads();
+        // claim: atom.global in groups of 8 issued back to back, results stored afterwards
+        for (int t0 = 0; t0 < tg.ntiles; t0 += 8 * BIN_THREADS) {
+            int base[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int t = t0 + q * BIN_THREADS + threadIdx.x;
+                base[q] = -1;
+                if (t < tg.ntiles) {
+                    const int c = slot[t];
+                    if (c) base[q] = atomicAdd(&cursor[t], c);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (base[q] >= 0) slot[t0 + q * BIN_THREADS + threadIdx.x] = base[q];
+        }
+        __syncthreads();
+        // sweep B: re-read (L1/L2), rank inside the claimed range, write the payload
+#pragma unroll
+        for (int k0 = 0; k0 < BIN_PER_THREAD; k0 += BIN_MLP) {
+            float4 v[BIN_MLP];
+#pragma unroll
+            for (int u = 0; u < BIN_MLP; u++) {
+                if (keys[k0 + u] != 0xffffu) {
+                    const int i = lo + (k0 + u) * BIN_THREADS + threadIdx.x;
+                    const float *p = pos + (first + i) * ps0;
+                    v[u] = make_float4(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), HASW ? __ldg(W + first + i) : 1.0f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BIN_MLP; u++)
+                if (keys[k0 + u] != 0xffffu) out[atomicAdd(&slot[keys[k0 + u]], 1)] = v[u];
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RADIX fallback
+// ------------------------------------------------------------------------------------------------
+template <int MAS, class TC>
 __global__ void __launch_bounds__(256)
 tile_key_kernel(const float *__restrict__ pos, int64_t first, int n, int64_t ps0, int64_t ps1, float inv,
                 TileGeom tg, unsigned *keys, unsigned *vals) {
-    constexpr int S = Support<MAS>::S;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float *p = pos + (first + i) * ps0;
-    float C[S];
-    const int bx = wrap(axis_stencil<MAS>(__ldg(p), inv, C), tg.dims);
-    const int by = wrap(axis_stencil<MAS>(__ldg(p + ps1), inv, C), tg.dims);
-    const int bz = wrap(axis_stencil<MAS>(__ldg(p + 2 * ps1), inv, C), tg.dims);
-    keys[i] = (unsigned)(((bx / TX) * tg.nty + (by / TY)) * tg.ntz + (bz / TZ));
+    keys[i] = tile_key<MAS, TC>(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), inv, tg);
     vals[i] = (unsigned)i;
 }
 
 // tile_begin[t] = first sorted position whose key >= t  (t = 0..ntiles)
-__global__ void tile_begin_kernel(const unsigned *__restrict__ skeys, int n, int ntiles, int *tile_begin, int *nchunks) {
+__global__ void tile_begin_kernel(const unsigned *__restrict__ skeys, int n, int ntiles, int *tile_begin) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > ntiles) return;
     int lo = 0, hi = n;
@@ -73,11 +202,14 @@ __global__ void tile_chunks_kernel(const int *__restrict__ tile_begin, int ntile
     nchunks[t] = (t < ntiles) ? (tile_begin[t + 1] - tile_begin[t] + CHUNK - 1) / CHUNK : 0;
 }
 
-template <int MAS>
+// ------------------------------------------------------------------------------------------------
+// tile accumulation
+// ------------------------------------------------------------------------------------------------
+template <int MAS, class TC>
 struct TileShape {
     static constexpr int S = Support<MAS>::S;
-    static constexpr int SX = TX + S - 1, SY = TY + S - 1;
-    static constexpr int SZ = ((TZ + S - 1) + 3) & ~3;  // padded to a multiple of 4 for the v4 flush
+    static constexpr int SX = TC::TX + S - 1, SY = TC::TY + S - 1;
+    static constexpr int SZ = ((TC::TZ + S - 1) + 3) & ~3;  // padded to a multiple of 4 for the v4 flush
     static constexpr int CELLS = SX * SY * SZ;
 };
 
@@ -86,13 +218,14 @@ __device__ __forceinline__ void red_add_v4(float *p, float4 v) {
                  : "memory");
 }
 
-template <int MAS, bool HASW>
+// SORTED: particles come as float4 (x,y,z,w) already in tile order.  Otherwise through the sorted index.
+template <int MAS, bool HASW, class TC, bool SORTED>
 __global__ void __launch_bounds__(TILE_THREADS)
 deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, int64_t ps1,
                     const float *__restrict__ W, float inv, TileGeom tg, const unsigned *__restrict__ svals,
-                    const int *__restrict__ tile_begin, const int *__restrict__ chunk_off,
-                    float *__restrict__ grid) {
-    using TS = TileShape<MAS>;
+                    const float4 *__restrict__ sorted, const int *__restrict__ tile_begin,
+                    const int *__restrict__ chunk_off, float *__restrict__ grid) {
+    using TS = TileShape<MAS, TC>;
     constexpr int S = TS::S;
     extern __shared__ __align__(16) float tile[];
     __shared__ int s_tile, s_lo, s_hi;
@@ -123,16 +256,23 @@ deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, i
         reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     const int tz = t % tg.ntz, ty = (t / tg.ntz) % tg.nty, tx = t / (tg.ntz * tg.nty);
-    const int ox = tx * TX, oy = ty * TY, oz = tz * TZ;
+    const int ox = tx * TC::TX, oy = ty * TC::TY, oz = tz * TC::TZ;
 
     for (int i = s_lo + threadIdx.x; i < s_hi; i += TILE_THREADS) {
-        const int64_t pi = first + (int64_t)svals[i];
-        const float *p = pos + pi * ps0;
+        float x, y, z, w;
+        if (SORTED) {
+            const float4 q = __ldg(sorted + i);
+            x = q.x; y = q.y; z = q.z; w = q.w;
+        } else {
+            const int64_t pi = first + (int64_t)svals[i];
+            const float *p = pos + pi * ps0;
+            x = __ldg(p); y = __ldg(p + ps1); z = __ldg(p + 2 * ps1);
+            w = HASW ? __ldg(W + pi) : 1.0f;
+        }
         float C[3][S];
-        const int lx = wrap(axis_stencil<MAS>(__ldg(p), inv, C[0]), tg.dims) - ox;
-        const int ly = wrap(axis_stencil<MAS>(__ldg(p + ps1), inv, C[1]), tg.dims) - oy;
-        const int lz = wrap(axis_stencil<MAS>(__ldg(p + 2 * ps1), inv, C[2]), tg.dims) - oz;
-        const float w = HASW ? __ldg(W + pi) : 1.0f;
+        const int lx = wrap(axis_stencil<MAS>(x, inv, C[0]), tg.dims) - ox;
+        const int ly = wrap(axis_stencil<MAS>(y, inv, C[1]), tg.dims) - oy;
+        const int lz = wrap(axis_stencil<MAS>(z, inv, C[2]), tg.dims) - oz;
         float *base = tile + (lx * TS::SY + ly) * TS::SZ + lz;
 #pragma unroll
         for (int l = 0; l < S; l++)
@@ -180,14 +320,34 @@ deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, i
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
 static int bits_for(unsigned v) {
     int b = 1;
     while (b < 32 && (v >> b)) b++;
     return b;
 }
 
+enum { PATH_BIN_S = 0, PATH_BIN_L = 1, PATH_RADIX_S = 2 };
+
+static int g_force_path = -1;   // tests: exercise every path on small grids (pylb_ma_debug_path)
+void ma_tiled_force_path(int p) { g_force_path = p; }
+
+static int choose_path(int dims) {
+    if (g_force_path >= PATH_BIN_S && g_force_path <= PATH_RADIX_S) return g_force_path;
+    if (tile_geom<TileS>(dims).ntiles <= BIN_MAX_TILES) return PATH_BIN_S;
+    if (tile_geom<TileL>(dims).ntiles <= BIN_MAX_TILES) return PATH_BIN_L;
+    return PATH_RADIX_S;
+}
+
 struct TiledWs {
+    // binsort
+    int *H, *S;
+    float4 *sorted;
+    // radix
     unsigned *k0, *k1, *v0, *v1;
+    // common
     int *tile_begin, *nchunks, *chunk_off;
     void *tmp;
     size_t tmp_bytes, total;
@@ -195,26 +355,33 @@ struct TiledWs {
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static int plan_ws(int64_t np, int dims, TiledWs *ws, char *base) {
-    const TileGeom tg = tile_geom(dims);
+static void plan_ws(int64_t np, int dims, TiledWs *ws, char *base) {
+    const int path = choose_path(dims);
+    const int ntiles = path == PATH_BIN_L ? tile_geom<TileL>(dims).ntiles : tile_geom<TileS>(dims).ntiles;
     const int64_t nb = np < BATCH ? np : BATCH;
-    size_t sort_tmp = 0, scan_tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (unsigned *)nullptr, (unsigned *)nullptr, (unsigned *)nullptr,
-                                    (unsigned *)nullptr, (int)nb, 0, 32);
-    cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (int *)nullptr, (int *)nullptr, tg.ntiles + 1);
-    size_t o = 0;
+    size_t o = 0, t1 = 0, t2 = 0, t3 = 0;
     auto take = [&](size_t bytes) { char *p = base ? base + o : nullptr; o += align_up(bytes); return p; };
-    ws->k0 = (unsigned *)take(sizeof(unsigned) * nb);
-    ws->k1 = (unsigned *)take(sizeof(unsigned) * nb);
-    ws->v0 = (unsigned *)take(sizeof(unsigned) * nb);
-    ws->v1 = (unsigned *)take(sizeof(unsigned) * nb);
-    ws->tile_begin = (int *)take(sizeof(int) * (tg.ntiles + 2));
-    ws->nchunks = (int *)take(sizeof(int) * (tg.ntiles + 2));
-    ws->chunk_off = (int *)take(sizeof(int) * (tg.ntiles + 2));
-    ws->tmp_bytes = sort_tmp > scan_tmp ? sort_tmp : scan_tmp;
+    memset(ws, 0, sizeof(*ws));
+    if (path == PATH_RADIX_S) {
+        cub::DeviceRadixSort::SortPairs(nullptr, t1, (unsigned *)nullptr, (unsigned *)nullptr, (unsigned *)nullptr,
+                                        (unsigned *)nullptr, (int)nb, 0, 32);
+        ws->k0 = (unsigned *)take(sizeof(unsigned) * nb);
+        ws->k1 = (unsigned *)take(sizeof(unsigned) * nb);
+        ws->v0 = (unsigned *)take(sizeof(unsigned) * nb);
+        ws->v1 = (unsigned *)take(sizeof(unsigned) * nb);
+    } else {
+        ws->H = (int *)take(sizeof(int) * (size_t)(ntiles + 2));   // per-tile counts
+        ws->S = (int *)take(sizeof(int) * (size_t)(ntiles + 2));   // per-tile write cursors
+        ws->sorted = (float4 *)take(sizeof(float4) * nb);
+    }
+    cub::DeviceScan::ExclusiveSum(nullptr, t2, (int *)nullptr, (int *)nullptr, ntiles + 1);
+    ws->tile_begin = (int *)take(sizeof(int) * (ntiles + 2));
+    ws->nchunks = (int *)take(sizeof(int) * (ntiles + 2));
+    ws->chunk_off = (int *)take(sizeof(int) * (ntiles + 2));
+    ws->tmp_bytes = t1 > t2 ? t1 : t2;
+    if (t3 > ws->tmp_bytes) ws->tmp_bytes = t3;
     ws->tmp = take(ws->tmp_bytes ? ws->tmp_bytes : 16);
     ws->total = o;
-    return 0;
 }
 
 size_t ma_tiled_workspace(int64_t np, int dims, int mas, int has_w) {
@@ -227,28 +394,49 @@ size_t ma_tiled_workspace(int64_t np, int dims, int mas, int has_w) {
 
 bool ma_tiled_supported(int ndim, int dims, int grid_f64) { return ndim == 3 && !grid_f64 && dims >= 32; }
 
-template <int MAS, bool HASW>
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+    PYLB_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+template <int MAS, bool HASW, class TC, bool BINSORT>
 static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv,
                      const float *w, TiledWs &ws, cudaStream_t st) {
-    using TS = TileShape<MAS>;
-    const TileGeom tg = tile_geom(dims);
-    const size_t smem = sizeof(float) * TS::CELLS;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PYLB_CHECK(cudaFuncSetAttribute(deposit_tile_kernel<MAS, HASW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+    using TS = TileShape<MAS, TC>;
+    const TileGeom tg = tile_geom<TC>(dims);
+    const size_t tile_smem = sizeof(float) * TS::CELLS;
+    const size_t hist_smem = sizeof(int) * (size_t)tg.ntiles;
+    const int P = sm_count();
+    if (set_smem(deposit_tile_kernel<MAS, HASW, TC, BINSORT>, tile_smem)) return 1;
+    if (BINSORT) {
+        if (set_smem(bin_hist_kernel<MAS, TC>, hist_smem)) return 1;
+        if (set_smem(bin_scatter_kernel<MAS, TC, HASW>, hist_smem)) return 1;
     }
-    const int end_bit = bits_for((unsigned)(tg.ntiles - 1));
+    const int nt1 = tg.ntiles + 1;
     for (int64_t first = 0; first < np; first += BATCH) {
         const int n = (int)((np - first) < BATCH ? (np - first) : BATCH);
-        tile_key_kernel<MAS><<<(n + 255) / 256, 256, 0, st>>>(pos, first, n, ps0, ps1, inv, tg, ws.k0, ws.v0);
-        PYLB_LAUNCH_CHECK();
         size_t tb = ws.tmp_bytes;
-        PYLB_CHECK(cub::DeviceRadixSort::SortPairs(ws.tmp, tb, ws.k0, ws.k1, ws.v0, ws.v1, n, 0, end_bit, st));
-        count_launch(3);
-        const int nt1 = tg.ntiles + 1;
-        tile_begin_kernel<<<(nt1 + 255) / 256, 256, 0, st>>>(ws.k1, n, tg.ntiles, ws.tile_begin, ws.nchunks);
-        PYLB_LAUNCH_CHECK();
+        if (BINSORT) {
+            PYLB_CHECK(cudaMemsetAsync(ws.H, 0, sizeof(int) * (size_t)nt1, st));
+            bin_hist_kernel<MAS, TC><<<P, BIN_THREADS, hist_smem, st>>>(pos, first, n, ps0, ps1, inv, tg, ws.H);
+            PYLB_LAUNCH_CHECK();
+            // tile_begin[0..ntiles] = exclusive scan of the counts (counts[ntiles] = 0)
+            PYLB_CHECK(cub::DeviceScan::ExclusiveSum(ws.tmp, tb, ws.H, ws.tile_begin, nt1, st));
+            count_launch(2);
+            PYLB_CHECK(cudaMemcpyAsync(ws.S, ws.tile_begin, sizeof(int) * (size_t)nt1, cudaMemcpyDeviceToDevice, st));
+            bin_scatter_kernel<MAS, TC, HASW><<<P, BIN_THREADS, hist_smem, st>>>(pos, w, first, n, ps0, ps1, inv, tg,
+                                                                                  ws.S, ws.sorted);
+            PYLB_LAUNCH_CHECK();
+        } else {
+            tile_key_kernel<MAS, TC><<<(n + 255) / 256, 256, 0, st>>>(pos, first, n, ps0, ps1, inv, tg, ws.k0, ws.v0);
+            PYLB_LAUNCH_CHECK();
+            const int end_bit = bits_for((unsigned)(tg.ntiles - 1));
+            PYLB_CHECK(cub::DeviceRadixSort::SortPairs(ws.tmp, tb, ws.k0, ws.k1, ws.v0, ws.v1, n, 0, end_bit, st));
+            count_launch(3);
+            tile_begin_kernel<<<(nt1 + 255) / 256, 256, 0, st>>>(ws.k1, n, tg.ntiles, ws.tile_begin);
+            PYLB_LAUNCH_CHECK();
+        }
         tile_chunks_kernel<<<(nt1 + 255) / 256, 256, 0, st>>>(ws.tile_begin, tg.ntiles, ws.nchunks);
         PYLB_LAUNCH_CHECK();
         tb = ws.tmp_bytes;
@@ -257,12 +445,20 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
         // upper bound on work items: every non-empty tile has at most count/CHUNK + 1 chunks
         const int64_t max_items = (int64_t)n / CHUNK + tg.ntiles;
         timing_begin(PYLB_T_TILE, st);
-        deposit_tile_kernel<MAS, HASW><<<(unsigned)max_items, TILE_THREADS, smem, st>>>(
-            pos, first, ps0, ps1, w, inv, tg, ws.v1, ws.tile_begin, ws.chunk_off, grid);
+        deposit_tile_kernel<MAS, HASW, TC, BINSORT><<<(unsigned)max_items, TILE_THREADS, tile_smem, st>>>(
+            pos, first, ps0, ps1, w, inv, tg, ws.v1, ws.sorted, ws.tile_begin, ws.chunk_off, grid);
         timing_end(PYLB_T_TILE, st);
         PYLB_LAUNCH_CHECK();
     }
     return 0;
+}
+
+template <int MAS, bool HASW>
+static int tiled_path(int path, const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims,
+                      float inv, const float *w, TiledWs &ws, cudaStream_t st) {
+    if (path == PATH_BIN_S) return tiled_run<MAS, HASW, TileS, true>(pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
+    if (path == PATH_BIN_L) return tiled_run<MAS, HASW, TileL, true>(pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
+    return tiled_run<MAS, HASW, TileS, false>(pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
 }
 
 int ma_tiled(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv, int mas,
@@ -273,16 +469,17 @@ int ma_tiled(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid
     PYLB_REQUIRE(workspace != nullptr && workspace_bytes >= ws.total, "pylb_ma: tiled workspace too small (%zu < %zu)",
                  workspace_bytes, ws.total);
     PYLB_REQUIRE(((uintptr_t)grid & 15) == 0, "pylb_ma: grid must be 16-byte aligned");
+    const int path = choose_path(dims);
     const bool hw = w != nullptr;
     switch (mas) {
-        case PYLB_NGP: return hw ? tiled_run<PYLB_NGP, true>(pos, np, ps0, ps1, grid, dims, inv, w, ws, st)
-                                 : tiled_run<PYLB_NGP, false>(pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
-        case PYLB_CIC: return hw ? tiled_run<PYLB_CIC, true>(pos, np, ps0, ps1, grid, dims, inv, w, ws, st)
-                                 : tiled_run<PYLB_CIC, false>(pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
-        case PYLB_TSC: return hw ? tiled_run<PYLB_TSC, true>(pos, np, ps0, ps1, grid, dims, inv, w, ws, st)
-                                 : tiled_run<PYLB_TSC, false>(pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
-        case PYLB_PCS: return hw ? tiled_run<PYLB_PCS, true>(pos, np, ps0, ps1, grid, dims, inv, w, ws, st)
-                                 : tiled_run<PYLB_PCS, false>(pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
+        case PYLB_NGP: return hw ? tiled_path<PYLB_NGP, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st)
+                                 : tiled_path<PYLB_NGP, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
+        case PYLB_CIC: return hw ? tiled_path<PYLB_CIC, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st)
+                                 : tiled_path<PYLB_CIC, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
+        case PYLB_TSC: return hw ? tiled_path<PYLB_TSC, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st)
+                                 : tiled_path<PYLB_TSC, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
+        case PYLB_PCS: return hw ? tiled_path<PYLB_PCS, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st)
+                                 : tiled_path<PYLB_PCS, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
     }
     set_error("pylb_ma: unknown mass-assignment scheme %d", mas);
     return 1;

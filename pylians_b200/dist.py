@@ -1,0 +1,190 @@
+"""Slab-decomposed multi-GPU density-field -> power-spectrum pipeline (one process per GPU).
+
+The reference is single-process ("slab-transpose comm layer: does not exist");
+this module is the new component BASELINE.json's north_star asks for.  Per snapshot, on rank r of G:
+
+    particles (any shard)                       pos_r (n_r, 3)
+      -> deposit onto a FULL partial grid       MASL kernels, (N,N,N) float32          [local]
+      -> reduce-scatter (sum) into x-slabs      (N/G, N, N)                            [NCCL reduce_scatter]
+      -> overdensity with the GLOBAL mean       sum in float64, all-reduced            [NCCL all_reduce, 8 B]
+      -> batched 2-D R2C over (y,z)             (N/G, N, N/2+1) complex64              [cuFFT]
+      -> transpose pack + all-to-all            (G, N/G, N/G, N/2+1) blocks            [pack kernel + NCCL all_to_all]
+      -> 1-D C2C along x (strided, in place)    (N, N/G, N/2+1): rank r owns ky in [r N/G, (r+1) N/G)   [cuFFT]
+      -> fused deconvolve + bin + Legendre      on the transposed layout, no transpose back   [ring kernel]
+      -> all-reduce of the k-bins               float64 sums + int64 counts (<= 24 MB) [NCCL all_reduce]
+      -> units / normalisation on the host      identical on every rank
+
+The local operations come from an `ops` object so the host logic (partitioning, collectives, layout
+arithmetic) can be exercised on CPU with the gloo backend and a numpy stand-in (tests/cpu_slab_ops.py);
+the product always uses CudaOps -- there is no CPU fallback in this package.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import Pk_library as PKL
+from . import MAS_library as MASL
+
+
+class CudaOps(object):
+    """Local (per-rank) operations on the current CUDA device, through the C ABI."""
+
+    def __init__(self):
+        self.lib = _lib.load()
+        self.dev = MASL._device()
+
+    # ---- helpers -------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def zeros(self, shape, dtype=torch.float32):
+        return torch.zeros(shape, dtype=dtype, device=self.dev)
+
+    def empty(self, shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.dev)
+
+    def to_device(self, a):
+        return MASL._to_device(a, self.dev)
+
+    # ---- stages --------------------------------------------------------------------------------
+    def deposit(self, pos, W, grid, BoxSize, MAS):
+        MASL.MA(pos, grid, BoxSize, MAS, W=W)
+
+    def grid_sum(self, slab):
+        s = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.pylb_grid_sum(slab.data_ptr(), slab.numel(), s.data_ptr(), self._stream()), "pylb_grid_sum")
+        return s
+
+    def overdensity_apply(self, slab, total, n_total):
+        _lib.check(self.lib.pylb_overdensity_apply(slab.data_ptr(), slab.numel(), total.data_ptr(), int(n_total),
+                                                   self._stream()), "pylb_overdensity_apply")
+
+    def fft_yz(self, slab, dims):
+        nxl, nz = slab.shape[0], dims // 2 + 1
+        out = torch.empty((nxl, dims, nz), dtype=torch.complex64, device=self.dev)
+        wb = self.lib.pylb_fft_slab_yz_work_bytes(dims, nxl)
+        work = torch.empty(max(int(wb), 1), dtype=torch.uint8, device=self.dev)
+        _lib.check(self.lib.pylb_fft_slab_yz(slab.data_ptr(), out.data_ptr(), dims, nxl, work.data_ptr(), int(wb),
+                                             self._stream()), "pylb_fft_slab_yz")
+        return out
+
+    def pack(self, cplx, dims, G):
+        nxl, nz = cplx.shape[0], dims // 2 + 1
+        send = torch.empty((G, nxl, dims // G, nz), dtype=torch.complex64, device=self.dev)
+        _lib.check(self.lib.pylb_slab_pack(cplx.data_ptr(), send.data_ptr(), dims, nxl, G, self._stream()), "pylb_slab_pack")
+        return send
+
+    def fft_x(self, recv, dims):
+        nyl = recv.shape[1]
+        wb = self.lib.pylb_fft_slab_x_work_bytes(dims, nyl)
+        work = torch.empty(max(int(wb), 1), dtype=torch.uint8, device=self.dev)
+        _lib.check(self.lib.pylb_fft_slab_x(recv.data_ptr(), dims, nyl, work.data_ptr(), int(wb), self._stream()),
+                   "pylb_fft_slab_x")
+
+    def bin(self, fields, dims, axis, mas_index, want_phase, y0, nyl):
+        nz = dims // 2 + 1
+        ks = _lib.KSpace(dims, 0, dims, int(y0), int(nyl), nyl * nz, nz)
+        return PKL.bin_modes(fields, dims, axis, mas_index, want_phase, False, ks=ks)
+
+
+def _group_info(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def _reduce_scatter_sum(out, full, group, G):
+    """out (N/G,...) <- sum over ranks of full (N,...)[rank slab].  NCCL has the primitive; gloo does not."""
+    if G == 1:
+        out.copy_(full[: out.shape[0]])
+        return
+    if dist.get_backend(group) == "nccl":
+        dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+        r = dist.get_rank(group)
+        out.copy_(full[r * out.shape[0]:(r + 1) * out.shape[0]])
+
+
+class _Result(object):
+    pass
+
+
+class SlabPk(object):
+    """Distributed MA + Pk / XPk.  Every rank calls the same methods with its own particle shard."""
+
+    def __init__(self, dims, BoxSize, MAS="CIC", axis=2, group=None, ops=None):
+        self.rank, self.G = _group_info(group)
+        self.group = group
+        if dims % self.G != 0:
+            raise ValueError("dims (%d) must be divisible by the number of ranks (%d)" % (dims, self.G))
+        self.dims, self.BoxSize, self.MAS, self.axis = int(dims), BoxSize, MAS, int(axis)
+        self.nxl = self.nyl = dims // self.G
+        self.ops = ops if ops is not None else CudaOps()
+
+    # ---- stage 1: particles -> overdensity slab --------------------------------------------------
+    def density_slab(self, pos, W=None, MAS=None, overdensity=True):
+        """Deposit this rank's particles, reduce-scatter to the x-slab this rank owns, normalise."""
+        ops, N, G = self.ops, self.dims, self.G
+        partial = ops.zeros((N, N, N))
+        ops.deposit(pos, W, partial, self.BoxSize, MAS or self.MAS)
+        slab = ops.empty((self.nxl, N, N))
+        _reduce_scatter_sum(slab, partial, self.group, G)
+        del partial
+        if overdensity:
+            total = ops.grid_sum(slab)
+            if G > 1:
+                dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+            ops.overdensity_apply(slab, total, N ** 3)
+        return slab
+
+    # ---- stage 2: x-slab (real) -> ky-slab (k-space, transposed) --------------------------------
+    def fft_slab(self, slab):
+        """(N/G, N, N) real x-slab -> (N, N/G, N/2+1) complex: all kx, this rank's ky, kz >= 0."""
+        ops, N, G = self.ops, self.dims, self.G
+        cplx = ops.fft_yz(slab, N)
+        send = ops.pack(cplx, N, G)
+        del cplx
+        if G > 1:
+            recv = torch.empty_like(send)
+            dist.all_to_all_single(recv, send, group=self.group)
+        else:
+            recv = send
+        recv = recv.view(N, self.nyl, N // 2 + 1)          # block g holds x in [g N/G, (g+1) N/G)
+        ops.fft_x(recv, N)
+        return recv
+
+    # ---- stage 3: binning + all-reduce -----------------------------------------------------------
+    def bin(self, fields_k, mas_list, want_phase):
+        ops, N, G = self.ops, self.dims, self.G
+        mas_index = [PKL.MAS_function(m) for m in mas_list]
+        L, sums, counts = ops.bin(fields_k, N, self.axis, mas_index, want_phase, self.rank * self.nyl, self.nyl)
+        if G > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
+        return PKL._Bins(L, sums, counts)
+
+    # ---- whole pipelines -------------------------------------------------------------------------
+    def pk_from_slab(self, slab, MAS=None):
+        """Pk of an already slab-distributed overdensity field (each rank passes its (N/G,N,N) slab)."""
+        dk = self.fft_slab(slab)
+        out = _Result()
+        PKL._finish(out, self.bin([dk], [MAS or self.MAS], True), self.dims, self.BoxSize, False)
+        return out
+
+    def run(self, pos, W=None):
+        """particles -> Pk (same attributes as Pk_library.Pk), identical on every rank."""
+        return self.pk_from_slab(self.density_slab(pos, W))
+
+    def run_x(self, pos_list, W_list=None, MAS_list=None):
+        """Several particle sets -> XPk (same attributes as Pk_library.XPk)."""
+        F = len(pos_list)
+        W_list = W_list or [None] * F
+        MAS_list = list(MAS_list or [self.MAS] * F)
+        dks = [self.fft_slab(self.density_slab(p, w, m)) for p, w, m in zip(pos_list, W_list, MAS_list)]
+        out = _Result()
+        PKL._finish(out, self.bin(dks, MAS_list, False), self.dims, self.BoxSize, True)
+        return out

@@ -131,11 +131,16 @@ def test_reference_unit_tests_mass_conservation(MASL, mas, places, weighted):
     assert round(abs(suma / (3.0 * particles if weighted else particles) - 1.0), places) == 0
 
 
-@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("algo", [1, 2, 20, 21, 22])   # direct; tiled auto; tiled forced binsort-S / binsort-L / radix
 @pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
 @pytest.mark.parametrize("dims", [64, 80])
 def test_ma_vs_oracle_both_algorithms(MASL, algo, mas, dims):
-    """Seeded random + clustered particles, direct and tiled kernels against the oracle."""
+    """Seeded random + clustered particles, direct and tiled kernels (every sort path) against the oracle."""
+    from pylians_b200 import _lib
+    path = -1
+    if algo >= 20:
+        path, algo = algo - 20, 2
+    _lib.load().pylb_ma_debug_path(path)
     rng = np.random.default_rng(100 + dims)
     box, n = 1000.0, 300000
     pos = (rng.random((n, 3)) * box).astype(np.float32)
@@ -154,6 +159,7 @@ def test_ma_vs_oracle_both_algorithms(MASL, algo, mas, dims):
             parity.assert_grid_close(a, b, "%s algo %d" % (mas, algo))
     finally:
         M.ALGO = old
+        _lib.load().pylb_ma_debug_path(-1)
 
 
 def test_cabi_host_entry_points(gma):
