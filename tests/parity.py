@@ -49,7 +49,7 @@ def _get(o, n):
     return np.asarray(o[n] if isinstance(o, dict) else getattr(o, n))
 
 
-def check_pk(test, ref, phase=True):
+def check_pk(test, ref, phase=True, rtol=PK_RTOL):
     """test/ref: objects or dicts with the reference's Pk attribute names."""
     for n in ("Nmodes3D", "Nmodes1D", "Nmodes2D", "kpar", "kper"):
         assert_exact(_get(test, n), _get(ref, n), n)
@@ -58,18 +58,18 @@ def check_pk(test, ref, phase=True):
     P = _get(ref, "Pk")
     p0 = np.abs(P[:, 0])
     floor3 = p0 + np.median(p0)               # multipoles may cancel; floor at the monopole level
-    assert_spec_close(_get(test, "Pk"), P, floor3[:, None] * np.array([1.0, 5.0, 9.0])[None, :], "Pk3D")
+    assert_spec_close(_get(test, "Pk"), P, floor3[:, None] * np.array([1.0, 5.0, 9.0])[None, :], "Pk3D", rtol)
     if phase:
         ph = _get(ref, "Pkphase")
-        assert_spec_close(_get(test, "Pkphase"), ph, np.median(np.abs(ph)), "Pkphase", rtol=2e-5)
+        assert_spec_close(_get(test, "Pkphase"), ph, np.median(np.abs(ph)), "Pkphase", rtol=2 * rtol)
     p1 = _get(ref, "Pk1D")
-    assert_spec_close(_get(test, "Pk1D"), p1, np.median(np.abs(p1)), "Pk1D")
+    assert_spec_close(_get(test, "Pk1D"), p1, np.median(np.abs(p1)), "Pk1D", rtol)
     p2 = _get(ref, "Pk2D")
     # bins holding a single (or few) modes carry the FFT's own 1e-7..1e-6 noise; floor at the median
-    assert_spec_close(_get(test, "Pk2D"), p2, np.median(np.abs(p2)), "Pk2D")
+    assert_spec_close(_get(test, "Pk2D"), p2, np.median(np.abs(p2)), "Pk2D", rtol)
 
 
-def check_xpk(test, ref):
+def check_xpk(test, ref, rtol=PK_RTOL):
     for n in ("Nmodes3D", "Nmodes1D", "Nmodes2D", "kpar", "kper"):
         assert_exact(_get(test, n), _get(ref, n), n)
     assert_k_close(_get(test, "k3D"), _get(ref, "k3D"), "k3D")
@@ -79,16 +79,16 @@ def check_xpk(test, ref):
     p0 = np.abs(P[:, 0, :])
     floor = p0 + np.median(p0, axis=0)[None, :]
     ell = np.array([1.0, 5.0, 9.0])[None, :, None]
-    assert_spec_close(_get(test, "Pk"), P, floor[:, None, :] * ell, "XPk.Pk")
+    assert_spec_close(_get(test, "Pk"), P, floor[:, None, :] * ell, "XPk.Pk", rtol)
     XP = _get(ref, "XPk")
     pairs = [(i, j) for i in range(F) for j in range(i + 1, F)]
     if pairs:
         xfloor = np.stack([np.sqrt(floor[:, i] * floor[:, j]) for i, j in pairs], axis=1)
-        assert_spec_close(_get(test, "XPk"), XP, xfloor[:, None, :] * ell, "XPk.XPk")
+        assert_spec_close(_get(test, "XPk"), XP, xfloor[:, None, :] * ell, "XPk.XPk", rtol)
     for n, xn in (("Pk1D", "PkX1D"), ("Pk2D", "PkX2D")):
         p = _get(ref, n)
         med = np.median(np.abs(p), axis=0)
-        assert_spec_close(_get(test, n), p, med[None, :], n)
+        assert_spec_close(_get(test, n), p, med[None, :], n, rtol)
         if pairs:
             xmed = np.array([np.sqrt(med[i] * med[j]) for i, j in pairs])
-            assert_spec_close(_get(test, xn), _get(ref, xn), xmed[None, :], xn)
+            assert_spec_close(_get(test, xn), _get(ref, xn), xmed[None, :], xn, rtol)

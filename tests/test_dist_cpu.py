@@ -39,12 +39,15 @@ def _worker(rank, world, port, dims, axis, mas, xmode, q):
             d = np.zeros((dims,) * 3, np.float32); O.MA(p, d, box, m, W=w)
             d /= np.mean(d, dtype=np.float64); d -= 1.0
             return d
+        # Sharding the particles changes the fp32 summation order of the grid (~1e-7 per cell); the MAS
+        # deconvolution amplifies that by up to (pi/2)^(2p) = 15x (CIC) .. 226x (PCS) in amplitude at the
+        # Nyquist corner, so single-mode corner bins move by up to ~2e-4: this comparison uses 1e-3 (a layout bug gives O(1)).  Exact layout parity is test_slab_layout_single_process.
         if not xmode:
             got = eng.run(pos[rank::world])                       # each rank deposits its own shard
-            parity.check_pk(got, O.Pk(field(pos, mas), box, axis, mas, 1))
+            parity.check_pk(got, O.Pk(field(pos, mas), box, axis, mas, 1), rtol=1e-3)
         else:
             got = eng.run_x([pos[rank::world], pos2[rank::world]], [None, W2[rank::world]], [mas, "PCS"])
-            parity.check_xpk(got, O.XPk([field(pos, mas), field(pos2, "PCS", W2)], box, axis, [mas, "PCS"], 1))
+            parity.check_xpk(got, O.XPk([field(pos, mas), field(pos2, "PCS", W2)], box, axis, [mas, "PCS"], 1), rtol=1e-3)
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         import traceback

@@ -1,0 +1,100 @@
+"""GPU: slab-decomposed pipeline (pylians_b200.dist) with the real CUDA ops.
+  * G=1 on one GPU: slab FFT pieces + pack + windowed ring kernel against the single-GPU Pk and the oracle;
+  * world_size 2 over NCCL (needs 2 GPUs): reduce-scatter, all-to-all transpose, all-reduce."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import parity
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pylians_b200
+    pylians_b200.set_verbose(False)
+
+
+def _particles(dims, box, seed, n_per_cell=3):
+    rng = np.random.default_rng(seed)
+    return (rng.random((n_per_cell * dims ** 3, 3)) * box).astype(np.float32)
+
+
+@pytest.mark.parametrize("dims,mas,axis", [(64, "CIC", 2), (48, "PCS", 2), (40, "TSC", 0)])
+def test_slab_g1_matches_single_gpu_and_oracle(dims, mas, axis):
+    import MAS_library as MASL
+    import Pk_library as PKL
+    from oracle import pylians_oracle as O
+    from pylians_b200.dist import SlabPk
+    box = 800.0
+    pos = _particles(dims, box, dims)
+    got = SlabPk(dims, box, mas, axis).run(torch.from_numpy(pos).cuda())
+    d = np.zeros((dims,) * 3, np.float32); MASL.MA(pos, d, box, mas); MASL.overdensity(d)
+    parity.check_pk(got, PKL.Pk(d, box, axis, mas, 1))
+    r = np.zeros((dims,) * 3, np.float32); O.MA(pos, r, box, mas); r /= np.mean(r, dtype=np.float64); r -= 1.0
+    parity.check_pk(got, O.Pk(r, box, axis, mas, 1), rtol=1e-4 if mas != "CIC" else 1e-5)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import pylians_b200
+        pylians_b200.set_verbose(False)
+        import MAS_library as MASL
+        import Pk_library as PKL
+        import parity
+        from pylians_b200.dist import SlabPk
+        box, dims = 1000.0, 128
+        pos = _particles(dims, box, 11, 2)
+        pos2 = _particles(dims, box, 12, 1)
+        W2 = (np.random.default_rng(5).random(len(pos2)) + 0.5).astype(np.float32)
+        eng = SlabPk(dims, box, "CIC", 2)
+        got = eng.run(torch.from_numpy(pos[rank::world]).cuda())
+        d = np.zeros((dims,) * 3, np.float32); MASL.MA(pos, d, box, "CIC"); MASL.overdensity(d)
+        parity.check_pk(got, PKL.Pk(d, box, 2, "CIC", 1), rtol=1e-4)
+        gx = eng.run_x([torch.from_numpy(pos[rank::world]).cuda(), torch.from_numpy(pos2[rank::world]).cuda()],
+                       [None, torch.from_numpy(W2[rank::world]).cuda()], ["CIC", "TSC"])
+        d2 = np.zeros((dims,) * 3, np.float32); MASL.MA(pos2, d2, box, "TSC", W=W2); MASL.overdensity(d2)
+        parity.check_xpk(gx, PKL.XPk([d, d2], box, 2, ["CIC", "TSC"], 1), rtol=1e-3)
+        q.put((rank, "ok"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_nccl_world2():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == "ok", "rank %d failed:\n%s" % (rank, msg)
