@@ -70,8 +70,8 @@ __device__ __forceinline__ unsigned tile_key(float x, float y, float z, float in
 // ------------------------------------------------------------------------------------------------
 // BINSORT
 // ------------------------------------------------------------------------------------------------
-constexpr int BIN_PER_THREAD = 32;                            // particles per thread per sub-chunk
-constexpr int BIN_SUB = BIN_THREADS * BIN_PER_THREAD;         // 32768 particles per sub-chunk
+constexpr int BIN_PER_THREAD = 16;                            // particles per thread per sub-chunk
+constexpr int BIN_SUB = BIN_THREADS * BIN_PER_THREAD;         // 16384 particles per sub-chunk (a round of 148 CTAs must fit L2)
 constexpr int BIN_MLP = 8;                                    // particles whose loads are in flight per thread
 
 // per-tile particle counts: per-CTA shared histogram, merged with one red.global per (CTA, tile)
