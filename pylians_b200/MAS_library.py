@@ -59,8 +59,39 @@ def _to_device(a, dev):
     return t.to(dev, non_blocking=True)
 
 
+HOST_CHUNK = 1 << 24      # particles per H2D chunk when `pos` lives on the host (201 MB of float32 x 3)
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev):
+    s = _COPY_STREAMS.get(dev.index)
+    if s is None:
+        s = _COPY_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    return s
+
+
+def _as_cpu_tensor(a):
+    if _is_torch(a):
+        return a
+    return torch.from_numpy(a) if a.flags.writeable else torch.from_numpy(a.copy())
+
+
+def _launch_ma(lib, d_pos, d_w, d_grid, ndim, dims, BoxSize, mas, z_repeat, grid_f64, algo, stream):
+    npart = d_pos.shape[0]
+    ws_bytes = lib.pylb_ma_workspace_bytes(npart, ndim, dims, mas, int(d_w is not None), int(grid_f64), algo)
+    ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=d_grid.device)
+    s0, s1 = d_pos.stride()
+    _lib.check(lib.pylb_ma(d_pos.data_ptr(), npart, ndim, s0, s1, d_grid.data_ptr(), int(grid_f64), dims,
+                           float(BoxSize), mas, d_w.data_ptr() if d_w is not None else None, int(z_repeat),
+                           algo, ws.data_ptr(), int(ws_bytes), stream.cuda_stream), "pylb_ma")
+
+
 def _deposit(pos, number, BoxSize, mas, W, z_repeat, grid_f64=False, algo=None):
-    """Common device path: returns nothing, accumulates into `number` (numpy or tensor) in place."""
+    """Common device path: accumulates into `number` (numpy or tensor) in place.
+
+    Device-resident `pos`: one pylb_ma call.  Host `pos`: the particle array is streamed in chunks on a
+    side stream, double-buffered, so the H2D copy of chunk i+1 overlaps the deposit of chunk i (MA only
+    ever adds into the grid, so chunking changes nothing but the fp32 summation order)."""
     lib = _lib.load()
     dev = _device()
     ndim = pos.shape[1]
@@ -73,22 +104,62 @@ def _deposit(pos, number, BoxSize, mas, W, z_repeat, grid_f64=False, algo=None):
     elif not (number.flags["C_CONTIGUOUS"] and number.flags["WRITEABLE"]):
         raise ValueError("number must be a writeable C-contiguous array")
     stream = torch.cuda.current_stream(dev)
-    d_pos = _to_device(pos, dev)
-    d_w = None
-    if W is not None:
-        d_w = _to_device(W, dev)
-        if not d_w.is_contiguous():
-            d_w = d_w.contiguous()
-    d_grid = _to_device(number, dev) if host_grid else number
     algo = ALGO if algo is None else algo
-    ws_bytes = lib.pylb_ma_workspace_bytes(npart, ndim, dims, mas, int(W is not None), int(grid_f64), algo)
-    ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=dev)
-    s0, s1 = d_pos.stride()
-    _lib.check(lib.pylb_ma(d_pos.data_ptr(), npart, ndim, s0, s1, d_grid.data_ptr(), int(grid_f64), dims,
-                           float(BoxSize), mas, d_w.data_ptr() if d_w is not None else None, int(z_repeat),
-                           algo, ws.data_ptr(), int(ws_bytes), stream.cuda_stream), "pylb_ma")
-    if not host_grid and (d_pos is not pos or (W is not None and d_w is not W)):
-        stream.synchronize()        # host inputs were staged asynchronously: do not return before they are consumed
+    d_grid = _to_device(number, dev) if host_grid else number
+    pos_on_dev = _is_torch(pos) and pos.is_cuda
+    if pos_on_dev or npart <= HOST_CHUNK:
+        d_pos = _to_device(pos, dev)
+        d_w = None
+        if W is not None:
+            d_w = _to_device(W, dev)
+            if not d_w.is_contiguous():
+                d_w = d_w.contiguous()
+        _launch_ma(lib, d_pos, d_w, d_grid, ndim, dims, BoxSize, mas, z_repeat, grid_f64, algo, stream)
+        if not host_grid and (d_pos is not pos or (W is not None and d_w is not W)):
+            stream.synchronize()    # host inputs were staged asynchronously: do not return before they are consumed
+        return d_grid, host_grid, stream
+
+    # ---- host particles: chunked, double-buffered H2D on a side stream ----------------------------
+    h_pos = _as_cpu_tensor(pos)
+    h_w = None
+    if W is not None:
+        h_w = _as_cpu_tensor(W) if not (_is_torch(W) and W.is_cuda) else None
+        d_w_full = W if h_w is None else None
+    cs = _copy_stream(dev)
+    bufs = [torch.empty((HOST_CHUNK, ndim), dtype=torch.float32, device=dev) for _ in range(2)]
+    wbufs = [torch.empty(HOST_CHUNK, dtype=torch.float32, device=dev) for _ in range(2)] if h_w is not None else None
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    cs.wait_stream(stream)
+    nchunks = (npart + HOST_CHUNK - 1) // HOST_CHUNK
+
+    def issue_copy(i):
+        b = i % 2
+        lo, hi = i * HOST_CHUNK, min(npart, (i + 1) * HOST_CHUNK)
+        with torch.cuda.stream(cs):
+            if i >= 2:
+                cs.wait_event(consumed[b])
+            bufs[b][: hi - lo].copy_(h_pos[lo:hi], non_blocking=True)
+            if wbufs is not None:
+                wbufs[b][: hi - lo].copy_(h_w[lo:hi], non_blocking=True)
+            copied[b].record(cs)
+
+    issue_copy(0)
+    for i in range(nchunks):
+        b = i % 2
+        lo, hi = i * HOST_CHUNK, min(npart, (i + 1) * HOST_CHUNK)
+        if i + 1 < nchunks:
+            issue_copy(i + 1)
+        stream.wait_event(copied[b])
+        d_w = None
+        if W is not None:
+            d_w = wbufs[b][: hi - lo] if wbufs is not None else d_w_full[lo:hi]
+        _launch_ma(lib, bufs[b][: hi - lo], d_w, d_grid, ndim, dims, BoxSize, mas, z_repeat, grid_f64, algo, stream)
+        consumed[b].record(stream)
+    for t in bufs + (wbufs or []):
+        t.record_stream(stream)
+    if not host_grid:
+        stream.synchronize()
     return d_grid, host_grid, stream
 
 

@@ -140,8 +140,11 @@ def bin_modes(delta_k, dims, axis, mas_index, want_phase, write_back, ks=None, s
         nz = dims // 2 + 1
         ks = _lib.KSpace(dims, 0, dims, 0, dims, dims * nz, nz)
     if sums is None:
-        sums = torch.empty(L.n_doubles, dtype=torch.float64, device=dev)
-        counts = torch.empty(L.n_counts, dtype=torch.int64, device=dev)
+        # one allocation for both accumulator arrays so that a single D2H copy brings them back
+        raw = torch.empty(L.n_doubles + L.n_counts, dtype=torch.float64, device=dev)
+        sums = raw[:L.n_doubles]
+        counts = raw[L.n_doubles:].view(torch.int64)
+        sums._pylb_raw = raw
     ptrs = (ctypes.c_void_p * F)(*[t.data_ptr() for t in delta_k])
     mi = (ctypes.c_int * F)(*[int(m) for m in mas_index])
     stream = torch.cuda.current_stream(dev)
@@ -151,12 +154,49 @@ def bin_modes(delta_k, dims, axis, mas_index, want_phase, write_back, ks=None, s
     return L, sums, counts
 
 
+_PINNED = {}
+
+
+def _pinned(n):
+    t = _PINNED.get(n)
+    if t is None:
+        t = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        _PINNED.clear()
+        _PINNED[n] = t
+    return t
+
+
+_KGRID = {}
+
+
+def _kpar_kper(kmax_par, kmax_per, kF):
+    """Bin centres of the 2-D table (Pk_library.pyx:397-403): pure geometry, cached per shape."""
+    key = (kmax_par, kmax_per, kF)
+    v = _KGRID.get(key)
+    if v is None:
+        i2 = np.arange((kmax_par + 1) * (kmax_per + 1))
+        v = (0.5 * (2 * (i2 % (kmax_par + 1)) + 1) * kF, 0.5 * (2 * (i2 // (kmax_par + 1)) + 1) * kF)
+        _KGRID.clear()
+        _KGRID[key] = v
+    return v[0].copy(), v[1].copy()
+
+
 class _Bins(object):
     """Host view (numpy float64) of the raw sums laid out by pylb_pk_layout."""
 
     def __init__(self, L, sums, counts):
-        s = sums.cpu().numpy()
-        c = counts.cpu().numpy().astype(np.float64)     # counts < 2^53: exact in float64
+        raw = getattr(sums, "_pylb_raw", None)
+        if raw is not None and raw.is_cuda:
+            # single async copy into a cached pinned buffer + one stream sync
+            host = _pinned(raw.numel())
+            host.copy_(raw, non_blocking=True)
+            torch.cuda.current_stream(raw.device).synchronize()
+            h = host.numpy()
+            s = h[:L.n_doubles].copy()
+            c = h[L.n_doubles:].view(np.int64).astype(np.float64)   # counts < 2^53: exact in float64
+        else:
+            s = sums.cpu().numpy()
+            c = counts.cpu().numpy().astype(np.float64)
         F, X, n3, n1, B2 = L.F, L.X, L.kmax + 1, L.kmax_par + 1, L.B2
         self.F, self.X = F, X
         self.k3d = s[L.o_k3d:L.o_k3d + n3]
@@ -189,9 +229,7 @@ def _finish(obj, b, dims, BoxSize, is_x):
     # 2-D: the DC bin is kept; an empty bin is a ZeroDivisionError in the reference (cdivision False)
     if np.any(b.n2d == 0):
         raise ZeroDivisionError("float division")
-    i2 = np.arange((kmax_par + 1) * (kmax_per + 1))
-    obj.kpar = 0.5 * (2 * (i2 % (kmax_par + 1)) + 1) * kF
-    obj.kper = 0.5 * (2 * (i2 // (kmax_par + 1)) + 1) * kF
+    obj.kpar, obj.kper = _kpar_kper(kmax_par, kmax_per, kF)
     obj.Nmodes2D = b.n2d.copy()
     P2 = b.p2d * fact / b.n2d[:, None]
     X2 = b.x2d * fact / b.n2d[:, None]

@@ -410,6 +410,132 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// special columns kz = 0 and kz = dims/2 (even dims) for the ring path (line of sight = z).
+// These are the self-conjugate planes: one of each conjugate pair is kept (:326-330).  A thread owns
+// one (span of the r2-sorted row list, special kz).  With kz fixed, n = r2 + kz^2 grows along the
+// sorted list, so k_index and k_per are monotone: ONE running 3-D bin and ONE running 2-D bin per
+// thread, flushed with red.global when they change.  fp64 per mode (2*N^2 modes in total: irrelevant).
+// ------------------------------------------------------------------------------------------------
+constexpr int SPECIAL_ROWS = 64;   // rows per thread
+
+template <int F>
+__global__ void __launch_bounds__(128)
+special_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, int nplanes, int want_phase, int write_back) {
+    constexpr int X = F * (F - 1) / 2;
+    constexpr int Q = F + X;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int plane = gid % nplanes, span = gid / nplanes;
+    const int i0 = span * SPECIAL_ROWS, i1 = min(nrows, i0 + SPECIAL_ROWS);
+    if (i0 >= i1) return;
+    const int kz = plane == 0 ? 0 : g.middle;
+    const int kz2 = kz * kz, mid2 = g.middle * g.middle, m1 = g.middle + 1;
+    double cz[F];
+#pragma unroll
+    for (int f = 0; f < F; f++) cz[f] = g.mas_tab[f * m1 + kz];
+
+    int b3 = -1, b2 = -1, c3 = 0, c2 = 0, c1 = 0;
+    double s3[3][Q], ks = 0, ph = 0, s2[Q], s1[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) { s2[q] = 0; s1[q] = 0; s3[0][q] = s3[1][q] = s3[2][q] = 0; }
+
+    auto flush3 = [&]() {
+        if (c3) {
+            red_add(g.sums + g.o_k3d + b3, ks);
+            red_add_u64(g.counts + g.o_n3d + b3, (uint64_t)c3);
+#pragma unroll
+            for (int l = 0; l < 3; l++) {
+#pragma unroll
+                for (int f = 0; f < F; f++) red_add(g.sums + g.o_p3d + ((long long)b3 * 3 + l) * F + f, s3[l][f]);
+#pragma unroll
+                for (int x = 0; x < X; x++) red_add(g.sums + g.o_x3d + ((long long)b3 * 3 + l) * X + x, s3[l][F + x]);
+            }
+            if (want_phase) red_add(g.sums + g.o_phase + b3, ph);
+        }
+        c3 = 0; ks = 0; ph = 0;
+#pragma unroll
+        for (int q = 0; q < Q; q++) s3[0][q] = s3[1][q] = s3[2][q] = 0;
+    };
+    auto flush2 = [&]() {
+        if (c2) {
+            const long long i2 = (long long)g.kmax_par1 * b2 + kz;
+            red_add_u64(g.counts + g.o_n2d + i2, (uint64_t)c2);
+#pragma unroll
+            for (int f = 0; f < F; f++) red_add(g.sums + g.o_p2d + i2 * F + f, s2[f]);
+#pragma unroll
+            for (int x = 0; x < X; x++) red_add(g.sums + g.o_x2d + i2 * X + x, s2[F + x]);
+        }
+        c2 = 0;
+#pragma unroll
+        for (int q = 0; q < Q; q++) s2[q] = 0;
+    };
+
+    for (int i = i0; i < i1; i++) {
+        const RowEnt e = tab[i];
+        const int kx = e.kx, ky = e.ky;
+        // keep one of each conjugate pair, :326-330
+        if (kx < 0) continue;
+        if ((kx == 0 || (kx == g.middle && g.even)) && ky < 0) continue;
+        const int n = e.r2 + kz2;
+        const int k_index = isqrt_exact(n), k_per = isqrt_exact(e.r2);
+        if (k_index != b3) { flush3(); b3 = k_index; }
+        if (k_per != b2) { flush2(); b2 = k_per; }
+        const double k = sqrt((double)n);
+        const double mu = (n == 0) ? 0.0 : (double)kz / k;
+        const double mu2 = mu * mu;
+        const double w2 = (3.0 * mu2 - 1.0) / 2.0, w4 = (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0;
+        const bool in1d = n <= mid2;
+        const int ax = kx, ay = ky < 0 ? -ky : ky;
+        double re[F], im[F], v[Q];
+#pragma unroll
+        for (int f = 0; f < F; f++) {
+            const float mf = (float)(g.mas_tab[f * m1 + ax] * g.mas_tab[f * m1 + ay] * cz[f]);
+            float2 *zp = reinterpret_cast<float2 *>(reinterpret_cast<char *>(dk.p[f]) + e.off) + kz;
+            const float2 z = *zp;
+            const float r = __fmul_rn(z.x, mf), q = __fmul_rn(z.y, mf);
+            if (write_back) *zp = make_float2(r, q);
+            re[f] = (double)r; im[f] = (double)q;
+            v[f] = re[f] * re[f] + im[f] * im[f];
+        }
+        if (X > 0) {
+            int ix = 0;
+#pragma unroll
+            for (int a = 0; a < F; a++)
+#pragma unroll
+                for (int b = a + 1; b < F; b++) { v[F + ix] = re[a] * re[b] + im[a] * im[b]; ix++; }
+        }
+        if (want_phase) { const double p = atan2(re[0], sqrt(v[0])); ph += p * p; }
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            s3[0][q] += v[q]; s3[1][q] += v[q] * w2; s3[2][q] += v[q] * w4;
+            s2[q] += v[q];
+            if (in1d) s1[q] += v[q];
+        }
+        ks += k; c3++; c2++;
+        if (in1d) c1++;
+    }
+    flush3();
+    flush2();
+    if (c1) {
+        red_add_u64(g.counts + g.o_n1d + kz, (uint64_t)c1);
+#pragma unroll
+        for (int f = 0; f < F; f++) red_add(g.sums + g.o_p1d + (long long)kz * F + f, s1[f]);
+#pragma unroll
+        for (int x = 0; x < X; x++) red_add(g.sums + g.o_x1d + (long long)kz * X + x, s1[F + x]);
+    }
+}
+
+template <int F>
+static int launch_special(const BinGeom &g, const FieldPtrs &dk, const RowEnt *tab, int nrows, int want_phase,
+                          int write_back, cudaStream_t st) {
+    const int nplanes = (g.even && g.middle > 0) ? 2 : 1;
+    const long long nthreads = (long long)((nrows + SPECIAL_ROWS - 1) / SPECIAL_ROWS) * nplanes;
+    if (nthreads == 0) return 0;
+    special_kernel<F><<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(g, dk, tab, nrows, nplanes, want_phase, write_back);
+    PYLB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic kernel: one thread per mode, kzz = kz_start + j*kz_step for j < kz_num
 // ------------------------------------------------------------------------------------------------
 template <bool WB>
@@ -549,10 +675,7 @@ static int bits_for(unsigned v) {
 static int run_ring(const BinGeom &g, const FieldPtrs &dk, int want_phase, int write_back, int precise, cudaStream_t st) {
     const int nrows = g.nx * g.ny;
     const int kz_hi = g.even ? g.middle - 1 : g.middle;  // columns 1..kz_hi carry no skip rule
-    // special columns first (kz = 0 and, for even dims, kz = middle)
-    if (launch_generic(g, dk, 0, g.middle > 0 ? g.middle : 1, (g.even && g.middle > 0) ? 2 : 1, want_phase, write_back, st))
-        return 1;
-    if (kz_hi < 1 || nrows == 0) return 0;
+    if (nrows == 0) return 0;
 
     // scratch: keys/vals (double-buffered for the radix sort), row table, cub temp
     unsigned *buf = nullptr;
@@ -575,11 +698,15 @@ static int run_ring(const BinGeom &g, const FieldPtrs &dk, int want_phase, int w
     row_table_kernel<<<blocks, 256, 0, st>>>(k_out, v_out, tab, nrows, g);
     PYLB_LAUNCH_CHECK();
 
+    // special columns (kz = 0 and, for even dims, kz = middle), then the bulk kz in [1, kz_hi]
     int rc = 1;
     switch (g.F) {
-        case 1: rc = launch_ring_f<1>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st); break;
-        case 2: rc = launch_ring_f<2>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st); break;
-        case 3: rc = launch_ring_f<3>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st); break;
+        case 1: rc = launch_special<1>(g, dk, tab, nrows, want_phase, write_back, st) ||
+                     (kz_hi >= 1 && launch_ring_f<1>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st)); break;
+        case 2: rc = launch_special<2>(g, dk, tab, nrows, want_phase, write_back, st) ||
+                     (kz_hi >= 1 && launch_ring_f<2>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st)); break;
+        case 3: rc = launch_special<3>(g, dk, tab, nrows, want_phase, write_back, st) ||
+                     (kz_hi >= 1 && launch_ring_f<3>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st)); break;
         default: set_error("ring binning supports 1..3 fields, got %d", g.F);
     }
     cudaFreeAsync(buf, st);

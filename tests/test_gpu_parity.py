@@ -104,6 +104,22 @@ def test_ma_fortran_order_and_device_tensors(MASL, gma):
     parity.assert_grid_close(gt.cpu().numpy(), gma["grid_PCSW"], "device tensors")
 
 
+def test_ma_host_chunked_streaming(MASL, gma):
+    """Host particle arrays are streamed in chunks (H2D overlapped with the deposit); shrink the chunk so
+    the path is exercised, including a ragged last chunk, weights and Fortran-ordered positions."""
+    import pylians_b200.MAS_library as M
+    box, dims = float(gma["box"]), int(gma["dims"])
+    old, M.HOST_CHUNK = M.HOST_CHUNK, 1700
+    try:
+        g = np.zeros((dims,) * 3, np.float32); MASL.MA(gma["pos"], g, box, "TSC", W=gma["W"])
+        parity.assert_grid_close(g, gma["grid_TSCW"], "chunked host TSCW")
+        gt = torch.zeros((dims,) * 3, dtype=torch.float32, device="cuda")
+        MASL.MA(np.asfortranarray(gma["pos"]), gt, box, "CIC")
+        parity.assert_grid_close(gt.cpu().numpy(), gma["grid_CIC"], "chunked host CIC -> device grid")
+    finally:
+        M.HOST_CHUNK = old
+
+
 def test_ma_errors(MASL):
     pos = np.zeros((4, 3), np.float32)
     with pytest.raises(SystemExit):
