@@ -123,6 +123,49 @@ __device__ __forceinline__ float phase_sq(float re, float d2) {
     return q * s;
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FMUL2 / FFMA2): two independent IEEE-rounded lanes per instruction
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// phase^2 of two modes at once: same polynomial as phase_sq, one FFMA2 per coefficient
+__device__ __forceinline__ float2 phase_sq2(float re2a, float d2a, float re2b, float d2b) {
+    float ra, rb;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(fmaxf(d2a, 1e-37f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(fmaxf(d2b, 1e-37f)));
+    const unsigned long long s = pack2(fminf(re2a * ra, 1.0f), fminf(re2b * rb, 1.0f));
+#define PYLB_C2(c) pack2(c, c)
+    unsigned long long q = PYLB_C2(-6.465150895e-03f);
+    q = fma2(q, s, PYLB_C2(3.925943169e-02f));
+    q = fma2(q, s, PYLB_C2(-1.113286174e-01f));
+    q = fma2(q, s, PYLB_C2(2.034298861e-01f));
+    q = fma2(q, s, PYLB_C2(-2.851652190e-01f));
+    q = fma2(q, s, PYLB_C2(3.508593260e-01f));
+    q = fma2(q, s, PYLB_C2(-4.181177634e-01f));
+    q = fma2(q, s, PYLB_C2(5.110430921e-01f));
+    q = fma2(q, s, PYLB_C2(-6.666647075e-01f));
+    q = fma2(q, s, PYLB_C2(9.999999906e-01f));
+#undef PYLB_C2
+    return unpack2(mul2(q, s));
+}
+
 __device__ __forceinline__ float2 ld_stream(const float2 *p) {
     float2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
@@ -383,8 +426,30 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
 #pragma unroll
         for (int u = 0; u < RING_B; u++) prefetch(j + D + u);
         ModeVals v[RING_B];
+        if (F == 1 && !PRECISE && !WB) {
+            // packed path: (re,im) *= mf and (re^2, im^2) as one FMUL2 each, phase^2 of two rows per FFMA2 chain
 #pragma unroll
-        for (int u = 0; u < RING_B; u++) mode_math(j + u, z[u], v[u]);
+            for (int u = 0; u < RING_B; u += 2) {
+                const float mfa = (float)(sm.cxy[j + u][0] * cz[0]);          // double product -> float, :354
+                const float mfb = (float)(sm.cxy[j + u + 1][0] * cz[0]);
+                const unsigned long long da = mul2(pack2(z[u][0].x, z[u][0].y), pack2(mfa, mfa));          // :355
+                const unsigned long long db = mul2(pack2(z[u + 1][0].x, z[u + 1][0].y), pack2(mfb, mfb));
+                const float2 sa = unpack2(mul2(da, da)), sb = unpack2(mul2(db, db));                        // (re^2, im^2)
+                const float d2a = sa.x + sa.y, d2b = sb.x + sb.y;
+                v[u].q[0] = (acc_t)d2a;
+                v[u + 1].q[0] = (acc_t)d2b;
+                if (PHASE) {
+                    const float2 ph = phase_sq2(sa.x, d2a, sb.x, d2b);
+                    v[u].ph = (acc_t)ph.x;
+                    v[u + 1].ph = (acc_t)ph.y;
+                } else {
+                    v[u].ph = 0; v[u + 1].ph = 0;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < RING_B; u++) mode_math(j + u, z[u], v[u]);
+        }
 #pragma unroll
         for (int u = 0; u < RING_B; u++) mode_bin(j + u, v[u]);
     }
@@ -416,7 +481,7 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
 // sorted list, so k_index and k_per are monotone: ONE running 3-D bin and ONE running 2-D bin per
 // thread, flushed with red.global when they change.  fp64 per mode (2*N^2 modes in total: irrelevant).
 // ------------------------------------------------------------------------------------------------
-constexpr int SPECIAL_ROWS = 64;   // rows per thread
+constexpr int SPECIAL_ROWS = 16;   // rows per thread
 
 template <int F>
 __global__ void __launch_bounds__(128)

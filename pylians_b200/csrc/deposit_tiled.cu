@@ -29,16 +29,15 @@
 
 namespace pylb {
 
-template <int TX_, int TY_, int TZ_>
+template <int TX_, int TY_, int TZ_, int THREADS_>
 struct TileCfg {
-    static constexpr int TX = TX_, TY = TY_, TZ = TZ_;
+    static constexpr int TX = TX_, TY = TY_, TZ = TZ_, THREADS = THREADS_;
 };
-typedef TileCfg<16, 16, 32> TileS;   // default: 38-51 KB of shared memory per CTA, 4-5 CTAs/SM
-typedef TileCfg<32, 32, 32> TileL;   // large grids: 144-176 KB, 1 CTA/SM, 8x fewer tiles
+typedef TileCfg<16, 16, 32, 256> TileS;    // 38-51 KB of shared memory per CTA, 4-5 CTAs/SM
+typedef TileCfg<32, 32, 32, 1024> TileL;   // 144-176 KB, 1 CTA/SM of 32 warps, 4x fewer tiles
 
 constexpr int CHUNK = 8192;              // particles per work item
 constexpr int64_t BATCH = 1ll << 28;     // particles binned per pass (bounds the workspace)
-constexpr int TILE_THREADS = 256;
 constexpr int BIN_THREADS = 1024;        // binsort CTAs: one per SM, 32 warps
 constexpr int BIN_MAX_TILES = 32768;     // per-CTA histogram must fit shared memory (128 KB)
 
@@ -220,13 +219,14 @@ __device__ __forceinline__ void red_add_v4(float *p, float4 v) {
 
 // SORTED: particles come as float4 (x,y,z,w) already in tile order.  Otherwise through the sorted index.
 template <int MAS, bool HASW, class TC, bool SORTED>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TC::THREADS)
 deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, int64_t ps1,
                     const float *__restrict__ W, float inv, TileGeom tg, const unsigned *__restrict__ svals,
                     const float4 *__restrict__ sorted, const int *__restrict__ tile_begin,
                     const int *__restrict__ chunk_off, float *__restrict__ grid) {
     using TS = TileShape<MAS, TC>;
     constexpr int S = TS::S;
+    constexpr int TILE_THREADS = TC::THREADS;
     extern __shared__ __align__(16) float tile[];
     __shared__ int s_tile, s_lo, s_hi;
 
@@ -445,7 +445,7 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
         // upper bound on work items: every non-empty tile has at most count/CHUNK + 1 chunks
         const int64_t max_items = (int64_t)n / CHUNK + tg.ntiles;
         timing_begin(PYLB_T_TILE, st);
-        deposit_tile_kernel<MAS, HASW, TC, BINSORT><<<(unsigned)max_items, TILE_THREADS, tile_smem, st>>>(
+        deposit_tile_kernel<MAS, HASW, TC, BINSORT><<<(unsigned)max_items, TC::THREADS, tile_smem, st>>>(
             pos, first, ps0, ps1, w, inv, tg, ws.v1, ws.sorted, ws.tile_begin, ws.chunk_off, grid);
         timing_end(PYLB_T_TILE, st);
         PYLB_LAUNCH_CHECK();
