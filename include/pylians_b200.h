@@ -47,7 +47,8 @@ enum { PYLB_MA_AUTO = 0, PYLB_MA_DIRECT = 1, PYLB_MA_TILED = 2 };
  * mode is squared and accumulated in float64 exactly like Pk_library.pyx:358-360 (the default forms
  * |delta_k|^2 in fp32 and accumulates in fp64 from the first group sum on; the generic kernel is
  * always fp64). */
-enum { PYLB_BIN_AUTO = 0, PYLB_BIN_GENERIC = 1, PYLB_BIN_RING = 2, PYLB_BIN_PRECISE = 16 };
+enum { PYLB_BIN_AUTO = 0, PYLB_BIN_GENERIC = 1, PYLB_BIN_RING = 2, PYLB_BIN_PRECISE = 16,
+       PYLB_BIN_NOBULK = 32 /* ring kernel: per-thread cp.async instead of cp.async.bulk row loads */ };
 
 int pylb_version(void);
 const char *pylb_last_error(void);

@@ -194,6 +194,47 @@ struct RingSmem {
     double cxy[RING_SPAN_MAX][F];
 };
 
+// Bulk variant: one elected lane copies whole row segments with cp.async.bulk (the TMA engine's 1-D
+// path) into a ring of stages; full/empty mbarriers replace per-thread cp.async groups.  Rows are only
+// 8-byte aligned and bulk copies need 16 bytes, so a row's window starts one element early when needed
+// (dlt = 0|1) and a segment serves RING_T-1 kz values.
+constexpr int BULK_ROWS = 4;     // rows per stage (= rows per loop iteration)
+constexpr int BULK_SLOTS = 6;    // stages in the ring
+constexpr int BULK_AHEAD = 4;    // stages in flight ahead of the consumer (<= BULK_SLOTS - 2)
+
+template <int F>
+struct RingSmemBulk {
+    float2 z[BULK_SLOTS][BULK_ROWS][F][RING_T];   // 2 KB per (row, field): 16-byte aligned windows
+    RowEnt ent[RING_SPAN_MAX];
+    double cxy[RING_SPAN_MAX][F];
+    unsigned long long full[BULK_SLOTS], empty[BULK_SLOTS];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 template <bool PRECISE> struct AccT { typedef float type; };
 template <> struct AccT<true> { typedef double type; };
 
@@ -204,19 +245,25 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int F, bool PHASE, bool WB, bool PRECISE>
+template <int F, bool BULK> struct RingSmemSel { typedef RingSmem<F> type; };
+template <int F> struct RingSmemSel<F, true> { typedef RingSmemBulk<F> type; };
+
+template <int F, bool PHASE, bool WB, bool PRECISE, bool BULK>
 __global__ void __launch_bounds__(RING_T, F == 1 ? (PRECISE ? 2 : 3) : (F == 2 ? 2 : 1))
 ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, int rows_per_span, int kz_hi) {
     constexpr int X = F * (F - 1) / 2;
     constexpr int Q = F + X;
     constexpr int D = RingCfg<F>::D;
     typedef typename AccT<PRECISE>::type acc_t;
-    extern __shared__ __align__(16) unsigned char ring_smem_raw[];
-    RingSmem<F> &sm = *reinterpret_cast<RingSmem<F> *>(ring_smem_raw);
+    typedef typename RingSmemSel<F, BULK>::type Smem;
+    extern __shared__ __align__(128) unsigned char ring_smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(ring_smem_raw);
 
     const int tid = threadIdx.x;
-    const int kz = 1 + blockIdx.y * RING_T + tid;
-    const bool active = kz <= kz_hi;
+    constexpr int LANES = BULK ? RING_T - 1 : RING_T;          // kz values served by one segment
+    const int kz_first = 1 + blockIdx.y * LANES;
+    const int kz = kz_first + tid;
+    const bool active = tid < LANES && kz <= kz_hi;
     const int kzc = active ? kz : kz_hi;  // clamp so idle lanes stay in bounds
     const int kz2 = kzc * kzc;
     const int i0 = blockIdx.x * rows_per_span;
@@ -224,9 +271,24 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
     if (total <= 0) return;
 
     // stage this span's row table (and the per-row x*y MAS factors) once
+    if (BULK && tid == 0) {
+#pragma unroll
+        for (int q = 0; q < BULK_SLOTS; q++) {
+            mbar_init(&reinterpret_cast<RingSmemBulk<F> &>(sm).full[q], 1);            // the producer's expect_tx arrive
+            mbar_init(&reinterpret_cast<RingSmemBulk<F> &>(sm).empty[q], RING_T / 32);  // one lane per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int j = tid; j < total; j += RING_T) {
-        const RowEnt e = tab[i0 + j];
+        RowEnt e = tab[i0 + j];
+        if (BULK) {
+            // window start = kz_first - dlt must sit on a 16-byte boundary: (row element offset + start) even
+            const int dlt = (int)(((e.off >> 3) + kz_first) & 1);
+            e.kx = (short)dlt;   // kx/ky are not needed after the MAS factors below; reuse the slot
+        }
+        const RowEnt e0 = tab[i0 + j];
         sm.ent[j] = e;
+        e = e0;
         const int ax = e.kx < 0 ? -e.kx : e.kx, ay = e.ky < 0 ? -e.ky : e.ky;
 #pragma unroll
         for (int f = 0; f < F; f++)
@@ -239,15 +301,50 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
 #pragma unroll
     for (int f = 0; f < F; f++) base[f] = reinterpret_cast<const char *>(dk.p[f] + kzc);
 
-    auto prefetch = [&](int j) {   // this thread's element of row j -> ring slot j % D
-        if (j < total) {
-            const long long off = sm.ent[j].off;
+    auto prefetch = [&](int j) {   // this thread's element of row j -> ring slot j % D   (non-bulk path)
+        if constexpr (!BULK) {
+            if (j < total) {
+                const long long off = sm.ent[j].off;
 #pragma unroll
-            for (int f = 0; f < F; f++) cp_async8(&sm.z[j & (D - 1)][tid][f], base[f] + off);
+                for (int f = 0; f < F; f++) cp_async8(&sm.z[j & (D - 1)][tid][f], base[f] + off);
+            }
+            cp_async_commit();     // one group per row, even when empty, so wait_group<N> counts rows
         }
-        cp_async_commit();         // one group per row, even when empty, so wait_group<N> counts rows
     };
-    for (int j = 0; j < D; j++) prefetch(j);
+    // bulk path: thread 0 fills stage st (rows 4*st .. 4*st+3) with one cp.async.bulk per (row, field)
+    const int nstages = (total + BULK_ROWS - 1) / BULK_ROWS;
+    const int kz_last = min(kz_hi, kz_first + LANES - 1);
+    auto produce = [&](int st) {
+        if constexpr (BULK) {
+            if (st < nstages) {
+                RingSmemBulk<F> &sb = reinterpret_cast<RingSmemBulk<F> &>(sm);
+                const int slot = st % BULK_SLOTS;
+                if (st >= BULK_SLOTS) mbar_wait(&sb.empty[slot], (unsigned)((st / BULK_SLOTS - 1) & 1));
+                const int r0 = st * BULK_ROWS, nr = min(BULK_ROWS, total - r0);
+                unsigned bytes[BULK_ROWS], tot_bytes = 0;
+                for (int u = 0; u < nr; u++) {
+                    const int dlt = sb.ent[r0 + u].kx;
+                    const int cnt = kz_last - (kz_first - dlt) + 1;           // elements needed from the window start
+                    bytes[u] = (unsigned)(((cnt + 1) & ~1) * 8);               // even count: multiple of 16 bytes, stays inside the row (even dims)
+                    tot_bytes += bytes[u] * F;
+                }
+                mbar_expect_tx(&sb.full[slot], tot_bytes);
+                for (int u = 0; u < nr; u++) {
+                    const int dlt = sb.ent[r0 + u].kx;
+                    const long long off = sb.ent[r0 + u].off + 8ll * (kz_first - dlt);
+#pragma unroll
+                    for (int f = 0; f < F; f++)
+                        bulk_g2s(&sb.z[slot][u][f][0], reinterpret_cast<const char *>(dk.p[f]) + off, bytes[u], &sb.full[slot]);
+                }
+            }
+        }
+    };
+    if constexpr (BULK) {
+        if (tid == 0)
+            for (int st = 0; st < BULK_AHEAD; st++) produce(st);
+    } else {
+        for (int j = 0; j < D; j++) prefetch(j);
+    }
 
     double cz[F];
 #pragma unroll
@@ -413,19 +510,10 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
         gcnt++;
     };
 
-    constexpr int RING_B = (F == 1) ? 4 : 2;   // rows per loop iteration
+    constexpr int RING_B = BULK ? BULK_ROWS : ((F == 1) ? 4 : 2);   // rows per loop iteration
     static_assert(RING_B < D, "pipeline depth must exceed the batch");
     int j = 0;
-    for (; j + RING_B <= total; j += RING_B) {
-        cp_async_wait<D - RING_B>();   // rows complete in order: rows j .. j+RING_B-1 have landed
-        float2 z[RING_B][F];
-#pragma unroll
-        for (int u = 0; u < RING_B; u++)
-#pragma unroll
-            for (int f = 0; f < F; f++) z[u][f] = sm.z[(j + u) & (D - 1)][tid][f];
-#pragma unroll
-        for (int u = 0; u < RING_B; u++) prefetch(j + D + u);
-        ModeVals v[RING_B];
+    auto batch_math = [&](float2 (&z)[RING_B][F], ModeVals (&v)[RING_B]) {
         if (F == 1 && !PRECISE && !WB) {
             // packed path: (re,im) *= mf and (re^2, im^2) as one FMUL2 each, phase^2 of two rows per FFMA2 chain
 #pragma unroll
@@ -434,12 +522,12 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
                 const float mfb = (float)(sm.cxy[j + u + 1][0] * cz[0]);
                 const unsigned long long da = mul2(pack2(z[u][0].x, z[u][0].y), pack2(mfa, mfa));          // :355
                 const unsigned long long db = mul2(pack2(z[u + 1][0].x, z[u + 1][0].y), pack2(mfb, mfb));
-                const float2 sa = unpack2(mul2(da, da)), sb = unpack2(mul2(db, db));                        // (re^2, im^2)
-                const float d2a = sa.x + sa.y, d2b = sb.x + sb.y;
+                const float2 sa = unpack2(mul2(da, da)), sb2 = unpack2(mul2(db, db));                       // (re^2, im^2)
+                const float d2a = sa.x + sa.y, d2b = sb2.x + sb2.y;
                 v[u].q[0] = (acc_t)d2a;
                 v[u + 1].q[0] = (acc_t)d2b;
                 if (PHASE) {
-                    const float2 ph = phase_sq2(sa.x, d2a, sb.x, d2b);
+                    const float2 ph = phase_sq2(sa.x, d2a, sb2.x, d2b);
                     v[u].ph = (acc_t)ph.x;
                     v[u + 1].ph = (acc_t)ph.y;
                 } else {
@@ -450,6 +538,54 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
 #pragma unroll
             for (int u = 0; u < RING_B; u++) mode_math(j + u, z[u], v[u]);
         }
+    };
+
+    if constexpr (BULK) {
+        RingSmemBulk<F> &sb = reinterpret_cast<RingSmemBulk<F> &>(sm);
+        const int lane = tid & 31;
+        for (int st = 0; st * BULK_ROWS + BULK_ROWS <= total; st++, j += BULK_ROWS) {
+            const int slot = st % BULK_SLOTS;
+            if (tid == 0) produce(st + BULK_AHEAD);
+            mbar_wait(&sb.full[slot], (unsigned)((st / BULK_SLOTS) & 1));
+            float2 z[RING_B][F];
+#pragma unroll
+            for (int u = 0; u < RING_B; u++) {
+                const int idx = (active ? tid : 0) + sb.ent[j + u].kx;   // element kz sits at window index tid + dlt
+#pragma unroll
+                for (int f = 0; f < F; f++) z[u][f] = sb.z[slot][u][f][idx];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sb.empty[slot]);       // this warp is done with the stage
+            ModeVals v[RING_B];
+            batch_math(z, v);
+#pragma unroll
+            for (int u = 0; u < RING_B; u++) mode_bin(j + u, v[u]);
+        }
+        if (j < total) {   // last, partial stage
+            const int st = j / BULK_ROWS, slot = st % BULK_SLOTS;
+            mbar_wait(&sb.full[slot], (unsigned)((st / BULK_SLOTS) & 1));
+            for (int u = 0; j < total; j++, u++) {
+                float2 z0[F];
+                const int idx = (active ? tid : 0) + sb.ent[j].kx;
+#pragma unroll
+                for (int f = 0; f < F; f++) z0[f] = sb.z[slot][u][f][idx];
+                ModeVals v0;
+                mode_math(j, z0, v0);
+                mode_bin(j, v0);
+            }
+        }
+    } else {
+    for (; j + RING_B <= total; j += RING_B) {
+        cp_async_wait<D - RING_B>();   // rows complete in order: rows j .. j+RING_B-1 have landed
+        float2 z[RING_B][F];
+#pragma unroll
+        for (int u = 0; u < RING_B; u++)
+#pragma unroll
+            for (int f = 0; f < F; f++) z[u][f] = sm.z[(j + u) & (D - 1)][tid][f];
+#pragma unroll
+        for (int u = 0; u < RING_B; u++) prefetch(j + D + u);
+        ModeVals v[RING_B];
+        batch_math(z, v);
 #pragma unroll
         for (int u = 0; u < RING_B; u++) mode_bin(j + u, v[u]);
     }
@@ -461,6 +597,7 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
         ModeVals v0;
         mode_math(j, z0, v0);
         mode_bin(j, v0);
+    }
     }
     cp_async_wait<0>();
     apply_group();
@@ -688,18 +825,19 @@ static int launch_generic(const BinGeom &g, const FieldPtrs &dk, int kz_start, i
     return 0;
 }
 
-template <int F, bool PHASE, bool WB, bool PRECISE>
+template <int F, bool PHASE, bool WB, bool PRECISE, bool BULK>
 static int launch_ring_v(const BinGeom &g, const FieldPtrs &dk, const RowEnt *tab, int nrows, int kz_hi, cudaStream_t st) {
-    const int nseg = (kz_hi + RING_T - 1) / RING_T;
-    const size_t smem = sizeof(RingSmem<F>);
+    constexpr int LANES = BULK ? RING_T - 1 : RING_T;
+    const int nseg = (kz_hi + LANES - 1) / LANES;
+    const size_t smem = BULK ? sizeof(RingSmemBulk<F>) : sizeof(RingSmem<F>);
     static bool attr_set = false;
     if (!attr_set) {
-        PYLB_CHECK(cudaFuncSetAttribute(ring_kernel<F, PHASE, WB, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PYLB_CHECK(cudaFuncSetAttribute(ring_kernel<F, PHASE, WB, PRECISE, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     // two waves of resident CTAs; spans of 32..RING_SPAN_MAX rows
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, PHASE, WB, PRECISE>, RING_T, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, PHASE, WB, PRECISE, BULK>, RING_T, smem);
     if (occ < 1) occ = 1;
     int nspan = (sm_count() * occ * 2 + nseg - 1) / nseg;
     if (nspan > (nrows + 31) / 32) nspan = (nrows + 31) / 32;
@@ -709,26 +847,38 @@ static int launch_ring_v(const BinGeom &g, const FieldPtrs &dk, const RowEnt *ta
     nspan = (nrows + rows_per_span - 1) / rows_per_span;
     dim3 grid(nspan, nseg);
     timing_begin(PYLB_T_RING, st);
-    ring_kernel<F, PHASE, WB, PRECISE><<<grid, RING_T, smem, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
+    ring_kernel<F, PHASE, WB, PRECISE, BULK><<<grid, RING_T, smem, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
     timing_end(PYLB_T_RING, st);
     PYLB_LAUNCH_CHECK();
     return 0;
 }
 
-template <int F>
-static int launch_ring_f(const BinGeom &g, const FieldPtrs &dk, const RowEnt *tab, int nrows, int kz_hi,
+template <int F, bool BULK>
+static int launch_ring_b(const BinGeom &g, const FieldPtrs &dk, const RowEnt *tab, int nrows, int kz_hi,
                          int want_phase, int write_back, int precise, cudaStream_t st) {
     const int sel = (want_phase ? 4 : 0) | (write_back ? 2 : 0) | (precise ? 1 : 0);
     switch (sel) {
-        case 0: return launch_ring_v<F, false, false, false>(g, dk, tab, nrows, kz_hi, st);
-        case 1: return launch_ring_v<F, false, false, true>(g, dk, tab, nrows, kz_hi, st);
-        case 2: return launch_ring_v<F, false, true, false>(g, dk, tab, nrows, kz_hi, st);
-        case 3: return launch_ring_v<F, false, true, true>(g, dk, tab, nrows, kz_hi, st);
-        case 4: return launch_ring_v<F, true, false, false>(g, dk, tab, nrows, kz_hi, st);
-        case 5: return launch_ring_v<F, true, false, true>(g, dk, tab, nrows, kz_hi, st);
-        case 6: return launch_ring_v<F, true, true, false>(g, dk, tab, nrows, kz_hi, st);
-        default: return launch_ring_v<F, true, true, true>(g, dk, tab, nrows, kz_hi, st);
+        case 0: return launch_ring_v<F, false, false, false, BULK>(g, dk, tab, nrows, kz_hi, st);
+        case 1: return launch_ring_v<F, false, false, true, BULK>(g, dk, tab, nrows, kz_hi, st);
+        case 2: return launch_ring_v<F, false, true, false, BULK>(g, dk, tab, nrows, kz_hi, st);
+        case 3: return launch_ring_v<F, false, true, true, BULK>(g, dk, tab, nrows, kz_hi, st);
+        case 4: return launch_ring_v<F, true, false, false, BULK>(g, dk, tab, nrows, kz_hi, st);
+        case 5: return launch_ring_v<F, true, false, true, BULK>(g, dk, tab, nrows, kz_hi, st);
+        case 6: return launch_ring_v<F, true, true, false, BULK>(g, dk, tab, nrows, kz_hi, st);
+        default: return launch_ring_v<F, true, true, true, BULK>(g, dk, tab, nrows, kz_hi, st);
     }
+}
+
+// bulk (TMA 1-D) loads need even dims (the window may take one extra element, which exists only then),
+// 16-byte aligned field pointers and 8-byte-multiple row strides (always true)
+static bool g_allow_bulk = true;
+template <int F>
+static int launch_ring_f(const BinGeom &g, const FieldPtrs &dk, const RowEnt *tab, int nrows, int kz_hi,
+                         int want_phase, int write_back, int precise, cudaStream_t st) {
+    bool bulk = g_allow_bulk && g.even;
+    for (int f = 0; f < F; f++) bulk = bulk && (((uintptr_t)dk.p[f] & 15) == 0);
+    if (bulk) return launch_ring_b<F, true>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st);
+    return launch_ring_b<F, false>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st);
 }
 
 static int bits_for(unsigned v) {
@@ -854,7 +1004,8 @@ extern "C" int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int ax
     PYLB_LAUNCH_CHECK();
 
     const int precise = (algo & PYLB_BIN_PRECISE) ? 1 : 0;
-    algo &= ~PYLB_BIN_PRECISE;
+    g_allow_bulk = !(algo & PYLB_BIN_NOBULK);
+    algo &= ~(PYLB_BIN_PRECISE | PYLB_BIN_NOBULK);
     if (algo == PYLB_BIN_AUTO) algo = (axis == 2 && F <= 3) ? PYLB_BIN_RING : PYLB_BIN_GENERIC;
     int rc;
     if (algo == PYLB_BIN_RING) {
