@@ -48,7 +48,8 @@ enum { PYLB_MA_AUTO = 0, PYLB_MA_DIRECT = 1, PYLB_MA_TILED = 2 };
  * |delta_k|^2 in fp32 and accumulates in fp64 from the first group sum on; the generic kernel is
  * always fp64). */
 enum { PYLB_BIN_AUTO = 0, PYLB_BIN_GENERIC = 1, PYLB_BIN_RING = 2, PYLB_BIN_PRECISE = 16,
-       PYLB_BIN_NOBULK = 32 /* ring kernel: per-thread cp.async instead of cp.async.bulk row loads */ };
+       PYLB_BIN_BULK = 32 /* ring kernel: cp.async.bulk + mbarrier row loads by a producer warp instead of
+                             per-thread cp.async (even dims only) */ };
 
 int pylb_version(void);
 const char *pylb_last_error(void);

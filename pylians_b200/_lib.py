@@ -59,7 +59,7 @@ SIGNATURES = {
 }
 
 MA_AUTO, MA_DIRECT, MA_TILED = 0, 1, 2
-BIN_AUTO, BIN_GENERIC, BIN_RING, BIN_PRECISE, BIN_NOBULK = 0, 1, 2, 16, 32
+BIN_AUTO, BIN_GENERIC, BIN_RING, BIN_PRECISE, BIN_BULK = 0, 1, 2, 16, 32
 
 _lib = None
 

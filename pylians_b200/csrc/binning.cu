@@ -199,8 +199,7 @@ struct RingSmem {
 // 8-byte aligned and bulk copies need 16 bytes, so a row's window starts one element early when needed
 // (dlt = 0|1) and a segment serves RING_T-1 kz values.
 constexpr int BULK_ROWS = 4;     // rows per stage (= rows per loop iteration)
-constexpr int BULK_SLOTS = 6;    // stages in the ring
-constexpr int BULK_AHEAD = 4;    // stages in flight ahead of the consumer (<= BULK_SLOTS - 2)
+constexpr int BULK_SLOTS = 4;    // stages in the ring (16 rows in flight)
 
 template <int F>
 struct RingSmemBulk {
@@ -249,7 +248,7 @@ template <int F, bool BULK> struct RingSmemSel { typedef RingSmem<F> type; };
 template <int F> struct RingSmemSel<F, true> { typedef RingSmemBulk<F> type; };
 
 template <int F, bool PHASE, bool WB, bool PRECISE, bool BULK>
-__global__ void __launch_bounds__(RING_T, F == 1 ? (PRECISE ? 2 : 3) : (F == 2 ? 2 : 1))
+__global__ void __launch_bounds__(BULK ? RING_T + 32 : RING_T, F == 1 ? (PRECISE ? 2 : 3) : (F == 2 ? 2 : 1))
 ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, int rows_per_span, int kz_hi) {
     constexpr int X = F * (F - 1) / 2;
     constexpr int Q = F + X;
@@ -279,7 +278,7 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int j = tid; j < total; j += RING_T) {
+    for (int j = tid; j < total; j += (int)blockDim.x) {
         RowEnt e = tab[i0 + j];
         if (BULK) {
             // window start = kz_first - dlt must sit on a 16-byte boundary: (row element offset + start) even
@@ -340,8 +339,11 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
         }
     };
     if constexpr (BULK) {
-        if (tid == 0)
-            for (int st = 0; st < BULK_AHEAD; st++) produce(st);
+        if (tid >= RING_T) {                    // dedicated producer warp: one elected lane streams every stage
+            if (tid == RING_T)
+                for (int st = 0; st < nstages; st++) produce(st);
+            return;
+        }
     } else {
         for (int j = 0; j < D; j++) prefetch(j);
     }
@@ -350,7 +352,6 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
 #pragma unroll
     for (int f = 0; f < F; f++) cz[f] = g.mas_tab[f * (g.middle + 1) + kzc];
     const int mid2 = g.middle * g.middle;
-    const double dkz2 = (double)kz2;
 
     // ring state (bins b0 / b0+1, 2-D bin (p, kz)) and span state (1-D bin kz)
     double lo3[3][Q], hi3[3][Q], lok = 0, hik = 0, loph = 0, hiph = 0, a2[Q], a1[Q];
@@ -369,20 +370,28 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
     int cur_r2 = -1, ring_p = -1, ring_hi = 0, b0 = 0, thr = 0;
     bool sel = false, in1d = false;
     double w2 = 0, w4 = 0, kk = 0;
+    float w2f = 0, w4f = 0;   // default mode: Legendre weights in fp32 (1e-7), applied to the fp32 group sums
 
     auto apply_group = [&]() {
         if (gcnt == 0) return;
+        double v0[Q], v1[Q], v2[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            v0[q] = (double)gq[q];
+            if (PRECISE) { v1[q] = v0[q] * w2; v2[q] = v0[q] * w4; }
+            else { v1[q] = (double)((float)gq[q] * w2f); v2[q] = (double)((float)gq[q] * w4f); }
+        }
         if (sel) {
 #pragma unroll
-            for (int q = 0; q < Q; q++) { const double v = (double)gq[q]; hi3[0][q] += v; hi3[1][q] += v * w2; hi3[2][q] += v * w4; }
+            for (int q = 0; q < Q; q++) { hi3[0][q] += v0[q]; hi3[1][q] += v1[q]; hi3[2][q] += v2[q]; }
             hik += (double)gcnt * kk; hicn += gcnt; hiph += (double)gph;
         } else {
 #pragma unroll
-            for (int q = 0; q < Q; q++) { const double v = (double)gq[q]; lo3[0][q] += v; lo3[1][q] += v * w2; lo3[2][q] += v * w4; }
+            for (int q = 0; q < Q; q++) { lo3[0][q] += v0[q]; lo3[1][q] += v1[q]; lo3[2][q] += v2[q]; }
             lok += (double)gcnt * kk; locn += gcnt; loph += (double)gph;
         }
 #pragma unroll
-        for (int q = 0; q < Q; q++) { const double v = (double)gq[q]; a2[q] += v; if (in1d) a1[q] += v; gq[q] = 0; }
+        for (int q = 0; q < Q; q++) { a2[q] += v0[q]; if (in1d) a1[q] += v0[q]; gq[q] = 0; }
         c2 += gcnt;
         if (in1d) c1 += gcnt;
         gcnt = 0; gph = 0;
@@ -437,24 +446,27 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
         sel = n >= thr;
         in1d = n <= mid2;                       // k <= middle, :364
         const double dn = (double)n;
-        double mu2;
         if (PRECISE) {
             kk = sqrt(dn);                      // :334
             const double mu = (double)kzc / kk; // :347
-            mu2 = mu * mu;
+            const double mu2 = mu * mu;
+            w2 = (3.0 * mu2 - 1.0) / 2.0;                       // :378
+            w4 = (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0;   // :379
         } else {
-            // fp32 seed + one Newton step in fp64: relative error < 1e-13 on 1/n and 1/sqrt(n)
+            // Short dependency chains (every warp of the CTA takes this branch at the same time, so its
+            // latency is exposed):  |k| = fp32 sqrt + one fp64 Newton correction (3e-14 relative);
+            // mu^2 = kz^2/n and the Legendre weights in fp32 (1e-7 absolute on the weights).
             const float nf = (float)n;
-            double r = (double)__frcp_rn(nf);
-            r = r * (2.0 - dn * r);
-            double x = (double)rsqrtf(nf);
-            x = x * (1.5 - 0.5 * dn * x * x);
-            x = x * (1.5 - 0.5 * dn * x * x);
-            kk = dn * x;
-            mu2 = dkz2 * r;
+            float rs, rc;
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(nf));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(nf));
+            const double k0 = (double)(nf * rs);
+            kk = fma(fma(-k0, k0, dn), (double)(0.5f * rs), k0);
+            float mu2f = (float)kz2 * rc;
+            mu2f = fminf(mu2f, 1.0f);
+            w2f = fmaf(1.5f, mu2f, -0.5f);                                        // (3 mu^2 - 1)/2
+            w4f = fmaf(fmaf(4.375f, mu2f, -3.75f), mu2f, 0.375f);                 // (35 mu^4 - 30 mu^2 + 3)/8
         }
-        w2 = (3.0 * mu2 - 1.0) / 2.0;                       // :378
-        w4 = (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0;   // :379
     };
 
     // Per-mode work is split in two so that the arithmetic of several rows can overlap:
@@ -545,7 +557,6 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
         const int lane = tid & 31;
         for (int st = 0; st * BULK_ROWS + BULK_ROWS <= total; st++, j += BULK_ROWS) {
             const int slot = st % BULK_SLOTS;
-            if (tid == 0) produce(st + BULK_AHEAD);
             mbar_wait(&sb.full[slot], (unsigned)((st / BULK_SLOTS) & 1));
             float2 z[RING_B][F];
 #pragma unroll
@@ -837,7 +848,7 @@ static int launch_ring_v(const BinGeom &g, const FieldPtrs &dk, const RowEnt *ta
     }
     // two waves of resident CTAs; spans of 32..RING_SPAN_MAX rows
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, PHASE, WB, PRECISE, BULK>, RING_T, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_kernel<F, PHASE, WB, PRECISE, BULK>, BULK ? RING_T + 32 : RING_T, smem);
     if (occ < 1) occ = 1;
     int nspan = (sm_count() * occ * 2 + nseg - 1) / nseg;
     if (nspan > (nrows + 31) / 32) nspan = (nrows + 31) / 32;
@@ -847,7 +858,7 @@ static int launch_ring_v(const BinGeom &g, const FieldPtrs &dk, const RowEnt *ta
     nspan = (nrows + rows_per_span - 1) / rows_per_span;
     dim3 grid(nspan, nseg);
     timing_begin(PYLB_T_RING, st);
-    ring_kernel<F, PHASE, WB, PRECISE, BULK><<<grid, RING_T, smem, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
+    ring_kernel<F, PHASE, WB, PRECISE, BULK><<<grid, BULK ? RING_T + 32 : RING_T, smem, st>>>(g, dk, tab, nrows, rows_per_span, kz_hi);
     timing_end(PYLB_T_RING, st);
     PYLB_LAUNCH_CHECK();
     return 0;
@@ -871,7 +882,7 @@ static int launch_ring_b(const BinGeom &g, const FieldPtrs &dk, const RowEnt *ta
 
 // bulk (TMA 1-D) loads need even dims (the window may take one extra element, which exists only then),
 // 16-byte aligned field pointers and 8-byte-multiple row strides (always true)
-static bool g_allow_bulk = true;
+static bool g_allow_bulk = false;   // opt-in (PYLB_BIN_BULK): matches cp.async for Pk, loses for F >= 2 (profiles/r1_ring_variants.txt)
 template <int F>
 static int launch_ring_f(const BinGeom &g, const FieldPtrs &dk, const RowEnt *tab, int nrows, int kz_hi,
                          int want_phase, int write_back, int precise, cudaStream_t st) {
@@ -1004,8 +1015,8 @@ extern "C" int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int ax
     PYLB_LAUNCH_CHECK();
 
     const int precise = (algo & PYLB_BIN_PRECISE) ? 1 : 0;
-    g_allow_bulk = !(algo & PYLB_BIN_NOBULK);
-    algo &= ~(PYLB_BIN_PRECISE | PYLB_BIN_NOBULK);
+    g_allow_bulk = (algo & PYLB_BIN_BULK) != 0;
+    algo &= ~(PYLB_BIN_PRECISE | PYLB_BIN_BULK);
     if (algo == PYLB_BIN_AUTO) algo = (axis == 2 && F <= 3) ? PYLB_BIN_RING : PYLB_BIN_GENERIC;
     int rc;
     if (algo == PYLB_BIN_RING) {

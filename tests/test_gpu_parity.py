@@ -240,7 +240,7 @@ def _field(dims, box, seed, mas="CIC"):
     return d
 
 
-@pytest.mark.parametrize("algo", [1, 2, 2 | 16, 2 | 32, 2 | 16 | 32])   # generic; ring bulk fp32 / fp64 option; ring cp.async fp32 / fp64
+@pytest.mark.parametrize("algo", [1, 2, 2 | 16, 2 | 32, 2 | 16 | 32])   # generic; ring cp.async fp32 / fp64 option; ring bulk (TMA 1-D) fp32 / fp64
 @pytest.mark.parametrize("dims", [48, 64, 33])
 def test_pk_vs_oracle(PKL, algo, dims):
     import pylians_b200.Pk_library as P
