@@ -130,6 +130,12 @@ int pylb_pos_redshift_space(float *pos, const float *vel, int64_t np, float box,
 size_t pylb_fft_r2c_work_bytes(int dims, int inplace);
 int pylb_fft_r2c(const float *in, void *out, int dims, int inplace, void *work, size_t work_bytes, void *stream);
 
+/* Real-space axis swap feeding the FFT: out(i,j,k) = in(k,j,i) for axis 0, in(i,k,j) for axis 1, a copy
+ * for axis 2.  `out` rows have out_pitch floats (dims for a dense cube, 2*(dims/2+1) for the padded
+ * in-place R2C layout).  The power spectrum with the line of sight along `axis` equals the spectrum of
+ * the swapped field with the line of sight along z (the binning ring kernel's fast direction). */
+int pylb_swap_axes(const float *in, float *out, int dims, int axis, int64_t out_pitch, void *stream);
+
 /* Slab-decomposed pieces (multi-GPU).  Real slab [nx_local][dims][dims] -> batched 2-D R2C over
  * (y,z) -> complex [nx_local][dims][dims/2+1]; then, after the all-to-all, 1-D C2C along x on the
  * transposed layout [dims][ny_local][dims/2+1] (in place). */

@@ -24,6 +24,7 @@ from .MAS_library import _device, _is_torch, _dtype_name
 VERBOSE = True          # the reference prints progress lines unconditionally; set False to silence
 # binning algorithm override for tests / benchmarks: 0 auto, 1 generic (atomics), 2 ring (registers)
 ALGO = _lib.BIN_AUTO
+SWAP_AXES = True        # axis 0/1: swap the line of sight onto z in real space and use the ring kernel
 
 
 def _say(msg):
@@ -88,32 +89,45 @@ def _work(nbytes, dev):
     return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=dev)
 
 
-def _fft_field(lib, delta, dims, dev, stream):
+def _fft_field(lib, delta, dims, dev, stream, swap_axis=2):
     """FFT3Dr_f on the device.  Returns a complex64 tensor (dims,dims,dims/2+1); `delta` is never modified.
 
     Host input: one strided H2D copy into the padded in-place layout, then an in-place R2C, so the
-    device holds a single copy of the field.  Device input: out-of-place R2C into a fresh buffer."""
+    device holds a single copy of the field.  Device input: out-of-place R2C into a fresh buffer.
+    swap_axis 0|1: the real field is first axis-swapped (pylb_swap_axes) into the padded layout, so the
+    requested line of sight becomes the half-spectrum axis the ring kernel is fast along."""
     nz = dims // 2 + 1
-    if _is_torch(delta) and delta.is_cuda:
-        src = delta if delta.is_contiguous() else delta.contiguous()
-        out = torch.empty((dims, dims, nz), dtype=torch.complex64, device=dev)
-        wb = lib.pylb_fft_r2c_work_bytes(dims, 0)
+    on_dev = _is_torch(delta) and delta.is_cuda
+
+    def r2c(src_ptr, out_ptr, inplace):
+        wb = lib.pylb_fft_r2c_work_bytes(dims, inplace)
         if wb == ctypes.c_size_t(-1).value:
             raise _lib.PylbError("cuFFT plan failed: " + lib.pylb_last_error().decode())
         work = _work(wb, dev)
-        _lib.check(lib.pylb_fft_r2c(src.data_ptr(), out.data_ptr(), dims, 0, work.data_ptr(), int(wb),
-                                    stream.cuda_stream), "pylb_fft_r2c")
+        _lib.check(lib.pylb_fft_r2c(src_ptr, out_ptr, dims, inplace, work.data_ptr(), int(wb), stream.cuda_stream),
+                   "pylb_fft_r2c")
+
+    if swap_axis != 2:
+        if on_dev:
+            src = delta if delta.is_contiguous() else delta.contiguous()
+        else:
+            host = delta.contiguous() if _is_torch(delta) else np.ascontiguousarray(delta)
+            src = (host if _is_torch(host) else torch.from_numpy(host)).to(dev, non_blocking=True)
+        buf = torch.empty((dims, dims, 2 * nz), dtype=torch.float32, device=dev)
+        _lib.check(lib.pylb_swap_axes(src.data_ptr(), buf.data_ptr(), dims, int(swap_axis), 2 * nz, stream.cuda_stream),
+                   "pylb_swap_axes")
+        r2c(buf.data_ptr(), buf.data_ptr(), 1)
+        return torch.view_as_complex(buf.view(dims, dims, nz, 2))
+    if on_dev:
+        src = delta if delta.is_contiguous() else delta.contiguous()
+        out = torch.empty((dims, dims, nz), dtype=torch.complex64, device=dev)
+        r2c(src.data_ptr(), out.data_ptr(), 0)
         return out
     host = delta.contiguous() if _is_torch(delta) else np.ascontiguousarray(delta)
     buf = torch.empty((dims, dims, 2 * nz), dtype=torch.float32, device=dev)
     hptr = host.data_ptr() if _is_torch(host) else host.ctypes.data
     _lib.check(lib.pylb_h2d_padded(hptr, buf.data_ptr(), dims, stream.cuda_stream), "pylb_h2d_padded")
-    wb = lib.pylb_fft_r2c_work_bytes(dims, 1)
-    if wb == ctypes.c_size_t(-1).value:
-        raise _lib.PylbError("cuFFT plan failed: " + lib.pylb_last_error().decode())
-    work = _work(wb, dev)
-    _lib.check(lib.pylb_fft_r2c(buf.data_ptr(), buf.data_ptr(), dims, 1, work.data_ptr(), int(wb),
-                                stream.cuda_stream), "pylb_fft_r2c")
+    r2c(buf.data_ptr(), buf.data_ptr(), 1)
     out = torch.view_as_complex(buf.view(dims, dims, nz, 2))
     out._pylb_keepalive = host
     return out
@@ -263,9 +277,14 @@ class Pk(object):
         dev = _device()
         dims = len(delta)
         stream = torch.cuda.current_stream(dev)
-        delta_k = _fft_field(lib, delta, dims, dev, stream)
+        # line of sight along x or y: swap that axis with z in real space and bin along z (same bins, same
+        # mode counts; which member of each conjugate pair is kept differs, its |delta_k|^2 does not).
+        # keep_deltak must return the reference's (kx,ky,kz>=0) layout, so it keeps the original axes.
+        swap = int(axis) if (int(axis) in (0, 1) and not keep_deltak and (ALGO & 3) != _lib.BIN_GENERIC and SWAP_AXES) else 2
+        delta_k = _fft_field(lib, delta, dims, dev, stream, swap)
         start2 = time.time()
-        L, sums, counts = bin_modes([delta_k], dims, int(axis), [MAS_function(MAS)], True, bool(keep_deltak))
+        L, sums, counts = bin_modes([delta_k], dims, 2 if swap != 2 else int(axis), [MAS_function(MAS)], True,
+                                    bool(keep_deltak))
         bins = _Bins(L, sums, counts)       # D2H of a few KB; synchronises the stream
         _say("Time to complete loop = %.2f" % (time.time() - start2))
         _finish(self, bins, dims, BoxSize, False)
@@ -296,10 +315,11 @@ class XPk(object):
         lib = _lib.load()
         dev = _device()
         stream = torch.cuda.current_stream(dev)
-        delta_k = [_fft_field(lib, d, dims, dev, stream) for d in delta]
+        swap = int(axis) if (int(axis) in (0, 1) and fields <= 3 and (ALGO & 3) != _lib.BIN_GENERIC and SWAP_AXES) else 2
+        delta_k = [_fft_field(lib, d, dims, dev, stream, swap) for d in delta]
         _say("Time FFTS = %.2f" % (time.time() - start))
         start2 = time.time()
-        L, sums, counts = bin_modes(delta_k, dims, int(axis), mas_index[:fields], False, False)
+        L, sums, counts = bin_modes(delta_k, dims, 2 if swap != 2 else int(axis), mas_index[:fields], False, False)
         bins = _Bins(L, sums, counts)
         _say("Time loop = %.2f" % (time.time() - start2))
         _finish(self, bins, dims, BoxSize, True)

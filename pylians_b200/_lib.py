@@ -45,6 +45,7 @@ SIGNATURES = {
     "pylb_grid_sum": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "pylb_overdensity_apply": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "pylb_pos_redshift_space": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_int, c_void_p]),
+    "pylb_swap_axes": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
     "pylb_fft_r2c_work_bytes": (c_size_t, [c_int, c_int]),
     "pylb_fft_r2c": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pylb_fft_slab_yz_work_bytes": (c_size_t, [c_int, c_int]),

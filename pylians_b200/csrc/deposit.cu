@@ -160,6 +160,42 @@ rsd_kernel(float *pos, const float *__restrict__ vel, int64_t np, float box, flo
     }
 }
 
+// Tiled 2-D transposes (32x32 tile through padded shared memory, coalesced on both sides).
+//   MODE 1 (axis 1): out[i][k][j] = in[i][j][k]   one (j,k) plane per blockIdx.z = i
+//   MODE 0 (axis 0): out[k][j][i] = in[i][j][k]   one (i,k) plane per blockIdx.z = j
+template <int MODE>
+__global__ void __launch_bounds__(256) swap_axes_kernel(const float *__restrict__ in, float *__restrict__ out, int N, int64_t pitch) {
+    __shared__ float tile[32][33];
+    const int p = blockIdx.z;
+    const int a0 = blockIdx.y * 32, c0 = blockIdx.x * 32;   // tile origin: a = slow input index (j or i), c = k
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int a = a0 + r, c = c0 + tx;
+        if (a < N && c < N) {
+            const int64_t src = (MODE == 1) ? ((int64_t)p * N + a) * N + c : ((int64_t)a * N + p) * N + c;
+            tile[r][tx] = in[src];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, a = a0 + tx;                  // now a is the fast output index
+        if (a < N && c < N) {
+            const int64_t dst = (MODE == 1) ? ((int64_t)p * N + c) * pitch + a : ((int64_t)c * N + p) * pitch + a;
+            out[dst] = tile[tx][r];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) copy_pitched_kernel(const float *__restrict__ in, float *__restrict__ out, int N, int64_t pitch, int64_t nrows) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrows * N; i += stride) {
+        const int64_t r = i / N;
+        out[r * pitch + (i - r * N)] = in[i];
+    }
+}
+
 static unsigned grid_for(int64_t n, int threads, int per_sm) {
     int64_t b = (n + threads - 1) / threads;
     const int64_t cap = (int64_t)sm_count() * per_sm;
@@ -195,6 +231,23 @@ extern "C" int pylb_overdensity(float *grid, int64_t n, double *scratch, void *s
     sum_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, st>>>(grid, n, scratch);
     PYLB_LAUNCH_CHECK();
     overdensity_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, st>>>(grid, n, scratch, n);
+    PYLB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pylb_swap_axes(const float *in, float *out, int dims, int axis, int64_t out_pitch, void *stream) {
+    PYLB_REQUIRE(in && out && in != out && dims >= 1 && out_pitch >= dims, "pylb_swap_axes: bad arguments");
+    PYLB_REQUIRE(axis >= 0 && axis <= 2, "pylb_swap_axes: axis must be 0, 1 or 2");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (axis == 2) {
+        const int64_t nrows = (int64_t)dims * dims;
+        copy_pitched_kernel<<<grid_for(nrows * dims, 256, 16), 256, 0, st>>>(in, out, dims, out_pitch, nrows);
+    } else {
+        PYLB_REQUIRE(dims <= 65535, "pylb_swap_axes: dims too large for the launch grid");
+        dim3 grid((dims + 31) / 32, (dims + 31) / 32, dims);
+        if (axis == 1) swap_axes_kernel<1><<<grid, 256, 0, st>>>(in, out, dims, out_pitch);
+        else swap_axes_kernel<0><<<grid, 256, 0, st>>>(in, out, dims, out_pitch);
+    }
     PYLB_LAUNCH_CHECK();
     return 0;
 }

@@ -248,7 +248,7 @@ def test_pk_vs_oracle(PKL, algo, dims):
     d = _field(dims, box, dims)
     old, P.ALGO = P.ALGO, algo
     try:
-        for axis in ((2,) if (algo & 2) else (0, 1, 2)):
+        for axis in (0, 1, 2):     # ring algos reach axes 0/1 through the real-space axis swap
             parity.check_pk(PKL.Pk(d, box, axis, "CIC", 1), O.Pk(d, box, axis, "CIC", 1))
     finally:
         P.ALGO = old
@@ -275,6 +275,28 @@ def test_pk_device_tensor_input_and_untouched_delta(PKL):
     p = PKL.Pk(dt, box, 2, "CIC", 1)
     assert torch.equal(dt, keep)                       # Pk never mutates delta
     parity.check_pk(p, O.Pk(d, box, 2, "CIC", 1))
+
+
+def test_swap_axes_kernel():
+    from pylians_b200 import _lib
+    lib = _lib.load()
+    for N in (33, 64):
+        x = torch.randn((N, N, N), device="cuda")
+        for axis, perm in ((0, (2, 1, 0)), (1, (0, 2, 1)), (2, (0, 1, 2))):
+            for pitch in (N, 2 * (N // 2 + 1)):
+                out = torch.full((N, N, pitch), -7.0, device="cuda")
+                _lib.check(lib.pylb_swap_axes(x.data_ptr(), out.data_ptr(), N, axis, pitch,
+                                              torch.cuda.current_stream().cuda_stream), "pylb_swap_axes")
+                assert torch.equal(out[:, :, :N], x.permute(*perm).contiguous())
+                assert bool((out[:, :, N:] == -7.0).all())
+
+
+def test_pk_axis_keep_deltak_keeps_reference_layout(PKL, gpk):
+    # keep_deltak with axis != 2 must not swap axes: delta_k is returned in the reference's layout
+    p = PKL.Pk(gpk["delta_16"], float(gpk["box"]), 0, "TSC", 1, keep_deltak=True)
+    ref = gpk["pk_16_deltak"]          # deconvolution does not depend on the axis
+    np.testing.assert_allclose(p.delta_k, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+    parity.check_pk(p, {n: gpk["pk_16_a0_TSC_%s" % n] for n in PK_NAMES})
 
 
 def test_pk_errors(PKL):
