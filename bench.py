@@ -29,6 +29,7 @@ WORKLOADS = {
     "cfg1_128_cic": dict(nside=128, mas="CIC", axis=2),
     "cfg3_1024_tsc": dict(nside=1024, mas="TSC", axis=2),
     "256_pcs": dict(nside=256, mas="PCS", axis=2),
+    "cfg4_1024pg_pcs": dict(nside=1024, mas="PCS", axis=2),   # 8 GPUs -> 2048^3 particles onto a 2048^3 grid
 }
 GRID_FOR_GPUS = {1: 1.0, 2: 1.25, 4: 1.5625, 8: 2.0}     # grid side multiplier: 512 -> 640 / 800 / 1024
 BOX = 1000.0
