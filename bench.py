@@ -161,6 +161,32 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
+def zeldovich_particles(nside, box, gen, dev, sigma_cells=2.0, n_s=-1.0):
+    """Lattice q = (i+1/2) L/n displaced by psi = IFFT(i k/k^2 delta_k) of a Gaussian field with a power-law
+    spectrum k^n_s (the construction of density_field_library.pyx:106-124), scaled to an rms displacement
+    of sigma_cells cells per axis, wrapped into [0, L).  Particles stay in lattice (x-major) order."""
+    import torch
+    n = nside
+    k1 = torch.fft.fftfreq(n, d=1.0 / n, device=dev)
+    kz = torch.fft.rfftfreq(n, d=1.0 / n, device=dev)
+    k2 = k1[:, None, None] ** 2 + k1[None, :, None] ** 2 + kz[None, None, :] ** 2
+    k2[0, 0, 0] = 1.0
+    amp = k2 ** (n_s / 4.0)
+    dk = torch.randn((n, n, n // 2 + 1), dtype=torch.complex64, device=dev, generator=gen) * amp
+    dk[0, 0, 0] = 0
+    q = (torch.arange(n, device=dev, dtype=torch.float32) + 0.5) * (box / n)
+    pos = torch.empty((n, n, n, 3), dtype=torch.float32, device=dev)
+    for a, ka in enumerate((k1[:, None, None], k1[None, :, None], kz[None, None, :])):
+        psi = torch.fft.irfftn(1j * ka / k2 * dk, s=(n, n, n))
+        psi *= sigma_cells * (box / n) / psi.std()
+        shape = [1, 1, 1]; shape[a] = n
+        pos[..., a] = torch.remainder(q.view(shape) + psi, box)
+        del psi
+    pos = pos.view(-1, 3)
+    pos.clamp_(0.0, float(torch.nextafter(torch.tensor(box, dtype=torch.float32), torch.tensor(0.0))))
+    return pos
+
+
 def workload_config(args, wl):
     n = args.gpus
     gside = int(round(wl["nside"] * GRID_FOR_GPUS.get(n, 1.0)))
@@ -194,9 +220,12 @@ def run_ours(args, wl):
     gside = int(round(nside * GRID_FOR_GPUS.get(world, 1.0)))
     peaks, peak_src = read_peaks()
 
-    # synthetic particles, generated on the device (seed 1 + rank), uniform in the box
+    # synthetic particles, generated on the device (seed 1 + rank)
     gen = torch.Generator(device=dev); gen.manual_seed(1 + rank)
-    pos = torch.rand((npart, 3), device=dev, dtype=torch.float32, generator=gen) * BOX
+    if args.data == "uniform":
+        pos = torch.rand((npart, 3), device=dev, dtype=torch.float32, generator=gen) * BOX
+    else:
+        pos = zeldovich_particles(nside, BOX, gen, dev)
     if world > 1:
         from pylians_b200 import dist as pdist
         engine = pdist.SlabPk(gside, BOX, mas, axis)
@@ -314,7 +343,8 @@ def run_ours(args, wl):
         line = {"metric": "MA+Pk snapshot throughput", "value": value, "unit": "particles/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
                 "s_per_snapshot": ms_step * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic uniform random particles generated on device, seed 1+rank",
+                "dtype": "f32", "data": ("synthetic uniform random particles" if args.data == "uniform" else
+                                         "synthetic Zel'dovich-displaced lattice (rms 2 cells, lattice order)") + " generated on device, seed 1+rank",
                 "config": workload_config(args, wl), "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_val, "unit": "particles/s", "h2d_bytes_per_step": int(npart * 12),
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / e2e_steps,
@@ -323,7 +353,8 @@ def run_ours(args, wl):
                 "kernels": {"ring_ms": ring_ms / max(ring_n, 1), "tile_ms": tile_ms / max(tile_n, 1),
                             "direct_ms": dir_ms / max(dir_n, 1), "ring_launches": ring_n, "tile_launches": tile_n,
                             "direct_launches": dir_n},
-                "check": {"P0_first_bins": [float(x) for x in pk.Pk[:3, 0]], "shot_noise_expected": BOX ** 3 / (npart * world)}}
+                "check": {"P0_first_bins": [float(x) for x in pk.Pk[:3, 0]], "shot_noise_expected": BOX ** 3 / (npart * world),
+                          "Nmodes_sum_ok": bool(pk.Nmodes3D.sum() + 1 == (gside ** 3 - 8) // 2 + 8) if gside % 2 == 0 else None}}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -337,6 +368,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_512_cic", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--data", default="uniform", choices=["uniform", "zeldovich"])
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
