@@ -97,6 +97,25 @@ int pylb_ma(const float *pos, int64_t np, int ndim, int64_t pos_stride0, int64_t
             void *grid, int grid_f64, int dims, float box, int mas, const float *w, int z_repeat,
             int algo, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Deposit onto an x-window of the cube: `grid` holds planes x0 .. x0+xext-1 (mod dims), shape
+ * (xext, dims, dims) float32.  Updates that fall outside the window are dropped.  `w` is read with
+ * stride w_stride, so particles may come as packed (x,y,z,w) records (pos stride 4, w = pos+3, w_stride 4).
+ * Used by the multi-GPU particle-exchange mode: every rank deposits only the particles it owns onto its
+ * slab plus S-1 halo planes. */
+size_t pylb_ma_window_workspace_bytes(int64_t np, int dims, int xext, int mas, int algo);
+int pylb_ma_window(const float *pos, int64_t np, int64_t pos_stride0, int64_t pos_stride1, float *grid, int dims,
+                   int x0, int xext, float box, int mas, const float *w, int64_t w_stride, int algo,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* Group particles by the x-slab (of dims/G planes) that owns their lowest touched x-plane.
+ * out_xyzw: device float4[np]; offsets: device int[G+1] (offsets[g]..offsets[g+1] = slab g's particles). */
+int pylb_partition_xslab(const float *pos, int64_t np, int64_t pos_stride0, int64_t pos_stride1, const float *w,
+                         int64_t w_stride, int dims, float box, int mas, int G, void *out_xyzw, int *offsets,
+                         void *stream);
+
+/* dst[i] += src[i]  (adding received halo planes) */
+int pylb_add_f32(float *dst, const float *src, int64_t n, void *stream);
+
 /* Testing hook: force how the tiled deposit brings particles into tile order.
  * -1 automatic, 0 binsort with 16x16x32 tiles, 1 binsort with 32x32x32 tiles, 2 radix sort + gather. */
 void pylb_ma_debug_path(int path);

@@ -38,6 +38,12 @@ SIGNATURES = {
     "pylb_ma_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int, c_int, c_int, c_int]),
     "pylb_ma": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_float, c_int,
                         c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "pylb_ma_window_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int, c_int]),
+    "pylb_ma_window": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_float, c_int,
+                               c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    "pylb_partition_xslab": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_float, c_int,
+                                     c_int, c_void_p, c_void_p, c_void_p]),
+    "pylb_add_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "pylb_ma_debug_path": (None, [c_int]),
     "pylb_divide": (c_int, [c_void_p, c_int64, c_float, c_void_p]),
     "pylb_h2d_padded": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

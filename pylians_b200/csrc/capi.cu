@@ -46,12 +46,19 @@ void timing_end(int which, cudaStream_t st) {
 }
 
 int ma_direct(const float *pos, int64_t np, int ndim, int64_t ps0, int64_t ps1, void *grid, int f64,
-              int dims, float inv, int mas, const float *w, float zrep, cudaStream_t st);
+              int dims, float inv, int mas, const float *w, float zrep, int x0, int xext, int64_t wst, cudaStream_t st);
 int ma_tiled(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv,
-             int mas, const float *w, void *workspace, size_t workspace_bytes, cudaStream_t st);
-size_t ma_tiled_workspace(int64_t np, int dims, int mas, int has_w);
+             int mas, const float *w, int64_t wst, int x0, int xext, void *workspace, size_t workspace_bytes, cudaStream_t st);
+size_t ma_tiled_workspace(int64_t np, int dims, int xext, int mas, int has_w);
 bool ma_tiled_supported(int ndim, int dims, int grid_f64);
 void ma_tiled_force_path(int p);
+int ma_partition(const float *pos, int64_t np, int64_t ps0, int64_t ps1, const float *w, int64_t wst, int dims, float inv,
+                 int mas, int G, float4 *out, int *offsets, cudaStream_t st);
+
+__global__ void add_f32_kernel(float *__restrict__ dst, const float *__restrict__ src, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += src[i];
+}
 
 // ------------------------------------------------------------------------------------------------
 // slab transpose: src [nx][dims][nz] -> dst [G][nx][dims/G][nz]; 16-byte vector copies when the
@@ -125,7 +132,7 @@ extern "C" void pylb_ma_debug_path(int path) { ma_tiled_force_path(path); }
 extern "C" size_t pylb_ma_workspace_bytes(int64_t np, int ndim, int dims, int mas, int has_w, int grid_f64, int algo) {
     if (algo == PYLB_MA_DIRECT) return 0;
     if (!ma_tiled_supported(ndim, dims, grid_f64)) return 0;
-    return ma_tiled_workspace(np, dims, mas, has_w);
+    return ma_tiled_workspace(np, dims, dims, mas, has_w);
 }
 
 extern "C" int pylb_ma(const float *pos, int64_t np, int ndim, int64_t ps0, int64_t ps1, void *grid, int grid_f64,
@@ -144,16 +151,38 @@ extern "C" int pylb_ma(const float *pos, int64_t np, int ndim, int64_t ps0, int6
         // AUTO: the tiled path pays a binning pass; it wins once the grid no longer lives in L2
         const bool big = (size_t)dims * dims * dims * sizeof(float) > (size_t)48 << 20;
         tiled = (algo == PYLB_MA_TILED) || (big && np >= (int64_t)1 << 20);
-        if (tiled && workspace_bytes < ma_tiled_workspace(np, dims, mas, w != nullptr)) {
+        if (tiled && workspace_bytes < ma_tiled_workspace(np, dims, dims, mas, w != nullptr)) {
             PYLB_REQUIRE(algo != PYLB_MA_TILED, "pylb_ma: workspace too small for the tiled path (%zu < %zu)",
-                         workspace_bytes, ma_tiled_workspace(np, dims, mas, w != nullptr));
+                         workspace_bytes, ma_tiled_workspace(np, dims, dims, mas, w != nullptr));
             tiled = false;
         }
     } else {
         PYLB_REQUIRE(algo != PYLB_MA_TILED, "pylb_ma: tiled path needs a 3-D float32 grid with dims >= 32");
     }
-    if (tiled) return ma_tiled(pos, np, ps0, ps1, (float *)grid, dims, inv, mas, w, workspace, workspace_bytes, st);
-    return ma_direct(pos, np, ndim, ps0, ps1, grid, grid_f64, dims, inv, mas, w, zrep, st);
+    if (tiled) return ma_tiled(pos, np, ps0, ps1, (float *)grid, dims, inv, mas, w, 1, 0, dims, workspace, workspace_bytes, st);
+    return ma_direct(pos, np, ndim, ps0, ps1, grid, grid_f64, dims, inv, mas, w, zrep, 0, dims, 1, st);
+}
+
+// ---- x-window deposit: the grid holds planes x0 .. x0+xext-1 (mod dims) of a dims^3 cube -------------
+extern "C" size_t pylb_ma_window_workspace_bytes(int64_t np, int dims, int xext, int mas, int algo) {
+    if (algo == PYLB_MA_DIRECT || dims < 32) return 0;
+    return ma_tiled_workspace(np, dims, xext, mas, 1);
+}
+
+extern "C" int pylb_ma_window(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, int x0,
+                              int xext, float box, int mas, const float *w, int64_t w_stride, int algo,
+                              void *workspace, size_t workspace_bytes, void *stream) {
+    PYLB_REQUIRE(mas >= PYLB_NGP && mas <= PYLB_PCS, "pylb_ma_window: unknown mass-assignment scheme %d", mas);
+    PYLB_REQUIRE(dims >= 1 && np >= 0 && x0 >= 0 && x0 < dims && xext >= 1 && xext <= dims, "pylb_ma_window: bad window");
+    PYLB_REQUIRE(np == 0 || (pos != nullptr && grid != nullptr), "pylb_ma_window: NULL pointer");
+    PYLB_REQUIRE(box > 0.0f, "pylb_ma_window: BoxSize must be positive");
+    const float inv = (float)dims / box;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool tiled = algo != PYLB_MA_DIRECT && dims >= 32 && np >= ((int64_t)1 << 16) &&
+                 workspace_bytes >= ma_tiled_workspace(np, dims, xext, mas, 1) && workspace != nullptr;
+    PYLB_REQUIRE(tiled || algo != PYLB_MA_TILED, "pylb_ma_window: tiled path unavailable (dims < 32, tiny input or workspace too small)");
+    if (tiled) return ma_tiled(pos, np, ps0, ps1, grid, dims, inv, mas, w, w_stride, x0, xext, workspace, workspace_bytes, st);
+    return ma_direct(pos, np, 3, ps0, ps1, grid, 0, dims, inv, mas, w, 1.0f, x0, xext, w_stride, st);
 }
 
 // ---- reference-compatible host entry points (MAS_c.h:3-10) -------------------------------------
@@ -196,6 +225,28 @@ extern "C" void TSC(float *pos, float *number, float *W, long particles, int dim
 }
 extern "C" void PCS(float *pos, float *number, float *W, long particles, int dims, int axes, float BoxSize, int threads) {
     (void)threads; masc_host(PYLB_PCS, pos, number, W, particles, dims, axes, BoxSize);
+}
+
+extern "C" int pylb_partition_xslab(const float *pos, int64_t np, int64_t ps0, int64_t ps1, const float *w,
+                                    int64_t w_stride, int dims, float box, int mas, int G, void *out_xyzw,
+                                    int *offsets, void *stream) {
+    PYLB_REQUIRE(G >= 1 && G <= 1024 && dims % G == 0, "pylb_partition_xslab: dims must be divisible by G (1..1024)");
+    PYLB_REQUIRE(np >= 0 && np < ((int64_t)1 << 31), "pylb_partition_xslab: particle count out of range");
+    PYLB_REQUIRE(offsets != nullptr && (np == 0 || (pos && out_xyzw)), "pylb_partition_xslab: NULL pointer");
+    PYLB_REQUIRE(box > 0.0f, "pylb_partition_xslab: BoxSize must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (np == 0) { PYLB_CHECK(cudaMemsetAsync(offsets, 0, sizeof(int) * (G + 1), st)); return 0; }
+    return ma_partition(pos, np, ps0, ps1, w, w_stride, dims, (float)dims / box, mas, G, (float4 *)out_xyzw, offsets, st);
+}
+
+extern "C" int pylb_add_f32(float *dst, const float *src, int64_t n, void *stream) {
+    if (n <= 0) return 0;
+    PYLB_REQUIRE(dst && src, "pylb_add_f32: NULL pointer");
+    int64_t b = (n + 255) / 256;
+    if (b > (int64_t)sm_count() * 16) b = (int64_t)sm_count() * 16;
+    add_f32_kernel<<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>(dst, src, n);
+    PYLB_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int pylb_slab_pack(const void *src, void *dst, int dims, int nx_local, int G, void *stream) {

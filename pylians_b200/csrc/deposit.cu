@@ -13,7 +13,7 @@ template <int MAS, bool HASW, typename GT, int NDIM>
 __global__ void __launch_bounds__(256)
 deposit_direct_kernel(const float *__restrict__ pos, int64_t np, int64_t ps0, int64_t ps1,
                       GT *__restrict__ grid, int dims, float inv, const float *__restrict__ W,
-                      float zrep) {
+                      float zrep, int x0, int xext, int64_t wst) {
     constexpr int S = Support<MAS>::S;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += stride) {
@@ -22,12 +22,12 @@ deposit_direct_kernel(const float *__restrict__ pos, int64_t np, int64_t ps0, in
         const float *p = pos + i * ps0;
 #pragma unroll
         for (int a = 0; a < NDIM; a++) base[a] = axis_stencil<MAS>(__ldg(p + a * ps1), inv, C[a]);
-        float w = HASW ? __ldg(W + i) : 1.0f;
+        float w = HASW ? __ldg(W + i * wst) : 1.0f;
         if constexpr (NDIM == 2) w = (zrep == 1.0f) ? w : w * zrep;
         int ix[S], iy[S];
 #pragma unroll
         for (int j = 0; j < S; j++) {
-            ix[j] = wrap(base[0] + j, dims);
+            ix[j] = wrap(base[0] + j - x0, dims);   // x window: local plane index; planes >= xext are not held here
             iy[j] = wrap(base[1] + j, dims);
         }
         if constexpr (NDIM == 3) {
@@ -38,6 +38,7 @@ deposit_direct_kernel(const float *__restrict__ pos, int64_t np, int64_t ps0, in
             for (int l = 0; l < S; l++)
 #pragma unroll
                 for (int m = 0; m < S; m++) {
+                    if (ix[l] >= xext) continue;
                     const int64_t row = ((int64_t)ix[l] * dims + iy[m]) * dims;
                     const float cxy = C[0][l] * C[1][m];  // left-to-right product, :159-166
 #pragma unroll
@@ -54,7 +55,7 @@ deposit_direct_kernel(const float *__restrict__ pos, int64_t np, int64_t ps0, in
                 for (int m = 0; m < S; m++) {
                     float v = C[0][l] * C[1][m];
                     if (HASW || zrep != 1.0f) v *= w;
-                    red_add(grid + (int64_t)ix[l] * dims + iy[m], v);
+                    if (ix[l] < xext) red_add(grid + (int64_t)ix[l] * dims + iy[m], v);
                 }
         }
     }
@@ -62,7 +63,7 @@ deposit_direct_kernel(const float *__restrict__ pos, int64_t np, int64_t ps0, in
 
 template <int MAS, bool HASW, typename GT, int NDIM>
 static int launch_direct(const float *pos, int64_t np, int64_t ps0, int64_t ps1, void *grid, int dims,
-                         float inv, const float *w, float zrep, cudaStream_t st) {
+                         float inv, const float *w, float zrep, int x0, int xext, int64_t wst, cudaStream_t st) {
     if (np == 0) return 0;
     const int threads = 256;
     int64_t blocks = (np + threads - 1) / threads;
@@ -70,7 +71,7 @@ static int launch_direct(const float *pos, int64_t np, int64_t ps0, int64_t ps1,
     if (blocks > cap) blocks = cap;
     timing_begin(PYLB_T_DIRECT, st);
     deposit_direct_kernel<MAS, HASW, GT, NDIM><<<(unsigned)blocks, threads, 0, st>>>(
-        pos, np, ps0, ps1, (GT *)grid, dims, inv, w, zrep);
+        pos, np, ps0, ps1, (GT *)grid, dims, inv, w, zrep, x0, xext, wst);
     timing_end(PYLB_T_DIRECT, st);
     PYLB_LAUNCH_CHECK();
     return 0;
@@ -78,30 +79,30 @@ static int launch_direct(const float *pos, int64_t np, int64_t ps0, int64_t ps1,
 
 template <int MAS, bool HASW, typename GT>
 static int direct_ndim(int ndim, const float *pos, int64_t np, int64_t ps0, int64_t ps1, void *grid,
-                       int dims, float inv, const float *w, float zrep, cudaStream_t st) {
-    if (ndim == 3) return launch_direct<MAS, HASW, GT, 3>(pos, np, ps0, ps1, grid, dims, inv, w, zrep, st);
-    return launch_direct<MAS, HASW, GT, 2>(pos, np, ps0, ps1, grid, dims, inv, w, zrep, st);
+                       int dims, float inv, const float *w, float zrep, int x0, int xext, int64_t wst, cudaStream_t st) {
+    if (ndim == 3) return launch_direct<MAS, HASW, GT, 3>(pos, np, ps0, ps1, grid, dims, inv, w, zrep, x0, xext, wst, st);
+    return launch_direct<MAS, HASW, GT, 2>(pos, np, ps0, ps1, grid, dims, inv, w, zrep, x0, xext, wst, st);
 }
 
 template <int MAS>
 static int direct_mas(bool hasw, bool f64, int ndim, const float *pos, int64_t np, int64_t ps0,
                       int64_t ps1, void *grid, int dims, float inv, const float *w, float zrep,
-                      cudaStream_t st) {
+                      int x0, int xext, int64_t wst, cudaStream_t st) {
     if (hasw) {
-        if (f64) return direct_ndim<MAS, true, double>(ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, st);
-        return direct_ndim<MAS, true, float>(ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, st);
+        if (f64) return direct_ndim<MAS, true, double>(ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, x0, xext, wst, st);
+        return direct_ndim<MAS, true, float>(ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, x0, xext, wst, st);
     }
-    if (f64) return direct_ndim<MAS, false, double>(ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, st);
-    return direct_ndim<MAS, false, float>(ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, st);
+    if (f64) return direct_ndim<MAS, false, double>(ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, x0, xext, wst, st);
+    return direct_ndim<MAS, false, float>(ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, x0, xext, wst, st);
 }
 
 int ma_direct(const float *pos, int64_t np, int ndim, int64_t ps0, int64_t ps1, void *grid, int f64,
-              int dims, float inv, int mas, const float *w, float zrep, cudaStream_t st) {
+              int dims, float inv, int mas, const float *w, float zrep, int x0, int xext, int64_t wst, cudaStream_t st) {
     switch (mas) {
-        case PYLB_NGP: return direct_mas<PYLB_NGP>(w != nullptr, f64, ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, st);
-        case PYLB_CIC: return direct_mas<PYLB_CIC>(w != nullptr, f64, ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, st);
-        case PYLB_TSC: return direct_mas<PYLB_TSC>(w != nullptr, f64, ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, st);
-        case PYLB_PCS: return direct_mas<PYLB_PCS>(w != nullptr, f64, ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, st);
+        case PYLB_NGP: return direct_mas<PYLB_NGP>(w != nullptr, f64, ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, x0, xext, wst, st);
+        case PYLB_CIC: return direct_mas<PYLB_CIC>(w != nullptr, f64, ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, x0, xext, wst, st);
+        case PYLB_TSC: return direct_mas<PYLB_TSC>(w != nullptr, f64, ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, x0, xext, wst, st);
+        case PYLB_PCS: return direct_mas<PYLB_PCS>(w != nullptr, f64, ndim, pos, np, ps0, ps1, grid, dims, inv, w, zrep, x0, xext, wst, st);
     }
     set_error("pylb_ma: unknown mass-assignment scheme %d", mas);
     return 1;

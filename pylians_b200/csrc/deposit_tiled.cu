@@ -41,15 +41,20 @@ constexpr int64_t BATCH = 1ll << 28;     // particles binned per pass (bounds th
 constexpr int BIN_THREADS = 1024;        // binsort CTAs: one per SM, 32 warps
 constexpr int BIN_MAX_TILES = 32768;     // per-CTA histogram must fit shared memory (128 KB)
 
+// x0 / xext: x window held by the grid (planes x0 .. x0+xext-1 modulo dims; the whole cube when xext == dims)
 struct TileGeom {
-    int dims, ntx, nty, ntz, ntiles;
+    int dims, ntx, nty, ntz, ntiles, x0, xext;
+    int slab_w;   // > 0: partition mode -- the key is the x-slab (of slab_w planes) owning the particle's lowest touched cell
 };
 
 template <class TC>
-static TileGeom tile_geom(int dims) {
+static TileGeom tile_geom(int dims, int x0 = 0, int xext = -1) {
     TileGeom t;
     t.dims = dims;
-    t.ntx = (dims + TC::TX - 1) / TC::TX;
+    t.x0 = x0;
+    t.slab_w = 0;
+    t.xext = xext < 0 ? dims : xext;
+    t.ntx = (t.xext + TC::TX - 1) / TC::TX;
     t.nty = (dims + TC::TY - 1) / TC::TY;
     t.ntz = (dims + TC::TZ - 1) / TC::TZ;
     t.ntiles = t.ntx * t.nty * t.ntz;
@@ -60,7 +65,9 @@ static TileGeom tile_geom(int dims) {
 template <int MAS, class TC>
 __device__ __forceinline__ unsigned tile_key(float x, float y, float z, float inv, const TileGeom &tg) {
     float C[Support<MAS>::S];
-    const int bx = wrap(axis_stencil<MAS>(x, inv, C), tg.dims);
+    int bx = wrap(axis_stencil<MAS>(x, inv, C) - tg.x0, tg.dims);
+    if (tg.slab_w > 0) return (unsigned)(bx / tg.slab_w);
+    if (bx >= tg.xext) bx = tg.xext - 1;   // particle routed to the wrong slab: keep the key in range (its updates are dropped)
     const int by = wrap(axis_stencil<MAS>(y, inv, C), tg.dims);
     const int bz = wrap(axis_stencil<MAS>(z, inv, C), tg.dims);
     return (unsigned)(((bx / TC::TX) * tg.nty + (by / TC::TY)) * tg.ntz + (bz / TC::TZ));
@@ -99,7 +106,7 @@ bin_hist_kernel(const float *__restrict__ pos, int64_t first, int n, int64_t ps0
 //   sweep B  re-read the particles (L1/L2 hits), rank inside the range with a shared atomic, write float4.
 template <int MAS, class TC, bool HASW>
 __global__ void __launch_bounds__(BIN_THREADS, 1)
-bin_scatter_kernel(const float *__restrict__ pos, const float *__restrict__ W, int64_t first, int n, int64_t ps0,
+bin_scatter_kernel(const float *__restrict__ pos, const float *__restrict__ W, int64_t wst, int64_t first, int n, int64_t ps0,
                    int64_t ps1, float inv, TileGeom tg, int *__restrict__ cursor, float4 *__restrict__ out) {
     extern __shared__ int slot[];
     const int nsub = (n + BIN_SUB - 1) / BIN_SUB;
@@ -157,7 +164,7 @@ bin_scatter_kernel(const float *__restrict__ pos, const float *__restrict__ W, i
                 if (keys[k0 + u] != 0xffffu) {
                     const int i = lo + (k0 + u) * BIN_THREADS + threadIdx.x;
                     const float *p = pos + (first + i) * ps0;
-                    v[u] = make_float4(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), HASW ? __ldg(W + first + i) : 1.0f);
+                    v[u] = make_float4(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), HASW ? __ldg(W + (first + i) * wst) : 1.0f);
                 }
             }
 #pragma unroll
@@ -221,7 +228,7 @@ __device__ __forceinline__ void red_add_v4(float *p, float4 v) {
 template <int MAS, bool HASW, class TC, bool SORTED>
 __global__ void __launch_bounds__(TC::THREADS)
 deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, int64_t ps1,
-                    const float *__restrict__ W, float inv, TileGeom tg, const unsigned *__restrict__ svals,
+                    const float *__restrict__ W, int64_t wst, float inv, TileGeom tg, const unsigned *__restrict__ svals,
                     const float4 *__restrict__ sorted, const int *__restrict__ tile_begin,
                     const int *__restrict__ chunk_off, float *__restrict__ grid) {
     using TS = TileShape<MAS, TC>;
@@ -267,10 +274,11 @@ deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, i
             const int64_t pi = first + (int64_t)svals[i];
             const float *p = pos + pi * ps0;
             x = __ldg(p); y = __ldg(p + ps1); z = __ldg(p + 2 * ps1);
-            w = HASW ? __ldg(W + pi) : 1.0f;
+            w = HASW ? __ldg(W + pi * wst) : 1.0f;
         }
         float C[3][S];
-        const int lx = wrap(axis_stencil<MAS>(x, inv, C[0]), tg.dims) - ox;
+        const int lx = wrap(axis_stencil<MAS>(x, inv, C[0]) - tg.x0, tg.dims) - ox;
+        if (lx < 0 || lx >= TC::TX) continue;   // not this tile's particle (only possible for a mis-routed particle)
         const int ly = wrap(axis_stencil<MAS>(y, inv, C[1]), tg.dims) - oy;
         const int lz = wrap(axis_stencil<MAS>(z, inv, C[2]), tg.dims) - oz;
         float *base = tile + (lx * TS::SY + ly) * TS::SZ + lz;
@@ -298,7 +306,8 @@ deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, i
             const float4 v = reinterpret_cast<const float4 *>(tile)[i];
             if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
             int gx = ox + x, gy = oy + y, gz = oz + zv * 4;
-            if (gx >= dims) gx -= dims;
+            if (tg.xext == dims) { if (gx >= dims) gx -= dims; }
+            else if (gx >= tg.xext) continue;   // beyond the x window: nothing was deposited there
             if (gy >= dims) gy -= dims;
             if (gz >= dims) gz -= dims;  // dims%4==0 and gz%4==0: the 4 cells never straddle the wrap
             if (gx >= dims || gy >= dims || gz >= dims) {  // only when dims < tile extent: scalar, full modulo
@@ -315,7 +324,10 @@ deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, i
             const float v = tile[i];
             if (v == 0.f) continue;
             const int z = i % TS::SZ, y = (i / TS::SZ) % TS::SY, x = i / (TS::SZ * TS::SY);
-            atomicAdd(grid + ((int64_t)((ox + x) % dims) * dims + (oy + y) % dims) * dims + (oz + z) % dims, v);
+            int gx = ox + x;
+            if (tg.xext == dims) gx %= dims;
+            else if (gx >= tg.xext) continue;
+            atomicAdd(grid + ((int64_t)gx * dims + (oy + y) % dims) * dims + (oz + z) % dims, v);
         }
     }
 }
@@ -331,13 +343,62 @@ static int bits_for(unsigned v) {
 
 enum { PATH_BIN_S = 0, PATH_BIN_L = 1, PATH_RADIX_S = 2 };
 
+// ------------------------------------------------------------------------------------------------
+// partition particles by owning x-slab (multi-GPU particle exchange): the binsort kernels with a slab key.
+// out[offsets[g] .. offsets[g+1]) = (x,y,z,w) of the particles whose lowest touched x-plane lies in slab g.
+// ------------------------------------------------------------------------------------------------
+template <int MAS, bool HASW>
+static int partition_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, const float *w, int64_t wst, int dims,
+                         float inv, int G, float4 *out, int *offsets, cudaStream_t st) {
+    TileGeom tg = tile_geom<TileS>(dims);
+    tg.slab_w = dims / G;
+    tg.ntiles = G;
+    const int n = (int)np;
+    const size_t hist_smem = sizeof(int) * (size_t)(G < 32 ? 32 : G);
+    int *counts = nullptr, *cursor = nullptr;
+    void *tmp = nullptr;
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, (int *)nullptr, (int *)nullptr, G + 1);
+    PYLB_CHECK(cudaMallocAsync(&counts, sizeof(int) * (G + 2), st));
+    PYLB_CHECK(cudaMallocAsync(&cursor, sizeof(int) * (G + 2), st));
+    PYLB_CHECK(cudaMallocAsync(&tmp, tb ? tb : 16, st));
+    PYLB_CHECK(cudaMemsetAsync(counts, 0, sizeof(int) * (G + 2), st));
+    const int P = sm_count();
+    bin_hist_kernel<MAS, TileS><<<P, BIN_THREADS, hist_smem, st>>>(pos, 0, n, ps0, ps1, inv, tg, counts);
+    PYLB_LAUNCH_CHECK();
+    PYLB_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tb, counts, offsets, G + 1, st));
+    count_launch(2);
+    PYLB_CHECK(cudaMemcpyAsync(cursor, offsets, sizeof(int) * (G + 1), cudaMemcpyDeviceToDevice, st));
+    bin_scatter_kernel<MAS, TileS, HASW><<<P, BIN_THREADS, hist_smem, st>>>(pos, w, wst, 0, n, ps0, ps1, inv, tg, cursor, out);
+    PYLB_LAUNCH_CHECK();
+    cudaFreeAsync(counts, st); cudaFreeAsync(cursor, st); cudaFreeAsync(tmp, st);
+    return 0;
+}
+
+int ma_partition(const float *pos, int64_t np, int64_t ps0, int64_t ps1, const float *w, int64_t wst, int dims, float inv,
+                 int mas, int G, float4 *out, int *offsets, cudaStream_t st) {
+    const bool hw = w != nullptr;
+    switch (mas) {
+        case PYLB_NGP: return hw ? partition_run<PYLB_NGP, true>(pos, np, ps0, ps1, w, wst, dims, inv, G, out, offsets, st)
+                                 : partition_run<PYLB_NGP, false>(pos, np, ps0, ps1, w, wst, dims, inv, G, out, offsets, st);
+        case PYLB_CIC: return hw ? partition_run<PYLB_CIC, true>(pos, np, ps0, ps1, w, wst, dims, inv, G, out, offsets, st)
+                                 : partition_run<PYLB_CIC, false>(pos, np, ps0, ps1, w, wst, dims, inv, G, out, offsets, st);
+        case PYLB_TSC: return hw ? partition_run<PYLB_TSC, true>(pos, np, ps0, ps1, w, wst, dims, inv, G, out, offsets, st)
+                                 : partition_run<PYLB_TSC, false>(pos, np, ps0, ps1, w, wst, dims, inv, G, out, offsets, st);
+        case PYLB_PCS: return hw ? partition_run<PYLB_PCS, true>(pos, np, ps0, ps1, w, wst, dims, inv, G, out, offsets, st)
+                                 : partition_run<PYLB_PCS, false>(pos, np, ps0, ps1, w, wst, dims, inv, G, out, offsets, st);
+    }
+    set_error("pylb_partition_xslab: unknown mass-assignment scheme %d", mas);
+    return 1;
+}
+
 static int g_force_path = -1;   // tests: exercise every path on small grids (pylb_ma_debug_path)
 void ma_tiled_force_path(int p) { g_force_path = p; }
 
-static int choose_path(int dims) {
+static int choose_path(int dims, int xext) {
     if (g_force_path >= PATH_BIN_S && g_force_path <= PATH_RADIX_S) return g_force_path;
-    if (tile_geom<TileS>(dims).ntiles <= BIN_MAX_TILES) return PATH_BIN_S;
-    if (tile_geom<TileL>(dims).ntiles <= BIN_MAX_TILES) return PATH_BIN_L;
+    if (tile_geom<TileS>(dims, 0, xext).ntiles <= BIN_MAX_TILES) return PATH_BIN_S;
+    if (tile_geom<TileL>(dims, 0, xext).ntiles <= BIN_MAX_TILES) return PATH_BIN_L;
     return PATH_RADIX_S;
 }
 
@@ -355,9 +416,9 @@ struct TiledWs {
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static void plan_ws(int64_t np, int dims, TiledWs *ws, char *base) {
-    const int path = choose_path(dims);
-    const int ntiles = path == PATH_BIN_L ? tile_geom<TileL>(dims).ntiles : tile_geom<TileS>(dims).ntiles;
+static void plan_ws(int64_t np, int dims, int xext, TiledWs *ws, char *base) {
+    const int path = choose_path(dims, xext);
+    const int ntiles = path == PATH_BIN_L ? tile_geom<TileL>(dims, 0, xext).ntiles : tile_geom<TileS>(dims, 0, xext).ntiles;
     const int64_t nb = np < BATCH ? np : BATCH;
     size_t o = 0, t1 = 0, t2 = 0, t3 = 0;
     auto take = [&](size_t bytes) { char *p = base ? base + o : nullptr; o += align_up(bytes); return p; };
@@ -384,11 +445,11 @@ static void plan_ws(int64_t np, int dims, TiledWs *ws, char *base) {
     ws->total = o;
 }
 
-size_t ma_tiled_workspace(int64_t np, int dims, int mas, int has_w) {
+size_t ma_tiled_workspace(int64_t np, int dims, int xext, int mas, int has_w) {
     (void)mas; (void)has_w;
     if (np <= 0) return 0;
     TiledWs ws;
-    plan_ws(np, dims, &ws, nullptr);
+    plan_ws(np, dims, xext, &ws, nullptr);
     return ws.total;
 }
 
@@ -402,9 +463,9 @@ static int set_smem(K kernel, size_t bytes) {
 
 template <int MAS, bool HASW, class TC, bool BINSORT>
 static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv,
-                     const float *w, TiledWs &ws, cudaStream_t st) {
+                     const float *w, int64_t wst, int x0, int xext, TiledWs &ws, cudaStream_t st) {
     using TS = TileShape<MAS, TC>;
-    const TileGeom tg = tile_geom<TC>(dims);
+    const TileGeom tg = tile_geom<TC>(dims, x0, xext);
     const size_t tile_smem = sizeof(float) * TS::CELLS;
     const size_t hist_smem = sizeof(int) * (size_t)tg.ntiles;
     const int P = sm_count();
@@ -425,7 +486,7 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
             PYLB_CHECK(cub::DeviceScan::ExclusiveSum(ws.tmp, tb, ws.H, ws.tile_begin, nt1, st));
             count_launch(2);
             PYLB_CHECK(cudaMemcpyAsync(ws.S, ws.tile_begin, sizeof(int) * (size_t)nt1, cudaMemcpyDeviceToDevice, st));
-            bin_scatter_kernel<MAS, TC, HASW><<<P, BIN_THREADS, hist_smem, st>>>(pos, w, first, n, ps0, ps1, inv, tg,
+            bin_scatter_kernel<MAS, TC, HASW><<<P, BIN_THREADS, hist_smem, st>>>(pos, w, wst, first, n, ps0, ps1, inv, tg,
                                                                                   ws.S, ws.sorted);
             PYLB_LAUNCH_CHECK();
         } else {
@@ -446,7 +507,7 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
         const int64_t max_items = (int64_t)n / CHUNK + tg.ntiles;
         timing_begin(PYLB_T_TILE, st);
         deposit_tile_kernel<MAS, HASW, TC, BINSORT><<<(unsigned)max_items, TC::THREADS, tile_smem, st>>>(
-            pos, first, ps0, ps1, w, inv, tg, ws.v1, ws.sorted, ws.tile_begin, ws.chunk_off, grid);
+            pos, first, ps0, ps1, w, wst, inv, tg, ws.v1, ws.sorted, ws.tile_begin, ws.chunk_off, grid);
         timing_end(PYLB_T_TILE, st);
         PYLB_LAUNCH_CHECK();
     }
@@ -455,31 +516,31 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
 
 template <int MAS, bool HASW>
 static int tiled_path(int path, const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims,
-                      float inv, const float *w, TiledWs &ws, cudaStream_t st) {
-    if (path == PATH_BIN_S) return tiled_run<MAS, HASW, TileS, true>(pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
-    if (path == PATH_BIN_L) return tiled_run<MAS, HASW, TileL, true>(pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
-    return tiled_run<MAS, HASW, TileS, false>(pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
+                      float inv, const float *w, int64_t wst, int x0, int xext, TiledWs &ws, cudaStream_t st) {
+    if (path == PATH_BIN_S) return tiled_run<MAS, HASW, TileS, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+    if (path == PATH_BIN_L) return tiled_run<MAS, HASW, TileL, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+    return tiled_run<MAS, HASW, TileS, false>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
 }
 
 int ma_tiled(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv, int mas,
-             const float *w, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+             const float *w, int64_t wst, int x0, int xext, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     if (np == 0) return 0;
     TiledWs ws;
-    plan_ws(np, dims, &ws, (char *)workspace);
+    plan_ws(np, dims, xext, &ws, (char *)workspace);
     PYLB_REQUIRE(workspace != nullptr && workspace_bytes >= ws.total, "pylb_ma: tiled workspace too small (%zu < %zu)",
                  workspace_bytes, ws.total);
     PYLB_REQUIRE(((uintptr_t)grid & 15) == 0, "pylb_ma: grid must be 16-byte aligned");
-    const int path = choose_path(dims);
+    const int path = choose_path(dims, xext);
     const bool hw = w != nullptr;
     switch (mas) {
-        case PYLB_NGP: return hw ? tiled_path<PYLB_NGP, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st)
-                                 : tiled_path<PYLB_NGP, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
-        case PYLB_CIC: return hw ? tiled_path<PYLB_CIC, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st)
-                                 : tiled_path<PYLB_CIC, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
-        case PYLB_TSC: return hw ? tiled_path<PYLB_TSC, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st)
-                                 : tiled_path<PYLB_TSC, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
-        case PYLB_PCS: return hw ? tiled_path<PYLB_PCS, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st)
-                                 : tiled_path<PYLB_PCS, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, ws, st);
+        case PYLB_NGP: return hw ? tiled_path<PYLB_NGP, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st)
+                                 : tiled_path<PYLB_NGP, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+        case PYLB_CIC: return hw ? tiled_path<PYLB_CIC, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st)
+                                 : tiled_path<PYLB_CIC, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+        case PYLB_TSC: return hw ? tiled_path<PYLB_TSC, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st)
+                                 : tiled_path<PYLB_TSC, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+        case PYLB_PCS: return hw ? tiled_path<PYLB_PCS, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st)
+                                 : tiled_path<PYLB_PCS, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
     }
     set_error("pylb_ma: unknown mass-assignment scheme %d", mas);
     return 1;

@@ -4,8 +4,10 @@ The reference is single-process ("slab-transpose comm layer
 this module is the new component BASELINE.json's north_star asks for.  Per snapshot, on rank r of G:
 
     particles (any shard)                       pos_r (n_r, 3)
-      -> deposit onto a FULL partial grid       MASL kernels, (N,N,N) float32          [local]
-      -> reduce-scatter (sum) into x-slabs      (N/G, N, N)                            [NCCL reduce_scatter]
+      -> EITHER deposit onto a FULL partial grid, (N,N,N) float32                      [local]
+                reduce-scatter (sum) into x-slabs (N/G, N, N)                          [NCCL reduce_scatter, 4 N^3 B]
+         OR     route particles to the rank owning their lowest x-plane                [partition kernel + NCCL all_to_all, 16 B/particle]
+                deposit onto slab + S-1 halo planes, pass the halo to the next rank    [windowed deposit + NCCL send/recv]
       -> overdensity with the GLOBAL mean       sum in float64, all-reduced            [NCCL all_reduce, 8 B]
       -> batched 2-D R2C over (y,z)             (N/G, N, N/2+1) complex64              [cuFFT]
       -> transpose pack + all-to-all            (G, N/G, N/G, N/2+1) blocks            [pack kernel + NCCL all_to_all]
@@ -52,6 +54,34 @@ class CudaOps(object):
     # ---- stages --------------------------------------------------------------------------------
     def deposit(self, pos, W, grid, BoxSize, MAS):
         MASL.MA(pos, grid, BoxSize, MAS, W=W)
+
+    def partition(self, pos, W, BoxSize, MAS, G, dims):
+        """Group this rank's particles by owning x-slab: (float32 (n,4) x,y,z,w in slab order, int32 offsets[G+1])."""
+        d_pos = MASL._to_device(pos, self.dev)
+        d_w = MASL._to_device(W, self.dev) if W is not None else None
+        n = d_pos.shape[0]
+        out = torch.empty((n, 4), dtype=torch.float32, device=self.dev)
+        offsets = torch.empty(G + 1, dtype=torch.int32, device=self.dev)
+        s0, s1 = d_pos.stride()
+        _lib.check(self.lib.pylb_partition_xslab(d_pos.data_ptr(), n, s0, s1, d_w.data_ptr() if d_w is not None else None,
+                                                 d_w.stride(0) if d_w is not None else 1, dims, float(BoxSize),
+                                                 MASL._MAS_ID[MAS], G, out.data_ptr(), offsets.data_ptr(), self._stream()),
+                   "pylb_partition_xslab")
+        return out, offsets
+
+    def deposit_window(self, xyzw, grid, x0, BoxSize, MAS, weighted, dims):
+        """Deposit packed (x,y,z,w) particles onto `grid` = planes x0 .. x0+grid.shape[0]-1 (mod dims)."""
+        n, xext = xyzw.shape[0], grid.shape[0]
+        mas = MASL._MAS_ID[MAS]
+        wb = self.lib.pylb_ma_window_workspace_bytes(n, dims, xext, mas, 0)
+        ws = torch.empty(max(int(wb), 1), dtype=torch.uint8, device=self.dev)
+        wptr = xyzw.data_ptr() + 12 if weighted else None
+        _lib.check(self.lib.pylb_ma_window(xyzw.data_ptr(), n, 4, 1, grid.data_ptr(), dims, int(x0), int(xext),
+                                           float(BoxSize), mas, wptr, 4, 0, ws.data_ptr(), int(wb), self._stream()),
+                   "pylb_ma_window")
+
+    def add(self, dst, src):
+        _lib.check(self.lib.pylb_add_f32(dst.data_ptr(), src.data_ptr(), dst.numel(), self._stream()), "pylb_add_f32")
 
     def grid_sum(self, slab):
         s = torch.zeros(1, dtype=torch.float64, device=self.dev)
@@ -116,7 +146,13 @@ class _Result(object):
 class SlabPk(object):
     """Distributed MA + Pk / XPk.  Every rank calls the same methods with its own particle shard."""
 
-    def __init__(self, dims, BoxSize, MAS="CIC", axis=2, group=None, ops=None):
+    def __init__(self, dims, BoxSize, MAS="CIC", axis=2, group=None, ops=None, exchange="auto"):
+        """exchange: how per-rank deposits become x-slabs --
+             "grid"      every rank deposits onto a full partial grid, then reduce-scatter (4 N^3 bytes per rank);
+             "particles" particles are routed to the rank owning their lowest touched x-plane (16 B per particle),
+                         deposited onto slab + S-1 halo planes, halo planes are passed to the next rank;
+             "auto"      whichever moves fewer bytes for this call."""
+        self.exchange = exchange
         self.rank, self.G = _group_info(group)
         self.group = group
         if dims % self.G != 0:
@@ -127,19 +163,66 @@ class SlabPk(object):
 
     # ---- stage 1: particles -> overdensity slab --------------------------------------------------
     def density_slab(self, pos, W=None, MAS=None, overdensity=True):
-        """Deposit this rank's particles, reduce-scatter to the x-slab this rank owns, normalise."""
+        """Deposit this rank's particles and return the x-slab this rank owns (optionally as overdensity)."""
         ops, N, G = self.ops, self.dims, self.G
-        partial = ops.zeros((N, N, N))
-        ops.deposit(pos, W, partial, self.BoxSize, MAS or self.MAS)
-        slab = ops.empty((self.nxl, N, N))
-        _reduce_scatter_sum(slab, partial, self.group, G)
-        del partial
+        MAS = MAS or self.MAS
+        halo = {"NGP": 0, "CIC": 1, "TSC": 2, "PCS": 3}[MAS]
+        mode = self.exchange
+        if mode == "auto":
+            # grid mode moves 4 N^3 bytes per rank AND pays a full-grid zero + flush (~8 B/cell); particle mode moves
+            # 16 B per particle and deposits onto the slab only
+            mode = "particles" if (16 * int(pos.shape[0]) < 8 * N ** 3 and self.nxl >= max(halo, 1)) else "grid"
+        if mode == "particles" and self.nxl < halo:
+            raise ValueError("particle exchange needs at least %d planes per rank for %s" % (halo, MAS))
+        slab = self._slab_from_particles(pos, W, MAS, halo) if mode == "particles" else self._slab_from_grids(pos, W, MAS)
         if overdensity:
             total = ops.grid_sum(slab)
             if G > 1:
                 dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
             ops.overdensity_apply(slab, total, N ** 3)
         return slab
+
+    def _slab_from_grids(self, pos, W, MAS):
+        ops, N, G = self.ops, self.dims, self.G
+        partial = ops.zeros((N, N, N))
+        ops.deposit(pos, W, partial, self.BoxSize, MAS)
+        slab = ops.empty((self.nxl, N, N))
+        _reduce_scatter_sum(slab, partial, self.group, G)
+        return slab
+
+    def _slab_from_particles(self, pos, W, MAS, halo):
+        ops, N, G, r = self.ops, self.dims, self.G, self.rank
+        send, offsets = ops.partition(pos, W, self.BoxSize, MAS, G, N)
+        if G > 1:
+            off = offsets.to("cpu").tolist()                      # G+1 ints: the split sizes must be known on the host
+            send_splits = [off[g + 1] - off[g] for g in range(G)]
+            t_send = torch.tensor(send_splits, dtype=torch.int64, device=send.device)
+            t_recv = torch.empty_like(t_send)
+            dist.all_to_all_single(t_recv, t_send, group=self.group)
+            recv_splits = t_recv.to("cpu").tolist()
+            recv = send.new_empty((sum(recv_splits), 4))
+            dist.all_to_all_single(recv, send, output_split_sizes=recv_splits, input_split_sizes=send_splits, group=self.group)
+        else:
+            recv = send
+        del send
+        if G == 1:
+            halo = 0                                              # the window is the whole periodic cube
+        grid = ops.zeros((self.nxl + halo, N, N))
+        ops.deposit_window(recv, grid, r * self.nxl, self.BoxSize, MAS, W is not None, N)
+        del recv
+        if halo:
+            mine = grid[self.nxl:]                                # planes that belong to the next rank
+            if True:
+                got = torch.empty_like(mine)
+                nxt, prv = (r + 1) % G, (r - 1) % G
+                if self.group is not None:
+                    nxt, prv = dist.get_global_rank(self.group, nxt), dist.get_global_rank(self.group, prv)
+                reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, mine, nxt, group=self.group),
+                                               dist.P2POp(dist.irecv, got, prv, group=self.group)])
+                for q in reqs:
+                    q.wait()
+            ops.add(grid[:halo], got)
+        return grid[: self.nxl]
 
     # ---- stage 2: x-slab (real) -> ky-slab (k-space, transposed) --------------------------------
     def fft_slab(self, slab):

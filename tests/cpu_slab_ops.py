@@ -23,6 +23,32 @@ class CpuOps(object):
     def deposit(self, pos, W, grid, BoxSize, MAS):
         O.MA(np.ascontiguousarray(pos), grid.numpy(), BoxSize, MAS, W=W)
 
+    def partition(self, pos, W, BoxSize, MAS, G, dims):
+        pos = np.ascontiguousarray(pos)
+        inv = np.float32(dims) / np.float32(BoxSize)
+        dist = (pos[:, 0].astype(np.float32) * inv).astype(np.float32)
+        d64 = dist.astype(np.float64)
+        base = {"NGP": np.trunc(d64 + 0.5), "CIC": np.trunc(d64), "TSC": np.floor(d64 - 1.5) + 1,
+                "PCS": np.floor(d64 - 2.0) + 1}[MAS].astype(np.int64) % dims      # lowest touched x-plane
+        dest = base // (dims // G)
+        order = np.argsort(dest, kind="stable")
+        w = np.ones(len(pos), np.float32) if W is None else np.asarray(W, np.float32)
+        out = np.concatenate([pos[order], w[order, None]], axis=1).astype(np.float32)
+        offsets = np.searchsorted(dest[order], np.arange(G + 1)).astype(np.int32)
+        return torch.from_numpy(out), torch.from_numpy(offsets)
+
+    def deposit_window(self, xyzw, grid, x0, BoxSize, MAS, weighted, dims):
+        a = xyzw.numpy()
+        full = np.zeros((dims,) * 3, np.float32)
+        O.MA(np.ascontiguousarray(a[:, :3]), full, BoxSize, MAS, W=np.ascontiguousarray(a[:, 3]) if weighted else None)
+        planes = (x0 + np.arange(grid.shape[0])) % dims
+        outside = np.ones(dims, bool); outside[planes] = False
+        assert not full[outside].any(), "a particle was routed to the wrong slab"
+        grid.numpy()[...] += full[planes]
+
+    def add(self, dst, src):
+        dst += src
+
     def grid_sum(self, slab):
         return torch.tensor([float(np.sum(slab.numpy(), dtype=np.float64))], dtype=torch.float64)
 

@@ -19,7 +19,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, dims, axis, mas, xmode, q):
+def _worker(rank, world, port, dims, axis, mas, xmode, exchange, q):
     sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -33,7 +33,7 @@ def _worker(rank, world, port, dims, axis, mas, xmode, q):
         pos = (rng.random((6 * dims ** 3, 3)) * box).astype(np.float32)
         pos2 = (rng.random((5 * dims ** 3, 3)) * box).astype(np.float32)
         W2 = (rng.random(len(pos2)) + 0.5).astype(np.float32)
-        eng = SlabPk(dims, box, mas, axis, ops=CpuOps())
+        eng = SlabPk(dims, box, mas, axis, ops=CpuOps(), exchange=exchange)
         # single-process oracle on the full particle set
         def field(p, m, w=None):
             d = np.zeros((dims,) * 3, np.float32); O.MA(p, d, box, m, W=w)
@@ -56,12 +56,13 @@ def _worker(rank, world, port, dims, axis, mas, xmode, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("exchange", ["grid", "particles"])
 @pytest.mark.parametrize("dims,axis,mas,xmode", [(16, 2, "CIC", False), (16, 0, "CIC", False), (16, 2, "CIC", True)])
-def test_slab_pipeline_world2_gloo(dims, axis, mas, xmode):
+def test_slab_pipeline_world2_gloo(dims, axis, mas, xmode, exchange):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, dims, axis, mas, xmode, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, dims, axis, mas, xmode, exchange, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
@@ -82,4 +83,5 @@ def test_slab_layout_single_process():
     rng = np.random.default_rng(3)
     pos = (rng.random((4 * dims ** 3, 3)) * box).astype(np.float32)
     d = np.zeros((dims,) * 3, np.float32); O.MA(pos, d, box, "PCS"); d /= np.mean(d, dtype=np.float64); d -= 1.0
-    parity.check_pk(SlabPk(dims, box, "PCS", 1, ops=CpuOps()).run(pos), O.Pk(d, box, 1, "PCS", 1))
+    parity.check_pk(SlabPk(dims, box, "PCS", 1, ops=CpuOps(), exchange="grid").run(pos), O.Pk(d, box, 1, "PCS", 1))
+    parity.check_pk(SlabPk(dims, box, "PCS", 1, ops=CpuOps(), exchange="particles").run(pos), O.Pk(d, box, 1, "PCS", 1))

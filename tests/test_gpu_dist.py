@@ -47,6 +47,38 @@ def test_slab_g1_matches_single_gpu_and_oracle(dims, mas, axis):
     parity.check_pk(got, O.Pk(r, box, axis, mas, 1), rtol=1e-3 if mas != "CIC" else 1e-5)
 
 
+@pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_particle_exchange_pieces_with_logical_ranks(mas, weighted):
+    """pylb_partition_xslab + pylb_ma_window + halo add, with G = 4 logical ranks on one GPU, must rebuild
+    exactly the grid a single full deposit gives (and the oracle's)."""
+    import MAS_library as MASL
+    from oracle import pylians_oracle as O
+    from pylians_b200.dist import CudaOps
+    dims, box, G = 64, 500.0, 4
+    rng = np.random.default_rng(21)
+    pos = (rng.random((400000, 3)) * box).astype(np.float32)
+    pos[0] = 0.0; pos[1] = box; pos[2] = np.nextafter(np.float32(box), np.float32(0))
+    W = (rng.random(len(pos)) + 0.5).astype(np.float32) if weighted else None
+    ops = CudaOps()
+    halo = {"NGP": 0, "CIC": 1, "TSC": 2, "PCS": 3}[mas]
+    nxl = dims // G
+    xyzw, offsets = ops.partition(torch.from_numpy(pos).cuda(), torch.from_numpy(W).cuda() if weighted else None, box, mas, G, dims)
+    off = offsets.cpu().tolist()
+    assert off[0] == 0 and off[-1] == len(pos)
+    full = torch.zeros((dims,) * 3, device="cuda")
+    for r in range(G):
+        grid = torch.zeros((nxl + halo, dims, dims), device="cuda")
+        ops.deposit_window(xyzw[off[r]:off[r + 1]], grid, r * nxl, box, mas, weighted, dims)
+        full[r * nxl:(r + 1) * nxl] += grid[:nxl]
+        for h in range(halo):
+            full[((r + 1) * nxl + h) % dims] += grid[nxl + h]
+    ref = np.zeros((dims,) * 3, np.float32); O.MA(pos, ref, box, mas, W=W)
+    parity.assert_grid_close(full.cpu().numpy(), ref, "exchange pieces " + mas)
+    one = torch.zeros((dims,) * 3, device="cuda"); MASL.MA(torch.from_numpy(pos).cuda(), one, box, mas, W=torch.from_numpy(W).cuda() if weighted else None)
+    parity.assert_grid_close(full.cpu().numpy(), one.cpu().numpy(), "exchange vs single deposit " + mas)
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
@@ -69,10 +101,11 @@ def _worker(rank, world, port, q):
         pos = _particles(dims, box, 11, 2)
         pos2 = _particles(dims, box, 12, 1)
         W2 = (np.random.default_rng(5).random(len(pos2)) + 0.5).astype(np.float32)
-        eng = SlabPk(dims, box, "CIC", 2)
-        got = eng.run(torch.from_numpy(pos[rank::world]).cuda())
         d = np.zeros((dims,) * 3, np.float32); MASL.MA(pos, d, box, "CIC"); MASL.overdensity(d)
-        parity.check_pk(got, PKL.Pk(d, box, 2, "CIC", 1), rtol=1e-4)
+        for exchange in ("grid", "particles"):
+            eng = SlabPk(dims, box, "CIC", 2, exchange=exchange)
+            got = eng.run(torch.from_numpy(pos[rank::world]).cuda())
+            parity.check_pk(got, PKL.Pk(d, box, 2, "CIC", 1), rtol=1e-4)
         gx = eng.run_x([torch.from_numpy(pos[rank::world]).cuda(), torch.from_numpy(pos2[rank::world]).cuda()],
                        [None, torch.from_numpy(W2[rank::world]).cuda()], ["CIC", "TSC"])
         d2 = np.zeros((dims,) * 3, np.float32); MASL.MA(pos2, d2, box, "TSC", W=W2); MASL.overdensity(d2)
