@@ -471,8 +471,10 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
     const int P = sm_count();
     if (set_smem(deposit_tile_kernel<MAS, HASW, TC, BINSORT>, tile_smem)) return 1;
     if (BINSORT) {
-        if (set_smem(bin_hist_kernel<MAS, TC>, hist_smem)) return 1;
-        if (set_smem(bin_scatter_kernel<MAS, TC, HASW>, hist_smem)) return 1;
+        // always the maximum these kernels may ever need: the attribute is a limit, and a smaller value set
+        // here would make a later, larger launch of the same instantiation fail
+        if (set_smem(bin_hist_kernel<MAS, TC>, sizeof(int) * (size_t)BIN_MAX_TILES)) return 1;
+        if (set_smem(bin_scatter_kernel<MAS, TC, HASW>, sizeof(int) * (size_t)BIN_MAX_TILES)) return 1;
     }
     const int nt1 = tg.ntiles + 1;
     for (int64_t first = 0; first < np; first += BATCH) {
