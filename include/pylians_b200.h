@@ -117,7 +117,8 @@ int pylb_partition_xslab(const float *pos, int64_t np, int64_t pos_stride0, int6
 int pylb_add_f32(float *dst, const float *src, int64_t n, void *stream);
 
 /* Testing hook: force how the tiled deposit brings particles into tile order.
- * -1 automatic, 0 binsort with 16x16x32 tiles, 1 binsort with 32x32x32 tiles, 2 radix sort + gather. */
+ * -1 automatic, 0 binsort with 16x16x32 tiles, 1 binsort with 32x32x32 tiles, 2 radix sort + gather;
+ * 10 / 11: like 0 / 1 but moving the payload with the one-pass scatter instead of the two-pass block sort. */
 void pylb_ma_debug_path(int path);
 
 /* grid[i] /= divisor  (the `number2 /= 2|3|4` of MAS_library.pyx:90-107; applies to the WHOLE array) */

@@ -12,7 +12,7 @@ def T(f,n=5):
     for _ in range(n): f()
     torch.cuda.synchronize(); return (time.perf_counter()-t)/n*1e3
 for mas in ('CIC','TSC','PCS'):
-    for path,name in ((0,'binsort 16x16x32'),(1,'binsort 32^3'),(2,'radix+gather')):
+    for path,name in ((0,'2-pass sort 16x16x32'),(10,'1-pass scatter 16x16x32'),(1,'2-pass sort 32^3'),(2,'radix+gather')):
         lib.pylb_ma_debug_path(path); _lib.timing_enable(True); _lib.timing_collect(1)
         t=T(lambda: MASL.MA(pos,grid,box,mas)); ms,n=_lib.timing_collect(1)
         print("%s %-18s MA %.3f ms  tile kernel %.3f ms"%(mas,name,t,ms/max(n,1)))

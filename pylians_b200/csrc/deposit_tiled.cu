@@ -39,7 +39,7 @@ typedef TileCfg<32, 32, 32, 1024> TileL;   // 144-176 KB, 1 CTA/SM of 32 warps, 
 constexpr int CHUNK = 8192;              // particles per work item
 constexpr int64_t BATCH = 1ll << 28;     // particles binned per pass (bounds the workspace)
 constexpr int BIN_THREADS = 1024;        // binsort CTAs: one per SM, 32 warps
-constexpr int BIN_MAX_TILES = 32768;     // per-CTA histogram must fit shared memory (128 KB)
+constexpr int BIN_MAX_TILES = 53248;     // per-CTA histogram must fit shared memory (208 KB of 227 KB); keys are 16-bit
 
 // x0 / xext: x window held by the grid (planes x0 .. x0+xext-1 modulo dims; the whole cube when xext == dims)
 struct TileGeom {
@@ -172,6 +172,135 @@ bin_scatter_kernel(const float *__restrict__ pos, const float *__restrict__ W, i
                 if (keys[k0 + u] != 0xffffu) out[atomicAdd(&slot[keys[k0 + u]], 1)] = v[u];
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two-pass block-local counting sort of the payload (default for ntiles <= 65536).
+//   tile id = (hi digit << lo_bits) | lo digit, both digits <= 256 values.
+//   pass 0: raw particles  -> buckets of equal hi digit          (cursor = per-bucket write position)
+//   pass 1: bucket by bucket -> tiles (lo digit inside a bucket) (cursor = per-tile write position)
+// One CTA sorts a chunk of PART_CHUNK particles in shared memory (rank by a shared atomic per digit, exclusive
+// scan of the <= 256 counters), reserves ONE contiguous output range per digit present with a single
+// atom.global (<= 256 per 4096 particles), and copies the staged chunk out so that consecutive threads write
+// consecutive addresses inside each run.  ~40 B (pass 0) + 32 B (pass 1) of streaming traffic per particle.
+// ------------------------------------------------------------------------------------------------
+constexpr int PART_THREADS = 512;
+constexpr int PART_PER_THREAD = 8;
+constexpr int PART_CHUNK = PART_THREADS * PART_PER_THREAD;   // 4096 particles, 64 KB of float4 staging
+constexpr int PART_MAXBINS = 256;
+
+struct PartSmem {
+    float4 stage[PART_CHUNK];
+    unsigned char dig[PART_CHUNK];
+    int cnt[PART_MAXBINS], start[PART_MAXBINS], gbase[PART_MAXBINS];
+    int lo, hi, bucket;
+};
+
+// chunk list of pass 1: bucket b (tiles [b << lo_bits, (b+1) << lo_bits)) owns ceil(size_b / PART_CHUNK) chunks
+__global__ void part_buckets_kernel(const int *__restrict__ tile_begin, int ntiles, int lo_bits, int nb0, int *bcursor,
+                                    int *bchunk_off) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < nb0; b++) {
+            const int t0 = b << lo_bits, t1 = min(ntiles, (b + 1) << lo_bits);
+            bcursor[b] = tile_begin[t0];
+            bchunk_off[b] = acc;
+            acc += (tile_begin[t1] - tile_begin[t0] + PART_CHUNK - 1) / PART_CHUNK;
+        }
+        bchunk_off[nb0] = acc;
+    }
+}
+
+template <int MAS, class TC, bool HASW, bool FIRST>
+__global__ void __launch_bounds__(PART_THREADS, 2)
+bin_pass_kernel(const float *__restrict__ pos, const float *__restrict__ W, int64_t wst, int64_t first, int n, int64_t ps0,
+                int64_t ps1, float inv, TileGeom tg, const float4 *__restrict__ in, float4 *__restrict__ out,
+                int *__restrict__ cursor, const int *__restrict__ tile_begin, const int *__restrict__ bchunk_off,
+                int lo_bits, int nb0) {
+    extern __shared__ __align__(16) unsigned char part_raw[];
+    PartSmem &sm = *reinterpret_cast<PartSmem *>(part_raw);
+    const int tid = threadIdx.x;
+    const int nbins = FIRST ? nb0 : (1 << lo_bits);
+    if (tid == 0) {
+        if (FIRST) {
+            sm.lo = blockIdx.x * PART_CHUNK;
+            sm.hi = min(n, sm.lo + PART_CHUNK);
+            sm.bucket = 0;
+        } else {
+            const int blk = blockIdx.x, total = bchunk_off[nb0];
+            if (blk >= total) { sm.lo = sm.hi = 0; sm.bucket = 0; }
+            else {
+                int lo = 0, hi = nb0;          // bchunk_off[lo] <= blk < bchunk_off[hi]
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (bchunk_off[mid] <= blk) lo = mid; else hi = mid; }
+                const int t0 = lo << lo_bits, t1 = min(tg.ntiles, (lo + 1) << lo_bits);
+                sm.bucket = lo;
+                sm.lo = tile_begin[t0] + (blk - bchunk_off[lo]) * PART_CHUNK;
+                sm.hi = min(tile_begin[t1], sm.lo + PART_CHUNK);
+            }
+        }
+    }
+    if (tid < PART_MAXBINS) sm.cnt[tid] = 0;
+    __syncthreads();
+    const int lo = sm.lo, hi = sm.hi;
+    if (lo >= hi) return;                       // CTA-uniform
+    const int cbase = FIRST ? 0 : (sm.bucket << lo_bits);
+
+    float4 v[PART_PER_THREAD];
+    int d[PART_PER_THREAD], r[PART_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < PART_PER_THREAD; k++) {
+        const int i = lo + k * PART_THREADS + tid;
+        d[k] = -1;
+        if (i < hi) {
+            if (FIRST) {
+                const float *p = pos + (first + i) * ps0;
+                v[k] = make_float4(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), HASW ? __ldg(W + (first + i) * wst) : 1.0f);
+            } else {
+                v[k] = __ldg(in + i);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PART_PER_THREAD; k++) {
+        const int i = lo + k * PART_THREADS + tid;
+        if (i < hi) {
+            const unsigned t = tile_key<MAS, TC>(v[k].x, v[k].y, v[k].z, inv, tg);
+            d[k] = FIRST ? (int)(t >> lo_bits) : (int)(t & ((1u << lo_bits) - 1u));
+            r[k] = atomicAdd(&sm.cnt[d[k]], 1);
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the <= 256 counters by warp 0 (8 per lane) + one global claim per digit present
+    if (tid < 32) {
+        int loc[8], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { loc[q] = sum; sum += sm.cnt[tid * 8 + q]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
+        const int excl = incl - sum;
+#pragma unroll
+        for (int q = 0; q < 8; q++) sm.start[tid * 8 + q] = excl + loc[q];
+    }
+    if (tid >= 32 && tid < 32 + PART_MAXBINS) {
+        const int b = tid - 32;
+        const int c = (b < nbins) ? sm.cnt[b] : 0;
+        if (c) sm.gbase[b] = atomicAdd(&cursor[cbase + b], c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PART_PER_THREAD; k++) {
+        if (d[k] >= 0) {
+            const int p = sm.start[d[k]] + r[k];
+            sm.stage[p] = v[k];
+            sm.dig[p] = (unsigned char)d[k];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < hi - lo; i += PART_THREADS) {
+        const int dd = sm.dig[i];
+        out[sm.gbase[dd] + (i - sm.start[dd])] = sm.stage[i];
     }
 }
 
@@ -393,7 +522,8 @@ int ma_partition(const float *pos, int64_t np, int64_t ps0, int64_t ps1, const f
 }
 
 static int g_force_path = -1;   // tests: exercise every path on small grids (pylb_ma_debug_path)
-void ma_tiled_force_path(int p) { g_force_path = p; }
+static bool g_two_pass = true;  // binsort payload movement: two-pass block-local sort (default) or the one-pass scatter
+void ma_tiled_force_path(int p) { g_two_pass = !(p >= 10); g_force_path = p >= 10 ? p - 10 : p; }
 
 static int choose_path(int dims, int xext) {
     if (g_force_path >= PATH_BIN_S && g_force_path <= PATH_RADIX_S) return g_force_path;
@@ -404,8 +534,8 @@ static int choose_path(int dims, int xext) {
 
 struct TiledWs {
     // binsort
-    int *H, *S;
-    float4 *sorted;
+    int *H, *S, *bcursor, *bchunk_off;
+    float4 *sorted, *sorted_tmp;
     // radix
     unsigned *k0, *k1, *v0, *v1;
     // common
@@ -434,6 +564,9 @@ static void plan_ws(int64_t np, int dims, int xext, TiledWs *ws, char *base) {
         ws->H = (int *)take(sizeof(int) * (size_t)(ntiles + 2));   // per-tile counts
         ws->S = (int *)take(sizeof(int) * (size_t)(ntiles + 2));   // per-tile write cursors
         ws->sorted = (float4 *)take(sizeof(float4) * nb);
+        ws->sorted_tmp = (float4 *)take(sizeof(float4) * nb);
+        ws->bcursor = (int *)take(sizeof(int) * (PART_MAXBINS + 2));
+        ws->bchunk_off = (int *)take(sizeof(int) * (PART_MAXBINS + 2));
     }
     cub::DeviceScan::ExclusiveSum(nullptr, t2, (int *)nullptr, (int *)nullptr, ntiles + 1);
     ws->tile_begin = (int *)take(sizeof(int) * (ntiles + 2));
@@ -488,9 +621,26 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
             PYLB_CHECK(cub::DeviceScan::ExclusiveSum(ws.tmp, tb, ws.H, ws.tile_begin, nt1, st));
             count_launch(2);
             PYLB_CHECK(cudaMemcpyAsync(ws.S, ws.tile_begin, sizeof(int) * (size_t)nt1, cudaMemcpyDeviceToDevice, st));
-            bin_scatter_kernel<MAS, TC, HASW><<<P, BIN_THREADS, hist_smem, st>>>(pos, w, wst, first, n, ps0, ps1, inv, tg,
-                                                                                  ws.S, ws.sorted);
-            PYLB_LAUNCH_CHECK();
+            if (g_two_pass) {
+                int lo_bits = (bits_for((unsigned)(tg.ntiles - 1)) + 1) / 2;
+                if (lo_bits > 8) lo_bits = 8;
+                const int nb0 = (tg.ntiles + (1 << lo_bits) - 1) >> lo_bits;      // <= 256 because ntiles <= 65536
+                part_buckets_kernel<<<1, 32, 0, st>>>(ws.tile_begin, tg.ntiles, lo_bits, nb0, ws.bcursor, ws.bchunk_off);
+                PYLB_LAUNCH_CHECK();
+                const size_t psm = sizeof(PartSmem);
+                if (set_smem(bin_pass_kernel<MAS, TC, HASW, true>, psm) || set_smem(bin_pass_kernel<MAS, TC, HASW, false>, psm)) return 1;
+                const unsigned g0 = (unsigned)((n + PART_CHUNK - 1) / PART_CHUNK);
+                bin_pass_kernel<MAS, TC, HASW, true><<<g0, PART_THREADS, psm, st>>>(
+                    pos, w, wst, first, n, ps0, ps1, inv, tg, nullptr, ws.sorted_tmp, ws.bcursor, ws.tile_begin, ws.bchunk_off, lo_bits, nb0);
+                PYLB_LAUNCH_CHECK();
+                bin_pass_kernel<MAS, TC, HASW, false><<<g0 + (unsigned)nb0, PART_THREADS, psm, st>>>(
+                    pos, w, wst, first, n, ps0, ps1, inv, tg, ws.sorted_tmp, ws.sorted, ws.S, ws.tile_begin, ws.bchunk_off, lo_bits, nb0);
+                PYLB_LAUNCH_CHECK();
+            } else {
+                bin_scatter_kernel<MAS, TC, HASW><<<P, BIN_THREADS, hist_smem, st>>>(pos, w, wst, first, n, ps0, ps1, inv, tg,
+                                                                                      ws.S, ws.sorted);
+                PYLB_LAUNCH_CHECK();
+            }
         } else {
             tile_key_kernel<MAS, TC><<<(n + 255) / 256, 256, 0, st>>>(pos, first, n, ps0, ps1, inv, tg, ws.k0, ws.v0);
             PYLB_LAUNCH_CHECK();

@@ -169,9 +169,11 @@ class SlabPk(object):
         halo = {"NGP": 0, "CIC": 1, "TSC": 2, "PCS": 3}[MAS]
         mode = self.exchange
         if mode == "auto":
-            # grid mode moves 4 N^3 bytes per rank AND pays a full-grid zero + flush (~8 B/cell); particle mode moves
-            # 16 B per particle and deposits onto the slab only
-            mode = "particles" if (16 * int(pos.shape[0]) < 8 * N ** 3 and self.nxl >= max(halo, 1)) else "grid"
+            # Measured on 8xB200 (profiles/r1_bench_scaling_8gpu*.jsonl): with Np ~ N^3 the reduce-scatter mode wins
+            # up to N = 1024 (27 vs 34 ms at N=1024, G=8: particle mode sorts twice and needs two host syncs for the
+            # split sizes); beyond that the full partial grid (34 GB at 2048^3: zero + flush + 4 N^3-byte
+            # reduce-scatter, and its deposit leaves the fast binsort path) loses to routing particles (219 vs 295 ms).
+            mode = "particles" if (N > 1024 and G > 1 and self.nxl >= max(halo, 1)) else "grid"
         if mode == "particles" and self.nxl < halo:
             raise ValueError("particle exchange needs at least %d planes per rank for %s" % (halo, MAS))
         slab = self._slab_from_particles(pos, W, MAS, halo) if mode == "particles" else self._slab_from_grids(pos, W, MAS)

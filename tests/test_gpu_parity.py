@@ -147,7 +147,7 @@ def test_reference_unit_tests_mass_conservation(MASL, mas, places, weighted):
     assert round(abs(suma / (3.0 * particles if weighted else particles) - 1.0), places) == 0
 
 
-@pytest.mark.parametrize("algo", [1, 2, 20, 21, 22])   # direct; tiled auto; tiled forced binsort-S / binsort-L / radix
+@pytest.mark.parametrize("algo", [1, 2, 20, 21, 22, 30, 31])   # direct; tiled auto; forced two-pass binsort S / L, radix; one-pass scatter S / L
 @pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
 @pytest.mark.parametrize("dims", [64, 80])
 def test_ma_vs_oracle_both_algorithms(MASL, algo, mas, dims):
