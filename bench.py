@@ -43,51 +43,45 @@ def read_peaks():
 
 
 class ClockSampler(object):
-    """SM clock and throttle reasons sampled DURING the timed region by an in-process NVML thread
-    (an external `nvidia-smi -lms` process perturbs short runs)."""
+    """SM clock and throttle reasons sampled DURING the timed region: one NVML query pair per step, issued
+    inline from the timing loop while the GPU is busy (each query costs ~1 us).  A sampler *thread* or an
+    external `nvidia-smi -lms` process perturbs short runs by milliseconds per step (GIL hand-offs / process
+    start-up: profiles/loop_overhead.py), so neither is used."""
 
-    def __init__(self, index, period=0.02):
-        self.index, self.period = index, period
-        self.sm, self.reasons, self.max_mhz = [], set(), None
-        self._stop, self._thr, self._ok = None, None, False
+    def __init__(self, index):
+        self.index = index
+        self.sm, self.reasons, self.max_mhz, self._ok = [], set(), None, False
 
     def start(self):
-        import threading
         try:
             import pynvml
             pynvml.nvmlInit()
             self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.nv = pynvml
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.names = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                          "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                          "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                          "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
             self._ok = True
         except Exception:
-            return
-        self._stop = threading.Event()
+            self._ok = False
 
-        def loop():
-            nv = self.nv
-            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
-                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
-                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
-                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
-            while not self._stop.is_set():
-                try:
-                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                    for n, bit in names.items():
-                        if r & bit:
-                            self.reasons.add(n)
-                except Exception:
-                    pass
-                self._stop.wait(self.period)
-        self._thr = threading.Thread(target=loop, daemon=True)
-        self._thr.start()
+    def sample(self):
+        if not self._ok:
+            return
+        try:
+            self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for n, bit in self.names.items():
+                if r & bit:
+                    self.reasons.add(n)
+        except Exception:
+            pass
 
     def stop(self):
         if not self._ok:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
-        self._stop.set()
-        self._thr.join(timeout=2)
         return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
                 "samples": len(self.sm), "reasons": sorted(self.reasons)}
 
@@ -246,12 +240,14 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(fn, steps):
+    def timed_loop(fn, steps, sampler=None):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
         for _ in range(steps):
             out = fn()
+            if sampler is not None:
+                sampler.sample()        # GPU still busy with this step's tail / the next step follows immediately
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -269,7 +265,7 @@ def run_ours(args, wl):
         _lib.timing_collect(w)
     sampler = ClockSampler(local_rank); sampler.start()
     l0 = _lib.launch_count()
-    ms, pk = timed_loop(lambda: snapshot(pos), args.steps)
+    ms, pk = timed_loop(lambda: snapshot(pos), args.steps, sampler)
     launches = _lib.launch_count() - l0
     clocks = sampler.stop()
     ring_ms, ring_n = _lib.timing_collect(_lib.T_RING)
