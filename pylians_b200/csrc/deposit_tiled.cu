@@ -88,9 +88,21 @@ bin_hist_kernel(const float *__restrict__ pos, int64_t first, int n, int64_t ps0
     extern __shared__ int hist[];
     for (int t = threadIdx.x; t < tg.ntiles; t += BIN_THREADS) hist[t] = 0;
     __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * BIN_THREADS) {
-        const float *p = pos + (first + i) * ps0;
-        atomicAdd(&hist[tile_key<MAS, TC>(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), inv, tg)], 1);
+    // 4 particles per iteration: all 12 loads are issued before the first key is computed
+    const int64_t stride = (int64_t)gridDim.x * BIN_THREADS;
+    for (int64_t i0 = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        float x[4], y[4], z[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t i = i0 + u * stride;
+            if (i < n) {
+                const float *p = pos + (first + i) * ps0;
+                x[u] = __ldg(p); y[u] = __ldg(p + ps1); z[u] = __ldg(p + 2 * ps1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i0 + u * stride < n) atomicAdd(&hist[tile_key<MAS, TC>(x[u], y[u], z[u], inv, tg)], 1);
     }
     __syncthreads();
     for (int t = threadIdx.x; t < tg.ntiles; t += BIN_THREADS) {
