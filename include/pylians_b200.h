@@ -49,7 +49,8 @@ enum { PYLB_MA_AUTO = 0, PYLB_MA_DIRECT = 1, PYLB_MA_TILED = 2 };
  * always fp64). */
 enum { PYLB_BIN_AUTO = 0, PYLB_BIN_GENERIC = 1, PYLB_BIN_RING = 2, PYLB_BIN_PRECISE = 16,
        PYLB_BIN_BULK = 32 /* ring kernel: cp.async.bulk + mbarrier row loads by a producer warp instead of
-                             per-thread cp.async (even dims only) */ };
+                             per-thread cp.async (even dims only) */,
+       PYLB_BIN_RING1 = 64 /* one field: use the one-kz-per-thread ring kernel instead of ring2 */ };
 
 int pylb_version(void);
 const char *pylb_last_error(void);
@@ -127,6 +128,8 @@ int pylb_divide(float *grid, int64_t n, float divisor, void *stream);
 /* Host (dims,dims,dims) float32 -> device padded in-place-FFT layout (dims,dims,2*(dims/2+1)), one
  * strided copy (cudaMemcpy2DAsync).  Lets Pk() transform a host field with a single device buffer. */
 int pylb_h2d_padded(const float *host, float *dev, int dims, void *stream);
+/* Same with an explicit device row pitch (floats per z-row), for pylb_fft_r2c_pitched. */
+int pylb_h2d_pitched(const float *host, float *dev, int dims, int64_t dev_pitch, void *stream);
 
 /* delta = grid/mean(grid) - 1 in place, mean accumulated in float64 (np.mean(dtype=float64) in the
  * callers).  `scratch` is a device double[2].  The two halves are exposed separately for slab-
@@ -149,6 +152,13 @@ int pylb_pos_redshift_space(float *pos, const float *vel, int64_t np, float box,
  * work: device scratch of pylb_fft_r2c_work_bytes(dims) bytes. */
 size_t pylb_fft_r2c_work_bytes(int dims, int inplace);
 int pylb_fft_r2c(const float *in, void *out, int dims, int inplace, void *work, size_t work_bytes, void *stream);
+/* Same transform with explicit z-row pitches: in_pitch floats per input row, out_pitch complex elements per
+ * output row (>= dims/2+1).  in == out needs in_pitch == 2*out_pitch.  Pk() uses out_pitch = dims/2+2 when
+ * dims/2+1 is odd, so that every k-space row starts on a 16-byte boundary (the binning kernel then reads
+ * aligned element pairs from a single row table). */
+size_t pylb_fft_r2c_pitched_work_bytes(int dims, int64_t in_pitch, int64_t out_pitch);
+int pylb_fft_r2c_pitched(const float *in, int64_t in_pitch, void *out, int64_t out_pitch, int dims, void *work,
+                         size_t work_bytes, void *stream);
 
 /* Real-space axis swap feeding the FFT: out(i,j,k) = in(k,j,i) for axis 0, in(i,k,j) for axis 1, a copy
  * for axis 2.  `out` rows have out_pitch floats (dims for a dense cube, 2*(dims/2+1) for the padded

@@ -89,23 +89,30 @@ def _work(nbytes, dev):
     return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=dev)
 
 
-def _fft_field(lib, delta, dims, dev, stream, swap_axis=2):
+def _fft_field(lib, delta, dims, dev, stream, swap_axis=2, pad=False):
     """FFT3Dr_f on the device.  Returns a complex64 tensor (dims,dims,dims/2+1); `delta` is never modified.
 
     Host input: one strided H2D copy into the padded in-place layout, then an in-place R2C, so the
     device holds a single copy of the field.  Device input: out-of-place R2C into a fresh buffer.
     swap_axis 0|1: the real field is first axis-swapped (pylb_swap_axes) into the padded layout, so the
-    requested line of sight becomes the half-spectrum axis the ring kernel is fast along."""
+    requested line of sight becomes the half-spectrum axis the ring kernel is fast along.
+    pad: give the k-space rows an even pitch (dims/2+2 complex when dims/2+1 is odd), so that every row starts
+    on a 16-byte boundary; the result is then a strided view, not a contiguous tensor."""
     nz = dims // 2 + 1
+    nzp = nz + (nz & 1) if pad else nz          # k-space row pitch in complex elements
     on_dev = _is_torch(delta) and delta.is_cuda
 
-    def r2c(src_ptr, out_ptr, inplace):
-        wb = lib.pylb_fft_r2c_work_bytes(dims, inplace)
+    def r2c(src_ptr, in_pitch, out_ptr):
+        wb = lib.pylb_fft_r2c_pitched_work_bytes(dims, in_pitch, nzp)
         if wb == ctypes.c_size_t(-1).value:
             raise _lib.PylbError("cuFFT plan failed: " + lib.pylb_last_error().decode())
         work = _work(wb, dev)
-        _lib.check(lib.pylb_fft_r2c(src_ptr, out_ptr, dims, inplace, work.data_ptr(), int(wb), stream.cuda_stream),
-                   "pylb_fft_r2c")
+        _lib.check(lib.pylb_fft_r2c_pitched(src_ptr, in_pitch, out_ptr, nzp, dims, work.data_ptr(), int(wb),
+                                            stream.cuda_stream), "pylb_fft_r2c_pitched")
+
+    def as_complex(buf):
+        out = torch.view_as_complex(buf.view(dims, dims, nzp, 2))
+        return out if nzp == nz else out[:, :, :nz]
 
     if swap_axis != 2:
         if on_dev:
@@ -113,22 +120,22 @@ def _fft_field(lib, delta, dims, dev, stream, swap_axis=2):
         else:
             host = delta.contiguous() if _is_torch(delta) else np.ascontiguousarray(delta)
             src = (host if _is_torch(host) else torch.from_numpy(host)).to(dev, non_blocking=True)
-        buf = torch.empty((dims, dims, 2 * nz), dtype=torch.float32, device=dev)
-        _lib.check(lib.pylb_swap_axes(src.data_ptr(), buf.data_ptr(), dims, int(swap_axis), 2 * nz, stream.cuda_stream),
+        buf = torch.empty((dims, dims, 2 * nzp), dtype=torch.float32, device=dev)
+        _lib.check(lib.pylb_swap_axes(src.data_ptr(), buf.data_ptr(), dims, int(swap_axis), 2 * nzp, stream.cuda_stream),
                    "pylb_swap_axes")
-        r2c(buf.data_ptr(), buf.data_ptr(), 1)
-        return torch.view_as_complex(buf.view(dims, dims, nz, 2))
+        r2c(buf.data_ptr(), 2 * nzp, buf.data_ptr())
+        return as_complex(buf)
     if on_dev:
         src = delta if delta.is_contiguous() else delta.contiguous()
-        out = torch.empty((dims, dims, nz), dtype=torch.complex64, device=dev)
-        r2c(src.data_ptr(), out.data_ptr(), 0)
-        return out
+        buf = torch.empty((dims, dims, 2 * nzp), dtype=torch.float32, device=dev)
+        r2c(src.data_ptr(), dims, buf.data_ptr())
+        return as_complex(buf)
     host = delta.contiguous() if _is_torch(delta) else np.ascontiguousarray(delta)
-    buf = torch.empty((dims, dims, 2 * nz), dtype=torch.float32, device=dev)
+    buf = torch.empty((dims, dims, 2 * nzp), dtype=torch.float32, device=dev)
     hptr = host.data_ptr() if _is_torch(host) else host.ctypes.data
-    _lib.check(lib.pylb_h2d_padded(hptr, buf.data_ptr(), dims, stream.cuda_stream), "pylb_h2d_padded")
-    r2c(buf.data_ptr(), buf.data_ptr(), 1)
-    out = torch.view_as_complex(buf.view(dims, dims, nz, 2))
+    _lib.check(lib.pylb_h2d_pitched(hptr, buf.data_ptr(), dims, 2 * nzp, stream.cuda_stream), "pylb_h2d_pitched")
+    r2c(buf.data_ptr(), 2 * nzp, buf.data_ptr())
+    out = as_complex(buf)
     out._pylb_keepalive = host
     return out
 
@@ -151,8 +158,11 @@ def bin_modes(delta_k, dims, axis, mas_index, want_phase, write_back, ks=None, s
     F = len(delta_k)
     L = get_layout(dims, F)
     if ks is None:
-        nz = dims // 2 + 1
-        ks = _lib.KSpace(dims, 0, dims, 0, dims, dims * nz, nz)
+        # the whole cube, rows along kz; strides in complex elements (a padded row pitch is fine)
+        t0 = delta_k[0]
+        if t0.stride(2) != 1 or any(t.stride() != t0.stride() for t in delta_k):
+            raise ValueError("bin_modes: k-space fields must share strides and be contiguous along kz")
+        ks = _lib.KSpace(dims, 0, dims, 0, dims, t0.stride(0), t0.stride(1))
     if sums is None:
         # one allocation for both accumulator arrays so that a single D2H copy brings them back
         raw = torch.empty(L.n_doubles + L.n_counts, dtype=torch.float64, device=dev)
@@ -281,7 +291,7 @@ class Pk(object):
         # mode counts; which member of each conjugate pair is kept differs, its |delta_k|^2 does not).
         # keep_deltak must return the reference's (kx,ky,kz>=0) layout, so it keeps the original axes.
         swap = int(axis) if (int(axis) in (0, 1) and not keep_deltak and (ALGO & 3) != _lib.BIN_GENERIC and SWAP_AXES) else 2
-        delta_k = _fft_field(lib, delta, dims, dev, stream, swap)
+        delta_k = _fft_field(lib, delta, dims, dev, stream, swap, pad=not keep_deltak)
         start2 = time.time()
         L, sums, counts = bin_modes([delta_k], dims, 2 if swap != 2 else int(axis), [MAS_function(MAS)], True,
                                     bool(keep_deltak))

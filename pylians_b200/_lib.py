@@ -47,6 +47,7 @@ SIGNATURES = {
     "pylb_ma_debug_path": (None, [c_int]),
     "pylb_divide": (c_int, [c_void_p, c_int64, c_float, c_void_p]),
     "pylb_h2d_padded": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "pylb_h2d_pitched": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "pylb_overdensity": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "pylb_grid_sum": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "pylb_overdensity_apply": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
@@ -54,6 +55,8 @@ SIGNATURES = {
     "pylb_swap_axes": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
     "pylb_fft_r2c_work_bytes": (c_size_t, [c_int, c_int]),
     "pylb_fft_r2c": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "pylb_fft_r2c_pitched_work_bytes": (c_size_t, [c_int, c_int64, c_int64]),
+    "pylb_fft_r2c_pitched": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "pylb_fft_slab_yz_work_bytes": (c_size_t, [c_int, c_int]),
     "pylb_fft_slab_yz": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pylb_fft_slab_x_work_bytes": (c_size_t, [c_int, c_int]),
@@ -66,7 +69,7 @@ SIGNATURES = {
 }
 
 MA_AUTO, MA_DIRECT, MA_TILED = 0, 1, 2
-BIN_AUTO, BIN_GENERIC, BIN_RING, BIN_PRECISE, BIN_BULK = 0, 1, 2, 16, 32
+BIN_AUTO, BIN_GENERIC, BIN_RING, BIN_PRECISE, BIN_BULK, BIN_RING1 = 0, 1, 2, 16, 32, 64
 
 _lib = None
 

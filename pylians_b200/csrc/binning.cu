@@ -22,6 +22,8 @@
 //     as the any-axis path.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace pylb {
@@ -623,17 +625,463 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// ring2 kernel: the production path for one field (class Pk), fp32 mode math, no write-back.
+//
+// Same idea as ring_kernel (rows sorted by r2, register accumulation, geometry once per r2-group), re-cut
+// around what limited it on sm_100a (ncu: short-scoreboard/MIO stalls from ~7 shared-memory instructions and
+// 2 XU conversions per mode, 13-19 % of the SM time idle in the tail of a static 2-wave grid):
+//   * a thread owns TWO adjacent kz and every row access is one aligned 16-byte element pair (cp.async 16).
+//     Rows are 8-byte aligned only in general (N/2+1 complex per row), so the row table is split by the parity
+//     of the row's start element: in the even table a thread owns kz = (2t, 2t+1), in the odd table
+//     (2t+1, 2t+2); both are then 16-byte aligned.  Pk() pads its own k-space rows to an even pitch
+//     (pylb_fft_r2c_pitched), so there everything is in the even table and r2-groups keep their full length.
+//     All per-row work (table reads, group test, loop control) is shared by two modes and the mode arithmetic
+//     runs as packed f32x2 (FMUL2/FFMA2) across the two kz;
+//   * the MAS factor (float)(Cx*Cy*Cz) (Pk_library.pyx:354) is formed from float-float splits of Cx*Cy and Cz
+//     with 5 packed FMAs: error 2^-46 before the final rounding, i.e. the same float as the double product
+//     except for ~2e-7 of the modes, which then differ by one fp32 ulp; no DMUL, no F2F;
+//   * n = r2 + kz^2 grows along the sorted rows, so each kz walks its 3-D bins monotonically: ONE running 3-D
+//     accumulator set per kz, flushed (red.global) when the bin changes; the 2-D bin (k_per = floor(sqrt(r2)))
+//     changes CTA-uniformly; the 1-D bin is the kz itself;
+//   * persistent CTAs with guided self-scheduling: a CTA takes spans of consecutive table rows from an atomic
+//     counter; the first span of every CTA is long (pipeline fill/drain, the table prologue and the epilogue's
+//     ~12 red.global per kz are paid per span: 443-row spans run 1.8x faster than 100-row spans), later spans
+//     shrink geometrically, so the SMs finish together.  (Interleaving short chunks statically instead makes
+//     every CTA flush the same few bins at the same time: 4x slower, red.global serialises per address.)
+// Skipped here and left to special_kernel: kz = 0 and kz = N/2 (self-conjugate columns).  Even dims only.
+// ------------------------------------------------------------------------------------------------
+struct __align__(8) Row2 {
+    long long off;   // BYTE offset of the row start
+    int r2;
+    float chi, clo;  // Cx*Cy split into two floats: chi = (float)c, clo = (float)(c - chi)
+    short kx, ky;    // for special_kernel (skip rule, per-axis MAS factors)
+};
+
+constexpr int R2_T = 128;          // threads = kz pairs per CTA
+constexpr int R2_ROWS = 4;         // rows per loop iteration
+constexpr int R2_D = 16;           // rows in flight per thread (cp.async ring depth)
+constexpr int R2_SPAN_MAX = 1024;  // rows per span (their table entries are staged in shared memory once)
+constexpr int R2_SPAN_MIN = 32;
+constexpr int R2_LEVELS = 16;
+constexpr int R2_T3_VALS = 6;       // P0, P2, P4 sums, sum |k|, mode count, phase^2 per (3-D bin, kz)
+
+struct Ring2Smem {
+    float4 z[R2_D][R2_T];                     // 32 KB: thread t only ever touches z[.][t]
+    long long off[R2_SPAN_MAX];
+    int r2[R2_SPAN_MAX + 4];
+    float2 c[R2_SPAN_MAX];
+    int item;
+};
+
+// Guided schedule of one parity table: level l holds `per_level` spans of size[l] rows starting at base[l].
+struct Ring2Sched {
+    int nlevels, per_level;                   // per_level = spans per level and (parity, kz segment) group
+    int base[2][R2_LEVELS + 1], size[2][R2_LEVELS];
+};
+
+// parity of the row's first element address in units of 8 bytes (bp = that of the field base pointer)
+__device__ __forceinline__ int row_parity(int ix, int iy, const BinGeom &g, int bp) {
+    return (int)(((long long)ix * g.stride_x + (long long)iy * g.stride_y + bp) & 1);
+}
+
+__global__ void row_keys2_kernel(unsigned *keys, unsigned *vals, int nrows, BinGeom g, int bp, int par_bit) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const int ix = r / g.ny, iy = r - ix * g.ny;
+    const int kx = wavenumber(g.x0 + ix, g.dims, g.middle), ky = wavenumber(g.y0 + iy, g.dims, g.middle);
+    keys[r] = (unsigned)(kx * kx + ky * ky) | ((unsigned)row_parity(ix, iy, g, bp) << par_bit);
+    vals[r] = (unsigned)r;
+}
+
+__global__ void row_table2_kernel(const unsigned *keys, const unsigned *vals, Row2 *tab, int nrows, BinGeom g, int par_bit) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const int r = (int)vals[i];
+    const int ix = r / g.ny, iy = r - ix * g.ny;
+    const int kx = wavenumber(g.x0 + ix, g.dims, g.middle), ky = wavenumber(g.y0 + iy, g.dims, g.middle);
+    const double c = g.mas_tab[kx < 0 ? -kx : kx] * g.mas_tab[ky < 0 ? -ky : ky];   // field 0
+    Row2 e;
+    e.off = 8ll * ((long long)ix * g.stride_x + (long long)iy * g.stride_y);
+    e.r2 = (int)(keys[i] & ((1u << par_bit) - 1u));
+    e.chi = (float)c;
+    e.clo = (float)(c - (double)e.chi);
+    e.kx = (short)kx; e.ky = (short)ky;
+    tab[i] = e;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+
+template <bool PHASE>
+__global__ void __launch_bounds__(R2_T, 4)
+ring2_kernel(BinGeom g, const float2 *__restrict__ dk, const Row2 *__restrict__ tab_all, int n0, int kz_hi, int nseg,
+             int npar, Ring2Sched sc, int *__restrict__ counter, double *__restrict__ t3, int t3_kz, long long *__restrict__ trace) {
+    extern __shared__ __align__(128) unsigned char ring2_raw[];
+    Ring2Smem &sm = *reinterpret_cast<Ring2Smem *>(ring2_raw);
+    const int tid = threadIdx.x;
+    const int groups = nseg * npar;
+    const int nitems = sc.nlevels * sc.per_level * groups;
+    const int mid2 = g.middle * g.middle;
+    const unsigned long long m1 = pack2(-1.0f, -1.0f);
+
+    for (;;) {
+        // ---- next span: item -> (level, span k, group = (parity, kz segment))
+        __syncthreads();                        // everyone is done with the previous span's tables
+        if (tid == 0) sm.item = atomicAdd(counter, 1);
+        __syncthreads();
+        const int item = sm.item;
+        if (item >= nitems) break;
+        const int lev = item / (sc.per_level * groups), w = item - lev * (sc.per_level * groups);
+        const int grp = w % groups, k = w / groups;
+        const int seg = grp % nseg;
+        const int P = npar == 2 ? grp / nseg : (sc.base[0][sc.nlevels] > 0 ? 0 : 1);   // parity table of this span
+        const int i0 = sc.base[P][lev] + k * sc.size[P][lev];
+        const int total = min(sc.size[P][lev], sc.base[P][lev + 1] - i0);
+        if (total <= 0) continue;
+        const int npairs = P ? (kz_hi - 1) / 2 + 1 : kz_hi / 2 + 1;
+        const int first_pair = seg * R2_T;
+        const int cnt = min(R2_T, npairs - first_pair);            // kz pairs served by this span
+        if (cnt <= 0) continue;
+        const Row2 *tab = tab_all + (P ? n0 : 0) + i0;
+        long long t_begin = 0;
+        if (trace && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+        for (int j = tid; j < total; j += R2_T) {
+            const Row2 e = tab[j];
+            sm.off[j] = e.off; sm.r2[j] = e.r2; sm.c[j] = make_float2(e.chi, e.clo);
+        }
+        __syncthreads();
+
+        // this thread's 16 bytes inside a row: kz = 2*(first_pair + tid) + P, 16-byte aligned by construction
+        const char *colbase = reinterpret_cast<const char *>(dk) + 8ll * (2 * (first_pair + tid) + P);
+        const bool loader = tid < cnt;
+        auto prefetch = [&](int j) {
+            if (j < total && loader) cp_async16(&sm.z[j & (R2_D - 1)][tid], colbase + sm.off[j]);
+            cp_async_commit();                  // one group per row, even when empty, so wait_group<N> counts rows
+        };
+        for (int j = 0; j < R2_D; j++) prefetch(j);
+
+        // ---- per-kz constants (s = 0: kzA, s = 1: kzB = kzA + 1)
+        const int kzA = 2 * (first_pair + tid) + P;
+        int kz[2], kz2[2];
+        bool act[2];
+        float kz2f[2], czh[2], czl[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            kz[s] = kzA + s;
+            act[s] = loader && kz[s] >= 1 && kz[s] <= kz_hi;
+            const int kc = min(kz[s], g.middle);
+            kz2[s] = kc * kc;
+            kz2f[s] = (float)kz2[s];
+            const double czd = g.mas_tab[kc];
+            czh[s] = (float)czd;
+            czl[s] = (float)(czd - (double)czh[s]);
+        }
+        const unsigned long long czh2 = pack2(czh[0], czh[1]);
+        const unsigned long long nczh2 = pack2(-czh[0], -czh[1]), nczl2 = pack2(-czl[0], -czl[1]);
+
+        // ---- accumulators
+        double s3[2][3], ks[2], ph[2], a2[2], a1[2], kk[2];
+        int cn[2], c1[2], bin[2], thr[2];
+        float w2f[2], w4f[2], gq[2], gph[2];
+        bool in1d[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            s3[s][0] = s3[s][1] = s3[s][2] = 0; ks[s] = ph[s] = a2[s] = a1[s] = 0; kk[s] = 0;
+            cn[s] = c1[s] = 0; bin[s] = 0; thr[s] = 0; w2f[s] = w4f[s] = 0; gq[s] = gph[s] = 0; in1d[s] = false;
+        }
+        int gcnt = 0, c2 = 0, cur_r2 = -1, ring_p = 0, ring_hi = 0;
+
+        auto apply_group = [&]() {
+            if (gcnt == 0) return;
+            const double dg = (double)gcnt;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const double v0 = (double)gq[s];
+                s3[s][0] += v0;
+                s3[s][1] += (double)(gq[s] * w2f[s]);
+                s3[s][2] += (double)(gq[s] * w4f[s]);
+                ks[s] = fma(dg, kk[s], ks[s]);
+                cn[s] += gcnt;
+                if (PHASE) ph[s] += (double)gph[s];
+                a2[s] += v0;
+                if (in1d[s]) { a1[s] += v0; c1[s] += gcnt; }
+                gq[s] = 0; gph[s] = 0;
+            }
+            c2 += gcnt;
+            gcnt = 0;
+        };
+        // 3-D bins go to a kz-private table t3[bin][value][kz] (no two lanes, and hardly any two CTAs, ever hit
+        // the same address; red.global on the shared bins themselves serialises: 47 G/s measured, and a kernel
+        // whose CTAs flush together then spends longer draining atomics than streaming data).  ring2_finish_kernel
+        // folds the table into the bins.
+        auto flush3 = [&](int s) {
+            if (act[s] && cn[s] > 0) {
+                double *t = t3 + ((long long)bin[s] * R2_T3_VALS) * t3_kz + kz[s];
+                red_add(t, s3[s][0]);
+                red_add(t + t3_kz, s3[s][1]);
+                red_add(t + 2 * t3_kz, s3[s][2]);
+                red_add(t + 3 * t3_kz, ks[s]);
+                red_add(t + 4 * t3_kz, (double)cn[s]);        // exact: counts < 2^53
+                if (PHASE) red_add(t + 5 * t3_kz, ph[s]);
+            }
+            s3[s][0] = s3[s][1] = s3[s][2] = 0; ks[s] = 0; ph[s] = 0; cn[s] = 0;
+        };
+        auto flush2 = [&]() {
+            if (c2 > 0) {
+#pragma unroll
+                for (int s = 0; s < 2; s++)
+                    if (act[s]) {
+                        const long long i2 = (long long)g.kmax_par1 * ring_p + kz[s];   // (kmax_par+1)*k_per + k_par, :371
+                        red_add_u64(g.counts + g.o_n2d + i2, (uint64_t)c2);
+                        red_add(g.sums + g.o_p2d + i2, a2[s]);
+                    }
+            }
+            a2[0] = a2[1] = 0; c2 = 0;
+        };
+        // new r2 group: CTA-uniform branch.  Bins, |k|, mu^2 and the Legendre weights once per (group, kz).
+        auto new_group = [&](int r2) {
+            apply_group();
+            cur_r2 = r2;
+            if (r2 >= ring_hi) {                   // k_per = floor(sqrt(r2)) changes, uniform
+                flush2();
+                ring_p = isqrt_exact(r2);
+                ring_hi = (ring_p + 1) * (ring_p + 1);
+            }
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const int n = r2 + kz2[s];         // >= 1 for active lanes (kz >= 1)
+                if (n >= thr[s]) {                 // k_index changes for this kz (divergent, about once per ring)
+                    flush3(s);
+                    bin[s] = isqrt_exact(n);
+                    thr[s] = (bin[s] + 1) * (bin[s] + 1);
+                }
+                in1d[s] = n <= mid2;               // k <= middle, :364
+                const float nf = (float)n;
+                float rs;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(nf, 1.0f)));
+                const float h = nf * rs;                                              // ~sqrt(n)
+                const double k0 = (double)h;
+                kk[s] = fma(fma(-k0, k0, (double)n), (double)(0.5f * rs), k0);       // fp32 sqrt + one fp64 Newton step: 3e-14
+                const float rs2 = rs * rs;
+                const float rn = fmaf(rs2, fmaf(-h, rs, 1.0f), rs2);                  // 1/n = rs^2 (1 + (1 - n rs^2)): ~1 ulp, no second MUFU
+                const float mu2f = fminf(kz2f[s] * rn, 1.0f);                         // mu^2 = kz^2/n, :347
+                w2f[s] = fmaf(1.5f, mu2f, -0.5f);                                     // (3 mu^2 - 1)/2, :378
+                w4f[s] = fmaf(fmaf(4.375f, mu2f, -3.75f), mu2f, 0.375f);              // (35 mu^4 - 30 mu^2 + 3)/8, :379
+            }
+        };
+
+        // deconvolve + square (+ phase^2) of one row's element pair
+        auto row_math = [&](const float4 z, const float2 c, float (&d2)[2], float (&p2)[2]) {
+            const unsigned long long chi2 = pack2(c.x, c.x), clo2 = pack2(c.y, c.y);
+            const unsigned long long p = mul2(chi2, czh2);
+            unsigned long long t = fma2(chi2, nczh2, p);            // -(chi*czh - p), exact
+            t = fma2(chi2, nczl2, t);
+            t = fma2(clo2, nczh2, t);
+            const float2 mf = unpack2(fma2(t, m1, p));              // (float)(Cx*Cy*Cz) for kzA, kzB, :354
+            const unsigned long long dA = mul2(pack2(z.x, z.y), pack2(mf.x, mf.x));   // complex64 *= float, :355
+            const unsigned long long dB = mul2(pack2(z.z, z.w), pack2(mf.y, mf.y));
+            const float2 sA = unpack2(mul2(dA, dA)), sB = unpack2(mul2(dB, dB));      // (re^2, im^2)
+            d2[0] = sA.x + sA.y;
+            d2[1] = sB.x + sB.y;
+            if (PHASE) {
+                const float2 q = phase_sq2(sA.x, d2[0], sB.x, d2[1]);
+                p2[0] = q.x; p2[1] = q.y;
+            } else {
+                p2[0] = p2[1] = 0.f;
+            }
+        };
+        auto row_bin = [&](int r2, const float (&d2)[2], const float (&p2)[2]) {
+            if (r2 != cur_r2) new_group(r2);       // CTA-uniform
+            gq[0] += d2[0]; gq[1] += d2[1];
+            if (PHASE) { gph[0] += p2[0]; gph[1] += p2[1]; }
+            gcnt++;
+        };
+
+        int j = 0;
+        for (; j + R2_ROWS <= total; j += R2_ROWS) {
+            cp_async_wait<R2_D - R2_ROWS>();      // rows complete in order: rows j .. j+3 have landed
+            float4 z[R2_ROWS];
+#pragma unroll
+            for (int u = 0; u < R2_ROWS; u++) z[u] = sm.z[(j + u) & (R2_D - 1)][tid];
+#pragma unroll
+            for (int u = 0; u < R2_ROWS; u++) prefetch(j + R2_D + u);
+            const int4 r2v = *reinterpret_cast<const int4 *>(&sm.r2[j]);
+            const float4 c01 = *reinterpret_cast<const float4 *>(&sm.c[j]);
+            const float4 c23 = *reinterpret_cast<const float4 *>(&sm.c[j + 2]);
+            float d2[R2_ROWS][2], p2[R2_ROWS][2];
+            row_math(z[0], make_float2(c01.x, c01.y), d2[0], p2[0]);
+            row_math(z[1], make_float2(c01.z, c01.w), d2[1], p2[1]);
+            row_math(z[2], make_float2(c23.x, c23.y), d2[2], p2[2]);
+            row_math(z[3], make_float2(c23.z, c23.w), d2[3], p2[3]);
+            row_bin(r2v.x, d2[0], p2[0]);
+            row_bin(r2v.y, d2[1], p2[1]);
+            row_bin(r2v.z, d2[2], p2[2]);
+            row_bin(r2v.w, d2[3], p2[3]);
+        }
+        cp_async_wait<0>();
+        for (; j < total; j++) {
+            float d2[2], p2[2];
+            row_math(sm.z[j & (R2_D - 1)][tid], sm.c[j], d2, p2);
+            row_bin(sm.r2[j], d2, p2);
+        }
+        apply_group();
+        flush3(0);
+        flush3(1);
+        flush2();
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+            if (act[s] && c1[s] > 0) {
+                red_add_u64(g.counts + g.o_n1d + kz[s], (uint64_t)c1[s]);
+                red_add(g.sums + g.o_p1d + kz[s], a1[s]);
+            }
+        if (trace && tid == 0) {                // PYLB_RING2_TRACE: per-span (start ns, end ns, SM, rows, first r2)
+            long long t_end;
+            unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            trace[5 * item + 0] = t_begin; trace[5 * item + 1] = t_end; trace[5 * item + 2] = smid;
+            trace[5 * item + 3] = total; trace[5 * item + 4] = sm.r2[0];
+        }
+    }
+}
+
+// t3[bin][value][kz] -> the 3-D bins.  One warp per (bin, value).
+__global__ void __launch_bounds__(256)
+ring2_finish_kernel(BinGeom g, const double *__restrict__ t3, int t3_kz, int nbins, int want_phase) {
+    const int wid = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (wid >= nbins * R2_T3_VALS) return;
+    const int b = wid / R2_T3_VALS, v = wid - b * R2_T3_VALS;
+    if (v == 5 && !want_phase) return;
+    const double *row = t3 + (long long)wid * t3_kz;
+    double acc = 0;
+    // n = r2 + kz^2 >= kz^2: bin b only ever holds kz <= b
+    const int kz_end = min(t3_kz, b + 1);
+    for (int k = lane; k < kz_end; k += 32) acc += row[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane != 0 || acc == 0.0) return;
+    if (v < 3) red_add(g.sums + g.o_p3d + (long long)b * 3 + v, acc);
+    else if (v == 3) red_add(g.sums + g.o_k3d + b, acc);
+    else if (v == 4) red_add_u64(g.counts + g.o_n3d + b, (uint64_t)(acc + 0.5));
+    else red_add(g.sums + g.o_phase + b, acc);
+}
+
+static double ring2_first_share() {
+    static double f = 0;
+    if (f == 0) {
+        const char *e = getenv("PYLB_RING2_SHARE");
+        f = e ? atof(e) : 0.8;
+        if (f < 0.05) f = 0.05;
+        if (f > 1.0) f = 1.0;
+    }
+    return f;
+}
+
+// level sizes for a table of `rows` rows worked on by `per_level` CTAs: the first level takes `share` of the
+// rows, every later level the same share of what is left, down to R2_SPAN_MIN rows per span
+static void ring2_levels(int rows, int per_level, int P, Ring2Sched &sc, int &nlev) {
+    int done = 0, l = 0;
+    const double share = ring2_first_share();
+    while (done < rows && l < R2_LEVELS) {
+        const int left = rows - done;
+        long long sz = (long long)(share * left / per_level) + 1;
+        if (l == R2_LEVELS - 1) sz = (left + per_level - 1) / per_level;
+        sz = (sz + R2_ROWS - 1) / R2_ROWS * R2_ROWS;
+        if (sz < R2_SPAN_MIN) sz = R2_SPAN_MIN;
+        if (sz > R2_SPAN_MAX) sz = R2_SPAN_MAX;
+        sc.base[P][l] = done;
+        sc.size[P][l] = (int)sz;
+        const long long cover = sz * per_level;
+        done = cover >= left ? rows : done + (int)cover;
+        l++;
+    }
+    for (int q = l; q <= R2_LEVELS; q++) sc.base[P][q] = done;     // done == rows unless the table is huge (checked by the caller)
+    for (int q = l; q < R2_LEVELS; q++) sc.size[P][q] = R2_SPAN_MIN;
+    if (l > nlev) nlev = l;
+}
+
+template <bool PHASE>
+static int launch_ring2(const BinGeom &g, const float2 *dk, const Row2 *tab, int n0, int n1, int kz_hi, int *counter, int nbins3, cudaStream_t st) {
+    const size_t smem = sizeof(Ring2Smem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PYLB_CHECK(cudaFuncSetAttribute(ring2_kernel<PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring2_kernel<PHASE>, R2_T, smem);
+    if (occ < 1) occ = 1;
+    const int npairs = kz_hi / 2 + 1;                           // parity 0 (never fewer than parity 1)
+    const int nseg = (npairs + R2_T - 1) / R2_T;
+    const int npar = (n0 > 0) + (n1 > 0);
+    const int ctas = sm_count() * occ;                          // persistent: one resident wave
+    int per_level = ctas / (nseg * npar);
+    if (per_level < 1) per_level = 1;
+    {   // large tables: more spans per level than resident CTAs, so that level 0 still covers its share
+        const long long need = (long long)(ring2_first_share() * (n0 > n1 ? n0 : n1) / R2_SPAN_MAX) + 1;
+        if (need > per_level) per_level = (int)need;
+    }
+    Ring2Sched sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.per_level = per_level;
+    int nlev = 0;
+    ring2_levels(n0, per_level, 0, sc, nlev);
+    ring2_levels(n1, per_level, 1, sc, nlev);
+    sc.nlevels = nlev;
+    PYLB_REQUIRE(sc.base[0][nlev] == n0 && sc.base[1][nlev] == n1, "ring2: row table too large for the span schedule");
+    PYLB_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    double *t3 = nullptr;
+    const int t3_kz = (kz_hi + 1 + 3) & ~3;                     // kz = 0 .. kz_hi, rows padded to 32 bytes
+    const size_t t3_bytes = sizeof(double) * (size_t)nbins3 * R2_T3_VALS * t3_kz;
+    PYLB_CHECK(cudaMallocAsync(&t3, t3_bytes, st));
+    PYLB_CHECK(cudaMemsetAsync(t3, 0, t3_bytes, st));
+    long long *trace = nullptr;
+    const char *trace_path = getenv("PYLB_RING2_TRACE");
+    const int nitems = sc.nlevels * sc.per_level * nseg * npar;
+    if (trace_path) {
+        PYLB_CHECK(cudaMalloc(&trace, sizeof(long long) * 5 * (size_t)nitems));
+        PYLB_CHECK(cudaMemset(trace, 0, sizeof(long long) * 5 * (size_t)nitems));
+    }
+    timing_begin(PYLB_T_RING, st);
+    ring2_kernel<PHASE><<<ctas, R2_T, smem, st>>>(g, dk, tab, n0, kz_hi, nseg, npar, sc, counter, t3, t3_kz, trace);
+    timing_end(PYLB_T_RING, st);
+    PYLB_LAUNCH_CHECK();
+    ring2_finish_kernel<<<(unsigned)(((long long)nbins3 * R2_T3_VALS * 32 + 255) / 256), 256, 0, st>>>(g, t3, t3_kz, nbins3, PHASE ? 1 : 0);
+    PYLB_LAUNCH_CHECK();
+    cudaFreeAsync(t3, st);
+    if (trace) {                                // debugging aid: dump the per-span timeline (synchronises)
+        std::vector<long long> h(5 * (size_t)nitems);
+        PYLB_CHECK(cudaStreamSynchronize(st));
+        PYLB_CHECK(cudaMemcpy(h.data(), trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+        cudaFree(trace);
+        if (FILE *f = fopen(trace_path, "w")) {
+            fprintf(f, "# item start_ns end_ns smid rows first_r2   (levels %d, spans per level %d, groups %d)\n", sc.nlevels,
+                    sc.per_level, nseg * npar);
+            long long t0 = 0;
+            for (int i = 0; i < nitems; i++) if (h[5 * i + 3] && (!t0 || h[5 * i] < t0)) t0 = h[5 * i];
+            for (int i = 0; i < nitems; i++)
+                if (h[5 * i + 3])
+                    fprintf(f, "%d %lld %lld %lld %lld %lld\n", i, h[5 * i] - t0, h[5 * i + 1] - t0, h[5 * i + 2], h[5 * i + 3], h[5 * i + 4]);
+            fclose(f);
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // special columns kz = 0 and kz = dims/2 (even dims) for the ring path (line of sight = z).
 // These are the self-conjugate planes: one of each conjugate pair is kept (:326-330).  A thread owns
 // one (span of the r2-sorted row list, special kz).  With kz fixed, n = r2 + kz^2 grows along the
 // sorted list, so k_index and k_per are monotone: ONE running 3-D bin and ONE running 2-D bin per
 // thread, flushed with red.global when they change.  fp64 per mode (2*N^2 modes in total: irrelevant).
 // ------------------------------------------------------------------------------------------------
-constexpr int SPECIAL_ROWS = 16;   // rows per thread
+constexpr int SPECIAL_ROWS = 4;    // rows per thread (latency-bound: few rows per thread, many threads)
 
-template <int F>
+template <int F, class ROW>
 __global__ void __launch_bounds__(128)
-special_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, int nplanes, int want_phase, int write_back) {
+special_kernel(BinGeom g, FieldPtrs dk, const ROW *__restrict__ tab, int nrows, int nplanes, int want_phase, int write_back) {
     constexpr int X = F * (F - 1) / 2;
     constexpr int Q = F + X;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -683,7 +1131,7 @@ special_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrow
     };
 
     for (int i = i0; i < i1; i++) {
-        const RowEnt e = tab[i];
+        const ROW e = tab[i];
         const int kx = e.kx, ky = e.ky;
         // keep one of each conjugate pair, :326-330
         if (kx < 0) continue;
@@ -716,7 +1164,7 @@ special_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrow
 #pragma unroll
                 for (int b = a + 1; b < F; b++) { v[F + ix] = re[a] * re[b] + im[a] * im[b]; ix++; }
         }
-        if (want_phase) { const double p = atan2(re[0], sqrt(v[0])); ph += p * p; }
+        if (want_phase) ph += (double)phase_sq((float)re[0], (float)v[0]);   // atan2(re, |delta_k|)^2, :361 (1e-7 polynomial)
 #pragma unroll
         for (int q = 0; q < Q; q++) {
             s3[0][q] += v[q]; s3[1][q] += v[q] * w2; s3[2][q] += v[q] * w4;
@@ -737,13 +1185,13 @@ special_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrow
     }
 }
 
-template <int F>
-static int launch_special(const BinGeom &g, const FieldPtrs &dk, const RowEnt *tab, int nrows, int want_phase,
+template <int F, class ROW>
+static int launch_special(const BinGeom &g, const FieldPtrs &dk, const ROW *tab, int nrows, int want_phase,
                           int write_back, cudaStream_t st) {
     const int nplanes = (g.even && g.middle > 0) ? 2 : 1;
     const long long nthreads = (long long)((nrows + SPECIAL_ROWS - 1) / SPECIAL_ROWS) * nplanes;
     if (nthreads == 0) return 0;
-    special_kernel<F><<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(g, dk, tab, nrows, nplanes, want_phase, write_back);
+    special_kernel<F, ROW><<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(g, dk, tab, nrows, nplanes, want_phase, write_back);
     PYLB_LAUNCH_CHECK();
     return 0;
 }
@@ -898,10 +1346,59 @@ static int bits_for(unsigned v) {
     return b;
 }
 
+static bool g_allow_ring2 = true;
+
+// one field, even dims, default arithmetic, no write-back: parity-split row table + ring2_kernel
+static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cudaStream_t st) {
+    const int nrows = g.nx * g.ny;
+    const int kz_hi = g.middle - 1;
+    const int bp = (int)(((uintptr_t)dk.p[0] >> 3) & 1);
+    // rows whose first element sits on an odd multiple of 8 bytes
+    const long long sxo = g.stride_x & 1, syo = g.stride_y & 1;
+    const long long ox = sxo ? g.nx / 2 : 0, ex = g.nx - ox, oy = syo ? g.ny / 2 : 0, ey = g.ny - oy;
+    long long n1 = ox * ey + ex * oy;
+    if (bp) n1 = (long long)nrows - n1;
+    const int n0 = (int)(nrows - n1);
+
+    unsigned *buf = nullptr;
+    Row2 *tab = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    const int kmaxsq = 2 * (g.dims / 2 + 1) * (g.dims / 2 + 1);
+    const int par_bit = bits_for((unsigned)kmaxsq);
+    PYLB_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned *)nullptr, (unsigned *)nullptr,
+                                               (unsigned *)nullptr, (unsigned *)nullptr, nrows, 0, par_bit + 1, st));
+    PYLB_CHECK(cudaMallocAsync(&buf, sizeof(unsigned) * (4 * (size_t)nrows + 4), st));   // + the span counter
+    PYLB_CHECK(cudaMallocAsync(&tab, sizeof(Row2) * (size_t)nrows, st));
+    PYLB_CHECK(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st));
+    unsigned *k_in = buf, *v_in = buf + nrows, *k_out = buf + 2 * (size_t)nrows, *v_out = buf + 3 * (size_t)nrows;
+    const unsigned blocks = (unsigned)((nrows + 255) / 256);
+    row_keys2_kernel<<<blocks, 256, 0, st>>>(k_in, v_in, nrows, g, bp, par_bit);
+    PYLB_LAUNCH_CHECK();
+    PYLB_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, nrows, 0, par_bit + 1, st));
+    count_launch(3);
+    row_table2_kernel<<<blocks, 256, 0, st>>>(k_out, v_out, tab, nrows, g, par_bit);
+    PYLB_LAUNCH_CHECK();
+
+    int rc = launch_special<1, Row2>(g, dk, tab, nrows, want_phase, 0, st);
+    if (!rc && kz_hi >= 1) {
+        int *counter = reinterpret_cast<int *>(buf + 4 * (size_t)nrows);
+        const int nbins3 = isqrt_exact(3 * g.middle * g.middle) + 1;     // kmax + 1
+        rc = want_phase ? launch_ring2<true>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, st)
+                        : launch_ring2<false>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, st);
+    }
+    cudaFreeAsync(buf, st);
+    cudaFreeAsync(tab, st);
+    cudaFreeAsync(tmp, st);
+    return rc;
+}
+
 static int run_ring(const BinGeom &g, const FieldPtrs &dk, int want_phase, int write_back, int precise, cudaStream_t st) {
     const int nrows = g.nx * g.ny;
     const int kz_hi = g.even ? g.middle - 1 : g.middle;  // columns 1..kz_hi carry no skip rule
     if (nrows == 0) return 0;
+    if (g_allow_ring2 && g.F == 1 && !write_back && !precise && g.even && g.middle >= 2 && ((uintptr_t)dk.p[0] & 7) == 0)
+        return run_ring2(g, dk, want_phase, st);
 
     // scratch: keys/vals (double-buffered for the radix sort), row table, cub temp
     unsigned *buf = nullptr;
@@ -927,11 +1424,11 @@ static int run_ring(const BinGeom &g, const FieldPtrs &dk, int want_phase, int w
     // special columns (kz = 0 and, for even dims, kz = middle), then the bulk kz in [1, kz_hi]
     int rc = 1;
     switch (g.F) {
-        case 1: rc = launch_special<1>(g, dk, tab, nrows, want_phase, write_back, st) ||
+        case 1: rc = launch_special<1, RowEnt>(g, dk, tab, nrows, want_phase, write_back, st) ||
                      (kz_hi >= 1 && launch_ring_f<1>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st)); break;
-        case 2: rc = launch_special<2>(g, dk, tab, nrows, want_phase, write_back, st) ||
+        case 2: rc = launch_special<2, RowEnt>(g, dk, tab, nrows, want_phase, write_back, st) ||
                      (kz_hi >= 1 && launch_ring_f<2>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st)); break;
-        case 3: rc = launch_special<3>(g, dk, tab, nrows, want_phase, write_back, st) ||
+        case 3: rc = launch_special<3, RowEnt>(g, dk, tab, nrows, want_phase, write_back, st) ||
                      (kz_hi >= 1 && launch_ring_f<3>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st)); break;
         default: set_error("ring binning supports 1..3 fields, got %d", g.F);
     }
@@ -1016,7 +1513,8 @@ extern "C" int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int ax
 
     const int precise = (algo & PYLB_BIN_PRECISE) ? 1 : 0;
     g_allow_bulk = (algo & PYLB_BIN_BULK) != 0;
-    algo &= ~(PYLB_BIN_PRECISE | PYLB_BIN_BULK);
+    g_allow_ring2 = (algo & PYLB_BIN_RING1) == 0;
+    algo &= ~(PYLB_BIN_PRECISE | PYLB_BIN_BULK | PYLB_BIN_RING1);
     if (algo == PYLB_BIN_AUTO) algo = (axis == 2 && F <= 3) ? PYLB_BIN_RING : PYLB_BIN_GENERIC;
     int rc;
     if (algo == PYLB_BIN_RING) {

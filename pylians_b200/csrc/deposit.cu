@@ -224,6 +224,13 @@ extern "C" int pylb_h2d_padded(const float *host, float *dev, int dims, void *st
     return 0;
 }
 
+extern "C" int pylb_h2d_pitched(const float *host, float *dev, int dims, int64_t dev_pitch, void *stream) {
+    PYLB_REQUIRE(host && dev && dims >= 2 && dev_pitch >= dims, "pylb_h2d_pitched: bad arguments");
+    PYLB_CHECK(cudaMemcpy2DAsync(dev, (size_t)dev_pitch * sizeof(float), host, (size_t)dims * sizeof(float),
+                                 (size_t)dims * sizeof(float), (size_t)dims * dims, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
 extern "C" int pylb_overdensity(float *grid, int64_t n, double *scratch, void *stream) {
     PYLB_REQUIRE(n > 0 && scratch != nullptr, "pylb_overdensity: empty grid or NULL scratch");
     PYLB_REQUIRE(((uintptr_t)grid & 15) == 0, "pylb_overdensity: grid must be 16-byte aligned");

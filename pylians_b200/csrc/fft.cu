@@ -38,17 +38,18 @@ static const char *cufft_str(cufftResult r) {
         }                                                                                         \
     } while (0)
 
-enum { KIND_R2C_3D = 0, KIND_SLAB_YZ = 1, KIND_SLAB_X = 2 };
+enum { KIND_R2C_3D = 0, KIND_SLAB_YZ = 1, KIND_SLAB_X = 2, KIND_R2C_3D_PITCHED = 3 };
 
 struct Plan {
     cufftHandle h = 0;
     size_t work = 0;
 };
 
-typedef std::tuple<int, int, int, int, int> PlanKey;  // device, kind, dims, nloc, inplace
+typedef std::tuple<int, int, int, long long, long long> PlanKey;  // device, kind, dims, nloc | in_pitch, inplace | out_pitch
 static std::map<PlanKey, Plan> g_plans;
 
-static int get_plan(int kind, int dims, int nloc, int inplace, Plan **out) {
+// KIND_R2C_3D_PITCHED: nloc = input row pitch in floats, inplace = output row pitch in complex elements
+static int get_plan(int kind, int dims, long long nloc, long long inplace, Plan **out) {
     int dev = 0;
     PYLB_CHECK(cudaGetDevice(&dev));
     PlanKey key(dev, kind, dims, nloc, inplace);
@@ -70,6 +71,10 @@ static int get_plan(int kind, int dims, int nloc, int inplace, Plan **out) {
         } else {
             PYLB_CUFFT(cufftMakePlanMany64(p.h, 3, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, 1, &p.work));
         }
+    } else if (kind == KIND_R2C_3D_PITCHED) {
+        long long n[3] = {N, N, N};
+        long long inembed[3] = {N, N, nloc}, onembed[3] = {N, N, inplace};
+        PYLB_CUFFT(cufftMakePlanMany64(p.h, 3, n, inembed, 1, N * N * nloc, onembed, 1, N * N * inplace, CUFFT_R2C, 1, &p.work));
     } else if (kind == KIND_SLAB_YZ) {
         long long n[2] = {N, N};
         long long inembed[2] = {N, N}, onembed[2] = {N, nz};
@@ -109,6 +114,26 @@ extern "C" int pylb_fft_r2c(const float *in, void *out, int dims, int inplace, v
     PYLB_REQUIRE(inplace || (const void *)in != out, "pylb_fft_r2c: in == out requires inplace=1 (padded layout)");
     Plan *p = nullptr;
     if (get_plan(KIND_R2C_3D, dims, 0, inplace ? 1 : 0, &p)) return 1;
+    if (exec_setup(p, work, work_bytes, (cudaStream_t)stream)) return 1;
+    PYLB_CUFFT(cufftExecR2C(p->h, (cufftReal *)in, (cufftComplex *)out));
+    count_launch();
+    return 0;
+}
+
+extern "C" size_t pylb_fft_r2c_pitched_work_bytes(int dims, int64_t in_pitch, int64_t out_pitch) {
+    Plan *p = nullptr;
+    if (dims < 2 || in_pitch < dims || out_pitch < dims / 2 + 1 || get_plan(KIND_R2C_3D_PITCHED, dims, in_pitch, out_pitch, &p))
+        return (size_t)-1;
+    return p->work;
+}
+
+extern "C" int pylb_fft_r2c_pitched(const float *in, int64_t in_pitch, void *out, int64_t out_pitch, int dims, void *work,
+                                    size_t work_bytes, void *stream) {
+    PYLB_REQUIRE(dims >= 2 && in_pitch >= dims && out_pitch >= dims / 2 + 1, "pylb_fft_r2c_pitched: bad shape");
+    PYLB_REQUIRE((const void *)in != out || in_pitch == 2 * out_pitch,
+                 "pylb_fft_r2c_pitched: in == out requires in_pitch == 2*out_pitch");
+    Plan *p = nullptr;
+    if (get_plan(KIND_R2C_3D_PITCHED, dims, in_pitch, out_pitch, &p)) return 1;
     if (exec_setup(p, work, work_bytes, (cudaStream_t)stream)) return 1;
     PYLB_CUFFT(cufftExecR2C(p->h, (cufftReal *)in, (cufftComplex *)out));
     count_launch();

@@ -261,7 +261,8 @@ def _field(dims, box, seed, mas="CIC"):
     return d
 
 
-@pytest.mark.parametrize("algo", [1, 2, 2 | 16, 2 | 32, 2 | 16 | 32])   # generic; ring cp.async fp32 / fp64 option; ring bulk (TMA 1-D) fp32 / fp64
+# generic; ring2 (two kz per thread); one-kz ring cp.async fp32 / fp64 option / bulk fp32 / bulk fp64
+@pytest.mark.parametrize("algo", [1, 2, 2 | 64, 2 | 16, 2 | 64 | 32, 2 | 16 | 32])
 @pytest.mark.parametrize("dims", [48, 64, 33])
 def test_pk_vs_oracle(PKL, algo, dims):
     import pylians_b200.Pk_library as P
@@ -284,6 +285,36 @@ def test_xpk_vs_oracle(PKL, algo):
     try:
         parity.check_xpk(PKL.XPk(fs[:2], box, 2, ["CIC", "TSC"], 1), O.XPk(fs[:2], box, 2, ["CIC", "TSC"], 1))
         parity.check_xpk(PKL.XPk(fs, box, 2, ["CIC", "TSC", "PCS"], 1), O.XPk(fs, box, 2, ["CIC", "TSC", "PCS"], 1))
+    finally:
+        P.ALGO = old
+
+
+@pytest.mark.parametrize("dims", [520, 258])
+def test_ring2_segments_and_unaligned_rows(PKL, dims):
+    """ring2 against the one-thread-per-mode kernel where the oracle is too slow: 520 -> two kz segments (the
+    second with two pairs), 258 -> N/2+1 even, so every row starts on the same 16-byte parity; plus a field whose
+    base pointer is only 8-byte aligned (the parity tables swap roles)."""
+    import pylians_b200.Pk_library as P
+    gen = torch.Generator(device="cuda"); gen.manual_seed(dims)
+    d = torch.randn((dims,) * 3, device="cuda", dtype=torch.float32, generator=gen)
+    old = P.ALGO
+    try:
+        P.ALGO = 1
+        ref = PKL.Pk(d, 1000.0, 2, "PCS", 1)
+        for algo in (2, 2 | 64):
+            P.ALGO = algo
+            parity.check_pk(PKL.Pk(d, 1000.0, 2, "PCS", 1), ref)
+        # bins straight from a k-space field at an odd 8-byte offset
+        m = dims // 2 + 1
+        buf = torch.randn((dims * dims * m + 1, 2), device="cuda", dtype=torch.float32, generator=gen)
+        dk = torch.view_as_complex(buf[1:]).reshape(dims, dims, m)
+        assert dk.data_ptr() % 16 == 8
+        _, ws, wc = P.bin_modes([dk], dims, 2, [2], True, False, algo=1)
+        ws, wc = ws.cpu().numpy(), wc.cpu().numpy()
+        for algo in (2, 2 | 64):
+            _, gs, gc = P.bin_modes([dk], dims, 2, [2], True, False, algo=algo)
+            assert np.array_equal(gc.cpu().numpy(), wc)              # mode counts: bit-exact
+            np.testing.assert_allclose(gs.cpu().numpy(), ws, rtol=2e-6, atol=1e-7 * float(np.abs(ws).max()))
     finally:
         P.ALGO = old
 
