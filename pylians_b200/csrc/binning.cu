@@ -1077,7 +1077,7 @@ static int launch_ring2(const BinGeom &g, const float2 *dk, const Row2 *tab, int
 // sorted list, so k_index and k_per are monotone: ONE running 3-D bin and ONE running 2-D bin per
 // thread, flushed with red.global when they change.  fp64 per mode (2*N^2 modes in total: irrelevant).
 // ------------------------------------------------------------------------------------------------
-constexpr int SPECIAL_ROWS = 4;    // rows per thread (latency-bound: few rows per thread, many threads)
+constexpr int SPECIAL_ROWS = 16;   // rows per thread
 
 template <int F, class ROW>
 __global__ void __launch_bounds__(128)
@@ -1183,6 +1183,87 @@ special_kernel(BinGeom g, FieldPtrs dk, const ROW *__restrict__ tab, int nrows, 
 #pragma unroll
         for (int x = 0; x < X; x++) red_add(g.sums + g.o_x1d + (long long)kz * X + x, s1[F + x]);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// special columns for the ring2 path (one field, no write-back): one thread per (row, plane), then a warp-level
+// reduce-by-key -- neighbouring rows of the r2-sorted table share their bins, so a warp issues one red.global
+// per value for each of its 1-2 distinct bins instead of one per thread (red.global on the hot 3-D bins
+// serialises; the 16-rows-per-thread kernel above spends 50-75 us there at 512^3).
+// ------------------------------------------------------------------------------------------------
+template <int NV, class FLUSH>
+__device__ __forceinline__ void warp_reduce_by_key(int key, bool valid, const double (&v)[NV], FLUSH flush) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(full, valid);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int k = __shfl_sync(full, key, leader);
+        const bool mine = valid && key == k;
+        double s[NV];
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            s[q] = mine ? v[q] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(full, s[q], o);
+        }
+        if (lane == leader) flush(k, s);
+        todo &= ~__ballot_sync(full, mine);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+special2_kernel(BinGeom g, const float2 *__restrict__ dk, const Row2 *__restrict__ tab, int nrows, int want_phase) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // whole warps stay alive: shuffles below use the full mask
+    const int kz = blockIdx.y == 0 ? 0 : g.middle;
+    bool valid = i < nrows;
+    Row2 e;
+    e.off = 0; e.r2 = 0; e.chi = e.clo = 0.f; e.kx = e.ky = 0;
+    if (valid) e = tab[i];
+    const int kx = e.kx, ky = e.ky;
+    // keep one of each conjugate pair, :326-330
+    if (kx < 0) valid = false;
+    if ((kx == 0 || (kx == g.middle && g.even)) && ky < 0) valid = false;
+    const int n = e.r2 + kz * kz;
+    const int b3 = isqrt_exact(n), b2 = isqrt_exact(e.r2);
+    double v3[6] = {0, 0, 0, 0, 0, 0}, v2[2] = {0, 0}, v1[2] = {0, 0};
+    if (valid) {
+        const double k = sqrt((double)n);
+        const double mu = (n == 0) ? 0.0 : (double)kz / k;
+        const double mu2 = mu * mu;
+        const int ax = kx, ay = ky < 0 ? -ky : ky;
+        const float mf = (float)(g.mas_tab[ax] * g.mas_tab[ay] * g.mas_tab[kz]);   // :354
+        const float2 z = *(reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(dk) + e.off) + kz);
+        const float r = __fmul_rn(z.x, mf), q = __fmul_rn(z.y, mf);                // :355
+        const double d2 = (double)r * (double)r + (double)q * (double)q;           // :358-360
+        v3[0] = d2;
+        v3[1] = d2 * ((3.0 * mu2 - 1.0) / 2.0);
+        v3[2] = d2 * ((35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0);
+        v3[3] = k;
+        v3[4] = 1.0;
+        v3[5] = want_phase ? (double)phase_sq(r, (float)d2) : 0.0;                 // atan2(re, |delta_k|)^2, :361
+        v2[0] = d2; v2[1] = 1.0;
+        if (n <= g.middle * g.middle) { v1[0] = d2; v1[1] = 1.0; }
+    }
+    warp_reduce_by_key<6>(b3, valid, v3, [&](int b, const double (&s)[6]) {
+        red_add(g.sums + g.o_p3d + (long long)b * 3 + 0, s[0]);
+        red_add(g.sums + g.o_p3d + (long long)b * 3 + 1, s[1]);
+        red_add(g.sums + g.o_p3d + (long long)b * 3 + 2, s[2]);
+        red_add(g.sums + g.o_k3d + b, s[3]);
+        red_add_u64(g.counts + g.o_n3d + b, (uint64_t)(s[4] + 0.5));
+        if (want_phase) red_add(g.sums + g.o_phase + b, s[5]);
+    });
+    warp_reduce_by_key<2>(b2, valid, v2, [&](int b, const double (&s)[2]) {
+        const long long i2 = (long long)g.kmax_par1 * b + kz;
+        red_add(g.sums + g.o_p2d + i2, s[0]);
+        red_add_u64(g.counts + g.o_n2d + i2, (uint64_t)(s[1] + 0.5));
+    });
+    warp_reduce_by_key<2>(0, valid, v1, [&](int, const double (&s)[2]) {
+        if (s[1] > 0.5) {
+            red_add(g.sums + g.o_p1d + kz, s[0]);
+            red_add_u64(g.counts + g.o_n1d + kz, (uint64_t)(s[1] + 0.5));
+        }
+    });
 }
 
 template <int F, class ROW>
@@ -1348,6 +1429,18 @@ static int bits_for(unsigned v) {
 
 static bool g_allow_ring2 = true;
 
+struct Ring2Key {
+    int dims, x0, nx, y0, ny;
+    long long stride_x, stride_y;
+    int bp, mas;
+};
+struct Ring2Cache {
+    Ring2Key key;
+    Row2 *tab = nullptr;
+    cudaEvent_t ready = nullptr;
+};
+static Ring2Cache g_ring2_cache[16];
+
 // one field, even dims, default arithmetic, no write-back: parity-split row table + ring2_kernel
 static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cudaStream_t st) {
     const int nrows = g.nx * g.ny;
@@ -1360,36 +1453,53 @@ static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cuda
     if (bp) n1 = (long long)nrows - n1;
     const int n0 = (int)(nrows - n1);
 
-    unsigned *buf = nullptr;
-    Row2 *tab = nullptr;
-    void *tmp = nullptr;
-    size_t tmp_bytes = 0;
-    const int kmaxsq = 2 * (g.dims / 2 + 1) * (g.dims / 2 + 1);
-    const int par_bit = bits_for((unsigned)kmaxsq);
-    PYLB_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned *)nullptr, (unsigned *)nullptr,
-                                               (unsigned *)nullptr, (unsigned *)nullptr, nrows, 0, par_bit + 1, st));
-    PYLB_CHECK(cudaMallocAsync(&buf, sizeof(unsigned) * (4 * (size_t)nrows + 4), st));   // + the span counter
-    PYLB_CHECK(cudaMallocAsync(&tab, sizeof(Row2) * (size_t)nrows, st));
-    PYLB_CHECK(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st));
-    unsigned *k_in = buf, *v_in = buf + nrows, *k_out = buf + 2 * (size_t)nrows, *v_out = buf + 3 * (size_t)nrows;
-    const unsigned blocks = (unsigned)((nrows + 255) / 256);
-    row_keys2_kernel<<<blocks, 256, 0, st>>>(k_in, v_in, nrows, g, bp, par_bit);
-    PYLB_LAUNCH_CHECK();
-    PYLB_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, nrows, 0, par_bit + 1, st));
-    count_launch(3);
-    row_table2_kernel<<<blocks, 256, 0, st>>>(k_out, v_out, tab, nrows, g, par_bit);
-    PYLB_LAUNCH_CHECK();
+    // The row table depends only on the k-space window, the strides, the pointer parity and the MAS exponent:
+    // keep the last one per device (24 B per row; rebuilding costs a radix sort of N^2 keys and ~8 launches).
+    int dev = 0;
+    PYLB_CHECK(cudaGetDevice(&dev));
+    Ring2Cache &c = g_ring2_cache[dev & 15];
+    const Ring2Key key = {g.dims, g.x0, g.nx, g.y0, g.ny, g.stride_x, g.stride_y, bp, g.mas_idx[0]};
+    if (!c.tab || memcmp(&c.key, &key, sizeof(key)) != 0) {
+        if (c.tab) { cudaFree(c.tab); c.tab = nullptr; }          // synchronises: nobody is reading it any more
+        if (!c.ready) PYLB_CHECK(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
+        unsigned *buf = nullptr;
+        void *tmp = nullptr;
+        size_t tmp_bytes = 0;
+        const int kmaxsq = 2 * (g.dims / 2 + 1) * (g.dims / 2 + 1);
+        const int par_bit = bits_for((unsigned)kmaxsq);
+        PYLB_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned *)nullptr, (unsigned *)nullptr,
+                                                   (unsigned *)nullptr, (unsigned *)nullptr, nrows, 0, par_bit + 1, st));
+        PYLB_CHECK(cudaMalloc(&c.tab, sizeof(Row2) * (size_t)nrows));
+        PYLB_CHECK(cudaMallocAsync(&buf, sizeof(unsigned) * 4 * (size_t)nrows, st));
+        PYLB_CHECK(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st));
+        unsigned *k_in = buf, *v_in = buf + nrows, *k_out = buf + 2 * (size_t)nrows, *v_out = buf + 3 * (size_t)nrows;
+        const unsigned blocks = (unsigned)((nrows + 255) / 256);
+        row_keys2_kernel<<<blocks, 256, 0, st>>>(k_in, v_in, nrows, g, bp, par_bit);
+        PYLB_LAUNCH_CHECK();
+        PYLB_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, nrows, 0, par_bit + 1, st));
+        count_launch(3);
+        row_table2_kernel<<<blocks, 256, 0, st>>>(k_out, v_out, c.tab, nrows, g, par_bit);
+        PYLB_LAUNCH_CHECK();
+        cudaFreeAsync(buf, st);
+        cudaFreeAsync(tmp, st);
+        PYLB_CHECK(cudaEventRecord(c.ready, st));
+        c.key = key;
+    } else {
+        PYLB_CHECK(cudaStreamWaitEvent(st, c.ready, 0));           // built on another stream, perhaps
+    }
+    Row2 *tab = c.tab;
+    int *counter = nullptr;
+    PYLB_CHECK(cudaMallocAsync(&counter, 16, st));
 
-    int rc = launch_special<1, Row2>(g, dk, tab, nrows, want_phase, 0, st);
+    special2_kernel<<<dim3((unsigned)((nrows + 255) / 256), (g.middle > 0) ? 2 : 1), 256, 0, st>>>(g, dk.p[0], tab, nrows, want_phase);
+    PYLB_LAUNCH_CHECK();
+    int rc = 0;
     if (!rc && kz_hi >= 1) {
-        int *counter = reinterpret_cast<int *>(buf + 4 * (size_t)nrows);
         const int nbins3 = isqrt_exact(3 * g.middle * g.middle) + 1;     // kmax + 1
         rc = want_phase ? launch_ring2<true>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, st)
                         : launch_ring2<false>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, st);
     }
-    cudaFreeAsync(buf, st);
-    cudaFreeAsync(tab, st);
-    cudaFreeAsync(tmp, st);
+    cudaFreeAsync(counter, st);
     return rc;
 }
 

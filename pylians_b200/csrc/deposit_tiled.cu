@@ -88,6 +88,33 @@ bin_hist_kernel(const float *__restrict__ pos, int64_t first, int n, int64_t ps0
     extern __shared__ int hist[];
     for (int t = threadIdx.x; t < tg.ntiles; t += BIN_THREADS) hist[t] = 0;
     __syncthreads();
+    const float *base = pos + first * ps0;
+    if (ps0 == 3 && ps1 == 1 && ((uintptr_t)base & 15) == 0) {
+        // dense (np,3) array: 4 particles = 3 aligned float4, 8 particles (6 x 16 B) in flight per thread
+        const float4 *p4 = reinterpret_cast<const float4 *>(base);
+        const int n4 = n >> 2;
+        const int stride = gridDim.x * BIN_THREADS;
+        for (int q0 = blockIdx.x * BIN_THREADS + threadIdx.x; q0 < n4; q0 += 2 * stride) {
+            float4 a[2], b[2], c[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int q = q0 + u * stride;
+                if (q < n4) { a[u] = __ldg(p4 + 3 * (int64_t)q); b[u] = __ldg(p4 + 3 * (int64_t)q + 1); c[u] = __ldg(p4 + 3 * (int64_t)q + 2); }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (q0 + u * stride < n4) {
+                    atomicAdd(&hist[tile_key<MAS, TC>(a[u].x, a[u].y, a[u].z, inv, tg)], 1);
+                    atomicAdd(&hist[tile_key<MAS, TC>(a[u].w, b[u].x, b[u].y, inv, tg)], 1);
+                    atomicAdd(&hist[tile_key<MAS, TC>(b[u].z, b[u].w, c[u].x, inv, tg)], 1);
+                    atomicAdd(&hist[tile_key<MAS, TC>(c[u].y, c[u].z, c[u].w, inv, tg)], 1);
+                }
+        }
+        if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+            const float *p = base + 3 * (int64_t)(4 * n4 + threadIdx.x);
+            atomicAdd(&hist[tile_key<MAS, TC>(p[0], p[1], p[2], inv, tg)], 1);
+        }
+    } else {
     // 4 particles per iteration: all 12 loads are issued before the first key is computed
     const int64_t stride = (int64_t)gridDim.x * BIN_THREADS;
     for (int64_t i0 = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x; i0 < n; i0 += 4 * stride) {
@@ -103,6 +130,7 @@ bin_hist_kernel(const float *__restrict__ pos, int64_t first, int n, int64_t ps0
 #pragma unroll
         for (int u = 0; u < 4; u++)
             if (i0 + u * stride < n) atomicAdd(&hist[tile_key<MAS, TC>(x[u], y[u], z[u], inv, tg)], 1);
+    }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < tg.ntiles; t += BIN_THREADS) {
@@ -260,10 +288,34 @@ bin_pass_kernel(const float *__restrict__ pos, const float *__restrict__ W, int6
 
     float4 v[PART_PER_THREAD];
     int d[PART_PER_THREAD], r[PART_PER_THREAD];
+    // dense (np,3) input: a thread takes 2 x 4 consecutive particles as 3 aligned float4 each (lo is a multiple of 4096)
+    const float *rawbase = FIRST ? pos + first * ps0 : nullptr;
+    const bool vec = FIRST && ps0 == 3 && ps1 == 1 && (((uintptr_t)rawbase) & 15) == 0 && hi - lo == PART_CHUNK;
+    auto index_of = [&](int k) { return vec ? lo + ((k >> 2) * PART_THREADS + tid) * 4 + (k & 3) : lo + k * PART_THREADS + tid; };
+    if (vec) {
+        const float4 *p4 = reinterpret_cast<const float4 *>(rawbase);
+        float4 a[2], b[2], c[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int64_t q = ((int64_t)lo >> 2) + u * PART_THREADS + tid;
+            a[u] = __ldg(p4 + 3 * q); b[u] = __ldg(p4 + 3 * q + 1); c[u] = __ldg(p4 + 3 * q + 2);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            float wv[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+            if (HASW) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) wv[j] = __ldg(W + (first + index_of(4 * u + j)) * wst);
+            }
+            v[4 * u + 0] = make_float4(a[u].x, a[u].y, a[u].z, wv[0]);
+            v[4 * u + 1] = make_float4(a[u].w, b[u].x, b[u].y, wv[1]);
+            v[4 * u + 2] = make_float4(b[u].z, b[u].w, c[u].x, wv[2]);
+            v[4 * u + 3] = make_float4(c[u].y, c[u].z, c[u].w, wv[3]);
+        }
+    } else {
 #pragma unroll
     for (int k = 0; k < PART_PER_THREAD; k++) {
         const int i = lo + k * PART_THREADS + tid;
-        d[k] = -1;
         if (i < hi) {
             if (FIRST) {
                 const float *p = pos + (first + i) * ps0;
@@ -273,9 +325,11 @@ bin_pass_kernel(const float *__restrict__ pos, const float *__restrict__ W, int6
             }
         }
     }
+    }
 #pragma unroll
     for (int k = 0; k < PART_PER_THREAD; k++) {
-        const int i = lo + k * PART_THREADS + tid;
+        const int i = index_of(k);
+        d[k] = -1;
         if (i < hi) {
             const unsigned t = tile_key<MAS, TC>(v[k].x, v[k].y, v[k].z, inv, tg);
             d[k] = FIRST ? (int)(t >> lo_bits) : (int)(t & ((1u << lo_bits) - 1u));
@@ -358,6 +412,7 @@ struct TileShape {
     static constexpr int SX = TC::TX + S - 1, SY = TC::TY + S - 1;
     static constexpr int SZ = ((TC::TZ + S - 1) + 3) & ~3;  // padded to a multiple of 4 for the v4 flush
     static constexpr int CELLS = SX * SY * SZ;
+    static constexpr int HI_WORDS = ((CELLS / 2) + 3) & ~3;   // fixed-point tiles: 16-bit carry counters, two per word
 };
 
 __device__ __forceinline__ void red_add_v4(float *p, float4 v) {
@@ -366,7 +421,14 @@ __device__ __forceinline__ void red_add_v4(float *p, float4 v) {
 }
 
 // SORTED: particles come as float4 (x,y,z,w) already in tile order.  Otherwise through the sorted index.
-template <int MAS, bool HASW, class TC, bool SORTED>
+// FIXED (unweighted only): the tile is accumulated as 48-bit fixed point, unit 2^-31, with NATIVE 32-bit shared
+//   atomics: `lo` takes the update (ATOMS.ADD with return), a wrap-around of `lo` adds one to a 16-bit carry counter
+//   packed two per word in `hi`.  A weight is in [0,1], so an update is at most 2^31 and a CTA's <= 8192 particles
+//   can never overflow the 16-bit carry.  Rounding: 2.3e-10 absolute per update (fp32 accumulation rounds every
+//   partial sum to 6e-8 relative), the sum itself is exact and order independent -- the tile result is
+//   deterministic.  Why: atomicAdd(float) on shared memory is an ATOMS.CAST.SPIN loop on sm_100a (2.9
+//   updates/clk/SM measured against 9.2 for native integer atomics).
+template <int MAS, bool HASW, class TC, bool SORTED, bool FIXED>
 __global__ void __launch_bounds__(TC::THREADS)
 deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, int64_t ps1,
                     const float *__restrict__ W, int64_t wst, float inv, TileGeom tg, const unsigned *__restrict__ svals,
@@ -400,7 +462,10 @@ deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, i
     __syncthreads();
     const int t = s_tile;
     if (t < 0) return;  // CTA-uniform: beyond the last work item
-    for (int i = threadIdx.x; i < TS::CELLS / 4; i += TILE_THREADS)
+    static_assert(!(FIXED && HASW), "fixed-point accumulation needs weights in [0,1]");
+    unsigned *lo = reinterpret_cast<unsigned *>(tile);
+    unsigned *hi = lo + TS::CELLS;             // HI_WORDS words
+    for (int i = threadIdx.x; i < (FIXED ? (TS::CELLS + TS::HI_WORDS) / 4 : TS::CELLS / 4); i += TILE_THREADS)
         reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     const int tz = t % tg.ntz, ty = (t / tg.ntz) % tg.nty, tx = t / (tg.ntz * tg.nty);
@@ -422,7 +487,8 @@ deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, i
         if (lx < 0 || lx >= TC::TX) continue;   // not this tile's particle (only possible for a mis-routed particle)
         const int ly = wrap(axis_stencil<MAS>(y, inv, C[1]), tg.dims) - oy;
         const int lz = wrap(axis_stencil<MAS>(z, inv, C[2]), tg.dims) - oz;
-        float *base = tile + (lx * TS::SY + ly) * TS::SZ + lz;
+        const int cell0 = (lx * TS::SY + ly) * TS::SZ + lz;
+        float *base = tile + cell0;
 #pragma unroll
         for (int l = 0; l < S; l++)
 #pragma unroll
@@ -432,11 +498,26 @@ deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, i
                 for (int n = 0; n < S; n++) {
                     float v = cxy * C[2][n];
                     if (HASW) v *= w;
-                    atomicAdd(base + (l * TS::SY + m) * TS::SZ + n, v);
+                    if (FIXED) {
+                        const int c = cell0 + (l * TS::SY + m) * TS::SZ + n;
+                        const unsigned u = __float2uint_rn(v * 2147483648.0f);
+                        const unsigned old = atomicAdd(lo + c, u);
+                        if (old + u < old) atomicAdd(hi + (c >> 1), 1u << ((c & 1) * 16));
+                    } else {
+                        atomicAdd(base + (l * TS::SY + m) * TS::SZ + n, v);
+                    }
                 }
             }
     }
     __syncthreads();
+    // fixed point -> float in place (cell i: carry << 32 | lo, unit 2^-31), then the common flush
+    if (FIXED) {
+        for (int i = threadIdx.x; i < TS::CELLS; i += TILE_THREADS) {
+            const unsigned long long t = ((unsigned long long)((hi[i >> 1] >> ((i & 1) * 16)) & 0xffffu) << 32) | lo[i];
+            tile[i] = (float)t * 4.656612873077393e-10f;
+        }
+        __syncthreads();
+    }
 
     // flush: local (x,y,z) -> global ((ox+x)%dims, (oy+y)%dims, (oz+z)%dims)
     const int dims = tg.dims;
@@ -535,7 +616,25 @@ int ma_partition(const float *pos, int64_t np, int64_t ps0, int64_t ps1, const f
 
 static int g_force_path = -1;   // tests: exercise every path on small grids (pylb_ma_debug_path)
 static bool g_two_pass = true;  // binsort payload movement: two-pass block-local sort (default) or the one-pass scatter
-void ma_tiled_force_path(int p) { g_two_pass = !(p >= 10); g_force_path = p >= 10 ? p - 10 : p; }
+static int g_fixed = -1;        // tile accumulation: -1 default (float, or PYLB_MA_FIXED), 0 float, 1 fixed point
+void ma_tiled_force_path(int p) {
+    g_fixed = -1;
+    if (p >= 200) { g_fixed = 1; p -= 200; }          // 2xx: force fixed-point tiles (unweighted deposits)
+    else if (p >= 100) { g_fixed = 0; p -= 100; }     // 1xx: force float tiles
+    g_two_pass = !(p >= 10);
+    g_force_path = p >= 10 ? p - 10 : p;
+}
+static bool use_fixed(int64_t np, int dims, int xext) {
+    static int env = -2;
+    if (env == -2) { const char *e = getenv("PYLB_MA_FIXED"); env = e ? atoi(e) : -1; }
+    const int f = g_fixed >= 0 ? g_fixed : env;
+    (void)np; (void)dims; (void)xext;
+    // Opt-in (PYLB_MA_FIXED=1 or pylb_ma_debug_path(2xx)): measured 1.68 ms against 1.59 ms for the float CAS loop at
+    // 512^3 CIC -- both saturate the shared-memory data pipe (95 % of LSU wavefronts, ~13 wavefronts per warp
+    // update from bank conflicts of randomly placed cells), so the native atomic buys determinism, not speed.
+    // Its 2.3e-10 absolute rounding per update needs a mean density well above 1e-4 particles per cell.
+    return f > 0;
+}
 
 static int choose_path(int dims, int xext) {
     if (g_force_path >= PATH_BIN_S && g_force_path <= PATH_RADIX_S) return g_force_path;
@@ -606,15 +705,15 @@ static int set_smem(K kernel, size_t bytes) {
     return 0;
 }
 
-template <int MAS, bool HASW, class TC, bool BINSORT>
+template <int MAS, bool HASW, class TC, bool BINSORT, bool FIXED>
 static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv,
                      const float *w, int64_t wst, int x0, int xext, TiledWs &ws, cudaStream_t st) {
     using TS = TileShape<MAS, TC>;
     const TileGeom tg = tile_geom<TC>(dims, x0, xext);
-    const size_t tile_smem = sizeof(float) * TS::CELLS;
+    const size_t tile_smem = sizeof(float) * (FIXED ? TS::CELLS + TS::HI_WORDS : TS::CELLS);
     const size_t hist_smem = sizeof(int) * (size_t)tg.ntiles;
     const int P = sm_count();
-    if (set_smem(deposit_tile_kernel<MAS, HASW, TC, BINSORT>, tile_smem)) return 1;
+    if (set_smem(deposit_tile_kernel<MAS, HASW, TC, BINSORT, FIXED>, tile_smem)) return 1;
     if (BINSORT) {
         // always the maximum these kernels may ever need: the attribute is a limit, and a smaller value set
         // here would make a later, larger launch of the same instantiation fail
@@ -670,7 +769,7 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
         // upper bound on work items: every non-empty tile has at most count/CHUNK + 1 chunks
         const int64_t max_items = (int64_t)n / CHUNK + tg.ntiles;
         timing_begin(PYLB_T_TILE, st);
-        deposit_tile_kernel<MAS, HASW, TC, BINSORT><<<(unsigned)max_items, TC::THREADS, tile_smem, st>>>(
+        deposit_tile_kernel<MAS, HASW, TC, BINSORT, FIXED><<<(unsigned)max_items, TC::THREADS, tile_smem, st>>>(
             pos, first, ps0, ps1, w, wst, inv, tg, ws.v1, ws.sorted, ws.tile_begin, ws.chunk_off, grid);
         timing_end(PYLB_T_TILE, st);
         PYLB_LAUNCH_CHECK();
@@ -681,9 +780,16 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
 template <int MAS, bool HASW>
 static int tiled_path(int path, const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims,
                       float inv, const float *w, int64_t wst, int x0, int xext, TiledWs &ws, cudaStream_t st) {
-    if (path == PATH_BIN_S) return tiled_run<MAS, HASW, TileS, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
-    if (path == PATH_BIN_L) return tiled_run<MAS, HASW, TileL, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
-    return tiled_run<MAS, HASW, TileS, false>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+    if constexpr (!HASW) {
+        // TileL + fixed point would need 264 KB of shared memory: fixed point only with the small tile
+        if (path != PATH_BIN_L && use_fixed(np, dims, xext < 0 ? dims : xext)) {
+            if (path == PATH_BIN_S) return tiled_run<MAS, HASW, TileS, true, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+            return tiled_run<MAS, HASW, TileS, false, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+        }
+    }
+    if (path == PATH_BIN_S) return tiled_run<MAS, HASW, TileS, true, false>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+    if (path == PATH_BIN_L) return tiled_run<MAS, HASW, TileL, true, false>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+    return tiled_run<MAS, HASW, TileS, false, false>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
 }
 
 int ma_tiled(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv, int mas,

@@ -147,7 +147,9 @@ def test_reference_unit_tests_mass_conservation(MASL, mas, places, weighted):
     assert round(abs(suma / (3.0 * particles if weighted else particles) - 1.0), places) == 0
 
 
-@pytest.mark.parametrize("algo", [1, 2, 20, 21, 22, 30, 31])   # direct; tiled auto; forced two-pass binsort S / L, radix; one-pass scatter S / L
+# direct; tiled auto; forced two-pass binsort S / L, radix; one-pass scatter S / L; binsort S with float tiles (1xx) and
+# with fixed-point tiles (2xx); radix with fixed-point tiles
+@pytest.mark.parametrize("algo", [1, 2, 20, 21, 22, 30, 31, 120, 220, 222])
 @pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
 @pytest.mark.parametrize("dims", [64, 80])
 def test_ma_vs_oracle_both_algorithms(MASL, algo, mas, dims):
