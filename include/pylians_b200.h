@@ -160,6 +160,32 @@ size_t pylb_fft_r2c_pitched_work_bytes(int dims, int64_t in_pitch, int64_t out_p
 int pylb_fft_r2c_pitched(const float *in, int64_t in_pitch, void *out, int64_t out_pitch, int dims, void *work,
                          size_t work_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Siblings of Pk/XPk that share the FFT and the mode loop (library/Pk_library/Pk_library.pyx)
+ * ------------------------------------------------------------------------------------------- */
+
+/* IFFT3Dr_f :152-165 (unnormalised backward c2r; `in` is destroyed), FFT2Dr_f :184-197, IFFT2Dr_f :216-229 */
+int pylb_fft_c2r(void *in, float *out, int dims, void *stream);
+int pylb_fft2d_r2c(const float *in, void *out, int dims, void *stream);
+int pylb_fft2d_c2r(void *in, float *out, int dims, void *stream);
+
+/* In-place pass over a (dims,dims,dims/2+1) complex64 field.  mode 0: the loop of correct_MAS :1770-1797
+ * (independent modes times the MAS factor; the self-conjugate planes are left Hermitian-averaged, which is what
+ * FFTW/pocketfft's c2r make of the reference's half-corrected planes).  mode 1: the first loop of Xi :2063-2083
+ * (every stored mode becomes (|M delta_k|^2, 0)). */
+int pylb_mas_correct(void *dk, int dims, int mas_index, int mode, void *stream);
+
+/* Mode loop of Pk_theta :1283-1325.  sums: device double[3][kmax+1] = sum |k|, sum |theta|^2, Nmodes. */
+int pylb_theta_bin(const void *vx, const void *vy, const void *vz, int dims, int mas_index, double *sums, void *stream);
+
+/* Mode loops of Pk_plane :472-502 and XPk_plane :871-925 on (dims,dims/2+1) complex64 fields (d2 may be NULL).
+ * sums: device double[5][kmax2d+1] = sum |k|, sum |d1|^2, sum |d2|^2, sum Re(d1 conj d2), Nmodes. */
+int pylb_plane_bin(const void *d1, const void *d2, int dims, int mas1, int mas2, double *sums, void *stream);
+
+/* Real-space loop of Xi :2097-2133 over the unnormalised inverse transform.
+ * sums: device double[5][kmax+1] = sum r, sum xi, sum xi*L2(mu), sum xi*L4(mu), Nmodes. */
+int pylb_xi_bin(const float *xi, int dims, int axis, double *sums, void *stream);
+
 /* Real-space axis swap feeding the FFT: out(i,j,k) = in(k,j,i) for axis 0, in(i,k,j) for axis 1, a copy
  * for axis 2.  `out` rows have out_pitch floats (dims for a dense cube, 2*(dims/2+1) for the padded
  * in-place R2C layout).  The power spectrum with the line of sight along `axis` equals the spectrum of

@@ -239,3 +239,184 @@ class XPk(object):
         ell = np.array([1.0, 5.0, 9.0])[None, :, None]
         self.Pk = (o["p3d"][1:] * ell / N3[:, None, None]) * fact
         self.XPk = (o["x3d"][1:] * ell / N3[:, None, None]) * fact
+
+
+# --------------------------------------------------------------------------------------------------
+# Siblings sharing the FFT and the mode loop, restated with vectorised numpy.  TEST INFRASTRUCTURE.
+# Arithmetic notes follow the reference's C types: MAS_factor is a C float (double product rounded once), a
+# complex64 times a float stays fp32 per component, |.|^2 and all sums are double.
+# --------------------------------------------------------------------------------------------------
+import scipy.fft as _sf
+
+
+def _wavenumbers(dims):
+    i = np.arange(dims)
+    return np.where(i > dims // 2, i - dims, i)
+
+
+def _mas_axis(dims, mas_index):
+    """MAS_correction(pi*k/dims, MAS_index) for every FFT index, Pk_library.pyx:86-87."""
+    x = (np.pi / dims) * _wavenumbers(dims).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        c = np.where(x == 0.0, 1.0, (x / np.sin(x)) ** mas_index)
+    return c
+
+
+def _deconv(dk, mf):
+    """complex64 *= C float, component-wise fp32 rounding (e.g. :355, :490)."""
+    mf = mf.astype(np.float32)
+    out = np.empty(dk.shape, np.complex64)
+    out.real = dk.real * mf
+    out.imag = dk.imag * mf
+    return out
+
+
+def frequencies_2D(BoxSize, dims):                   # :67-72
+    kF = 2.0 * np.pi / BoxSize
+    middle = dims // 2
+    return kF, middle * kF, middle, middle, int(np.sqrt(middle ** 2 + middle ** 2))
+
+
+def _plane_modes(grid):
+    """(kx, ky) of the stored half plane and the mask of independent modes, :474-485."""
+    middle = grid // 2
+    kx = _wavenumbers(grid)[:, None] * np.ones((1, middle + 1), np.int64)
+    ky = np.arange(middle + 1)[None, :] * np.ones((grid, 1), np.int64)
+    special = (ky == 0) | ((ky == middle) & (grid % 2 == 0))
+    keep = ~(special & (kx < 0))
+    return kx, ky, keep
+
+
+class Pk_plane(object):
+    """Pk_library.pyx:440-516."""
+
+    def __init__(self, delta, BoxSize, MAS="CIC", threads=1):
+        grid = len(delta)
+        kF, kN, kmax_par, kmax_per, kmax = frequencies_2D(BoxSize, grid)
+        c = _mas_axis(grid, MAS_function(MAS))
+        dk = _sf.rfftn(np.asarray(delta, np.float32), axes=(0, 1)).astype(np.complex64)
+        kx, ky, keep = _plane_modes(grid)
+        k = np.sqrt((kx * kx + ky * ky).astype(np.float64))
+        dk = _deconv(dk, c[:, None] * c[None, :grid // 2 + 1])
+        d2 = dk.real.astype(np.float64) ** 2 + dk.imag.astype(np.float64) ** 2
+        idx = k.astype(np.int64)[keep]
+        k2D = np.bincount(idx, k[keep], kmax + 1)
+        Pk2D = np.bincount(idx, d2[keep], kmax + 1)
+        Nmodes = np.bincount(idx, None, kmax + 1).astype(np.float64)
+        self.k = (k2D[1:] / Nmodes[1:]) * kF
+        self.Nmodes = Nmodes[1:]
+        self.Pk = (Pk2D[1:] / Nmodes[1:]) * (BoxSize / grid ** 2) ** 2
+
+
+class XPk_plane(object):
+    """Pk_library.pyx:814-941."""
+
+    def __init__(self, delta1, delta2, BoxSize, MAS1=None, MAS2=None, threads=1):
+        grid = delta1.shape[0]
+        kF, kN, kmax_par, kmax_per, kmax = frequencies_2D(BoxSize, grid)
+        kx, ky, keep = _plane_modes(grid)
+        k = np.sqrt((kx * kx + ky * ky).astype(np.float64))
+        idx = k.astype(np.int64)[keep]
+        dks = []
+        for d, m in ((delta1, MAS1), (delta2, MAS2)):
+            c = _mas_axis(grid, MAS_function(m))
+            dk = _sf.rfftn(np.asarray(d, np.float32), axes=(0, 1)).astype(np.complex64)
+            dks.append(_deconv(dk, c[:, None] * c[None, :grid // 2 + 1]))
+        re = [d.real.astype(np.float64) for d in dks]
+        im = [d.imag.astype(np.float64) for d in dks]
+        Nmodes = np.bincount(idx, None, kmax + 1).astype(np.float64)[1:]
+        fact = (BoxSize / grid ** 2) ** 3
+        self.k = (np.bincount(idx, k[keep], kmax + 1)[1:] / Nmodes) * kF
+        self.Nmodes = Nmodes
+        self.Pk = np.stack([np.bincount(idx, (re[i] ** 2 + im[i] ** 2)[keep], kmax + 1)[1:] / Nmodes * fact
+                            for i in range(2)], axis=1)
+        self.XPk = np.bincount(idx, (re[0] * re[1] + im[0] * im[1])[keep], kmax + 1)[1:] / Nmodes * fact
+        self.r = self.XPk / np.sqrt(self.Pk[:, 0] * self.Pk[:, 1])
+
+
+def _cube_modes(dims):
+    """(kx, ky, kz) of the stored half spectrum and the mask of independent modes, :326-330."""
+    middle = dims // 2
+    w = _wavenumbers(dims)
+    kx = w[:, None, None] + np.zeros((1, dims, middle + 1), np.int64)
+    ky = w[None, :, None] + np.zeros((dims, 1, middle + 1), np.int64)
+    kz = np.arange(middle + 1)[None, None, :] + np.zeros((dims, dims, 1), np.int64)
+    even = dims % 2 == 0
+    plane = (kz == 0) | ((kz == middle) & even)
+    drop = plane & ((kx < 0) | (((kx == 0) | ((kx == middle) & even)) & (ky < 0)))
+    return kx, ky, kz, ~drop
+
+
+def _mas_cube(dims, mas_index):
+    c = _mas_axis(dims, mas_index)
+    return (c[:, None, None] * c[None, :, None]) * c[None, None, :dims // 2 + 1]
+
+
+def Pk_theta(Vx, Vy, Vz, BoxSize, axis=2, MAS="CIC", threads=1):
+    """Pk_library.pyx:1245-1336."""
+    dims = len(Vx)
+    kF, kN, kmax_par, kmax_per, kmax = frequencies(BoxSize, dims)
+    kx, ky, kz, keep = _cube_modes(dims)
+    mf = _mas_cube(dims, MAS_function(MAS))
+    V = [_deconv(FFT3Dr_f(np.asarray(v, np.float32)), mf) for v in (Vx, Vy, Vz)]
+    f = [a.astype(np.float32) for a in (kx, ky, kz)]
+    # int * float products and their sum are fp32 in the reference's C (:1308-1314)
+    real = -(f[0] * V[0].imag + f[1] * V[1].imag + f[2] * V[2].imag)
+    imag = f[0] * V[0].real + f[1] * V[1].real + f[2] * V[2].real
+    theta2 = real.astype(np.float64) ** 2 + imag.astype(np.float64) ** 2
+    kmod = np.sqrt((kx * kx + ky * ky + kz * kz).astype(np.float64))
+    idx = kmod.astype(np.int64)[keep]
+    k = np.bincount(idx, kmod[keep], kmax + 1)
+    Pk_ = np.bincount(idx, theta2[keep], kmax + 1)
+    Nmodes = np.bincount(idx, None, kmax + 1).astype(np.float64)
+    check_number_modes(Nmodes, dims)
+    k, Nmodes = k[1:], Nmodes[1:]
+    k = (k / Nmodes) * kF
+    Pk_ = Pk_[1:] * (BoxSize / dims ** 2) ** 3 * kF ** 2
+    Pk_ *= (1.0 / Nmodes)
+    return [k, Pk_, Nmodes]
+
+
+def correct_MAS(delta, BoxSize, MAS="CIC", threads=1):
+    """Pk_library.pyx:1749-1806.  The backward transform (pyfftw -> FFTW, un-vendored) is restated with pocketfft's
+    irfftn, unnormalised; it takes the real part after the complex passes, which fixes what the half-corrected
+    self-conjugate planes mean."""
+    dims = len(delta)
+    kx, ky, kz, keep = _cube_modes(dims)
+    dk = FFT3Dr_f(np.asarray(delta, np.float32))
+    corrected = _deconv(dk, _mas_cube(dims, MAS_function(MAS)))
+    dk = np.where(keep, corrected, dk)
+    return (_sf.irfftn(dk, s=(dims,) * 3, axes=(0, 1, 2)) * dims ** 3).astype(np.float32)
+
+
+class Xi(object):
+    """Pk_library.pyx:2035-2150."""
+
+    def __init__(self, delta, BoxSize, MAS="CIC", axis=2, threads=1):
+        BoxSize = float(np.float32(BoxSize))
+        dims = delta.shape[0]
+        kF, kN, kmax_par, kmax_per, kmax = frequencies(BoxSize, dims)
+        dk = _deconv(FFT3Dr_f(np.asarray(delta, np.float32)), _mas_cube(dims, MAS_function(MAS)))
+        p = np.zeros(dk.shape, np.complex64)
+        p.real = dk.real * dk.real + dk.imag * dk.imag          # `float real, imag`, :2078-2082
+        xi = (_sf.irfftn(p, s=(dims,) * 3, axes=(0, 1, 2)) * dims ** 3).astype(np.float32)
+        w = _wavenumbers(dims)
+        kx = w[:, None, None] + np.zeros((1, dims, dims), np.int64)
+        ky = w[None, :, None] + np.zeros((dims, 1, dims), np.int64)
+        kz = w[None, None, :] + np.zeros((dims, dims, 1), np.int64)
+        k = np.sqrt((kx * kx + ky * ky + kz * kz).astype(np.float64))
+        kpar = (kx, ky, kz)[axis].astype(np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            mu = np.where(k == 0, 0.0, kpar / k)
+        mu2 = mu * mu
+        idx = k.astype(np.int64).ravel()
+        x = xi.astype(np.float64).ravel()
+        N = np.bincount(idx, None, kmax + 1).astype(np.float64)[1:]
+        self.r3D = np.bincount(idx, k.ravel(), kmax + 1)[1:] / N * (BoxSize * 1.0 / dims)
+        self.Nmodes3D = N
+        norm = 1.0 / dims ** 3
+        l2 = ((3.0 * mu2 - 1.0) / 2.0).ravel()
+        l4 = ((35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0).ravel()
+        self.xi = np.stack([np.bincount(idx, x, kmax + 1)[1:] / N * norm,
+                            np.bincount(idx, x * l2, kmax + 1)[1:] * 5.0 / N * norm,
+                            np.bincount(idx, x * l4, kmax + 1)[1:] * 9.0 / N * norm], axis=1)

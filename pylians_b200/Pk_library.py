@@ -216,7 +216,7 @@ class _Bins(object):
             host.copy_(raw, non_blocking=True)
             torch.cuda.current_stream(raw.device).synchronize()
             h = host.numpy()
-            s = h[:L.n_doubles].copy()
+            s = h[:L.n_doubles]          # view of the pinned buffer: _finish only derives new arrays from it
             c = h[L.n_doubles:].view(np.int64).astype(np.float64)   # counts < 2^53: exact in float64
         else:
             s = sums.cpu().numpy()
@@ -251,12 +251,13 @@ def _finish(obj, b, dims, BoxSize, is_x):
     X1 = b.x1d[1:] * fact * s1[:, None]
 
     # 2-D: the DC bin is kept; an empty bin is a ZeroDivisionError in the reference (cdivision False)
-    if np.any(b.n2d == 0):
+    if b.n2d.min() == 0:
         raise ZeroDivisionError("float division")
     obj.kpar, obj.kper = _kpar_kper(kmax_par, kmax_per, kF)
-    obj.Nmodes2D = b.n2d.copy()
-    P2 = b.p2d * fact / b.n2d[:, None]
-    X2 = b.x2d * fact / b.n2d[:, None]
+    obj.Nmodes2D = b.n2d            # already a fresh array (astype in _Bins)
+    inv2 = (fact / b.n2d)[:, None]
+    P2 = b.p2d * inv2
+    X2 = b.x2d * inv2
 
     # 3-D
     check_number_modes(b.n3d, dims)
@@ -344,3 +345,215 @@ def FFT3Dr_f(a, threads=1):
     dev = _device()
     out = _fft_field(lib, a, len(a), dev, torch.cuda.current_stream(dev))
     return out if (_is_torch(a) and a.is_cuda) else out.cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------------------
+# Siblings that share the FFT and the mode loop.  Same host conventions as Pk/XPk: numpy or
+# CUDA-tensor inputs, float64 numpy spectra out, fields come back in the container they came in.
+# --------------------------------------------------------------------------------------------------
+def frequencies_2D(BoxSize, dims):
+    """Pk_library.pyx:67-72."""
+    kF = 2.0 * np.pi / BoxSize
+    middle = dims // 2
+    kN = middle * kF
+    return kF, kN, middle, middle, int(np.sqrt(middle ** 2 + middle ** 2))
+
+
+def check_number_modes_2D(Nmodes, dims):
+    """Pk_library.pyx:105-118."""
+    own_modes = 1 if dims % 2 == 1 else 4
+    indep_modes = (dims ** 2 - own_modes) // 2 + own_modes
+    if int(np.sum(Nmodes)) != indep_modes:
+        print("WARNING: Not all modes counted")
+        print("Counted  %d independent modes" % (int(np.sum(Nmodes))))
+        print("Expected %d independent modes" % indep_modes)
+        sys.exit()
+
+
+def _dev_f32(a, ndim, dev):
+    """float32 C-contiguous device tensor of a numpy array / tensor with `ndim` equal sides."""
+    if _is_torch(a):
+        if a.dtype != torch.float32:
+            raise ValueError("Buffer dtype mismatch, expected 'float32_t' but got '%s'" % _dtype_name(a))
+        t = a
+    else:
+        a = np.asarray(a)
+        if a.dtype != np.float32:
+            raise ValueError("Buffer dtype mismatch, expected 'float32_t' but got '%s'" % _dtype_name(a))
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.ndim != ndim:
+        raise ValueError("Buffer has wrong number of dimensions (expected %d, got %d)" % (ndim, t.ndim))
+    return t.to(dev, non_blocking=True).contiguous()
+
+
+def _like_input(t, ref):
+    return t if (_is_torch(ref) and ref.is_cuda) else t.cpu().numpy()
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def FFT2Dr_f(a, threads=1):
+    """Pk_library.pyx:184-197: unnormalised forward R2C of a (grid,grid) float32 image -> complex64 (grid,grid/2+1)."""
+    lib, dev = _lib.load(), _device()
+    src = _dev_f32(a, 2, dev)
+    n = src.shape[0]
+    out = torch.empty((n, n // 2 + 1), dtype=torch.complex64, device=dev)
+    _lib.check(lib.pylb_fft2d_r2c(src.data_ptr(), out.data_ptr(), n, _stream(dev)), "pylb_fft2d_r2c")
+    return _like_input(out, a)
+
+
+def _dev_c64(a, dev):
+    t = a if _is_torch(a) else torch.from_numpy(np.ascontiguousarray(np.asarray(a)))
+    if t.dtype != torch.complex64:
+        raise ValueError("Buffer dtype mismatch, expected 'complex64_t' but got '%s'" % _dtype_name(a))
+    return t.to(dev).contiguous().clone()          # the C2R transform destroys its input
+
+
+def IFFT2Dr_f(a, threads=1):
+    """Pk_library.pyx:216-229: unnormalised backward C2R, complex64 (grid,grid/2+1) -> float32 (grid,grid)."""
+    lib, dev = _lib.load(), _device()
+    src = _dev_c64(a, dev)
+    n = src.shape[0]
+    out = torch.empty((n, n), dtype=torch.float32, device=dev)
+    _lib.check(lib.pylb_fft2d_c2r(src.data_ptr(), out.data_ptr(), n, _stream(dev)), "pylb_fft2d_c2r")
+    return _like_input(out, a)
+
+
+def IFFT3Dr_f(a, threads=1):
+    """Pk_library.pyx:152-165: unnormalised backward C2R, complex64 (dims,dims,dims/2+1) -> float32 (dims,dims,dims)."""
+    lib, dev = _lib.load(), _device()
+    src = _dev_c64(a, dev)
+    n = src.shape[0]
+    out = torch.empty((n, n, n), dtype=torch.float32, device=dev)
+    _lib.check(lib.pylb_fft_c2r(src.data_ptr(), out.data_ptr(), n, _stream(dev)), "pylb_fft_c2r")
+    return _like_input(out, a)
+
+
+def _sums_host(sums):
+    torch.cuda.current_stream(sums.device).synchronize()
+    return sums.cpu().numpy()
+
+
+class Pk_plane(object):
+    """Power spectrum of a 2-D field (image).  Pk_library.pyx:440-516.  Attributes k, Nmodes, Pk."""
+
+    def __init__(self, delta, BoxSize, MAS="CIC", threads=1):
+        start = time.time()
+        _say("\nComputing power spectrum of the field...")
+        lib, dev = _lib.load(), _device()
+        img = _dev_f32(delta, 2, dev)
+        grid = img.shape[0]
+        kF, kN, kmax_par, kmax_per, kmax = frequencies_2D(BoxSize, grid)
+        dk = torch.empty((grid, grid // 2 + 1), dtype=torch.complex64, device=dev)
+        _lib.check(lib.pylb_fft2d_r2c(img.data_ptr(), dk.data_ptr(), grid, _stream(dev)), "pylb_fft2d_r2c")
+        sums = torch.empty((5, kmax + 1), dtype=torch.float64, device=dev)
+        _lib.check(lib.pylb_plane_bin(dk.data_ptr(), None, grid, MAS_function(MAS), 0, sums.data_ptr(), _stream(dev)),
+                   "pylb_plane_bin")
+        s = _sums_host(sums)
+        check_number_modes_2D(s[4], grid)
+        Nmodes = s[4, 1:].copy()
+        self.k = (s[0, 1:] / Nmodes) * kF
+        self.Nmodes = Nmodes
+        self.Pk = (s[1, 1:] / Nmodes) * (BoxSize / grid ** 2) ** 2          # :507
+        _say("Time taken = %.2f seconds" % (time.time() - start))
+
+
+class XPk_plane(object):
+    """Auto- and cross-power spectrum of two images.  Pk_library.pyx:814-941.  Attributes k, Nmodes, Pk[:,2], XPk, r."""
+
+    def __init__(self, delta1, delta2, BoxSize, MAS1=None, MAS2=None, threads=1):
+        start = time.time()
+        _say("\nComputing power spectra of the fields...")
+        if delta1.shape[0] != delta2.shape[1]:                             # :839-840
+            raise Exception("Images have different grid sizes!!!")
+        lib, dev = _lib.load(), _device()
+        a, b = _dev_f32(delta1, 2, dev), _dev_f32(delta2, 2, dev)
+        grid = a.shape[0]
+        kF, kN, kmax_par, kmax_per, kmax = frequencies_2D(BoxSize, grid)
+        dk = torch.empty((2, grid, grid // 2 + 1), dtype=torch.complex64, device=dev)
+        for i, t in enumerate((a, b)):
+            _lib.check(lib.pylb_fft2d_r2c(t.data_ptr(), dk[i].data_ptr(), grid, _stream(dev)), "pylb_fft2d_r2c")
+        sums = torch.empty((5, kmax + 1), dtype=torch.float64, device=dev)
+        _lib.check(lib.pylb_plane_bin(dk[0].data_ptr(), dk[1].data_ptr(), grid, MAS_function(MAS1), MAS_function(MAS2),
+                                      sums.data_ptr(), _stream(dev)), "pylb_plane_bin")
+        s = _sums_host(sums)
+        fact = (BoxSize / grid ** 2) ** 3                                  # :928 (sic: cubed for a 2-D field)
+        Nmodes = s[4, 1:].copy()
+        self.k = (s[0, 1:] / Nmodes) * kF
+        self.Nmodes = Nmodes
+        self.Pk = np.ascontiguousarray((s[1:3, 1:] / Nmodes).T * fact)
+        self.XPk = (s[3, 1:] / Nmodes) * fact
+        self.r = self.XPk / np.sqrt(self.Pk[:, 0] * self.Pk[:, 1])
+        _say("Time taken = %.2f seconds" % (time.time() - start))
+
+
+def _fft3(lib, field, dims, dev):
+    return _fft_field(lib, _check_field(field), dims, dev, torch.cuda.current_stream(dev))
+
+
+def Pk_theta(Vx, Vy, Vz, BoxSize, axis=2, MAS="CIC", threads=1):
+    """Power spectrum of theta = div V.  Pk_library.pyx:1245-1336.  Returns [k, Pk, Nmodes]."""
+    start = time.time()
+    _say("Computing power spectrum of theta...")
+    lib, dev = _lib.load(), _device()
+    dims = len(Vx)
+    kF, kN, kmax_par, kmax_per, kmax = frequencies(BoxSize, dims)
+    vk = [_fft3(lib, v, dims, dev) for v in (Vx, Vy, Vz)]
+    sums = torch.empty((3, kmax + 1), dtype=torch.float64, device=dev)
+    _lib.check(lib.pylb_theta_bin(vk[0].data_ptr(), vk[1].data_ptr(), vk[2].data_ptr(), dims, MAS_function(MAS),
+                                  sums.data_ptr(), _stream(dev)), "pylb_theta_bin")
+    s = _sums_host(sums)
+    check_number_modes(s[2], dims)
+    Nmodes = s[2, 1:].copy()
+    k = (s[0, 1:] / Nmodes) * kF
+    Pk_ = s[1, 1:] * (BoxSize / dims ** 2) ** 3 * kF ** 2                  # :1331
+    Pk_ *= (1.0 / Nmodes)
+    _say("Time taken = %.2f seconds" % (time.time() - start))
+    return [k, Pk_, Nmodes]
+
+
+def correct_MAS(delta, BoxSize, MAS="CIC", threads=1):
+    """Deconvolve the MAS window from a density field.  Pk_library.pyx:1749-1806.  Like the reference the result is
+    the UNNORMALISED inverse transform (dims^3 times the corrected field), float32 (dims,dims,dims)."""
+    start = time.time()
+    _say("\nComputing power spectrum of the field...")
+    lib, dev = _lib.load(), _device()
+    delta = _check_field(delta)
+    dims = len(delta)
+    dk = _fft_field(lib, delta, dims, dev, torch.cuda.current_stream(dev))      # a fresh buffer, never `delta` itself
+    _lib.check(lib.pylb_mas_correct(dk.data_ptr(), dims, MAS_function(MAS), 0, _stream(dev)), "pylb_mas_correct")
+    out = torch.empty((dims, dims, dims), dtype=torch.float32, device=dev)
+    _lib.check(lib.pylb_fft_c2r(dk.data_ptr(), out.data_ptr(), dims, _stream(dev)), "pylb_fft_c2r")
+    _say("Time taken = %.2f seconds" % (time.time() - start))
+    return _like_input(out, delta)
+
+
+class Xi(object):
+    """Correlation function multipoles from the inverse transform of |delta_k|^2.  Pk_library.pyx:2035-2150.
+    Attributes r3D, xi[:,0..2] (l = 0, 2, 4), Nmodes3D."""
+
+    def __init__(self, delta, BoxSize, MAS="CIC", axis=2, threads=1):
+        start = time.time()
+        _say("\nComputing correlation function of the field...")
+        lib, dev = _lib.load(), _device()
+        delta = _check_field(delta)
+        dims = delta.shape[0]
+        BoxSize = float(np.float32(BoxSize))                               # `float BoxSize` in the signature
+        kF, kN, kmax_par, kmax_per, kmax = frequencies(BoxSize, dims)
+        dk = _fft_field(lib, delta, dims, dev, torch.cuda.current_stream(dev))
+        _lib.check(lib.pylb_mas_correct(dk.data_ptr(), dims, MAS_function(MAS), 1, _stream(dev)), "pylb_mas_correct")
+        xi = torch.empty((dims, dims, dims), dtype=torch.float32, device=dev)
+        _lib.check(lib.pylb_fft_c2r(dk.data_ptr(), xi.data_ptr(), dims, _stream(dev)), "pylb_fft_c2r")
+        del dk
+        sums = torch.empty((5, kmax + 1), dtype=torch.float64, device=dev)
+        _lib.check(lib.pylb_xi_bin(xi.data_ptr(), dims, int(axis), sums.data_ptr(), _stream(dev)), "pylb_xi_bin")
+        s = _sums_host(sums)
+        Nmodes = s[4, 1:].copy()
+        norm = 1.0 / dims ** 3
+        self.r3D = (s[0, 1:] / Nmodes) * (BoxSize * 1.0 / dims)           # :2139
+        self.Nmodes3D = Nmodes
+        self.xi = np.ascontiguousarray(np.stack([(s[1, 1:] / Nmodes) * norm, (s[2, 1:] * 5.0 / Nmodes) * norm,
+                                                 (s[3, 1:] * 9.0 / Nmodes) * norm], axis=1))
+        _say("Time taken = %.2f seconds" % (time.time() - start))

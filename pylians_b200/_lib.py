@@ -57,6 +57,13 @@ SIGNATURES = {
     "pylb_fft_r2c": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pylb_fft_r2c_pitched_work_bytes": (c_size_t, [c_int, c_int64, c_int64]),
     "pylb_fft_r2c_pitched": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    "pylb_fft_c2r": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "pylb_fft2d_r2c": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "pylb_fft2d_c2r": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "pylb_mas_correct": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pylb_theta_bin": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "pylb_plane_bin": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pylb_xi_bin": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "pylb_fft_slab_yz_work_bytes": (c_size_t, [c_int, c_int]),
     "pylb_fft_slab_yz": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pylb_fft_slab_x_work_bytes": (c_size_t, [c_int, c_int]),

@@ -1191,27 +1191,6 @@ special_kernel(BinGeom g, FieldPtrs dk, const ROW *__restrict__ tab, int nrows, 
 // per value for each of its 1-2 distinct bins instead of one per thread (red.global on the hot 3-D bins
 // serialises; the 16-rows-per-thread kernel above spends 50-75 us there at 512^3).
 // ------------------------------------------------------------------------------------------------
-template <int NV, class FLUSH>
-__device__ __forceinline__ void warp_reduce_by_key(int key, bool valid, const double (&v)[NV], FLUSH flush) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    unsigned todo = __ballot_sync(full, valid);
-    while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int k = __shfl_sync(full, key, leader);
-        const bool mine = valid && key == k;
-        double s[NV];
-#pragma unroll
-        for (int q = 0; q < NV; q++) {
-            s[q] = mine ? v[q] : 0.0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(full, s[q], o);
-        }
-        if (lane == leader) flush(k, s);
-        todo &= ~__ballot_sync(full, mine);
-    }
-}
-
 __global__ void __launch_bounds__(256)
 special2_kernel(BinGeom g, const float2 *__restrict__ dk, const Row2 *__restrict__ tab, int nrows, int want_phase) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;      // whole warps stay alive: shuffles below use the full mask

@@ -92,4 +92,28 @@ __device__ __forceinline__ void red_add_u64(uint64_t *p, uint64_t v) {
     atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
 }
 
+// Warp-level reduce-by-key for binning kernels whose neighbouring lanes mostly share a bin: for each distinct key
+// in the warp the NV values are summed by shuffles and `flush(key, sums)` runs on one lane.  Every lane of the
+// warp must call it (full-mask shuffles); lanes without a contribution pass valid = false.
+template <int NV, class FLUSH>
+__device__ __forceinline__ void warp_reduce_by_key(int key, bool valid, const double (&v)[NV], FLUSH flush) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(full, valid);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int k = __shfl_sync(full, key, leader);
+        const bool mine = valid && key == k;
+        double s[NV];
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            s[q] = mine ? v[q] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(full, s[q], o);
+        }
+        if (lane == leader) flush(k, s);
+        todo &= ~__ballot_sync(full, mine);
+    }
+}
+
 }  // namespace pylb

@@ -144,8 +144,40 @@ def gold_rsd():
     np.savez_compressed(os.path.join(HERE, "rsd.npz"), **out)
 
 
+def gold_siblings():
+    """Pk_plane / XPk_plane / Pk_theta / correct_MAS / Xi of the unmodified reference (Pk_library.pyx)."""
+    out = {}
+    box = 500.0
+    rng = np.random.default_rng(21)
+    for grid in (16, 18):                      # N/2+1 odd and even
+        a = rng.standard_normal((grid, grid)).astype(np.float32)
+        b = (0.5 * a + rng.standard_normal((grid, grid))).astype(np.float32)
+        out["img_a_%d" % grid], out["img_b_%d" % grid] = a, b
+        p = quiet(PKL.Pk_plane, a, box, "CIC", 1)
+        for n in ("k", "Nmodes", "Pk"):
+            out["plane_%d_%s" % (grid, n)] = np.asarray(getattr(p, n))
+        x = quiet(PKL.XPk_plane, a, b, box, "CIC", "TSC", 1)
+        for n in ("k", "Nmodes", "Pk", "XPk", "r"):
+            out["xplane_%d_%s" % (grid, n)] = np.asarray(getattr(x, n))
+        v = [rng.standard_normal((grid,) * 3).astype(np.float32) for _ in range(3)]
+        for i in range(3):
+            out["vel%d_%d" % (i, grid)] = v[i]
+        t = quiet(PKL.Pk_theta, v[0], v[1], v[2], box, 2, "PCS", 1)
+        for n, arr in zip(("k", "Pk", "Nmodes"), t):
+            out["theta_%d_%s" % (grid, n)] = np.asarray(arr)
+        (d,) = fields(grid, box, [(31 + grid, "CIC", False)])
+        out["delta_%d" % grid] = d
+        out["correct_%d" % grid] = np.asarray(quiet(PKL.correct_MAS, d, box, "CIC", 1))
+        for axis in (0, 1, 2):
+            xi = quiet(PKL.Xi, d, box, "CIC", axis, 1)
+            for n in ("r3D", "xi", "Nmodes3D"):
+                out["xi_%d_a%d_%s" % (grid, axis, n)] = np.asarray(getattr(xi, n))
+    out["box"] = box
+    np.savez_compressed(os.path.join(HERE, "siblings.npz"), **out)
+
+
 if __name__ == "__main__":
-    gold_ma(); gold_pk(); gold_xpk(); gold_rsd()
+    gold_ma(); gold_pk(); gold_xpk(); gold_rsd(); gold_siblings()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -92,3 +92,35 @@ def check_xpk(test, ref, rtol=PK_RTOL):
         if pairs:
             xmed = np.array([np.sqrt(med[i] * med[j]) for i, j in pairs])
             assert_spec_close(_get(test, xn), _get(ref, xn), xmed[None, :], xn, rtol)
+
+
+# ---- siblings (Pk_plane, XPk_plane, Pk_theta, correct_MAS, Xi): same contract -- counts exact, k means 1e-12,
+# spectra 1e-5 relative with an absolute floor at the typical auto-power level (cross terms and multipoles cancel)
+def check_plane(test, ref, rtol=PK_RTOL):
+    assert_exact(_get(test, "Nmodes"), _get(ref, "Nmodes"), "Nmodes")
+    assert_k_close(_get(test, "k"), _get(ref, "k"), "k")
+    p = _get(ref, "Pk")
+    assert_spec_close(_get(test, "Pk"), p, np.median(np.abs(p), axis=0), "Pk_plane", rtol)
+
+
+def check_xplane(test, ref, rtol=PK_RTOL):
+    check_plane(test, ref, rtol)
+    p = _get(ref, "Pk")
+    floor = np.sqrt(np.abs(p[:, 0] * p[:, 1])) + np.sqrt(np.prod(np.median(np.abs(p), axis=0)))
+    assert_spec_close(_get(test, "XPk"), _get(ref, "XPk"), floor, "XPk_plane", rtol)
+    np.testing.assert_allclose(_get(test, "r"), _get(ref, "r"), rtol=0, atol=5e-5)
+
+
+def check_theta(test, ref, rtol=PK_RTOL):
+    assert_exact(np.asarray(test[2]), np.asarray(ref[2]), "Nmodes")
+    assert_k_close(np.asarray(test[0]), np.asarray(ref[0]), "k")
+    assert_spec_close(test[1], ref[1], np.median(np.abs(ref[1])), "Pk_theta", rtol)
+
+
+def check_xi(test, ref, rtol=PK_RTOL):
+    assert_exact(_get(test, "Nmodes3D"), _get(ref, "Nmodes3D"), "Nmodes3D")
+    assert_k_close(_get(test, "r3D"), _get(ref, "r3D"), "r3D")
+    x = _get(ref, "xi")
+    # xi(r) oscillates around zero; every bin is a mean of cells whose values are of the order of xi(0..1 cell)
+    floor = np.max(np.abs(x[:, 0])) * np.array([1.0, 5.0, 9.0])[None, :]
+    assert_spec_close(_get(test, "xi"), x, floor, "xi", rtol)
