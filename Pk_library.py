@@ -2,4 +2,4 @@
 from pylians_b200.Pk_library import *  # noqa: F401,F403
 from pylians_b200.Pk_library import (Pk, XPk, frequencies, MAS_function, MAS_correction, check_number_modes, FFT3Dr_f,  # noqa: F401
                                      Pk_plane, XPk_plane, Pk_theta, correct_MAS, Xi, frequencies_2D, check_number_modes_2D,
-                                     FFT2Dr_f, IFFT2Dr_f, IFFT3Dr_f)
+                                     FFT2Dr_f, IFFT2Dr_f, IFFT3Dr_f, XPk_imag)

@@ -50,7 +50,8 @@ enum { PYLB_MA_AUTO = 0, PYLB_MA_DIRECT = 1, PYLB_MA_TILED = 2 };
 enum { PYLB_BIN_AUTO = 0, PYLB_BIN_GENERIC = 1, PYLB_BIN_RING = 2, PYLB_BIN_PRECISE = 16,
        PYLB_BIN_BULK = 32 /* ring kernel: cp.async.bulk + mbarrier row loads by a producer warp instead of
                              per-thread cp.async (even dims only) */,
-       PYLB_BIN_RING1 = 64 /* one field: use the one-kz-per-thread ring kernel instead of ring2 */ };
+       PYLB_BIN_RING1 = 64 /* one field: use the one-kz-per-thread ring kernel instead of ring2 */,
+       PYLB_BIN_XIMAG = 256 /* cross terms im_i*re_j - re_i*im_j (class XPk_imag :1131-1132) */ };
 
 int pylb_version(void);
 const char *pylb_last_error(void);

@@ -148,6 +148,10 @@ static double mas_correction(double x, int p) { /* :86-87 */
     return (x == 0.0) ? 1.0 : pow(x / sin(x), (double)p);
 }
 
+/* class XPk_imag (Pk_library.pyx:959-1225) is class XPk with the cross term im_i*re_j - re_i*im_j (:1131-1132) */
+static int g_cross_imag = 0;
+void orc_set_cross_imag(int on) { g_cross_imag = on; }
+
 void orc_pk_loop(float **dk, int F, int dims, int axis, const int *mas_index, int kmax_par,
                  int kmax_per, int kmax, double *k3d, double *n3d, double *p3d, double *x3d,
                  double *phase, double *k1d, double *n1d, double *p1d, double *x1d, double *n2d,
@@ -219,7 +223,7 @@ void orc_pk_loop(float **dk, int F, int dims, int axis, const int *mas_index, in
                 int ix = 0;
                 for (int i = 0; i < F; i++)
                     for (int j = i + 1; j < F; j++) { /* :719-736 */
-                        const double dx = re[i] * re[j] + im[i] * im[j];
+                        const double dx = g_cross_imag ? im[i] * re[j] - re[i] * im[j] : re[i] * re[j] + im[i] * im[j];
                         if (in1d) x1d[(long)k_par * X + ix] += dx;
                         x2d[i2 * X + ix] += dx;
                         x3d[((long)k_index * 3 + 0) * X + ix] += dx;

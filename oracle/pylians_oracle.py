@@ -241,6 +241,17 @@ class XPk(object):
         self.XPk = (o["x3d"][1:] * ell / N3[:, None, None]) * fact
 
 
+class XPk_imag(XPk):
+    """Pk_library.pyx:959-1225: class XPk with the imaginary cross term im_i*re_j - re_i*im_j (:1131-1132)."""
+
+    def __init__(self, delta, BoxSize, axis=2, MAS=None, threads=1):
+        lib().orc_set_cross_imag(1)
+        try:
+            XPk.__init__(self, delta, BoxSize, axis, MAS, threads)
+        finally:
+            lib().orc_set_cross_imag(0)
+
+
 # --------------------------------------------------------------------------------------------------
 # Siblings sharing the FFT and the mode loop (SURVEY 8f #3), restated with vectorised numpy.  TEST INFRASTRUCTURE.
 # Arithmetic notes follow the reference's C types: MAS_factor is a C float (double product rounded once), a

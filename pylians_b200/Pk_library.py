@@ -309,6 +309,7 @@ class XPk(object):
 
     Attributes: k3D, Nmodes3D, Pk[k, ell, field], XPk[k, ell, pair]; k1D, Nmodes1D, Pk1D, PkX1D;
     kpar, kper, Nmodes2D, Pk2D, PkX2D.  Pairs are ordered (0,1),(0,2),...,(1,2),..."""
+    _ALGO_FLAGS = 0
 
     def __init__(self, delta, BoxSize, axis=2, MAS=None, threads=1):
         start = time.time()
@@ -326,15 +327,24 @@ class XPk(object):
         lib = _lib.load()
         dev = _device()
         stream = torch.cuda.current_stream(dev)
-        swap = int(axis) if (int(axis) in (0, 1) and fields <= 3 and (ALGO & 3) != _lib.BIN_GENERIC and SWAP_AXES) else 2
+        swap = int(axis) if (int(axis) in (0, 1) and fields <= 3 and (ALGO & 3) != _lib.BIN_GENERIC and SWAP_AXES
+                             and not self._ALGO_FLAGS) else 2
         delta_k = [_fft_field(lib, d, dims, dev, stream, swap) for d in delta]
         _say("Time FFTS = %.2f" % (time.time() - start))
         start2 = time.time()
-        L, sums, counts = bin_modes(delta_k, dims, 2 if swap != 2 else int(axis), mas_index[:fields], False, False)
+        L, sums, counts = bin_modes(delta_k, dims, 2 if swap != 2 else int(axis), mas_index[:fields], False, False,
+                                    algo=ALGO | self._ALGO_FLAGS)
         bins = _Bins(L, sums, counts)
         _say("Time loop = %.2f" % (time.time() - start2))
         _finish(self, bins, dims, BoxSize, True)
         _say("Time taken = %.2f seconds" % (time.time() - start))
+
+
+class XPk_imag(XPk):
+    """Real auto- and IMAGINARY cross-power spectra.  Pk_library.pyx:959-1225: class XPk with the cross term
+    im_i*re_j - re_i*im_j (:1131-1132).  The imaginary part changes sign under k -> -k, so the line of sight is not
+    moved onto z by an axis swap here (that keeps the other member of each conjugate pair)."""
+    _ALGO_FLAGS = _lib.BIN_XIMAG
 
 
 def FFT3Dr_f(a, threads=1):

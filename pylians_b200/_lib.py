@@ -76,7 +76,7 @@ SIGNATURES = {
 }
 
 MA_AUTO, MA_DIRECT, MA_TILED = 0, 1, 2
-BIN_AUTO, BIN_GENERIC, BIN_RING, BIN_PRECISE, BIN_BULK, BIN_RING1 = 0, 1, 2, 16, 32, 64
+BIN_AUTO, BIN_GENERIC, BIN_RING, BIN_PRECISE, BIN_BULK, BIN_RING1, BIN_XIMAG = 0, 1, 2, 16, 32, 64, 256
 
 _lib = None
 

@@ -47,6 +47,7 @@ struct BinGeom {
     uint64_t *counts;
     const double *mas_tab;  // [F][middle+1]: (x/sin x)^p at |k| = 0..middle
     int mas_idx[MAX_F];
+    int ximag;              // class XPk_imag: cross term im_i*re_j - re_i*im_j (:1131-1132) instead of re_i*re_j + im_i*im_j
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -503,7 +504,10 @@ ring_kernel(BinGeom g, FieldPtrs dk, const RowEnt *__restrict__ tab, int nrows, 
             for (int a = 0; a < F; a++)
 #pragma unroll
                 for (int b = a + 1; b < F; b++) {  // :721-722
-                    if (PRECISE) v.q[F + ix] = (acc_t)((double)re[a] * (double)re[b] + (double)im[a] * (double)im[b]);
+                    if (g.ximag) {
+                        if (PRECISE) v.q[F + ix] = (acc_t)((double)im[a] * (double)re[b] - (double)re[a] * (double)im[b]);
+                        else v.q[F + ix] = (acc_t)fmaf(im[a], re[b], -(re[a] * im[b]));
+                    } else if (PRECISE) v.q[F + ix] = (acc_t)((double)re[a] * (double)re[b] + (double)im[a] * (double)im[b]);
                     else v.q[F + ix] = (acc_t)fmaf(re[a], re[b], im[a] * im[b]);
                     ix++;
                 }
@@ -1162,7 +1166,7 @@ special_kernel(BinGeom g, FieldPtrs dk, const ROW *__restrict__ tab, int nrows, 
 #pragma unroll
             for (int a = 0; a < F; a++)
 #pragma unroll
-                for (int b = a + 1; b < F; b++) { v[F + ix] = re[a] * re[b] + im[a] * im[b]; ix++; }
+                for (int b = a + 1; b < F; b++) { v[F + ix] = g.ximag ? im[a] * re[b] - re[a] * im[b] : re[a] * re[b] + im[a] * im[b]; ix++; }
         }
         if (want_phase) ph += (double)phase_sq((float)re[0], (float)v[0]);   // atan2(re, |delta_k|)^2, :361 (1e-7 polynomial)
 #pragma unroll
@@ -1323,7 +1327,8 @@ generic_kernel(BinGeom g, FieldPtrs dk, long long nmodes, int kz_start, int kz_s
     int xi = 0;
     for (int a = 0; a < F; a++)
         for (int b = a + 1; b < F; b++) {
-            const double dx = (double)re[a] * (double)re[b] + (double)im[a] * (double)im[b];
+            const double dx = g.ximag ? (double)im[a] * (double)re[b] - (double)re[a] * (double)im[b]
+                                      : (double)re[a] * (double)re[b] + (double)im[a] * (double)im[b];
             if (in1d) red_add(g.sums + g.o_x1d + (long long)k_par * X + xi, dx);
             red_add(g.sums + g.o_x2d + i2 * X + xi, dx);
             red_add(g.sums + g.o_x3d + ((long long)k_index * 3 + 0) * X + xi, dx);
@@ -1600,10 +1605,11 @@ extern "C" int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int ax
     mas_table_kernel<<<(ntab + 127) / 128, 128, 0, st>>>(tab, L.middle, ks->dims, F, g);
     PYLB_LAUNCH_CHECK();
 
+    g.ximag = (algo & PYLB_BIN_XIMAG) ? 1 : 0;
     const int precise = (algo & PYLB_BIN_PRECISE) ? 1 : 0;
     g_allow_bulk = (algo & PYLB_BIN_BULK) != 0;
     g_allow_ring2 = (algo & PYLB_BIN_RING1) == 0;
-    algo &= ~(PYLB_BIN_PRECISE | PYLB_BIN_BULK | PYLB_BIN_RING1);
+    algo &= ~(PYLB_BIN_PRECISE | PYLB_BIN_BULK | PYLB_BIN_RING1 | PYLB_BIN_XIMAG);
     if (algo == PYLB_BIN_AUTO) algo = (axis == 2 && F <= 3) ? PYLB_BIN_RING : PYLB_BIN_GENERIC;
     int rc;
     if (algo == PYLB_BIN_RING) {

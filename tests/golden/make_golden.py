@@ -172,6 +172,14 @@ def gold_siblings():
             xi = quiet(PKL.Xi, d, box, "CIC", axis, 1)
             for n in ("r3D", "xi", "Nmodes3D"):
                 out["xi_%d_a%d_%s" % (grid, axis, n)] = np.asarray(getattr(xi, n))
+    # XPk_imag: three fields, line of sight along z and along x
+    fs = fields(16, box, [(41, "CIC", False), (42, "TSC", True), (43, "PCS", False)])
+    for i, f in enumerate(fs):
+        out["ximag_delta%d" % i] = f
+    for axis in (2, 0):
+        x = quiet(PKL.XPk_imag, fs, box, axis, ["CIC", "TSC", "PCS"], 1)
+        for n, v in pk_attrs(x, XPK_NAMES).items():
+            out["ximag_a%d_%s" % (axis, n)] = v
     out["box"] = box
     np.savez_compressed(os.path.join(HERE, "siblings.npz"), **out)
 

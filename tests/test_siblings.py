@@ -113,3 +113,24 @@ def test_xi_is_the_transform_of_pk():
     want = np.mean((A * A / 2) * np.cos(2 * np.pi * m * rx[sel] / grid))
     assert abs(xi.xi[0, 0] / grid ** 3 - want) < 1e-6
     assert xi.Nmodes3D[0] == sel.sum()
+
+
+def _check_ximag(impl, gs, rtol=parity.PK_RTOL):
+    box = float(gs["box"])
+    fs = [gs["ximag_delta%d" % i] for i in range(3)]
+    for axis in (2, 0):
+        ref = {n: gs["ximag_a%d_%s" % (axis, n)] for n in
+               ("k3D", "Pk", "XPk", "Nmodes3D", "k1D", "Pk1D", "PkX1D", "Nmodes1D", "kpar", "kper", "Pk2D", "PkX2D", "Nmodes2D")}
+        parity.check_xpk(impl.XPk_imag(fs, box, axis, ["CIC", "TSC", "PCS"], 1), ref, rtol)
+
+
+def test_oracle_ximag_matches_reference_golden(gs):
+    _check_ximag(O, gs)
+
+
+@pytest.mark.gpu
+def test_gpu_ximag_matches_reference_golden(gs):
+    import pylians_b200
+    import Pk_library as PKL
+    pylians_b200.set_verbose(False)
+    _check_ximag(PKL, gs)
