@@ -225,12 +225,13 @@ bin_scatter_kernel(const float *__restrict__ pos, const float *__restrict__ W, i
 // atom.global (<= 256 per 4096 particles), and copies the staged chunk out so that consecutive threads write
 // consecutive addresses inside each run.  ~40 B (pass 0) + 32 B (pass 1) of streaming traffic per particle.
 // ------------------------------------------------------------------------------------------------
-constexpr int PART_THREADS = 512;
 constexpr int PART_PER_THREAD = 8;
-constexpr int PART_CHUNK = PART_THREADS * PART_PER_THREAD;   // 4096 particles, 64 KB of float4 staging
+constexpr int PART_CHUNK_MAX = 512 * PART_PER_THREAD;        // 4096 particles, 64 KB of float4 staging (512 threads)
 constexpr int PART_MAXBINS = 256;
 
+template <int PART_THREADS>
 struct PartSmem {
+    static constexpr int PART_CHUNK = PART_THREADS * PART_PER_THREAD;
     float4 stage[PART_CHUNK];
     unsigned char dig[PART_CHUNK];
     int cnt[PART_MAXBINS], start[PART_MAXBINS], gbase[PART_MAXBINS];
@@ -239,7 +240,7 @@ struct PartSmem {
 
 // chunk list of pass 1: bucket b (tiles [b << lo_bits, (b+1) << lo_bits)) owns ceil(size_b / PART_CHUNK) chunks
 __global__ void part_buckets_kernel(const int *__restrict__ tile_begin, int ntiles, int lo_bits, int nb0, int *bcursor,
-                                    int *bchunk_off) {
+                                    int *bchunk_off, int PART_CHUNK) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         int acc = 0;
         for (int b = 0; b < nb0; b++) {
@@ -252,14 +253,15 @@ __global__ void part_buckets_kernel(const int *__restrict__ tile_begin, int ntil
     }
 }
 
-template <int MAS, class TC, bool HASW, bool FIRST>
-__global__ void __launch_bounds__(PART_THREADS, 2)
+template <int MAS, class TC, bool HASW, bool FIRST, int PART_THREADS>
+__global__ void __launch_bounds__(PART_THREADS, 1024 / PART_THREADS)
 bin_pass_kernel(const float *__restrict__ pos, const float *__restrict__ W, int64_t wst, int64_t first, int n, int64_t ps0,
                 int64_t ps1, float inv, TileGeom tg, const float4 *__restrict__ in, float4 *__restrict__ out,
                 int *__restrict__ cursor, const int *__restrict__ tile_begin, const int *__restrict__ bchunk_off,
                 int lo_bits, int nb0) {
     extern __shared__ __align__(16) unsigned char part_raw[];
-    PartSmem &sm = *reinterpret_cast<PartSmem *>(part_raw);
+    constexpr int PART_CHUNK = PART_THREADS * PART_PER_THREAD;
+    PartSmem<PART_THREADS> &sm = *reinterpret_cast<PartSmem<PART_THREADS> *>(part_raw);
     const int tid = threadIdx.x;
     const int nbins = FIRST ? nb0 : (1 << lo_bits);
     if (tid == 0) {
@@ -280,7 +282,7 @@ bin_pass_kernel(const float *__restrict__ pos, const float *__restrict__ W, int6
             }
         }
     }
-    if (tid < PART_MAXBINS) sm.cnt[tid] = 0;
+    for (int b = tid; b < PART_MAXBINS; b += PART_THREADS) sm.cnt[b] = 0;
     __syncthreads();
     const int lo = sm.lo, hi = sm.hi;
     if (lo >= hi) return;                       // CTA-uniform
@@ -349,8 +351,7 @@ bin_pass_kernel(const float *__restrict__ pos, const float *__restrict__ W, int6
 #pragma unroll
         for (int q = 0; q < 8; q++) sm.start[tid * 8 + q] = excl + loc[q];
     }
-    if (tid >= 32 && tid < 32 + PART_MAXBINS) {
-        const int b = tid - 32;
+    for (int b = PART_THREADS - 1 - tid; b < PART_MAXBINS; b += PART_THREADS) {   // last warps first: warp 0 is scanning
         const int c = (b < nbins) ? sm.cnt[b] : 0;
         if (c) sm.gbase[b] = atomicAdd(&cursor[cbase + b], c);
     }
@@ -705,6 +706,32 @@ static int set_smem(K kernel, size_t bytes) {
     return 0;
 }
 
+static int part_threads() {
+    static int t = 0;
+    // 256-thread CTAs (2048-particle chunks, 4 CTAs/SM) overlap the load / rank / write-out phases of neighbouring CTAs
+    // better than 512-thread CTAs (4096, 2 CTAs/SM): 3.73 ms against 3.99 ms for the whole 512^3 CIC deposit
+    if (t == 0) { const char *e = getenv("PYLB_PART_THREADS"); const int v = e ? atoi(e) : 256; t = (v == 512 || v == 128) ? v : 256; }
+    return t;
+}
+
+template <int MAS, class TC, bool HASW, int PT>
+static int run_passes(const float *pos, const float *w, int64_t wst, int64_t first, int n, int64_t ps0, int64_t ps1, float inv,
+                      const TileGeom &tg, TiledWs &ws, int lo_bits, int nb0, cudaStream_t st) {
+    constexpr int CH = PT * PART_PER_THREAD;
+    part_buckets_kernel<<<1, 32, 0, st>>>(ws.tile_begin, tg.ntiles, lo_bits, nb0, ws.bcursor, ws.bchunk_off, CH);
+    PYLB_LAUNCH_CHECK();
+    const size_t psm = sizeof(PartSmem<PT>);
+    if (set_smem(bin_pass_kernel<MAS, TC, HASW, true, PT>, psm) || set_smem(bin_pass_kernel<MAS, TC, HASW, false, PT>, psm)) return 1;
+    const unsigned g0 = (unsigned)((n + CH - 1) / CH);
+    bin_pass_kernel<MAS, TC, HASW, true, PT><<<g0, PT, psm, st>>>(
+        pos, w, wst, first, n, ps0, ps1, inv, tg, nullptr, ws.sorted_tmp, ws.bcursor, ws.tile_begin, ws.bchunk_off, lo_bits, nb0);
+    PYLB_LAUNCH_CHECK();
+    bin_pass_kernel<MAS, TC, HASW, false, PT><<<g0 + (unsigned)nb0, PT, psm, st>>>(
+        pos, w, wst, first, n, ps0, ps1, inv, tg, ws.sorted_tmp, ws.sorted, ws.S, ws.tile_begin, ws.bchunk_off, lo_bits, nb0);
+    PYLB_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int MAS, bool HASW, class TC, bool BINSORT, bool FIXED>
 static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv,
                      const float *w, int64_t wst, int x0, int xext, TiledWs &ws, cudaStream_t st) {
@@ -736,17 +763,13 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
                 int lo_bits = (bits_for((unsigned)(tg.ntiles - 1)) + 1) / 2;
                 if (lo_bits > 8) lo_bits = 8;
                 const int nb0 = (tg.ntiles + (1 << lo_bits) - 1) >> lo_bits;      // <= 256 because ntiles <= 65536
-                part_buckets_kernel<<<1, 32, 0, st>>>(ws.tile_begin, tg.ntiles, lo_bits, nb0, ws.bcursor, ws.bchunk_off);
-                PYLB_LAUNCH_CHECK();
-                const size_t psm = sizeof(PartSmem);
-                if (set_smem(bin_pass_kernel<MAS, TC, HASW, true>, psm) || set_smem(bin_pass_kernel<MAS, TC, HASW, false>, psm)) return 1;
-                const unsigned g0 = (unsigned)((n + PART_CHUNK - 1) / PART_CHUNK);
-                bin_pass_kernel<MAS, TC, HASW, true><<<g0, PART_THREADS, psm, st>>>(
-                    pos, w, wst, first, n, ps0, ps1, inv, tg, nullptr, ws.sorted_tmp, ws.bcursor, ws.tile_begin, ws.bchunk_off, lo_bits, nb0);
-                PYLB_LAUNCH_CHECK();
-                bin_pass_kernel<MAS, TC, HASW, false><<<g0 + (unsigned)nb0, PART_THREADS, psm, st>>>(
-                    pos, w, wst, first, n, ps0, ps1, inv, tg, ws.sorted_tmp, ws.sorted, ws.S, ws.tile_begin, ws.bchunk_off, lo_bits, nb0);
-                PYLB_LAUNCH_CHECK();
+                if (part_threads() == 256) {
+                    if (run_passes<MAS, TC, HASW, 256>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, lo_bits, nb0, st)) return 1;
+                } else if (part_threads() == 128) {
+                    if (run_passes<MAS, TC, HASW, 128>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, lo_bits, nb0, st)) return 1;
+                } else {
+                    if (run_passes<MAS, TC, HASW, 512>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, lo_bits, nb0, st)) return 1;
+                }
             } else {
                 bin_scatter_kernel<MAS, TC, HASW><<<P, BIN_THREADS, hist_smem, st>>>(pos, w, wst, first, n, ps0, ps1, inv, tg,
                                                                                       ws.S, ws.sorted);
