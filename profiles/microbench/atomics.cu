@@ -14,6 +14,16 @@ __global__ void kA(unsigned* c, unsigned M, long n){ long i=(long)blockIdx.x*blo
   for(;i<n;i+=s) atomicAdd(&c[hash((unsigned)i)%M],1u); }
 __global__ void kB(unsigned* c, unsigned M, long n, unsigned* out){ long i=(long)blockIdx.x*blockDim.x+threadIdx.x, s=(long)gridDim.x*blockDim.x; unsigned acc=0;
   for(;i<n;i+=s) acc+=atomicAdd(&c[hash((unsigned)i)%M],1u); if(acc==0x12345678u) out[0]=acc; }
+// F: same update stream, but the 32 lanes of a warp always fall into 32 distinct banks (row = random, column = lane):
+// what a deposit would see if every warp's particles were regrouped by bank first
+template<typename T> __global__ void kF(T* out, int cells, int iters){
+  extern __shared__ unsigned char raw[]; T* s=(T*)raw;
+  for(int i=threadIdx.x;i<cells;i+=blockDim.x) s[i]=0; __syncthreads();
+  unsigned h=hash(blockIdx.x*blockDim.x+threadIdx.x+1); const int rows=cells/32-8, lane=threadIdx.x&31;
+  for(int it=0;it<iters;it++){ h=hash(h+it); int base=(h%rows)*32+lane;
+    #pragma unroll
+    for(int q=0;q<8;q++) atomicAdd(&s[base+((q*37)%8)*32], (T)1); }
+  __syncthreads(); T acc=0; for(int i=threadIdx.x;i<cells;i+=blockDim.x) acc+=s[i]; if(acc==(T)-1) out[0]=acc; }
 template<typename T> __global__ void kC(T* out, int cells, int iters){
   extern __shared__ unsigned char raw[]; T* s=(T*)raw;
   for(int i=threadIdx.x;i<cells;i+=blockDim.x) s[i]=0; __syncthreads();
@@ -49,6 +59,14 @@ int main(){
       int blocks=sms*cps; double ops=(double)blocks*256*iters*8;
       float f=timeit([&]{kC<float><<<blocks,256,sm>>>((float*)fo,cells,iters);}); float i=timeit([&]{kC<int><<<blocks,256,sm>>>((int*)out,cells,iters);});
       printf("C smem atomics cells=%5d CTAs/SM=%d: float(CAS) %7.3f ms %7.1f Gops/s (%.2f ops/clk/SM @1.9GHz) | int(native) %7.3f ms %7.1f Gops/s\n",cells,cps,f,ops/f/1e6,ops/f/1e6/148/1.9,i,ops/i/1e6);
+    }
+  }
+  { int cells=12635, iters=2048; size_t sm=cells*4;
+    CK(cudaFuncSetAttribute(kF<float>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)sm)); CK(cudaFuncSetAttribute(kF<int>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int)sm));
+    for(int cps: {2,4}){
+      int blocks=sms*cps; double ops=(double)blocks*256*iters*8;
+      float f=timeit([&]{kF<float><<<blocks,256,sm>>>((float*)fo,cells,iters);}); float i=timeit([&]{kF<int><<<blocks,256,sm>>>((int*)out,cells,iters);});
+      printf("F smem atomics, lanes in distinct banks, cells=%5d CTAs/SM=%d: float(CAS) %7.3f ms %7.1f Gops/s (%.2f ops/clk/SM @1.9GHz) | int(native) %7.3f ms %7.1f Gops/s\n",cells,cps,f,ops/f/1e6,ops/f/1e6/148/1.9,i,ops/i/1e6);
     }
   }
   float d=timeit([&]{kD<<<sms*16,256>>>(p,idx,n,fo);}); float e=timeit([&]{kE<<<sms*16,256>>>(p,n,fo);});

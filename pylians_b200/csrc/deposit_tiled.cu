@@ -37,6 +37,7 @@ typedef TileCfg<16, 16, 32, 256> TileS;    // 38-51 KB of shared memory per CTA,
 typedef TileCfg<32, 32, 32, 1024> TileL;   // 144-176 KB, 1 CTA/SM of 32 warps, 4x fewer tiles
 
 constexpr int CHUNK = 8192;              // particles per work item
+constexpr int REGROUP_BATCH = 1024;      // tile kernel: particles regrouped by shared-memory bank at a time
 constexpr int64_t BATCH = 1ll << 28;     // particles binned per pass (bounds the workspace)
 constexpr int BIN_THREADS = 1024;        // binsort CTAs: one per SM, 32 warps
 constexpr int BIN_MAX_TILES = 53248;     // per-CTA histogram must fit shared memory (208 KB of 227 KB); keys are 16-bit
@@ -429,7 +430,7 @@ __device__ __forceinline__ void red_add_v4(float *p, float4 v) {
 //   partial sum to 6e-8 relative), the sum itself is exact and order independent -- the tile result is
 //   deterministic.  Why: atomicAdd(float) on shared memory is an ATOMS.CAST.SPIN loop on sm_100a (2.9
 //   updates/clk/SM measured against 9.2 for native integer atomics).
-template <int MAS, bool HASW, class TC, bool SORTED, bool FIXED>
+template <int MAS, bool HASW, class TC, bool SORTED, bool FIXED, bool REGROUP>
 __global__ void __launch_bounds__(TC::THREADS)
 deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, int64_t ps1,
                     const float *__restrict__ W, int64_t wst, float inv, TileGeom tg, const unsigned *__restrict__ svals,
@@ -472,23 +473,21 @@ deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, i
     const int tz = t % tg.ntz, ty = (t / tg.ntz) % tg.nty, tx = t / (tg.ntz * tg.nty);
     const int ox = tx * TC::TX, oy = ty * TC::TY, oz = tz * TC::TZ;
 
-    for (int i = s_lo + threadIdx.x; i < s_hi; i += TILE_THREADS) {
-        float x, y, z, w;
-        if (SORTED) {
-            const float4 q = __ldg(sorted + i);
-            x = q.x; y = q.y; z = q.z; w = q.w;
-        } else {
-            const int64_t pi = first + (int64_t)svals[i];
-            const float *p = pos + pi * ps0;
-            x = __ldg(p); y = __ldg(p + ps1); z = __ldg(p + 2 * ps1);
-            w = HASW ? __ldg(W + pi * wst) : 1.0f;
-        }
-        float C[3][S];
-        const int lx = wrap(axis_stencil<MAS>(x, inv, C[0]) - tg.x0, tg.dims) - ox;
-        if (lx < 0 || lx >= TC::TX) continue;   // not this tile's particle (only possible for a mis-routed particle)
-        const int ly = wrap(axis_stencil<MAS>(y, inv, C[1]), tg.dims) - oy;
-        const int lz = wrap(axis_stencil<MAS>(z, inv, C[2]), tg.dims) - oz;
-        const int cell0 = (lx * TS::SY + ly) * TS::SZ + lz;
+    auto load = [&](int i) -> float4 {
+        if (SORTED) return __ldg(sorted + i);
+        const int64_t pi = first + (int64_t)svals[i];
+        const float *p = pos + pi * ps0;
+        return make_float4(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), HASW ? __ldg(W + pi * wst) : 1.0f);
+    };
+    // tile-local cell of the particle's lowest touched grid point, or -1 (mis-routed particle: its updates are dropped)
+    auto base_cell = [&](const float4 q, float (&C)[3][S]) -> int {
+        const int lx = wrap(axis_stencil<MAS>(q.x, inv, C[0]) - tg.x0, tg.dims) - ox;
+        if (lx < 0 || lx >= TC::TX) return -1;
+        const int ly = wrap(axis_stencil<MAS>(q.y, inv, C[1]), tg.dims) - oy;
+        const int lz = wrap(axis_stencil<MAS>(q.z, inv, C[2]), tg.dims) - oz;
+        return (lx * TS::SY + ly) * TS::SZ + lz;
+    };
+    auto put = [&](const int cell0, const float (&C)[3][S], const float w) {
         float *base = tile + cell0;
 #pragma unroll
         for (int l = 0; l < S; l++)
@@ -509,6 +508,79 @@ deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, i
                     }
                 }
             }
+    };
+    if (!REGROUP) {
+        for (int i = s_lo + threadIdx.x; i < s_hi; i += TILE_THREADS) {
+            const float4 q = load(i);
+            float C[3][S];
+            const int cell0 = base_cell(q, C);
+            if (cell0 >= 0) put(cell0, C, q.w);
+        }
+    } else {
+        // Regroup by shared-memory bank.  The tile's particles arrive in no particular order, so the 32 cells a warp
+        // updates at once fall into random banks: ~13 shared-memory wavefronts per warp update (LDS + CAS, each
+        // serialised ~3.4x), and that data pipe is what bounds this kernel (95 % busy).  Here a batch of REGROUP_BATCH
+        // particles is first bucketed by the bank of its base cell (one native shared atomic per particle, a 32-entry
+        // scan, one 16-byte shared store); warp r then takes the r-th particle of every bank, lane = bank.  All
+        // lanes of an update hit distinct banks -- every stencil offset shifts all of them alike -- and never the
+        // same address: 2.7x the update rate in profiles/microbench/atomics.cu (830 -> 2200 G updates/s).
+        constexpr int BATCH_P = REGROUP_BATCH;             // 1024 particles: 16 KB of staging
+        constexpr int RG = BATCH_P / TILE_THREADS;
+        float4 *pstage = reinterpret_cast<float4 *>(tile + (FIXED ? TS::CELLS + TS::HI_WORDS : TS::CELLS));
+        __shared__ int bcnt[32], boff[32], s_rows;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int b0 = s_lo; b0 < s_hi; b0 += BATCH_P) {
+            if (threadIdx.x < 32) bcnt[threadIdx.x] = 0;
+            __syncthreads();
+            float4 q[RG];
+            int bank[RG], rk[RG];
+#pragma unroll
+            for (int k = 0; k < RG; k++) {
+                const int i = b0 + k * TILE_THREADS + threadIdx.x;
+                bank[k] = -1;
+                if (i < s_hi) q[k] = load(i);
+            }
+#pragma unroll
+            for (int k = 0; k < RG; k++) {
+                const int i = b0 + k * TILE_THREADS + threadIdx.x;
+                if (i < s_hi) {
+                    float C[3][S];
+                    const int cell0 = base_cell(q[k], C);
+                    if (cell0 >= 0) {
+                        bank[k] = cell0 & 31;
+                        rk[k] = atomicAdd(&bcnt[bank[k]], 1);
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {            // exclusive scan of the 32 counts, and the longest list
+                const int c = bcnt[lane];
+                int incl = c, mx = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                }
+                boff[lane] = incl - c;
+                if (lane == 0) s_rows = mx;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < RG; k++)
+                if (bank[k] >= 0) pstage[boff[bank[k]] + rk[k]] = q[k];
+            __syncthreads();
+            const int mycnt = bcnt[lane], myoff = boff[lane], rows = s_rows;
+            for (int r = warp; r < rows; r += TILE_THREADS / 32) {
+                if (r < mycnt) {
+                    const float4 p = pstage[myoff + r];
+                    float C[3][S];
+                    const int cell0 = base_cell(p, C);
+                    put(cell0, C, p.w);
+                }
+            }
+            __syncthreads();                   // the next batch reuses bcnt / pstage
+        }
     }
     __syncthreads();
     // fixed point -> float in place (cell i: carry << 32 | lo, unit 2^-31), then the common flush
@@ -732,15 +804,28 @@ static int run_passes(const float *pos, const float *w, int64_t wst, int64_t fir
     return 0;
 }
 
+static bool use_regroup() {
+    static int env = -2;
+    // Opt-in (PYLB_MA_REGROUP=1).  Measured at 512^3: CIC 2.31 ms against 1.59 ms in arrival order, PCS 1.50 against
+    // 1.54 ms at 256^3 -- the update rate does go up 2.7x, but three barriers, the 32-counter ranking and the exposed
+    // particle load per 1024-particle batch cost more than the conflicts they remove (profiles/r1_ma_regroup_ab.txt).
+    if (env == -2) { const char *e = getenv("PYLB_MA_REGROUP"); env = e ? atoi(e) : 0; }
+    return env != 0;
+}
+
 template <int MAS, bool HASW, class TC, bool BINSORT, bool FIXED>
 static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv,
                      const float *w, int64_t wst, int x0, int xext, TiledWs &ws, cudaStream_t st) {
     using TS = TileShape<MAS, TC>;
     const TileGeom tg = tile_geom<TC>(dims, x0, xext);
-    const size_t tile_smem = sizeof(float) * (FIXED ? TS::CELLS + TS::HI_WORDS : TS::CELLS);
+    // NGP has one update per particle: nothing to gain from regrouping
+    const bool regroup = MAS != PYLB_NGP && use_regroup();
+    const size_t acc_smem = sizeof(float) * (FIXED ? TS::CELLS + TS::HI_WORDS : TS::CELLS);
+    const size_t tile_smem = acc_smem + (regroup ? sizeof(float4) * REGROUP_BATCH : 0);
     const size_t hist_smem = sizeof(int) * (size_t)tg.ntiles;
     const int P = sm_count();
-    if (set_smem(deposit_tile_kernel<MAS, HASW, TC, BINSORT, FIXED>, tile_smem)) return 1;
+    if (set_smem(deposit_tile_kernel<MAS, HASW, TC, BINSORT, FIXED, true>, acc_smem + sizeof(float4) * REGROUP_BATCH) ||
+        set_smem(deposit_tile_kernel<MAS, HASW, TC, BINSORT, FIXED, false>, acc_smem)) return 1;
     if (BINSORT) {
         // always the maximum these kernels may ever need: the attribute is a limit, and a smaller value set
         // here would make a later, larger launch of the same instantiation fail
@@ -792,8 +877,12 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
         // upper bound on work items: every non-empty tile has at most count/CHUNK + 1 chunks
         const int64_t max_items = (int64_t)n / CHUNK + tg.ntiles;
         timing_begin(PYLB_T_TILE, st);
-        deposit_tile_kernel<MAS, HASW, TC, BINSORT, FIXED><<<(unsigned)max_items, TC::THREADS, tile_smem, st>>>(
-            pos, first, ps0, ps1, w, wst, inv, tg, ws.v1, ws.sorted, ws.tile_begin, ws.chunk_off, grid);
+        if (regroup)
+            deposit_tile_kernel<MAS, HASW, TC, BINSORT, FIXED, true><<<(unsigned)max_items, TC::THREADS, tile_smem, st>>>(
+                pos, first, ps0, ps1, w, wst, inv, tg, ws.v1, ws.sorted, ws.tile_begin, ws.chunk_off, grid);
+        else
+            deposit_tile_kernel<MAS, HASW, TC, BINSORT, FIXED, false><<<(unsigned)max_items, TC::THREADS, tile_smem, st>>>(
+                pos, first, ps0, ps1, w, wst, inv, tg, ws.v1, ws.sorted, ws.tile_begin, ws.chunk_off, grid);
         timing_end(PYLB_T_TILE, st);
         PYLB_LAUNCH_CHECK();
     }
