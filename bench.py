@@ -325,8 +325,17 @@ def run_ours(args, wl):
         rows_local = gside * gside // world
         alg_bytes = 8.0 * rows_local * kz_hi                        # 8 B per complex mode, read once
         achieved = alg_bytes / (ring_ms / ring_n * 1e-3) / 1e9
-        roof = {"kernel": "ring2_kernel<phase>" if gside % 2 == 0 else "ring_kernel<1,phase>", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+        kname = "ring2_kernel<phase>" if gside % 2 == 0 else "ring_kernel<1,phase>"
+        traffic = None                       # DRAM bytes per launch from the committed ncu --set full capture, if one matches
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_traffic.json")) as f:
+                t = json.load(f).get(kname, {}).get(str(gside)) if world == 1 else None
+            if t:
+                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+        except (OSError, ValueError, KeyError):
+            pass
+        roof = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
                 "peak_source": peak_src, "avg_launch_ms": ring_ms / ring_n, "launches": ring_n,
                 "algorithmic_bytes_per_launch": alg_bytes}
 

@@ -194,15 +194,18 @@ _KGRID = {}
 
 
 def _kpar_kper(kmax_par, kmax_per, kF):
-    """Bin centres of the 2-D table (Pk_library.pyx:397-403): pure geometry, cached per shape."""
+    """Bin centres of the 2-D table (Pk_library.pyx:397-403): pure geometry, cached per shape and handed out as
+    read-only arrays (two 0.7 MB copies per call otherwise; a caller that wants to modify them copies)."""
     key = (kmax_par, kmax_per, kF)
     v = _KGRID.get(key)
     if v is None:
         i2 = np.arange((kmax_par + 1) * (kmax_per + 1))
         v = (0.5 * (2 * (i2 % (kmax_par + 1)) + 1) * kF, 0.5 * (2 * (i2 // (kmax_par + 1)) + 1) * kF)
+        for a in v:
+            a.flags.writeable = False
         _KGRID.clear()
         _KGRID[key] = v
-    return v[0].copy(), v[1].copy()
+    return v[0], v[1]
 
 
 class _Bins(object):

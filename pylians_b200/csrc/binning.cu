@@ -1419,7 +1419,7 @@ struct Ring2Key {
     int bp, mas;
 };
 struct Ring2Cache {
-    Ring2Key key;
+    Ring2Key key = {};
     Row2 *tab = nullptr;
     cudaEvent_t ready = nullptr;
 };
@@ -1442,7 +1442,10 @@ static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cuda
     int dev = 0;
     PYLB_CHECK(cudaGetDevice(&dev));
     Ring2Cache &c = g_ring2_cache[dev & 15];
-    const Ring2Key key = {g.dims, g.x0, g.nx, g.y0, g.ny, g.stride_x, g.stride_y, bp, g.mas_idx[0]};
+    Ring2Key key;
+    memset(&key, 0, sizeof(key));               // the struct has padding and is compared with memcmp
+    key.dims = g.dims; key.x0 = g.x0; key.nx = g.nx; key.y0 = g.y0; key.ny = g.ny;
+    key.stride_x = g.stride_x; key.stride_y = g.stride_y; key.bp = bp; key.mas = g.mas_idx[0];
     if (!c.tab || memcmp(&c.key, &key, sizeof(key)) != 0) {
         if (c.tab) { cudaFree(c.tab); c.tab = nullptr; }          // synchronises: nobody is reading it any more
         if (!c.ready) PYLB_CHECK(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
@@ -1573,6 +1576,7 @@ extern "C" int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int ax
     PYLB_REQUIRE(ks->nx >= 0 && ks->ny >= 0 && ks->x0 >= 0 && ks->y0 >= 0 && ks->x0 + ks->nx <= ks->dims &&
                  ks->y0 + ks->ny <= ks->dims, "pylb_pk_bin: k-space window out of range");
     PYLB_REQUIRE((long long)ks->nx * ks->ny < (1ll << 31), "pylb_pk_bin: too many rows");
+    keep_pool_memory();
     cudaStream_t st = (cudaStream_t)stream;
     pylb_pk_layout L;
     if (pylb_pk_get_layout(ks->dims, F, &L)) return 1;

@@ -42,6 +42,21 @@ void timing_end(int which, cudaStream_t st);
         }                                                                                         \
     } while (0)
 
+// The library's scratch comes from the stream-ordered allocator.  Its default pool hands unused memory back to
+// the driver at every synchronisation (release threshold 0), and Pk() synchronises once per call to read the bins:
+// without this the next call's cudaMallocAsync goes back to the driver (sporadic 30-700 ms stalls were measured).
+inline void keep_pool_memory() {
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[dev] = true;
+}
+
 inline int sm_count() {
     static int n = 0;
     if (n == 0) {

@@ -647,6 +647,7 @@ enum { PATH_BIN_S = 0, PATH_BIN_L = 1, PATH_RADIX_S = 2 };
 template <int MAS, bool HASW>
 static int partition_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, const float *w, int64_t wst, int dims,
                          float inv, int G, float4 *out, int *offsets, cudaStream_t st) {
+    keep_pool_memory();
     TileGeom tg = tile_geom<TileS>(dims);
     tg.slab_w = dims / G;
     tg.ntiles = G;

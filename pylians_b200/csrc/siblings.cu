@@ -214,6 +214,7 @@ static SibGeom sib_geom(int dims, int ndim) {
 }
 
 static int make_tab(double **tab, int dims, int mas_index, cudaStream_t st) {
+    keep_pool_memory();
     const int middle = dims / 2;
     PYLB_REQUIRE(mas_index >= 0 && mas_index <= 4, "MAS index %d out of range", mas_index);
     PYLB_CHECK(cudaMallocAsync(tab, sizeof(double) * (size_t)(middle + 1), st));
