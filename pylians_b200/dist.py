@@ -153,6 +153,7 @@ class SlabPk(object):
                          deposited onto slab + S-1 halo planes, halo planes are passed to the next rank;
              "auto"      whichever moves fewer bytes for this call."""
         self.exchange = exchange
+        self._auto_mode = None
         self.rank, self.G = _group_info(group)
         self.group = group
         if dims % self.G != 0:
@@ -169,11 +170,21 @@ class SlabPk(object):
         halo = {"NGP": 0, "CIC": 1, "TSC": 2, "PCS": 3}[MAS]
         mode = self.exchange
         if mode == "auto":
-            # Measured on 8xB200 (profiles/r1_bench_scaling_8gpu*.jsonl): with Np ~ N^3 the reduce-scatter mode wins
-            # up to N = 1024 (27 vs 34 ms at N=1024, G=8: particle mode sorts twice and needs two host syncs for the
-            # split sizes); beyond that the full partial grid (34 GB at 2048^3: zero + flush + 4 N^3-byte
-            # reduce-scatter, and its deposit leaves the fast binsort path) loses to routing particles (219 vs 295 ms).
-            mode = "particles" if (N > 1024 and G > 1 and self.nxl >= max(halo, 1)) else "grid"
+            # Whichever moves fewer bytes per rank: 4 N^3 (reduce-scatter of the partial grids, which also have to be
+            # zeroed and flushed in full) against 16 B per particle (all-to-all of the routed payload).  Measured on
+            # 8xB200, 512^3 particles per GPU (profiles/r1_dist_stages_8gpu.txt): N=1024, G=8: particles 14.4 ms vs grid
+            # 20.8 ms per snapshot; N=640, G=2: grid 9.7 vs particles 13.7 ms; 2048^3 PCS, G=8: particles 219 vs 295 ms.
+            # Every rank must take the same branch, so the particle count is agreed on once (max over ranks) and the
+            # choice is kept for the engine's lifetime.
+            if self._auto_mode is None:
+                npmax = int(pos.shape[0])
+                if G > 1:
+                    t = torch.tensor([npmax], dtype=torch.int64, device=getattr(ops, "dev", torch.device("cpu")))
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+                    npmax = int(t.item())
+                ok = G > 1 and self.nxl >= max(halo, 1)
+                self._auto_mode = "particles" if (ok and 4 * N ** 3 > 16 * npmax) else "grid"
+            mode = self._auto_mode
         if mode == "particles" and self.nxl < halo:
             raise ValueError("particle exchange needs at least %d planes per rank for %s" % (halo, MAS))
         slab = self._slab_from_particles(pos, W, MAS, halo) if mode == "particles" else self._slab_from_grids(pos, W, MAS)

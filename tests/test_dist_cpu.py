@@ -56,7 +56,7 @@ def _worker(rank, world, port, dims, axis, mas, xmode, exchange, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange", ["grid", "particles"])
+@pytest.mark.parametrize("exchange", ["grid", "particles", "auto"])
 @pytest.mark.parametrize("dims,axis,mas,xmode", [(16, 2, "CIC", False), (16, 0, "CIC", False), (16, 2, "CIC", True)])
 def test_slab_pipeline_world2_gloo(dims, axis, mas, xmode, exchange):
     ctx = mp.get_context("spawn")
