@@ -165,10 +165,12 @@ int pylb_fft_r2c_pitched(const float *in, int64_t in_pitch, void *out, int64_t o
  * Siblings of Pk/XPk that share the FFT and the mode loop (library/Pk_library/Pk_library.pyx)
  * ------------------------------------------------------------------------------------------- */
 
-/* IFFT3Dr_f :152-165 (unnormalised backward c2r; `in` is destroyed), FFT2Dr_f :184-197, IFFT2Dr_f :216-229 */
-int pylb_fft_c2r(void *in, float *out, int dims, void *stream);
+/* IFFT3Dr_f :152-165 (backward c2r; `in` is destroyed), FFT2Dr_f :184-197, IFFT2Dr_f :216-229.
+ * normalise != 0 scales the result by (float)(1/N) like pyfftw's FFTW.__call__ default (normalise_idft=True), which
+ * is what the reference's IFFT*Dr_f return; normalise == 0 is the raw FFTW/cuFFT backward transform. */
+int pylb_fft_c2r(void *in, float *out, int dims, int normalise, void *stream);
 int pylb_fft2d_r2c(const float *in, void *out, int dims, void *stream);
-int pylb_fft2d_c2r(void *in, float *out, int dims, void *stream);
+int pylb_fft2d_c2r(void *in, float *out, int dims, int normalise, void *stream);
 
 /* In-place pass over a (dims,dims,dims/2+1) complex64 field.  mode 0: the loop of correct_MAS :1770-1797
  * (independent modes times the MAS factor; the self-conjugate planes are left Hermitian-averaged, which is what
@@ -183,7 +185,7 @@ int pylb_theta_bin(const void *vx, const void *vy, const void *vz, int dims, int
  * sums: device double[5][kmax2d+1] = sum |k|, sum |d1|^2, sum |d2|^2, sum Re(d1 conj d2), Nmodes. */
 int pylb_plane_bin(const void *d1, const void *d2, int dims, int mas1, int mas2, double *sums, void *stream);
 
-/* Real-space loop of Xi :2097-2133 over the unnormalised inverse transform.
+/* Real-space loop of Xi :2097-2133 over the inverse transform.
  * sums: device double[5][kmax+1] = sum r, sum xi, sum xi*L2(mu), sum xi*L4(mu), Nmodes. */
 int pylb_xi_bin(const float *xi, int dims, int axis, double *sums, void *stream);
 
@@ -254,6 +256,31 @@ typedef struct {
 int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int axis, const int *mas_index,
                 int want_phase, int write_back, int algo, int accumulate, double *sums,
                 uint64_t *counts, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Callers and consumers either side of the path; csrc/consumers.cu
+ * ------------------------------------------------------------------------------------------- */
+/* x[i] *= mul in fp32: the `data *= math.sqrt(time)` of the snapshot reader (library/readsnap.py:376) */
+int pylb_scale_f32(float *x, int64_t n, float mul, void *stream);
+/* delta /= mean; delta -= 1.0 with the caller's mean, e.g. Np/dims^3 (Pk_library/Pk_snapshot.py:84-88, 191-194) */
+int pylb_overdensity_mean(float *grid, int64_t n, float mean, void *stream);
+/* dst[i] += a*src[i]: delta_tot += Omega*delta (Pk_snapshot.py:248-254) */
+int pylb_axpy_f32(float *dst, const float *src, float a, int64_t n, void *stream);
+
+/* smoothing_library.FT_filter (smoothing_library/smoothing_library.pyx:19-83) up to its FFT: fills the (dims^3)
+ * float32 grid with the Top-Hat (kind 0) or Gaussian (kind 1) filter of squared radius R2 (grid cells, float32),
+ * normalised to unit sum.  scratch: device double[1]. */
+int pylb_filter_real(float *field, int dims, float R2, int kind, double *scratch, void *stream);
+/* a[i] *= b[i], complex64: the mode loop of field_smoothing (:104-108) */
+int pylb_cmul_c64(void *a, const void *b, int64_t n, void *stream);
+
+/* bispectrum_library.Bk (Pk_library/bispectrum_library.pyx:88-130): out_d = MAS-deconvolved delta_k on the shell
+ * kmin <= |k| < kmax (units of kF) and 0 elsewhere; out_i = 1 on the shell, 0 elsewhere.  complex64
+ * (dims,dims,dims/2+1) buffers; dk is not modified. */
+int pylb_bk_shell(const void *dk, void *out_d, void *out_i, int dims, int mas_index, double kmin, double kmax,
+                  void *stream);
+/* *out = sum_i a[i]*b[i][*c[i]] (c may be NULL): fp32 products summed in float64 (:141-146, :187-193).  out: device double */
+int pylb_prod_sum(const float *a, const float *b, const float *c, int64_t n, double *out, void *stream);
 
 #ifdef __cplusplus
 }

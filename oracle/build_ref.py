@@ -1,4 +1,6 @@
-"""Build the UNMODIFIED reference hot path (MAS_library, Pk_library, redshift_space_library) into oracle/_ref/.
+"""Build the UNMODIFIED reference hot path (MAS_library, Pk_library, redshift_space_library) and its callers /
+consumers (readsnap, readgadget, MAS_gadget, Pk_snapshot, units_library, smoothing_library, bispectrum_library)
+into oracle/_ref/.
 
 TEST INFRASTRUCTURE ONLY.  Nothing in the product package imports this.
 
@@ -12,6 +14,7 @@ Accommodations (none touches arithmetic) -- see SURVEY.md section 8c / Appendix 
   * CC=/usr/bin/gcc (the default gcc in this image lacks libgomp.spec);
   * reference flags -O3 -ffast-math -fopenmp (library/setup.py:10-11,17-18) with
     -march=x86-64-v3 instead of -march=native so the .so also runs on the GPU box host;
+  * MAS_gadget.py is compiled from a tab-expanded scratch copy (mixed tabs/spaces are a Cython error);
   * at import time the harness (oracle/ref_loader.py) installs `time.clock` and a
     scipy-backed `pyfftw` stand-in (oracle/ref_shim/pyfftw.py) because pyfftw/FFTW are
     not in this image.
@@ -23,11 +26,21 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
 
 
+# callers / consumers of the hot path.  The pure-Python ones are Python-2 source, so they are
+# compiled with Cython (language_level=2) exactly like the .pyx files instead of being imported.
+EXTRA = ("readsnap", "readgadget", "MAS_gadget", "Pk_snapshot", "units_library", "smoothing_library",
+         "bispectrum_library")
+EXTRA_SRC = {"readsnap": "readsnap.py", "readgadget": "readgadget.py", "MAS_gadget": "MAS_library/MAS_gadget.py",
+             "Pk_snapshot": "Pk_library/Pk_snapshot.py", "units_library": "units_library.py",
+             "smoothing_library": "smoothing_library/smoothing_library.pyx",
+             "bispectrum_library": "Pk_library/bispectrum_library.pyx"}
+
+
 def build(force=False):
     if not os.path.isdir(REF):
         return False
     os.makedirs(OUT, exist_ok=True)
-    have = all(glob.glob(os.path.join(OUT, m + "*.so")) for m in ("MAS_library", "Pk_library", "redshift_space_library"))
+    have = all(glob.glob(os.path.join(OUT, m + "*.so")) for m in ("MAS_library", "Pk_library", "redshift_space_library") + EXTRA)
     if have and not force:
         return True
     os.environ["CC"] = "/usr/bin/gcc"
@@ -50,6 +63,24 @@ def build(force=False):
         Extension("redshift_space_library", [os.path.join(REF, "redshift_space_library.pyx")],
                   include_dirs=[numpy.get_include()]),
     ]
+    for name in EXTRA:
+        omp = name == "smoothing_library"
+        src = os.path.join(REF, EXTRA_SRC[name])
+        text = open(src).read()
+        if name == "readsnap":
+            # readsnap.py:193 prints an unassigned variable on its "file not found" error path; Cython makes that a
+            # compile error.  The scratch copy drops that one print (the sys.exit() after it stays).
+            text = text.replace('print "and:", curfilename;  sys.exit()', 'sys.exit()')
+        if "\t" in text or name == "readsnap":
+            # MAS_gadget.py mixes tabs and spaces (legal in Python 2, tab stops at 8); Cython refuses that, so the
+            # build compiles a tab-expanded scratch copy under /tmp.  Whitespace only; nothing lands in the repo.
+            os.makedirs(os.path.join(scratch, "src"), exist_ok=True)
+            src = os.path.join(scratch, "src", os.path.basename(src))
+            open(src, "w").write(text.expandtabs(8))
+        exts.append(Extension(name, [src],
+                              extra_compile_args=(flags if omp else ["-O2", "-w"]),
+                              extra_link_args=(["-fopenmp"] if omp else []), libraries=(["m"] if omp else []),
+                              include_dirs=[numpy.get_include()]))
     exts = cythonize(exts, compiler_directives={"language_level": 2},
                      build_dir=os.path.join(scratch, "cy"), quiet=True,
                      include_path=[os.path.join(REF, "MAS_library")])

@@ -390,14 +390,14 @@ def Pk_theta(Vx, Vy, Vz, BoxSize, axis=2, MAS="CIC", threads=1):
 
 def correct_MAS(delta, BoxSize, MAS="CIC", threads=1):
     """Pk_library.pyx:1749-1806.  The backward transform (pyfftw -> FFTW, un-vendored) is restated with pocketfft's
-    irfftn, unnormalised; it takes the real part after the complex passes, which fixes what the half-corrected
-    self-conjugate planes mean."""
+    irfftn, normalised by 1/dims^3 like pyfftw's FFTW.__call__ default (normalise_idft=True); it takes the real part
+    after the complex passes, which fixes what the half-corrected self-conjugate planes mean."""
     dims = len(delta)
     kx, ky, kz, keep = _cube_modes(dims)
     dk = FFT3Dr_f(np.asarray(delta, np.float32))
     corrected = _deconv(dk, _mas_cube(dims, MAS_function(MAS)))
     dk = np.where(keep, corrected, dk)
-    return (_sf.irfftn(dk, s=(dims,) * 3, axes=(0, 1, 2)) * dims ** 3).astype(np.float32)
+    return _sf.irfftn(dk, s=(dims,) * 3, axes=(0, 1, 2)).astype(np.float32)
 
 
 class Xi(object):
@@ -410,7 +410,7 @@ class Xi(object):
         dk = _deconv(FFT3Dr_f(np.asarray(delta, np.float32)), _mas_cube(dims, MAS_function(MAS)))
         p = np.zeros(dk.shape, np.complex64)
         p.real = dk.real * dk.real + dk.imag * dk.imag          # `float real, imag`, :2078-2082
-        xi = (_sf.irfftn(p, s=(dims,) * 3, axes=(0, 1, 2)) * dims ** 3).astype(np.float32)
+        xi = _sf.irfftn(p, s=(dims,) * 3, axes=(0, 1, 2)).astype(np.float32)      # pyfftw normalises the inverse
         w = _wavenumbers(dims)
         kx = w[:, None, None] + np.zeros((1, dims, dims), np.int64)
         ky = w[None, :, None] + np.zeros((dims, 1, dims), np.int64)

@@ -5,6 +5,13 @@ Covers exactly what Pk_library.pyx:120-245 touches: `empty_aligned(shape, dtype)
 `FFTW(a_in, a_out, axes, flags, direction, threads)(a_in, a_out)`.  Transforms are done by
 scipy.fft (pocketfft), which keeps float32 -> complex64 like the reference's FFT3Dr_f.
 Shapes arrive as floats because `dims/2+1` is true division under python 3.
+
+Normalisation follows pyfftw, not raw FFTW: `pyfftw.FFTW.__call__(input_array=None, output_array=None,
+normalise_idft=True, ortho=False)` scales a BACKWARD transform by 1/N unless told otherwise, and the reference
+calls its plans with two positional arguments only (Pk_library.pyx:165, 229), so IFFT3Dr_f / IFFT2Dr_f return the
+normalised inverse.  The reference's own arithmetic confirms it: `Xi` divides the inverse transform of
+|delta_k|^2 by dims^3 exactly once (Pk_library.pyx:2139-2143), which is the correlation function only if the
+inverse transform already carried the other 1/dims^3.  scipy's ifftn/irfftn have the same convention.
 """
 import numpy as np
 import scipy.fft as _sf
@@ -28,12 +35,8 @@ class FFTW(object):
                 a_out[...] = _sf.rfftn(a_in, axes=self.axes, workers=self.threads)
         else:
             if np.iscomplexobj(a_out):
-                a_out[...] = _sf.ifftn(a_in, axes=self.axes, workers=self.threads) * a_out.size
+                a_out[...] = _sf.ifftn(a_in, axes=self.axes, workers=self.threads)
             else:
                 s = [a_out.shape[ax] for ax in self.axes]
-                # FFTW's backward transform is unnormalised
-                n = 1
-                for v in s:
-                    n *= v
-                a_out[...] = _sf.irfftn(a_in, s=s, axes=self.axes, workers=self.threads) * n
+                a_out[...] = _sf.irfftn(a_in, s=s, axes=self.axes, workers=self.threads)
         return a_out

@@ -425,22 +425,24 @@ def _dev_c64(a, dev):
 
 
 def IFFT2Dr_f(a, threads=1):
-    """Pk_library.pyx:216-229: unnormalised backward C2R, complex64 (grid,grid/2+1) -> float32 (grid,grid)."""
+    """Pk_library.pyx:216-229: backward C2R, complex64 (grid,grid/2+1) -> float32 (grid,grid), scaled by 1/grid^2 like
+    the reference's pyfftw call (FFTW.__call__ normalises inverse transforms by default)."""
     lib, dev = _lib.load(), _device()
     src = _dev_c64(a, dev)
     n = src.shape[0]
     out = torch.empty((n, n), dtype=torch.float32, device=dev)
-    _lib.check(lib.pylb_fft2d_c2r(src.data_ptr(), out.data_ptr(), n, _stream(dev)), "pylb_fft2d_c2r")
+    _lib.check(lib.pylb_fft2d_c2r(src.data_ptr(), out.data_ptr(), n, 1, _stream(dev)), "pylb_fft2d_c2r")
     return _like_input(out, a)
 
 
 def IFFT3Dr_f(a, threads=1):
-    """Pk_library.pyx:152-165: unnormalised backward C2R, complex64 (dims,dims,dims/2+1) -> float32 (dims,dims,dims)."""
+    """Pk_library.pyx:152-165: backward C2R, complex64 (dims,dims,dims/2+1) -> float32 (dims,dims,dims), scaled by
+    1/dims^3 like the reference's pyfftw call (FFTW.__call__ normalises inverse transforms by default)."""
     lib, dev = _lib.load(), _device()
     src = _dev_c64(a, dev)
     n = src.shape[0]
     out = torch.empty((n, n, n), dtype=torch.float32, device=dev)
-    _lib.check(lib.pylb_fft_c2r(src.data_ptr(), out.data_ptr(), n, _stream(dev)), "pylb_fft_c2r")
+    _lib.check(lib.pylb_fft_c2r(src.data_ptr(), out.data_ptr(), n, 1, _stream(dev)), "pylb_fft_c2r")
     return _like_input(out, a)
 
 
@@ -528,8 +530,8 @@ def Pk_theta(Vx, Vy, Vz, BoxSize, axis=2, MAS="CIC", threads=1):
 
 
 def correct_MAS(delta, BoxSize, MAS="CIC", threads=1):
-    """Deconvolve the MAS window from a density field.  Pk_library.pyx:1749-1806.  Like the reference the result is
-    the UNNORMALISED inverse transform (dims^3 times the corrected field), float32 (dims,dims,dims)."""
+    """Deconvolve the MAS window from a density field.  Pk_library.pyx:1749-1806.  Returns the corrected field, float32
+    (dims,dims,dims) (the reference's IFFT3Dr_f is pyfftw's normalised inverse)."""
     start = time.time()
     _say("\nComputing power spectrum of the field...")
     lib, dev = _lib.load(), _device()
@@ -538,7 +540,7 @@ def correct_MAS(delta, BoxSize, MAS="CIC", threads=1):
     dk = _fft_field(lib, delta, dims, dev, torch.cuda.current_stream(dev))      # a fresh buffer, never `delta` itself
     _lib.check(lib.pylb_mas_correct(dk.data_ptr(), dims, MAS_function(MAS), 0, _stream(dev)), "pylb_mas_correct")
     out = torch.empty((dims, dims, dims), dtype=torch.float32, device=dev)
-    _lib.check(lib.pylb_fft_c2r(dk.data_ptr(), out.data_ptr(), dims, _stream(dev)), "pylb_fft_c2r")
+    _lib.check(lib.pylb_fft_c2r(dk.data_ptr(), out.data_ptr(), dims, 1, _stream(dev)), "pylb_fft_c2r")
     _say("Time taken = %.2f seconds" % (time.time() - start))
     return _like_input(out, delta)
 
@@ -558,7 +560,7 @@ class Xi(object):
         dk = _fft_field(lib, delta, dims, dev, torch.cuda.current_stream(dev))
         _lib.check(lib.pylb_mas_correct(dk.data_ptr(), dims, MAS_function(MAS), 1, _stream(dev)), "pylb_mas_correct")
         xi = torch.empty((dims, dims, dims), dtype=torch.float32, device=dev)
-        _lib.check(lib.pylb_fft_c2r(dk.data_ptr(), xi.data_ptr(), dims, _stream(dev)), "pylb_fft_c2r")
+        _lib.check(lib.pylb_fft_c2r(dk.data_ptr(), xi.data_ptr(), dims, 1, _stream(dev)), "pylb_fft_c2r")
         del dk
         sums = torch.empty((5, kmax + 1), dtype=torch.float64, device=dev)
         _lib.check(lib.pylb_xi_bin(xi.data_ptr(), dims, int(axis), sums.data_ptr(), _stream(dev)), "pylb_xi_bin")

@@ -57,9 +57,9 @@ SIGNATURES = {
     "pylb_fft_r2c": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pylb_fft_r2c_pitched_work_bytes": (c_size_t, [c_int, c_int64, c_int64]),
     "pylb_fft_r2c_pitched": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
-    "pylb_fft_c2r": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "pylb_fft_c2r": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pylb_fft2d_r2c": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
-    "pylb_fft2d_c2r": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "pylb_fft2d_c2r": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pylb_mas_correct": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "pylb_theta_bin": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "pylb_plane_bin": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -70,6 +70,13 @@ SIGNATURES = {
     "pylb_fft_slab_x": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pylb_slab_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pylb_slab_pack_push": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p]),
+    "pylb_scale_f32": (c_int, [c_void_p, c_int64, c_float, c_void_p]),
+    "pylb_overdensity_mean": (c_int, [c_void_p, c_int64, c_float, c_void_p]),
+    "pylb_axpy_f32": (c_int, [c_void_p, c_void_p, c_float, c_int64, c_void_p]),
+    "pylb_filter_real": (c_int, [c_void_p, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "pylb_cmul_c64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "pylb_bk_shell": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_void_p]),
+    "pylb_prod_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "pylb_pk_get_layout": (c_int, [c_int, c_int, ctypes.POINTER(PkLayout)]),
     "pylb_pk_bin": (c_int, [ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(KSpace), c_int, ctypes.POINTER(c_int),
                             c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libpylians_b200.so")
-SOURCES = ["capi.cu", "deposit.cu", "deposit_tiled.cu", "binning.cu", "fft.cu", "siblings.cu"]
+SOURCES = ["capi.cu", "deposit.cu", "deposit_tiled.cu", "binning.cu", "fft.cu", "siblings.cu", "consumers.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -174,7 +174,7 @@ plane_bin_kernel(const float2 *__restrict__ d1, const float2 *__restrict__ d2, S
 }
 
 // ------------------------------------------------------------------------------------------------
-// Xi real-space loop (:2097-2133): every cell of the (unnormalised) inverse transform, signed separations;
+// Xi real-space loop (:2097-2133): every cell of the inverse transform, signed separations;
 // sums[0..4][bin] = sum r, sum xi, sum xi L2(mu), sum xi L4(mu), Nmodes
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -213,6 +213,11 @@ static SibGeom sib_geom(int dims, int ndim) {
     return g;
 }
 
+__global__ void __launch_bounds__(256) scale_f32_kernel(float *x, int64_t n, float mul) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = __fmul_rn(x[i], mul);
+}
+
 static int make_tab(double **tab, int dims, int mas_index, cudaStream_t st) {
     keep_pool_memory();
     const int middle = dims / 2;
@@ -236,13 +241,27 @@ using namespace pylb;
         }                                                                                          \
     } while (0)
 
-extern "C" int pylb_fft_c2r(void *in, float *out, int dims, void *stream) {
+// pyfftw's FFTW.__call__ scales a backward transform by 1/N unless told otherwise (normalise_idft=True, the default
+// the reference relies on: Xi divides by dims^3 only once, Pk_library.pyx:2139-2143): one fp32 multiply per element
+// by (float)(1/N), as numpy's in-place `output_array *= scaling` does.
+static int c2r_normalise(float *out, int64_t n, cudaStream_t st) {
+    const float s = (float)(1.0 / (double)n);
+    int64_t b = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (b > cap) b = cap;
+    scale_f32_kernel<<<(unsigned)b, 256, 0, st>>>(out, n, s);
+    PYLB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pylb_fft_c2r(void *in, float *out, int dims, int normalise, void *stream) {
     PYLB_REQUIRE(in && out && dims >= 2 && in != (void *)out, "pylb_fft_c2r: bad arguments");
     cufftHandle h;
     if (sib_plan(SK_C2R_3D, dims, &h)) return 1;
     PYLB_CUFFT2(cufftSetStream(h, (cudaStream_t)stream));
     PYLB_CUFFT2(cufftExecC2R(h, (cufftComplex *)in, out));
     count_launch();
+    if (normalise) return c2r_normalise(out, (int64_t)dims * dims * dims, (cudaStream_t)stream);
     return 0;
 }
 
@@ -256,13 +275,14 @@ extern "C" int pylb_fft2d_r2c(const float *in, void *out, int dims, void *stream
     return 0;
 }
 
-extern "C" int pylb_fft2d_c2r(void *in, float *out, int dims, void *stream) {
+extern "C" int pylb_fft2d_c2r(void *in, float *out, int dims, int normalise, void *stream) {
     PYLB_REQUIRE(in && out && dims >= 2 && in != (void *)out, "pylb_fft2d_c2r: bad arguments");
     cufftHandle h;
     if (sib_plan(SK_C2R_2D, dims, &h)) return 1;
     PYLB_CUFFT2(cufftSetStream(h, (cudaStream_t)stream));
     PYLB_CUFFT2(cufftExecC2R(h, (cufftComplex *)in, out));
     count_launch();
+    if (normalise) return c2r_normalise(out, (int64_t)dims * dims, (cudaStream_t)stream);
     return 0;
 }
 

@@ -185,7 +185,10 @@ def gold_siblings():
 
 
 if __name__ == "__main__":
-    gold_ma(); gold_pk(); gold_xpk(); gold_rsd(); gold_siblings()
+    # python tests/golden/make_golden.py [ma pk xpk rsd siblings ...]   (default: all)
+    which = sys.argv[1:] or ["ma", "pk", "xpk", "rsd", "siblings"]
+    for name in which:
+        globals()["gold_" + name]()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

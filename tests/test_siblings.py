@@ -85,17 +85,17 @@ def test_gpu_matches_oracle(grid):
     # the helper transforms
     np.testing.assert_allclose(PKL.FFT2Dr_f(a, 1), np.fft.rfftn(a.astype(np.float64)), rtol=0, atol=2e-5 * grid)
     dk = np.fft.rfftn(d.astype(np.float64)).astype(np.complex64)
-    np.testing.assert_allclose(PKL.IFFT3Dr_f(dk, 1) / grid ** 3, d, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(PKL.IFFT3Dr_f(dk, 1), d, rtol=0, atol=1e-5)       # pyfftw normalises the inverse
     ak = np.fft.rfftn(a.astype(np.float64)).astype(np.complex64)
-    np.testing.assert_allclose(PKL.IFFT2Dr_f(ak, 1) / grid ** 2, a, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(PKL.IFFT2Dr_f(ak, 1), a, rtol=0, atol=1e-5)
 
 
 @pytest.mark.gpu
 def test_xi_is_the_transform_of_pk():
     """Known answer: a single plane wave delta = A cos(2 pi m x / L) has xi(r) = (A^2/2) cos(2 pi m r_x / L)
-    (MAS 'None').  The reference divides the unnormalised inverse transform of |delta_k|^2 (itself from an
-    unnormalised forward transform) by dims^3 once (:2139-2143), so its xi is dims^3 times that; correct_MAS with
-    'None' is the identity times dims^3."""
+    (MAS 'None').  The reference divides the inverse transform of |delta_k|^2 (delta_k from an unnormalised forward
+    transform) by dims^3 once (:2139-2143); together with the 1/dims^3 pyfftw applies to every inverse transform
+    (FFTW.__call__, normalise_idft=True) that is exactly xi.  correct_MAS with 'None' is the identity."""
     import pylians_b200
     import Pk_library as PKL
     pylians_b200.set_verbose(False)
@@ -103,7 +103,7 @@ def test_xi_is_the_transform_of_pk():
     x = np.arange(grid)
     d = np.broadcast_to((A * np.cos(2 * np.pi * m * x / grid))[:, None, None], (grid,) * 3).astype(np.float32).copy()
     same = PKL.correct_MAS(d, box, "None", 1)
-    np.testing.assert_allclose(same / grid ** 3, d, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(same, d, rtol=0, atol=1e-6)
     xi = PKL.Xi(d, box, "None", 0, 1)
     # bin 1 (r in [1,2) cells): mean over its 26 cells of (A^2/2) cos(2 pi m r_x / grid)
     w = np.where(x > grid // 2, x - grid, x)
@@ -111,7 +111,7 @@ def test_xi_is_the_transform_of_pk():
     r = np.sqrt(rx * rx + ry * ry + rz * rz)
     sel = (r >= 1) & (r < 2)
     want = np.mean((A * A / 2) * np.cos(2 * np.pi * m * rx[sel] / grid))
-    assert abs(xi.xi[0, 0] / grid ** 3 - want) < 1e-6
+    assert abs(xi.xi[0, 0] - want) < 1e-6
     assert xi.Nmodes3D[0] == sel.sum()
 
 
