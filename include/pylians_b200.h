@@ -274,6 +274,10 @@ int pylb_filter_real(float *field, int dims, float R2, int kind, double *scratch
 /* a[i] *= b[i], complex64: the mode loop of field_smoothing (:104-108) */
 int pylb_cmul_c64(void *a, const void *b, int64_t n, void *stream);
 
+/* void_library.gaussian_smoothing (void_library/void_library.pyx:45-80): dk *= top-hat window of kR = prefact*|k|,
+ * prefact = (float)(R*2*pi/BoxSize); complex64 (dims,dims,dims/2+1), in place, DC mode untouched */
+int pylb_tophat_k(void *dk, int dims, float prefact, void *stream);
+
 /* bispectrum_library.Bk (Pk_library/bispectrum_library.pyx:88-130): out_d = MAS-deconvolved delta_k on the shell
  * kmin <= |k| < kmax (units of kF) and 0 elsewhere; out_i = 1 on the shell, 0 elsewhere.  complex64
  * (dims,dims,dims/2+1) buffers; dk is not modified. */

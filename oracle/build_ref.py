@@ -29,11 +29,12 @@ OUT = os.path.join(HERE, "_ref")
 # callers / consumers of the hot path.  The pure-Python ones are Python-2 source, so they are
 # compiled with Cython (language_level=2) exactly like the .pyx files instead of being imported.
 EXTRA = ("readsnap", "readgadget", "MAS_gadget", "Pk_snapshot", "units_library", "smoothing_library",
-         "bispectrum_library")
+         "bispectrum_library", "void_library")
 EXTRA_SRC = {"readsnap": "readsnap.py", "readgadget": "readgadget.py", "MAS_gadget": "MAS_library/MAS_gadget.py",
              "Pk_snapshot": "Pk_library/Pk_snapshot.py", "units_library": "units_library.py",
              "smoothing_library": "smoothing_library/smoothing_library.pyx",
-             "bispectrum_library": "Pk_library/bispectrum_library.pyx"}
+             "bispectrum_library": "Pk_library/bispectrum_library.pyx",
+             "void_library": "void_library/void_library.pyx"}
 
 
 def build(force=False):
@@ -64,7 +65,7 @@ def build(force=False):
                   include_dirs=[numpy.get_include()]),
     ]
     for name in EXTRA:
-        omp = name == "smoothing_library"
+        omp = name in ("smoothing_library", "void_library")
         src = os.path.join(REF, EXTRA_SRC[name])
         text = open(src).read()
         if name == "readsnap":
@@ -77,13 +78,14 @@ def build(force=False):
             os.makedirs(os.path.join(scratch, "src"), exist_ok=True)
             src = os.path.join(scratch, "src", os.path.basename(src))
             open(src, "w").write(text.expandtabs(8))
-        exts.append(Extension(name, [src],
+        more = [os.path.join(REF, "void_library/void_openmp_library.c")] if name == "void_library" else []
+        exts.append(Extension(name, [src] + more,
                               extra_compile_args=(flags if omp else ["-O2", "-w"]),
                               extra_link_args=(["-fopenmp"] if omp else []), libraries=(["m"] if omp else []),
-                              include_dirs=[numpy.get_include()]))
+                              include_dirs=[numpy.get_include(), os.path.join(REF, "void_library")]))
     exts = cythonize(exts, compiler_directives={"language_level": 2},
                      build_dir=os.path.join(scratch, "cy"), quiet=True,
-                     include_path=[os.path.join(REF, "MAS_library")])
+                     include_path=[os.path.join(REF, "MAS_library"), os.path.join(REF, "void_library")])
     dist = Distribution({"ext_modules": exts})
     cmd = dist.get_command_obj("build_ext")
     cmd.build_lib = OUT

@@ -431,3 +431,90 @@ class Xi(object):
         self.xi = np.stack([np.bincount(idx, x, kmax + 1)[1:] / N * norm,
                             np.bincount(idx, x * l2, kmax + 1)[1:] * 5.0 / N * norm,
                             np.bincount(idx, x * l4, kmax + 1)[1:] * 9.0 / N * norm], axis=1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Consumers of the FFT either side of the path: smoothing_library, void_library.gaussian_smoothing,
+# bispectrum_library.Bk.  numpy restatements, pinned against the compiled reference by tests/golden/consumers.npz
+# and tests/test_oracle_vs_reference.py.  The inverse transform is pyfftw's normalised one (see ref_shim/pyfftw.py).
+# ---------------------------------------------------------------------------------------------------------------
+def _ifft3(dk, dims):
+    return _sf.irfftn(dk, s=(dims,) * 3, axes=(0, 1, 2)).astype(np.float32)
+
+
+def FT_filter(BoxSize, R, dims, Filter, threads=1):
+    """smoothing_library/smoothing_library.pyx:19-83."""
+    if Filter not in ["Top-Hat", "Gaussian"]:
+        raise Exception("Filter %s not implemented!" % Filter)
+    R_grid = np.float32(np.float32(np.float32(R) * np.float32(dims)) / np.float32(BoxSize))      # C floats, :31
+    R2 = np.float32(R_grid * R_grid)
+    w = _wavenumbers(dims)
+    d2 = (w[:, None, None] ** 2 + w[None, :, None] ** 2 + w[None, None, :] ** 2).astype(np.int64)
+    if Filter == "Top-Hat":
+        field = (d2.astype(np.float32) <= R2).astype(np.float32)                               # :47-50
+    else:
+        field = np.exp(-d2 / (2.0 * np.float64(R2))).astype(np.float32)                        # :66-67
+    normalization = np.sum(field, dtype=np.float64)
+    field = (field.astype(np.float64) / normalization).astype(np.float32)                      # :76-79
+    return FFT3Dr_f(field)
+
+
+def field_smoothing(field, filter_k, threads=1):
+    """smoothing_library.pyx:89-114."""
+    dims = field.shape[0]
+    if dims != filter_k.shape[0]:
+        raise Exception("field and filter have different grids!!!")
+    fk = FFT3Dr_f(np.asarray(field, np.float32))
+    return _ifft3((fk * np.asarray(filter_k, np.complex64)).astype(np.complex64), dims)
+
+
+def gaussian_smoothing(delta, BoxSize, R, threads=1):
+    """void_library/void_library.pyx:45-80 (a k-space top-hat, despite the name)."""
+    dims = delta.shape[0]
+    prefact = np.float32(float(np.float32(R)) * 2.0 * 3.141592653589793 / float(np.float32(BoxSize)))
+    kx, ky, kz, _ = _cube_modes(dims)
+    kR = (np.float64(prefact) * np.sqrt((kx * kx + ky * ky + kz * kz).astype(np.float64))).astype(np.float32)
+    x = kR.astype(np.float64)
+    kR3 = (kR * kR * kR).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        fact = np.where(np.abs(kR) < np.float32(1e-5), 1.0, 3.0 * (np.sin(x) - np.cos(x) * x) / kR3.astype(np.float64))
+    fact = fact.astype(np.float32)
+    fact[0, 0, 0] = 1.0                                                                        # DC mode skipped, :67-68
+    return _ifft3(_deconv(FFT3Dr_f(np.asarray(delta, np.float32)), fact), dims)
+
+
+class Bk(object):
+    """Pk_library/bispectrum_library.pyx:32-196."""
+
+    def __init__(self, delta, BoxSize, k1, k2, theta, MAS="CIC", threads=1):
+        dims = len(delta)
+        kF = frequencies(BoxSize, dims)[0]
+        theta = np.asarray(theta, np.float64)
+        bins = theta.shape[0]
+        k3 = np.sqrt((k2 * np.sin(theta)) ** 2 + (k2 * np.cos(theta) + k1) ** 2)
+        k_all = np.zeros(bins + 2)
+        k_all[0], k_all[1], k_all[2:] = k1, k2, k3
+        k_min, k_max = (k_all - kF) / kF, (k_all + kF) / kF
+        # every stored mode is deconvolved (the skip rule is commented out, :103-108)
+        dk = _deconv(FFT3Dr_f(np.asarray(delta, np.float32)), _mas_cube(dims, MAS_function(MAS)))
+        kx, ky, kz, _ = _cube_modes(dims)
+        k = np.sqrt((kx * kx + ky * ky + kz * kz).astype(np.float64))
+
+        def shell(i):
+            sel = (k >= k_min[i]) & (k < k_max[i])
+            d = _ifft3(np.where(sel, dk, 0).astype(np.complex64), dims)
+            ind = _ifft3(sel.astype(np.complex64), dims)
+            P = np.sum((d * d).astype(np.float64)) / np.sum((ind * ind).astype(np.float64)) * (BoxSize / dims ** 2) ** 3
+            return d, ind, P
+
+        Pk = np.zeros(bins + 2)
+        B, Q = np.zeros(bins), np.zeros(bins)
+        d1, I1, Pk[0] = shell(0)
+        d2, I2, Pk[1] = shell(1)
+        for j in range(bins):
+            d3, I3, Pk[j + 2] = shell(j + 2)
+            num = np.sum(((d1 * d2) * d3).astype(np.float64))
+            tri = np.sum(((I1 * I2) * I3).astype(np.float64))
+            B[j] = (num / tri) * (BoxSize ** 2 / dims ** 3) ** 3
+            Q[j] = B[j] / (Pk[0] * Pk[1] + Pk[0] * Pk[j + 2] + Pk[1] * Pk[j + 2])
+        self.B, self.Q, self.k, self.Pk = B, Q, k_all, Pk

@@ -71,7 +71,7 @@ def load_rsl():
 
 def load_extras():
     """The compiled reference callers / consumers of the hot path as a dict:
-    readsnap, readgadget, MAS_gadget, Pk_snapshot, units_library, smoothing_library, bispectrum_library.
+    readsnap, readgadget, MAS_gadget, Pk_snapshot, units_library, smoothing_library, bispectrum_library, void_library.
     They import their siblings by bare name (`import MAS_library as MASL`, `import readsnap`, `import h5py` ...), so
     the reference modules are registered under those names only while loading; afterwards sys.modules is restored
     and the product's drop-in modules of the same names are never shadowed."""
@@ -81,7 +81,7 @@ def load_extras():
     rsl = load_rsl()
     shim = os.path.join(HERE, "ref_shim")
     names = ["MAS_library", "Pk_library", "redshift_space_library", "h5py", "pyfftw", "units_library", "readsnap",
-             "readgadget", "MAS_gadget", "Pk_snapshot", "smoothing_library", "bispectrum_library"]
+             "readgadget", "MAS_gadget", "Pk_snapshot", "smoothing_library", "bispectrum_library", "void_library"]
     saved = {n: sys.modules.get(n) for n in names}
     out = {}
     sys.path.insert(0, shim)
@@ -90,7 +90,7 @@ def load_extras():
         sys.modules["redshift_space_library"] = rsl
         sys.modules.pop("h5py", None); sys.modules.pop("pyfftw", None)
         for n in ("units_library", "readsnap", "readgadget", "MAS_gadget", "Pk_snapshot", "smoothing_library",
-                  "bispectrum_library"):
+                  "bispectrum_library", "void_library"):
             spec = importlib.util.spec_from_file_location(n, glob.glob(os.path.join(HERE, "_ref", n + "*.so"))[0])
             mod = importlib.util.module_from_spec(spec)
             sys.modules[n] = mod
@@ -109,4 +109,5 @@ def load_extras():
 
 def extras_available():
     return all(glob.glob(os.path.join(HERE, "_ref", n + "*.so")) for n in
-               ("readsnap", "readgadget", "MAS_gadget", "Pk_snapshot", "smoothing_library", "bispectrum_library"))
+               ("readsnap", "readgadget", "MAS_gadget", "Pk_snapshot", "smoothing_library", "bispectrum_library",
+                "void_library"))

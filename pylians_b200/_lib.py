@@ -75,6 +75,7 @@ SIGNATURES = {
     "pylb_axpy_f32": (c_int, [c_void_p, c_void_p, c_float, c_int64, c_void_p]),
     "pylb_filter_real": (c_int, [c_void_p, c_int, c_float, c_int, c_void_p, c_void_p]),
     "pylb_cmul_c64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "pylb_tophat_k": (c_int, [c_void_p, c_int, c_float, c_void_p]),
     "pylb_bk_shell": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_void_p]),
     "pylb_prod_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "pylb_pk_get_layout": (c_int, [c_int, c_int, ctypes.POINTER(PkLayout)]),

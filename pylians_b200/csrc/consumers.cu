@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) axpy_kernel(float *dst, const float *__re
 
 // ---- smoothing_library.FT_filter :19-83: the filter on the grid, and its sum ----------------------------------
 // KIND 0 Top-Hat: 1 where d2 <= R2 (int compared with float, :47-50).  KIND 1 Gaussian: (float)exp(-d2/(2.0*R2))
-// evaluated in double (:66-67).  One thread per (i,j) row pair of 4 cells along k.
+// evaluated in double (:66-67).  Grid-stride over cells; the double sum of the written floats goes to *norm.
 template <int KIND>
 __global__ void __launch_bounds__(256) filter_fill_kernel(float *__restrict__ field, int dims, float R2, double *norm) {
     const int middle = dims / 2;
@@ -83,6 +83,30 @@ __global__ void __launch_bounds__(256) cmul_kernel(float2 *a, const float2 *__re
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float2 x = a[i], y = __ldg(b + i);
         a[i] = make_float2(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x);
+    }
+}
+
+// ---- void_library.gaussian_smoothing (void_library/void_library.pyx:45-80): despite its name a top-hat of radius R,
+// applied in k-space: delta_k *= 3 (sin kR - kR cos kR)/(kR)^3, kR = (float)(prefact*|k|); the DC mode is skipped.
+// The trigonometry is double like the reference's libm calls; kR*kR*kR is a float product (:74).
+__global__ void __launch_bounds__(256) tophat_k_kernel(float2 *dk, int dims, float prefact) {
+    const int middle = dims / 2, nz = middle + 1;
+    const int64_t total = (int64_t)dims * dims * nz;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        if (idx == 0) continue;
+        const int kz = (int)(idx % nz);
+        const int64_t r = idx / nz;
+        const int kx = wavenumber((int)(r / dims), dims, middle), ky = wavenumber((int)(r % dims), dims, middle);
+        const float kR = (float)((double)prefact * sqrt((double)(kx * kx + ky * ky + kz * kz)));
+        float fact = 1.0f;
+        if (fabsf(kR) >= 1e-5f) {
+            const double x = (double)kR;
+            const float kR3 = __fmul_rn(__fmul_rn(kR, kR), kR);
+            fact = (float)(3.0 * (sin(x) - cos(x) * x) / (double)kR3);
+        }
+        const float2 z = dk[idx];
+        dk[idx] = make_float2(__fmul_rn(z.x, fact), __fmul_rn(z.y, fact));
     }
 }
 
@@ -185,6 +209,14 @@ extern "C" int pylb_filter_real(float *field, int dims, float R2, int kind, doub
 extern "C" int pylb_cmul_c64(void *a, const void *b, int64_t n, void *stream) {
     PYLB_REQUIRE(a && b && n > 0, "pylb_cmul_c64: bad arguments");
     cmul_kernel<<<blocks_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>((float2 *)a, (const float2 *)b, n);
+    PYLB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pylb_tophat_k(void *dk, int dims, float prefact, void *stream) {
+    PYLB_REQUIRE(dk && dims >= 2 && dims <= 16384, "pylb_tophat_k: bad arguments");
+    const int64_t n = (int64_t)dims * dims * (dims / 2 + 1);
+    tophat_k_kernel<<<blocks_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>((float2 *)dk, dims, prefact);
     PYLB_LAUNCH_CHECK();
     return 0;
 }

@@ -184,9 +184,67 @@ def gold_siblings():
     np.savez_compressed(os.path.join(HERE, "siblings.npz"), **out)
 
 
+DRIVER_SNAPSHOT = dict(seed=9, counts=[3000, 5000, 0, 0, 1200, 0], box_kpc=40000.0, redshift=1.0,
+                       masstable=np.array([0.0, 0.7, 0.0, 0.0, 0.0, 0.0]), nfiles=3)
+
+
+def gold_drivers():
+    """Snapshot drivers: the reference's density_field_gadget / Pk_comp / Pk_Gadget, compiled
+    unmodified, on a synthetic 3-file format-1 snapshot that tests/gadget_writer.py regenerates from its seed."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import gadget_writer as GW
+    ex = ref_loader.load_extras()
+    MG, PS = ex["MAS_gadget"], ex["Pk_snapshot"]
+    S = DRIVER_SNAPSHOT
+    parts = GW.make_particles(S["seed"], S["counts"], S["box_kpc"], S["masstable"], clustered=True)
+    out = {"pos_checksum": np.array([float(np.sum(parts[t][0], dtype=np.float64)) for t in (0, 1, 4)])}
+    dims = 16
+    with tempfile.TemporaryDirectory() as tmp:
+        base = os.path.join(tmp, "snap_005")
+        GW.write_snapshot(base, parts, S["masstable"], S["box_kpc"], S["redshift"], S["nfiles"], 1)
+        # density fields: one species with a header mass (counts), one with a MASS block, RSD, two with MASS blocks
+        out["dens_cdm_CIC"] = quiet(MG.density_field_gadget, base, [1], dims, "CIC", False, 0, False)
+        out["dens_cdm_PCS_rsd1"] = quiet(MG.density_field_gadget, base, [1], dims, "PCS", True, 1, False)
+        out["dens_gas_TSC"] = quiet(MG.density_field_gadget, base, [0], dims, "TSC", False, 0, False)
+        out["dens_gas_stars_CIC_rsd2"] = quiet(MG.density_field_gadget, base, [0, 4], dims, "CIC", True, 2, False)
+        for tag, types, rsd, axis in (("cdm", [1], False, 0), ("cdm_rs2", [1], True, 2), ("gas_cdm", [0, 1], False, 0),
+                                      ("gas_cdm_stars_rs0", [0, 1, 4], True, 0)):
+            folder = os.path.join(tmp, tag)
+            os.makedirs(folder)
+            quiet(PS.Pk_Gadget, base, dims, types, rsd, axis, 1, folder)
+            for f in sorted(os.listdir(folder)):
+                out["pk_%s__%s" % (tag, f)] = np.loadtxt(os.path.join(folder, f))
+    np.savez_compressed(os.path.join(HERE, "drivers.npz"), **out)
+
+
+def gold_consumers():
+    """FFT consumers: smoothing_library, void_library.gaussian_smoothing, bispectrum_library.Bk of the
+    compiled, unmodified reference."""
+    ex = ref_loader.load_extras()
+    SL, VL, BL = ex["smoothing_library"], ex["void_library"], ex["bispectrum_library"]
+    out = {}
+    box = 200.0
+    for dims in (16, 18):
+        (d,) = fields(dims, box, [(51 + dims, "CIC", False)])
+        out["delta_%d" % dims] = d
+        for name, R in (("Top-Hat", 31.0), ("Gaussian", 17.5)):
+            W_k = np.asarray(SL.FT_filter(box, R, dims, name, 2))
+            out["filter_%d_%s" % (dims, name)] = W_k
+            out["smooth_%d_%s" % (dims, name)] = np.asarray(SL.field_smoothing(d, W_k, 2))
+        out["void_smooth_%d" % dims] = np.asarray(VL.gaussian_smoothing(d, box, 23.0, 2))
+        kF = 2.0 * np.pi / box
+        theta = np.array([0.3, 1.1, 2.0, 2.9])
+        b = quiet(BL.Bk, d, box, 3.0 * kF, 4.2 * kF, theta, "CIC", 1)
+        for n in ("B", "Q", "k", "Pk"):
+            out["bk_%d_%s" % (dims, n)] = np.asarray(getattr(b, n))
+    out["box"], out["theta"] = box, theta
+    np.savez_compressed(os.path.join(HERE, "consumers.npz"), **out)
+
+
 if __name__ == "__main__":
     # python tests/golden/make_golden.py [ma pk xpk rsd siblings ...]   (default: all)
-    which = sys.argv[1:] or ["ma", "pk", "xpk", "rsd", "siblings"]
+    which = sys.argv[1:] or ["ma", "pk", "xpk", "rsd", "siblings", "drivers", "consumers"]
     for name in which:
         globals()["gold_" + name]()
     for f in sorted(os.listdir(HERE)):
