@@ -434,3 +434,55 @@ def test_full_size_properties(MASL, PKL):
     finally:
         P.ALGO = old
     parity.check_pk(p, q)
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size properties at 1024^3 (BASELINE configs[2]: TSC, multipoles along axis 2; configs[4]: two fields, XPk)
+# ------------------------------------------------------------------------------------------------
+def _total_power(P0, Nmodes):
+    return float(np.sum(np.asarray(P0, np.float64) * np.asarray(Nmodes, np.float64)))
+
+
+def test_full_size_1024_tsc_multipoles_and_xpk(MASL, PKL):
+    dims, box = 1024, 1000.0
+    gen = torch.Generator(device="cuda"); gen.manual_seed(3)
+    fields = []
+    for mas, weighted in (("TSC", False), ("CIC", True)):
+        pos = torch.rand((dims ** 3, 3), device="cuda", dtype=torch.float32, generator=gen) * box
+        W = (torch.rand(dims ** 3, device="cuda", dtype=torch.float32, generator=gen) + 0.5) if weighted else None
+        grid = torch.zeros((dims,) * 3, device="cuda", dtype=torch.float32)
+        MASL.MA(pos, grid, box, mas, W=W)
+        want = float(W.sum(dtype=torch.float64)) if weighted else float(dims ** 3)
+        assert abs(float(grid.sum(dtype=torch.float64)) / want - 1.0) < 1e-6      # mass conservation
+        del pos, W
+        MASL.overdensity(grid)
+        assert abs(float(grid.mean(dtype=torch.float64))) < 1e-6
+        fields.append(grid)
+    # configs[2]: redshift-space-style multipoles along axis 2 of the TSC field
+    p = PKL.Pk(fields[0], box, 2, "TSC", 1)
+    assert p.Nmodes3D.sum() + 1 == (dims ** 3 - 8) // 2 + 8                       # Pk_library.pyx:90-102
+    assert p.Nmodes1D.sum() + p.Nmodes2D.sum() > 0
+    shot = box ** 3 / dims ** 3
+    w = p.Nmodes3D
+    assert abs(np.sum(p.Pk[5:60, 0] * w[5:60]) / np.sum(w[5:60]) / shot - 1.0) < 0.01
+    # isotropic input: quadrupole and hexadecapole vanish within the scatter of (2l+1) L_l(mu) |delta_k|^2 per bin
+    for ell, fac in ((1, 5.0), (2, 9.0)):
+        sig = fac * shot / np.sqrt(w[20:150])                                      # k < 0.3 k_Nyquist: aliasing still isotropic
+        assert np.all(np.abs(p.Pk[20:150, ell]) < 6.0 * sig), ell
+    # one mode set, three binnings: sum of |delta_k|^2 over the 2-D table equals the 3-D sum plus the DC mode's bin
+    tot3 = _total_power(p.Pk[:, 0], p.Nmodes3D)
+    tot2 = _total_power(p.Pk2D, p.Nmodes2D)
+    assert abs(tot2 / tot3 - 1.0) < 1e-7
+    # the line of sight only relabels modes: the monopole and the mode counts do not depend on it
+    q = PKL.Pk(fields[0], box, 0, "TSC", 1)
+    parity.assert_exact(q.Nmodes3D, p.Nmodes3D, "Nmodes3D axis 0 vs 2")
+    np.testing.assert_allclose(q.Pk[:, 0], p.Pk[:, 0], rtol=1e-5, atol=0)
+    del q
+    # configs[4]: auto and cross spectra of the two fields with per-field MAS deconvolution
+    x = PKL.XPk(fields, box, 2, ["TSC", "CIC"], 1)
+    parity.assert_exact(x.Nmodes3D, p.Nmodes3D, "XPk Nmodes3D")
+    np.testing.assert_allclose(x.Pk[:, :, 0], p.Pk, rtol=1e-5, atol=1e-5 * shot)   # same field, XPk path vs Pk path
+    assert np.all(np.abs(x.XPk[:, 0, 0]) <= np.sqrt(x.Pk[:, 0, 0] * x.Pk[:, 0, 1]) * (1 + 1e-6))   # Cauchy-Schwarz
+    y = PKL.XPk(fields[::-1], box, 2, ["CIC", "TSC"], 1)                          # the cross spectrum is symmetric
+    np.testing.assert_allclose(y.XPk[:, :, 0], x.XPk[:, :, 0], rtol=1e-6, atol=1e-7 * shot)
+    np.testing.assert_allclose(y.Pk[:, :, 1], x.Pk[:, :, 0], rtol=1e-6, atol=1e-7 * shot)
