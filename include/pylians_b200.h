@@ -257,6 +257,13 @@ int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int axis, const i
                 int want_phase, int write_back, int algo, int accumulate, double *sums,
                 uint64_t *counts, void *stream);
 
+/* After pylb_pk_bin (and, multi-GPU, after the all-reduce of sums/counts): the 2-D table's normalisation
+ * Pk2D = sum * (fact / Nmodes2D) (Pk_library.pyx:397-406, 771-786) for every field and pair, in place, and every
+ * mode count rewritten in place as a float64 (the reference's Nmodes arrays are float64), so that the host reads
+ * the finished tables with one copy.  fact = (BoxSize/dims^2)^3.  Bins with no mode become inf/nan; the caller
+ * checks min(Nmodes2D) first (ZeroDivisionError in the reference). */
+int pylb_pk_finish_tables(double *sums, uint64_t *counts, int dims, int F, double fact, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Callers and consumers either side of the path; csrc/consumers.cu
  * ------------------------------------------------------------------------------------------- */

@@ -22,7 +22,13 @@ for mode in ("grid", "particles"):
     if rank == 0:
         print("%-9s N=%d G=%d: density_slab %.2f ms  fft_slab %.2f ms  bin+allreduce %.2f ms  total %.2f ms" % (
             mode, N, world, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t3 - t0) * 1e3))
-# finer breakdown of the particle mode
+# particle mode: pieces of the routed payload overlapped with the windowed deposit (exchange_chunks), and the local kernels
+for chunks in (1, 2, 4, 8):
+    eng = pdist.SlabPk(N, box, "CIC", 2, exchange="particles", exchange_chunks=chunks)
+    for it in range(3):
+        sync(); t0 = time.perf_counter(); slab = eng.density_slab(pos); sync(); t1 = time.perf_counter()
+    if rank == 0:
+        print("particles, %d piece(s): density_slab %.2f ms" % (chunks, (t1 - t0) * 1e3))
 eng = pdist.SlabPk(N, box, "CIC", 2, exchange="particles"); ops = eng.ops
 for it in range(2):
     sync(); t0 = time.perf_counter()
@@ -32,6 +38,6 @@ for it in range(2):
     recv = send.new_empty((sum(rs), 4)); dist.all_to_all_single(recv, send, output_split_sizes=rs, input_split_sizes=ss); sync(); t3 = time.perf_counter()
     grid = ops.zeros((eng.nxl + 1, N, N)); ops.deposit_window(recv, grid, rank * eng.nxl, box, "CIC", False, N); sync(); t4 = time.perf_counter()
 if rank == 0:
-    print("particles: partition %.2f  splits %.2f  all_to_all(%.2f GB) %.2f  window deposit %.2f ms" % (
+    print("particles, stages one after the other: partition %.2f  splits %.2f  all_to_all(%.2f GB) %.2f  window deposit %.2f ms" % (
         (t1 - t0) * 1e3, (t2 - t1) * 1e3, send.numel() * 4 / 1e9, (t3 - t2) * 1e3, (t4 - t3) * 1e3))
 dist.destroy_process_group()

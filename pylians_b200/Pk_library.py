@@ -209,18 +209,32 @@ def _kpar_kper(kmax_par, kmax_per, kF):
 
 
 class _Bins(object):
-    """Host view (numpy float64) of the raw sums laid out by pylb_pk_layout."""
+    """Host view (numpy float64) of the raw sums laid out by pylb_pk_layout.
 
-    def __init__(self, L, sums, counts):
+    With `fact` = (BoxSize/dims^2)^3 and device-resident sums (the normal case) the 2-D table is normalised and the
+    mode counts are converted to float64 on the device first (pylb_pk_finish_tables), so the host makes exactly one
+    private copy of the buffer and every attribute is a view of it."""
+
+    def __init__(self, L, sums, counts, fact=None):
         raw = getattr(sums, "_pylb_raw", None)
+        self.tables_done = False
         if raw is not None and raw.is_cuda:
+            if fact is not None:
+                _lib.check(_lib.load().pylb_pk_finish_tables(sums.data_ptr(), counts.data_ptr(), int(L.dims), int(L.F),
+                                                             float(fact), torch.cuda.current_stream(raw.device).cuda_stream),
+                           "pylb_pk_finish_tables")
+                self.tables_done = True
             # single async copy into a cached pinned buffer + one stream sync
             host = _pinned(raw.numel())
             host.copy_(raw, non_blocking=True)
             torch.cuda.current_stream(raw.device).synchronize()
-            h = host.numpy()
-            s = h[:L.n_doubles]          # view of the pinned buffer: _finish only derives new arrays from it
-            c = h[L.n_doubles:].view(np.int64).astype(np.float64)   # counts < 2^53: exact in float64
+            if self.tables_done:
+                h = host.numpy().copy()  # the caller's private copy: the pinned buffer is reused by the next call
+                s, c = h[:L.n_doubles], h[L.n_doubles:]
+            else:
+                h = host.numpy()
+                s = h[:L.n_doubles]          # view of the pinned buffer: _finish only derives new arrays from it
+                c = h[L.n_doubles:].view(np.int64).astype(np.float64)   # counts < 2^53: exact in float64
         else:
             s = sums.cpu().numpy()
             c = counts.cpu().numpy().astype(np.float64)
@@ -257,10 +271,13 @@ def _finish(obj, b, dims, BoxSize, is_x):
     if b.n2d.min() == 0:
         raise ZeroDivisionError("float division")
     obj.kpar, obj.kper = _kpar_kper(kmax_par, kmax_per, kF)
-    obj.Nmodes2D = b.n2d            # already a fresh array (astype in _Bins)
-    inv2 = (fact / b.n2d)[:, None]
-    P2 = b.p2d * inv2
-    X2 = b.x2d * inv2
+    obj.Nmodes2D = b.n2d            # already private to this call (see _Bins)
+    if b.tables_done:               # normalised on the device: Pk2D = sum * (fact / Nmodes2D)
+        P2, X2 = b.p2d, b.x2d
+    else:
+        inv2 = (fact / b.n2d)[:, None]
+        P2 = b.p2d * inv2
+        X2 = b.x2d * inv2
 
     # 3-D
     check_number_modes(b.n3d, dims)
@@ -273,7 +290,8 @@ def _finish(obj, b, dims, BoxSize, is_x):
     if is_x:
         obj.Pk1D, obj.PkX1D, obj.Pk2D, obj.PkX2D, obj.Pk, obj.XPk = P1, X1, P2, X2, P3, X3
     else:
-        obj.Pk1D, obj.Pk2D, obj.Pk = P1[:, 0].copy(), P2[:, 0].copy(), np.ascontiguousarray(P3[:, :, 0])
+        obj.Pk1D, obj.Pk = P1[:, 0].copy(), np.ascontiguousarray(P3[:, :, 0])
+        obj.Pk2D = P2[:, 0] if b.tables_done else P2[:, 0].copy()     # F == 1: a contiguous view of the private copy
         obj.Pkphase = (b.phase[1:] / N3) * fact
 
 
@@ -299,7 +317,7 @@ class Pk(object):
         start2 = time.time()
         L, sums, counts = bin_modes([delta_k], dims, 2 if swap != 2 else int(axis), [MAS_function(MAS)], True,
                                     bool(keep_deltak))
-        bins = _Bins(L, sums, counts)       # D2H of a few KB; synchronises the stream
+        bins = _Bins(L, sums, counts, (BoxSize / dims ** 2) ** 3)       # one D2H of the bins; synchronises the stream
         _say("Time to complete loop = %.2f" % (time.time() - start2))
         _finish(self, bins, dims, BoxSize, False)
         if keep_deltak:
@@ -337,7 +355,7 @@ class XPk(object):
         start2 = time.time()
         L, sums, counts = bin_modes(delta_k, dims, 2 if swap != 2 else int(axis), mas_index[:fields], False, False,
                                     algo=ALGO | self._ALGO_FLAGS)
-        bins = _Bins(L, sums, counts)
+        bins = _Bins(L, sums, counts, (BoxSize / dims ** 2) ** 3)
         _say("Time loop = %.2f" % (time.time() - start2))
         _finish(self, bins, dims, BoxSize, True)
         _say("Time taken = %.2f seconds" % (time.time() - start))

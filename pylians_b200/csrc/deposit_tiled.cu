@@ -115,6 +115,19 @@ bin_hist_kernel(const float *__restrict__ pos, int64_t first, int n, int64_t ps0
             const float *p = base + 3 * (int64_t)(4 * n4 + threadIdx.x);
             atomicAdd(&hist[tile_key<MAS, TC>(p[0], p[1], p[2], inv, tg)], 1);
         }
+    } else if (ps0 == 4 && ps1 == 1 && ((uintptr_t)base & 15) == 0) {
+        // packed (x,y,z,w) records (the particle-exchange payload): one 16-byte load per particle, 4 in flight
+        const float4 *p4 = reinterpret_cast<const float4 *>(base);
+        const int64_t stride = (int64_t)gridDim.x * BIN_THREADS;
+        for (int64_t i0 = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x; i0 < n; i0 += 4 * stride) {
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (i0 + u * stride < n) q[u] = __ldg(p4 + i0 + u * stride);
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (i0 + u * stride < n) atomicAdd(&hist[tile_key<MAS, TC>(q[u].x, q[u].y, q[u].z, inv, tg)], 1);
+        }
     } else {
     // 4 particles per iteration: all 12 loads are issued before the first key is computed
     const int64_t stride = (int64_t)gridDim.x * BIN_THREADS;
@@ -316,11 +329,20 @@ bin_pass_kernel(const float *__restrict__ pos, const float *__restrict__ W, int6
             v[4 * u + 3] = make_float4(c[u].y, c[u].z, c[u].w, wv[3]);
         }
     } else {
+    // packed (x,y,z,w) records (the particle-exchange payload): one 16-byte load; the weight rides along when W
+    // points at the record's 4th float
+    const bool rec4 = FIRST && ps0 == 4 && ps1 == 1 && (((uintptr_t)rawbase) & 15) == 0;
+    const bool w_in_rec = HASW && rec4 && wst == 4 && W + first * wst == rawbase + 3;
 #pragma unroll
     for (int k = 0; k < PART_PER_THREAD; k++) {
         const int i = lo + k * PART_THREADS + tid;
         if (i < hi) {
             if (FIRST) {
+                if (rec4) {
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(rawbase) + i);
+                    v[k] = make_float4(q.x, q.y, q.z, HASW ? (w_in_rec ? q.w : __ldg(W + (first + i) * wst)) : 1.0f);
+                    continue;
+                }
                 const float *p = pos + (first + i) * ps0;
                 v[k] = make_float4(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), HASW ? __ldg(W + (first + i) * wst) : 1.0f);
             } else {
@@ -644,6 +666,9 @@ enum { PATH_BIN_S = 0, PATH_BIN_L = 1, PATH_RADIX_S = 2 };
 // partition particles by owning x-slab (multi-GPU particle exchange): the binsort kernels with a slab key.
 // out[offsets[g] .. offsets[g+1]) = (x,y,z,w) of the particles whose lowest touched x-plane lies in slab g.
 // ------------------------------------------------------------------------------------------------
+template <class K>
+static int set_smem(K kernel, size_t bytes);
+
 template <int MAS, bool HASW>
 static int partition_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, const float *w, int64_t wst, int dims,
                          float inv, int G, float4 *out, int *offsets, cudaStream_t st) {
@@ -667,7 +692,18 @@ static int partition_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1,
     PYLB_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tb, counts, offsets, G + 1, st));
     count_launch(2);
     PYLB_CHECK(cudaMemcpyAsync(cursor, offsets, sizeof(int) * (G + 1), cudaMemcpyDeviceToDevice, st));
-    bin_scatter_kernel<MAS, TileS, HASW><<<P, BIN_THREADS, hist_smem, st>>>(pos, w, wst, 0, n, ps0, ps1, inv, tg, cursor, out);
+    if (G <= PART_MAXBINS) {
+        // the block-local counting sort of the tiled deposit's pass 0 with the slab as its digit: one coalesced read
+        // of the particles, one contiguous run per (chunk, slab) written out (1.26 ms against 1.74 ms for the two-sweep
+        // scatter at 512^3 particles, G = 8)
+        constexpr int PT = 256, CH = PT * PART_PER_THREAD;
+        const size_t psm = sizeof(PartSmem<PT>);
+        if (set_smem(bin_pass_kernel<MAS, TileS, HASW, true, PT>, psm)) return 1;
+        bin_pass_kernel<MAS, TileS, HASW, true, PT><<<(unsigned)((n + CH - 1) / CH), PT, psm, st>>>(
+            pos, w, wst, 0, n, ps0, ps1, inv, tg, nullptr, out, cursor, nullptr, nullptr, 0, G);
+    } else {
+        bin_scatter_kernel<MAS, TileS, HASW><<<P, BIN_THREADS, hist_smem, st>>>(pos, w, wst, 0, n, ps0, ps1, inv, tg, cursor, out);
+    }
     PYLB_LAUNCH_CHECK();
     cudaFreeAsync(counts, st); cudaFreeAsync(cursor, st); cudaFreeAsync(tmp, st);
     return 0;

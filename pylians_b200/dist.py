@@ -6,8 +6,8 @@ this module is the new component BASELINE.json's north_star asks for.  Per snaps
     particles (any shard)                       pos_r (n_r, 3)
       -> EITHER deposit onto a FULL partial grid, (N,N,N) float32                      [local]
                 reduce-scatter (sum) into x-slabs (N/G, N, N)                          [NCCL reduce_scatter, 4 N^3 B]
-         OR     route particles to the rank owning their lowest x-plane                [partition kernel + NCCL all_to_all, 16 B/particle]
-                deposit onto slab + S-1 halo planes, pass the halo to the next rank    [windowed deposit + NCCL send/recv]
+         OR     route particles to the rank owning their lowest x-plane                [partition kernel + grouped NCCL send/recv, 16 B/particle,
+                deposit onto slab + S-1 halo planes, pass the halo to the next rank     in pieces overlapped with the windowed deposit; halo: send/recv]
       -> overdensity with the GLOBAL mean       sum in float64, all-reduced            [NCCL all_reduce, 8 B]
       -> batched 2-D R2C over (y,z)             (N/G, N, N/2+1) complex64              [cuFFT]
       -> transpose pack + all-to-all            (G, N/G, N/G, N/2+1) blocks            [pack kernel + NCCL all_to_all]
@@ -146,13 +146,16 @@ class _Result(object):
 class SlabPk(object):
     """Distributed MA + Pk / XPk.  Every rank calls the same methods with its own particle shard."""
 
-    def __init__(self, dims, BoxSize, MAS="CIC", axis=2, group=None, ops=None, exchange="auto"):
+    def __init__(self, dims, BoxSize, MAS="CIC", axis=2, group=None, ops=None, exchange="auto", exchange_chunks=2):
         """exchange: how per-rank deposits become x-slabs --
              "grid"      every rank deposits onto a full partial grid, then reduce-scatter (4 N^3 bytes per rank);
              "particles" particles are routed to the rank owning their lowest touched x-plane (16 B per particle),
                          deposited onto slab + S-1 halo planes, halo planes are passed to the next rank;
-             "auto"      whichever moves fewer bytes for this call."""
+             "auto"      whichever moves fewer bytes for this call.
+           exchange_chunks: pieces the routed particles travel in ("particles" mode), so that the deposit of one piece
+             overlaps the transfer of the next; must be the same on every rank."""
         self.exchange = exchange
+        self.exchange_chunks = max(1, int(exchange_chunks))
         self._auto_mode = None
         self.rank, self.G = _group_info(group)
         self.group = group
@@ -203,37 +206,67 @@ class SlabPk(object):
         _reduce_scatter_sum(slab, partial, self.group, G)
         return slab
 
+    def _peer(self, g):
+        return dist.get_global_rank(self.group, g) if self.group is not None else g
+
     def _slab_from_particles(self, pos, W, MAS, halo):
+        """Route every particle to the rank owning its lowest touched x-plane and deposit there.
+
+        The routed payload moves in `exchange_chunks` pieces: all pieces are queued on NCCL's stream at once (grouped
+        send/recv = all-to-all), and the windowed deposit of piece c runs on the compute stream as soon as piece c has
+        arrived, i.e. while piece c+1 is still crossing NVLink.  MA only ever adds into the grid, so depositing in
+        pieces changes nothing but the fp32 summation order."""
         ops, N, G, r = self.ops, self.dims, self.G, self.rank
         send, offsets = ops.partition(pos, W, self.BoxSize, MAS, G, N)
-        if G > 1:
-            off = offsets.to("cpu").tolist()                      # G+1 ints: the split sizes must be known on the host
-            send_splits = [off[g + 1] - off[g] for g in range(G)]
-            t_send = torch.tensor(send_splits, dtype=torch.int64, device=send.device)
-            t_recv = torch.empty_like(t_send)
-            dist.all_to_all_single(t_recv, t_send, group=self.group)
-            recv_splits = t_recv.to("cpu").tolist()
-            recv = send.new_empty((sum(recv_splits), 4))
-            dist.all_to_all_single(recv, send, output_split_sizes=recv_splits, input_split_sizes=send_splits, group=self.group)
-        else:
-            recv = send
-        del send
         if G == 1:
-            halo = 0                                              # the window is the whole periodic cube
+            grid = ops.zeros((self.nxl, N, N))                    # the window is the whole periodic cube
+            ops.deposit_window(send, grid, 0, self.BoxSize, MAS, W is not None, N)
+            return grid
+        off = offsets.to("cpu").tolist()                          # G+1 ints: the split sizes must be known on the host
+        send_tot = [off[g + 1] - off[g] for g in range(G)]
+        t_send = torch.tensor(send_tot, dtype=torch.int64, device=send.device)
+        t_recv = torch.empty_like(t_send)
+        dist.all_to_all_single(t_recv, t_send, group=self.group)
+        recv_tot = t_recv.to("cpu").tolist()
+        K = self.exchange_chunks
+
+        def part(c, total):                                       # rows [lo, hi) of a `total`-row range that travel in piece c
+            return (c * total) // K, ((c + 1) * total) // K       # same formula on the sending and the receiving side
+
+        pieces = []
+        for c in range(K):
+            spans = [part(c, recv_tot[s]) for s in range(G)]
+            buf = send.new_empty((sum(hi - lo for lo, hi in spans), 4))
+            p2p, row = [], 0
+            for s in range(G):
+                n = spans[s][1] - spans[s][0]
+                if n:
+                    if s == r:                                    # my own share stays on the device
+                        lo, hi = part(c, send_tot[r])
+                        buf[row:row + n].copy_(send[off[r] + lo:off[r] + hi])
+                    else:
+                        p2p.append(dist.P2POp(dist.irecv, buf[row:row + n], self._peer(s), group=self.group))
+                row += n
+            for g in range(G):
+                lo, hi = part(c, send_tot[g])
+                if hi > lo and g != r:
+                    p2p.append(dist.P2POp(dist.isend, send[off[g] + lo:off[g] + hi], self._peer(g), group=self.group))
+            pieces.append((buf, dist.batch_isend_irecv(p2p) if p2p else []))
         grid = ops.zeros((self.nxl + halo, N, N))
-        ops.deposit_window(recv, grid, r * self.nxl, self.BoxSize, MAS, W is not None, N)
-        del recv
+        for buf, reqs in pieces:
+            for q in reqs:
+                q.wait()
+            if buf.shape[0]:
+                ops.deposit_window(buf, grid, r * self.nxl, self.BoxSize, MAS, W is not None, N)
+        del pieces, send
         if halo:
             mine = grid[self.nxl:]                                # planes that belong to the next rank
-            if True:
-                got = torch.empty_like(mine)
-                nxt, prv = (r + 1) % G, (r - 1) % G
-                if self.group is not None:
-                    nxt, prv = dist.get_global_rank(self.group, nxt), dist.get_global_rank(self.group, prv)
-                reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, mine, nxt, group=self.group),
-                                               dist.P2POp(dist.irecv, got, prv, group=self.group)])
-                for q in reqs:
-                    q.wait()
+            got = torch.empty_like(mine)
+            nxt, prv = self._peer((r + 1) % G), self._peer((r - 1) % G)
+            reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, mine, nxt, group=self.group),
+                                           dist.P2POp(dist.irecv, got, prv, group=self.group)])
+            for q in reqs:
+                q.wait()
             ops.add(grid[:halo], got)
         return grid[: self.nxl]
 
@@ -261,7 +294,7 @@ class SlabPk(object):
         if G > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
             dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
-        return PKL._Bins(L, sums, counts)
+        return PKL._Bins(L, sums, counts, (self.BoxSize / N ** 2) ** 3 if getattr(sums, "is_cuda", False) else None)
 
     # ---- whole pipelines -------------------------------------------------------------------------
     def pk_from_slab(self, slab, MAS=None):

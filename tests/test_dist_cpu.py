@@ -85,3 +85,49 @@ def test_slab_layout_single_process():
     d = np.zeros((dims,) * 3, np.float32); O.MA(pos, d, box, "PCS"); d /= np.mean(d, dtype=np.float64); d -= 1.0
     parity.check_pk(SlabPk(dims, box, "PCS", 1, ops=CpuOps(), exchange="grid").run(pos), O.Pk(d, box, 1, "PCS", 1))
     parity.check_pk(SlabPk(dims, box, "PCS", 1, ops=CpuOps(), exchange="particles").run(pos), O.Pk(d, box, 1, "PCS", 1))
+
+
+def _worker_uneven(rank, world, port, q):
+    """Particle exchange with 4 ranks, very uneven shards (one rank holds 5 particles, all in one slab) and a chunk
+    count that divides nothing: the per-piece send/recv sizes must still agree on both ends."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import parity
+        from cpu_slab_ops import CpuOps
+        from oracle import pylians_oracle as O
+        from pylians_b200.dist import SlabPk
+        dims, box, mas = 16, 500.0, "PCS"
+        rng = np.random.default_rng(17)
+        pos = (rng.random((3 * dims ** 3, 3)) * box).astype(np.float32)
+        pos[-5:, 0] = box * 0.9                                   # the last rank's 5 particles all go to the last slab
+        bounds = [0, 7001, 7001 + 3, len(pos) - 5, len(pos)]      # 7001 / 3 / ~5279 / 5 particles
+        W = (rng.random(len(pos)) + 0.5).astype(np.float32)
+        for chunks in (3, 1, 7):
+            eng = SlabPk(dims, box, mas, 2, ops=CpuOps(), exchange="particles", exchange_chunks=chunks)
+            slab = eng.density_slab(pos[bounds[rank]:bounds[rank + 1]], W[bounds[rank]:bounds[rank + 1]], overdensity=False)
+            ref = np.zeros((dims,) * 3, np.float32); O.MA(pos, ref, box, mas, W=W)
+            nxl = dims // world
+            parity.assert_grid_close(slab.numpy(), ref[rank * nxl:(rank + 1) * nxl], "slab of rank %d, %d pieces" % (rank, chunks),
+                                     rtol=1e-4)
+        q.put((rank, "ok"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_particle_exchange_pieces_world4_uneven_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_uneven, args=(r, 4, port, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == "ok", "rank %d failed:\n%s" % (rank, msg)
