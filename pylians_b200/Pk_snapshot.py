@@ -92,10 +92,10 @@ def Pk_comp(snapshot_fname, ptype, dims, do_RSD, axis, cpus, folder_out):
     if do_RSD:
         _say("moving particles to redshift-space...")
     if ptype == -1:                                           # :70-82, masses from the header table or the MASS block
-        delta, count, mass_sum = _species_field(snap, [0, 1, 2, 3, 4, 5], dims, BoxSize, do_RSD, axis, True, True)
+        delta, count, mass_sum = _species_field(snap, [0, 1, 2, 3, 4, 5], dims, BoxSize, do_RSD, axis, True, PKL.VERBOSE)
         mean = mass_sum / dims ** 3
     else:                                                     # :84-86
-        delta, count, _ = _species_field(snap, [ptype], dims, BoxSize, do_RSD, axis, False, True)
+        delta, count, _ = _species_field(snap, [ptype], dims, BoxSize, do_RSD, axis, False, PKL.VERBOSE)
         mean = count * 1.0 / dims ** 3
     _overdensity_mean(delta, mean)
     Pk = PKL.Pk(delta, BoxSize, axis=axis, MAS="CIC", threads=cpus)

@@ -253,18 +253,30 @@ struct PartSmem {
 };
 
 // chunk list of pass 1: bucket b (tiles [b << lo_bits, (b+1) << lo_bits)) owns ceil(size_b / PART_CHUNK) chunks
-__global__ void part_buckets_kernel(const int *__restrict__ tile_begin, int ntiles, int lo_bits, int nb0, int *bcursor,
-                                    int *bchunk_off, int PART_CHUNK) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        int acc = 0;
-        for (int b = 0; b < nb0; b++) {
-            const int t0 = b << lo_bits, t1 = min(ntiles, (b + 1) << lo_bits);
-            bcursor[b] = tile_begin[t0];
-            bchunk_off[b] = acc;
-            acc += (tile_begin[t1] - tile_begin[t0] + PART_CHUNK - 1) / PART_CHUNK;
-        }
-        bchunk_off[nb0] = acc;
+__global__ void __launch_bounds__(PART_MAXBINS)
+part_buckets_kernel(const int *__restrict__ tile_begin, int ntiles, int lo_bits, int nb0, int *bcursor, int *bchunk_off,
+                    int PART_CHUNK) {
+    // one thread per bucket (nb0 <= PART_MAXBINS = blockDim.x) and a shared-memory scan of the chunk counts; the
+    // single-thread loop this replaces took 38 us of dependent global loads per deposit
+    __shared__ int s[PART_MAXBINS];
+    const int b = threadIdx.x;
+    int c = 0;
+    if (b < nb0) {
+        const int t0 = b << lo_bits, t1 = min(ntiles, (b + 1) << lo_bits);
+        const int begin = tile_begin[t0];
+        bcursor[b] = begin;
+        c = (tile_begin[t1] - begin + PART_CHUNK - 1) / PART_CHUNK;
     }
+    s[b] = c;
+    __syncthreads();
+    for (int o = 1; o < PART_MAXBINS; o <<= 1) {
+        const int v = b >= o ? s[b - o] : 0;
+        __syncthreads();
+        s[b] += v;
+        __syncthreads();
+    }
+    if (b < nb0) bchunk_off[b] = s[b] - c;
+    if (b == nb0 - 1) bchunk_off[nb0] = s[b];
 }
 
 template <int MAS, class TC, bool HASW, bool FIRST, int PART_THREADS>
@@ -829,7 +841,7 @@ template <int MAS, class TC, bool HASW, int PT>
 static int run_passes(const float *pos, const float *w, int64_t wst, int64_t first, int n, int64_t ps0, int64_t ps1, float inv,
                       const TileGeom &tg, TiledWs &ws, int lo_bits, int nb0, cudaStream_t st) {
     constexpr int CH = PT * PART_PER_THREAD;
-    part_buckets_kernel<<<1, 32, 0, st>>>(ws.tile_begin, tg.ntiles, lo_bits, nb0, ws.bcursor, ws.bchunk_off, CH);
+    part_buckets_kernel<<<1, PART_MAXBINS, 0, st>>>(ws.tile_begin, tg.ntiles, lo_bits, nb0, ws.bcursor, ws.bchunk_off, CH);
     PYLB_LAUNCH_CHECK();
     const size_t psm = sizeof(PartSmem<PT>);
     if (set_smem(bin_pass_kernel<MAS, TC, HASW, true, PT>, psm) || set_smem(bin_pass_kernel<MAS, TC, HASW, false, PT>, psm)) return 1;
