@@ -130,6 +130,29 @@ def cpu_measure(nside, mas, axis, repeats):
     return times, kind, threads
 
 
+def cpu_deposit_variants(nside, mas):
+    """The two deposit paths the reference offers, timed alone on the same sample: the serial Cython kernel
+    MA() dispatches to, and the OpenMP C kernel (MAS_c.c via <MAS>c3D, all host threads; valid for N < 1291 only)."""
+    import numpy as np
+    from oracle import ref_loader
+    if not ref_loader.available():
+        return None
+    MASL, _ = ref_loader.load()
+    threads = os.cpu_count() or 1
+    rng = np.random.default_rng(1)
+    pos = (rng.random((nside ** 3, 3), dtype=np.float32) * np.float32(BOX)).astype(np.float32)
+    out = {"sample": "%d^3 particles %s onto %d^3 grid" % (nside, mas, nside), "unit": "particles/s"}
+    d = np.zeros((nside,) * 3, np.float32)
+    t0 = time.perf_counter(); MASL.MA(pos, d, BOX, mas); out["serial_cython_1_core"] = nside ** 3 / (time.perf_counter() - t0)
+    try:
+        fn = getattr(MASL, mas + "c3D")
+        d[...] = 0
+        t0 = time.perf_counter(); fn(pos, d, BOX, threads); out["openmp_c_%d_threads" % threads] = nside ** 3 / (time.perf_counter() - t0)
+    except Exception as e:  # noqa: BLE001
+        out["openmp_c_error"] = repr(e)
+    return out
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -362,7 +385,8 @@ def run_ours(args, wl):
             sec = min(times)
             cpu = {"value": cn ** 3 / sec, "unit": "particles/s", "cores": threads, "kind": kind,
                    "sample": "%d^3 particles %s onto %d^3 grid + overdensity + Pk, best of 2 (%.1f s each); "
-                             "MA is the reference's serial kernel, threads feed only the FFT" % (cn, mas, cn, sec)}
+                             "MA is the reference's serial kernel, threads feed only the FFT" % (cn, mas, cn, sec),
+                   "deposit_only": cpu_deposit_variants(cn, mas)}
         line = {"metric": "MA+Pk snapshot throughput", "value": value, "unit": "particles/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
                 "s_per_snapshot": ms_step * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
