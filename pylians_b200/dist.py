@@ -119,6 +119,27 @@ class CudaOps(object):
         ks = _lib.KSpace(dims, 0, dims, int(y0), int(nyl), nyl * nz, nz)
         return PKL.bin_modes(fields, dims, axis, mas_index, want_phase, False, ks=ks)
 
+    def overdensity_mean(self, slab, mean):
+        """slab /= mean; slab -= 1 with the caller's mean (Pk_snapshot.py:84-88)."""
+        _lib.check(self.lib.pylb_overdensity_mean(slab.data_ptr(), slab.numel(), float(np.float32(mean)), self._stream()),
+                   "pylb_overdensity_mean")
+
+    def load_species(self, snapshot_fname, file_slice, ptype, do_RSD, axis):
+        """Positions (Mpc/h, redshift space if asked) of species `ptype` from the sub-files `file_slice` selects, as ONE
+        device tensor: every block goes disk -> pinned memory -> its place in the tensor (MAS_gadget.StreamedSnapshot)."""
+        from .MAS_gadget import StreamedSnapshot
+        snap = StreamedSnapshot(snapshot_fname)
+        snap.files = snap.files[file_slice]
+        BoxSize = snap.head.boxsize / 1e3
+        out = torch.empty((snap.count(ptype), 3), dtype=torch.float32, device=self.dev)
+        row = 0
+        for pos, vel, _, m in snap.blocks(ptype, want_vel=do_RSD):
+            if do_RSD:
+                snap.to_redshift_space(pos, vel, BoxSize, axis)
+            out[row:row + m].copy_(pos)
+            row += m
+        return out
+
 
 def _group_info(group):
     if dist.is_available() and dist.is_initialized():
@@ -307,6 +328,31 @@ class SlabPk(object):
     def run(self, pos, W=None):
         """particles -> Pk (same attributes as Pk_library.Pk), identical on every rank."""
         return self.pk_from_slab(self.density_slab(pos, W))
+
+    def pk_comp(self, snapshot_fname, ptype, do_RSD=False, folder_out=None):
+        """Distributed Pk_comp (Pk_library/Pk_snapshot.py:34-91) for one species of a binary Gadget snapshot: rank r
+        reads sub-files r, r+G, ... (each file is read by exactly one rank, straight into that GPU), the particles are
+        deposited with this engine's exchange mode, the overdensity uses the reference's mean Np/dims^3, and rank 0
+        writes the reference's output file.  Returns the Pk object (same attributes as Pk_library.Pk) on every rank."""
+        from . import readgadget
+        from .Pk_snapshot import name_dict
+        files = readgadget.subfiles(snapshot_fname)
+        head = readgadget.header(files[0][0])
+        BoxSize = head.boxsize / 1e3
+        if abs(BoxSize - self.BoxSize) > 1e-6 * BoxSize:
+            raise ValueError("snapshot BoxSize %g Mpc/h differs from the engine's %g" % (BoxSize, self.BoxSize))
+        total = sum(int(sf.npart[ptype]) for _, sf in files)
+        pos = self.ops.load_species(snapshot_fname, slice(self.rank, None, self.G), ptype, do_RSD, self.axis)
+        slab = self.density_slab(pos, None, "CIC", overdensity=False)
+        del pos
+        self.ops.overdensity_mean(slab, total * 1.0 / self.dims ** 3)
+        out = self.pk_from_slab(slab, "CIC")
+        if folder_out is not None and self.rank == 0:
+            z = "%.3f" % head.redshift
+            fout = folder_out + "/Pk_" + name_dict[str(ptype)]
+            fout += ("_RS_axis=" + str(self.axis) + "_z=" + z + ".dat") if do_RSD else ("_z=" + z + ".dat")
+            np.savetxt(fout, np.transpose([out.k3D, out.Pk[:, 0], out.Pk[:, 1], out.Pk[:, 2], out.Nmodes3D]))
+        return out
 
     def run_x(self, pos_list, W_list=None, MAS_list=None):
         """Several particle sets -> XPk (same attributes as Pk_library.XPk)."""

@@ -49,6 +49,25 @@ class CpuOps(object):
     def add(self, dst, src):
         dst += src
 
+    def overdensity_mean(self, slab, mean):
+        a = slab.numpy()
+        a /= np.float32(mean)
+        a -= np.float32(1.0)
+
+    def load_species(self, snapshot_fname, file_slice, ptype, do_RSD, axis):
+        from pylians_b200 import readgadget
+        head = readgadget.header(snapshot_fname)
+        parts = []
+        for name, sf in readgadget.subfiles(snapshot_fname)[file_slice]:
+            if int(sf.npart[ptype]) == 0:
+                continue
+            pos = readgadget.read_field(name, "POS ", ptype) / np.float32(1e3)
+            if do_RSD:
+                vel = readgadget.read_field(name, "VEL ", ptype)
+                O.pos_redshift_space(pos, vel, head.boxsize / 1e3, head.Hubble, head.redshift, axis)
+            parts.append(pos)
+        return np.concatenate(parts) if parts else np.zeros((0, 3), np.float32)
+
     def grid_sum(self, slab):
         return torch.tensor([float(np.sum(slab.numpy(), dtype=np.float64))], dtype=torch.float64)
 

@@ -131,3 +131,55 @@ def test_particle_exchange_pieces_world4_uneven_gloo():
         p.join(timeout=60)
     for rank, msg in res:
         assert msg == "ok", "rank %d failed:\n%s" % (rank, msg)
+
+
+def _worker_snapshot(rank, world, port, base, folder, q):
+    """Distributed Pk_comp: each rank reads its own sub-files; rank 0 writes the reference's output file."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cpu_slab_ops import CpuOps
+        from pylians_b200.dist import SlabPk
+        for exchange, rsd, axis in (("grid", False, 0), ("particles", True, 2)):
+            eng = SlabPk(16, 40.0, "CIC", axis, ops=CpuOps(), exchange=exchange)
+            eng.pk_comp(base, 1, rsd, folder)
+        q.put((rank, "ok"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_pk_comp_matches_reference_driver(tmp_path, golden_dir):
+    """3 sub-files over 2 ranks (rank 0 reads files 0 and 2, rank 1 reads file 1) against the output files of the
+    reference's own Pk_Gadget on the same snapshot (tests/golden/drivers.npz); 1e-3 because sharding changes the
+    fp32 summation order of the grid (see _worker)."""
+    sys.path.insert(0, HERE)
+    import gadget_writer as GW
+    import parity
+    from test_drivers import SNAP
+    parts = GW.make_particles(SNAP["seed"], SNAP["counts"], SNAP["box_kpc"], SNAP["masstable"], clustered=True)
+    base = str(tmp_path / "snap_005")
+    GW.write_snapshot(base, parts, SNAP["masstable"], SNAP["box_kpc"], SNAP["redshift"], SNAP["nfiles"], 1)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_snapshot, args=(r, 2, port, base, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == "ok", "rank %d failed:\n%s" % (rank, msg)
+    gd = np.load(os.path.join(golden_dir, "drivers.npz"))
+    for fname, key in (("Pk_CDM_z=1.000.dat", "pk_cdm__Pk_CDM_z=1.000.dat"),
+                       ("Pk_CDM_RS_axis=2_z=1.000.dat", "pk_cdm_rs2__Pk_CDM_RS_axis=2_z=1.000.dat")):
+        got, want = np.loadtxt(str(tmp_path / fname)), gd[key]
+        parity.assert_exact(got[:, 4], want[:, 4], fname + " Nmodes")
+        parity.assert_k_close(got[:, 0], want[:, 0], fname + " k")
+        p0 = np.abs(want[:, 1])
+        floor = (p0 + np.median(p0))[:, None] * np.array([1.0, 5.0, 9.0])[None, :]
+        parity.assert_spec_close(got[:, 1:4], want[:, 1:4], floor, fname, rtol=1e-3)

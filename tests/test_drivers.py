@@ -107,3 +107,19 @@ def test_pk_comp_total_matter_against_oracle(tmp_path, parts):
     delta -= np.float32(1.0)
     ref = O.Pk(delta, box, 0, "CIC", 1)
     _check_pk_file(got, np.transpose([ref.k3D, ref.Pk[:, 0], ref.Pk[:, 1], ref.Pk[:, 2], ref.Nmodes3D]), "Pk_matter")
+
+
+@pytest.mark.gpu
+def test_distributed_pk_comp_single_rank_matches_reference(tmp_path, gd, parts):
+    """pylians_b200.dist.SlabPk.pk_comp with one rank (no process group): the slab pipeline fed by the streamed reader
+    must write the same file as the reference's Pk_Gadget (world-2 is covered on CPU by tests/test_dist_cpu.py)."""
+    import pylians_b200
+    from pylians_b200.dist import SlabPk
+    pylians_b200.set_verbose(False)
+    base = _write(tmp_path, parts)
+    for exchange, rsd, axis, fname, key in (
+            ("grid", False, 0, "Pk_CDM_z=1.000.dat", "pk_cdm__Pk_CDM_z=1.000.dat"),
+            ("particles", True, 2, "Pk_CDM_RS_axis=2_z=1.000.dat", "pk_cdm_rs2__Pk_CDM_RS_axis=2_z=1.000.dat")):
+        out = SlabPk(DIMS, SNAP["box_kpc"] / 1e3, "CIC", axis, exchange=exchange).pk_comp(base, 1, rsd, str(tmp_path))
+        assert out.Nmodes3D.shape == (gd[key].shape[0],)
+        _check_pk_file(np.loadtxt(str(tmp_path / fname)), gd[key], fname)
