@@ -12,7 +12,7 @@ import os
 import numpy as np
 import torch
 
-from . import _lib, readgadget
+from . import _lib
 from . import MAS_library as MASL
 from . import Pk_library as PKL
 from . import units_library as UL

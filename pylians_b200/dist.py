@@ -20,8 +20,6 @@ The local operations come from an `ops` object so the host logic (partitioning, 
 arithmetic) can be exercised on CPU with the gloo backend and a numpy stand-in (tests/cpu_slab_ops.py);
 the product always uses CudaOps -- there is no CPU fallback in this package.
 """
-import ctypes
-
 import numpy as np
 import torch
 import torch.distributed as dist
