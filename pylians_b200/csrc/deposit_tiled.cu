@@ -469,12 +469,12 @@ __global__ void __launch_bounds__(TC::THREADS)
 deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, int64_t ps1,
                     const float *__restrict__ W, int64_t wst, float inv, TileGeom tg, const unsigned *__restrict__ svals,
                     const float4 *__restrict__ sorted, const int *__restrict__ tile_begin,
-                    const int *__restrict__ chunk_off, float *__restrict__ grid) {
+                    const int *__restrict__ chunk_off, float *__restrict__ grid, int agg) {
     using TS = TileShape<MAS, TC>;
     constexpr int S = TS::S;
     constexpr int TILE_THREADS = TC::THREADS;
     extern __shared__ __align__(16) float tile[];
-    __shared__ int s_tile, s_lo, s_hi;
+    __shared__ int s_tile, s_lo, s_hi, s_agg;
 
     if (threadIdx.x == 0) {
         // find the tile whose chunk range holds blockIdx.x: chunk_off[t] <= b < chunk_off[t+1]
@@ -493,6 +493,9 @@ deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, i
             const int begin = tile_begin[lo] + (b - chunk_off[lo]) * CHUNK;
             s_lo = begin;
             s_hi = min(begin + CHUNK, tile_begin[lo + 1]);
+            // a tile holding clearly more particles than the average tile is where a halo sits: only its CTAs
+            // pay for looking for lanes that share a cell (agg = that particle count, 0 = never)
+            s_agg = agg > 0 && tile_begin[lo + 1] - tile_begin[lo] >= agg;
         }
     }
     __syncthreads();
@@ -546,11 +549,60 @@ deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, i
     if (!REGROUP) {
         // (hoisting 4 particle loads ahead of the updates changes nothing for CIC and costs PCS 15 % in registers:
         //  the kernel waits on the shared-memory pipe, not on these loads)
-        for (int i = s_lo + threadIdx.x; i < s_hi; i += TILE_THREADS) {
-            const float4 q = load(i);
-            float C[3][S];
-            const int cell0 = base_cell(q, C);
-            if (cell0 >= 0) put(cell0, C, q.w);
+        if (FIXED || S > 2 || !s_agg) {
+            for (int i = s_lo + threadIdx.x; i < s_hi; i += TILE_THREADS) {
+                const float4 q = load(i);
+                float C[3][S];
+                const int cell0 = base_cell(q, C);
+                if (cell0 >= 0) put(cell0, C, q.w);
+            }
+        } else {
+            // Warp-aggregated updates for clustered inputs.  Lanes whose particles share a base cell update the same
+            // S^3 addresses; a shared atomicAdd(float) is a CAS loop, so n lanes on one address cost ~n rounds each.
+            // When a group of >= AGG_MIN lanes shares its base cell (a halo cell holding a large share of the tile's
+            // particles) the group's S^3 contributions are summed with warp shuffles and its first lane issues ONE
+            // atomic per cell.  Only CTAs of over-populated tiles (s_agg) run this loop, so uniform inputs never pay for it,
+            // and only NGP and CIC do: S^3 x 5 shuffles per group cost more than the contention they remove for TSC / PCS
+            // (measured on a clustered 512^3 set: CIC tile kernel 3.86 -> 2.99 ms, PCS 21.6 -> 25.0 ms).
+            constexpr int AGG_MIN = 4;
+            const unsigned full = 0xffffffffu;
+            const int lane = threadIdx.x & 31;
+            for (int i0 = s_lo + (threadIdx.x & ~31); i0 < s_hi; i0 += TILE_THREADS) {   // warp-uniform trip count
+                const int i = i0 + lane;
+                float C[3][S];
+                int cell0 = -1;
+                float w = 1.0f;
+                if (i < s_hi) {
+                    const float4 q = load(i);
+                    cell0 = base_cell(q, C);
+                    w = q.w;
+                }
+                const unsigned peers = __match_any_sync(full, cell0);
+                const bool heavy = cell0 >= 0 && __popc(peers) >= AGG_MIN;
+                unsigned todo = __ballot_sync(full, heavy);
+                while (todo) {                                   // one round per heavy group: at most 32 / AGG_MIN
+                    const int leader = __ffs(todo) - 1;
+                    const unsigned grp = __shfl_sync(full, peers, leader);
+                    const bool mine = (grp >> lane) & 1u;
+                    const int cell_l = __shfl_sync(full, cell0, leader);
+#pragma unroll
+                    for (int l = 0; l < S; l++)
+#pragma unroll
+                        for (int m = 0; m < S; m++) {
+                            const float cxy = mine ? C[0][l] * C[1][m] : 0.0f;
+#pragma unroll
+                            for (int n = 0; n < S; n++) {
+                                float v = mine ? cxy * C[2][n] : 0.0f;
+                                if (HASW && mine) v *= w;
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+                                if (lane == leader) atomicAdd(tile + cell_l + (l * TS::SY + m) * TS::SZ + n, v);
+                            }
+                        }
+                    todo &= ~grp;
+                }
+                if (cell0 >= 0 && !heavy) put(cell0, C, w);
+            }
         }
     } else {
         // Regroup by shared-memory bank.  The tile's particles arrive in no particular order, so the 32 cells a warp
@@ -855,6 +907,19 @@ static int run_passes(const float *pos, const float *w, int64_t wst, int64_t fir
     return 0;
 }
 
+// Particle count from which a tile's CTAs use the warp-aggregated branch: 1.25x the mean tile population (Poisson
+// fluctuations of a uniform set at >= 1000 particles per tile stay below 1.1x).  PYLB_MA_AGG=0 switches it off, =2 forces
+// it for every tile (A/B runs).
+static int agg_threshold(int n, int ntiles) {
+    static int env = -2;
+    if (env == -2) { const char *e = getenv("PYLB_MA_AGG"); env = e ? atoi(e) : 1; }
+    if (env == 0) return 0;
+    if (env == 2) return 1;
+    const double mean = (double)n / (double)(ntiles > 0 ? ntiles : 1);
+    const double thr = 1.25 * mean + 64.0;
+    return thr > 2.0e9 ? 2000000000 : (int)thr;
+}
+
 static bool use_regroup() {
     static int env = -2;
     // Opt-in (PYLB_MA_REGROUP=1).  Measured at 512^3: CIC 2.31 ms against 1.59 ms in arrival order, PCS 1.50 against
@@ -930,10 +995,10 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
         timing_begin(PYLB_T_TILE, st);
         if (regroup)
             deposit_tile_kernel<MAS, HASW, TC, BINSORT, FIXED, true><<<(unsigned)max_items, TC::THREADS, tile_smem, st>>>(
-                pos, first, ps0, ps1, w, wst, inv, tg, ws.v1, ws.sorted, ws.tile_begin, ws.chunk_off, grid);
+                pos, first, ps0, ps1, w, wst, inv, tg, ws.v1, ws.sorted, ws.tile_begin, ws.chunk_off, grid, agg_threshold(n, tg.ntiles));
         else
             deposit_tile_kernel<MAS, HASW, TC, BINSORT, FIXED, false><<<(unsigned)max_items, TC::THREADS, tile_smem, st>>>(
-                pos, first, ps0, ps1, w, wst, inv, tg, ws.v1, ws.sorted, ws.tile_begin, ws.chunk_off, grid);
+                pos, first, ps0, ps1, w, wst, inv, tg, ws.v1, ws.sorted, ws.tile_begin, ws.chunk_off, grid, agg_threshold(n, tg.ntiles));
         timing_end(PYLB_T_TILE, st);
         PYLB_LAUNCH_CHECK();
     }

@@ -486,3 +486,30 @@ def test_full_size_1024_tsc_multipoles_and_xpk(MASL, PKL):
     y = PKL.XPk(fields[::-1], box, 2, ["CIC", "TSC"], 1)                          # the cross spectrum is symmetric
     np.testing.assert_allclose(y.XPk[:, :, 0], x.XPk[:, :, 0], rtol=1e-6, atol=1e-7 * shot)
     np.testing.assert_allclose(y.Pk[:, :, 1], x.Pk[:, :, 0], rtol=1e-6, atol=1e-7 * shot)
+
+
+@pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_ma_clustered_input_warp_aggregation(MASL, mas, weighted):
+    """Half of one tile's particles sit in three cells (a halo): the tile kernel's warp-aggregated branch (groups of
+    lanes sharing a base cell are summed with shuffles, one shared atomic per cell) must give the oracle's grid."""
+    from oracle import pylians_oracle as O
+    import pylians_b200.MAS_library as M
+    dims, box = 64, 640.0                                   # 10 length units per cell
+    rng = np.random.default_rng(31)
+    uni = rng.random((150000, 3)) * box
+    hot = np.concatenate([c + rng.normal(0.0, 2.0, (1500, 3)) for c in
+                          (np.array([105.0, 85.0, 155.0]), np.array([104.0, 93.0, 161.0]), np.array([325.0, 325.0, 325.0]))])
+    pos = np.mod(np.concatenate([uni, hot]), box).astype(np.float32)
+    pos = pos[rng.permutation(len(pos))]
+    W = (rng.random(len(pos)) + 0.5).astype(np.float32) if weighted else None
+    ref = np.zeros((dims,) * 3, np.float32)
+    O.MA(pos, ref, box, mas, W=W)
+    old, M.ALGO = M.ALGO, 2                                 # the tiled (shared-memory) deposit, also on this small grid
+    try:
+        got = np.zeros((dims,) * 3, np.float32)
+        MASL.MA(pos, got, box, mas, W=W)
+    finally:
+        M.ALGO = old
+    assert ref.max() > 50 * ref.mean()                      # the halo cells really are hot
+    parity.assert_grid_close(got, ref, "clustered " + mas)
