@@ -1,0 +1,47 @@
+"""The JSON lines bench.py printed on the B200 this round (kept under profiles/) carry every key the driver's contract
+names, with consistent values.  CPU only: guards the contract against regressions in bench.py's output."""
+import json
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(name):
+    path = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(path):
+        pytest.skip("%s not recorded" % name)
+    return json.load(open(path))
+
+
+def test_own_arm_line():
+    d = _load("r1_bench_1gpu_final_v4.json")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "gpu_launches", "e2e", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["warmup"] >= 3 and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert abs(d["value"] - d["config"]["particles_total"] / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 12 * d["config"]["particles_total"] and e["d2h_bytes_per_step"] > 0
+    assert e["value"] < d["value"]                                   # host-fed can not beat HBM-resident
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert r["traffic"] is None or r["traffic"] >= r["algorithmic_bytes_per_launch"]
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["unit"] == d["unit"] and c["sample"]
+    assert d["gpu_launches"] > 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["check"]["Nmodes_sum_ok"] is True
+
+
+def test_reference_arm_line():
+    d = _load("r1_bench_1gpu_reference_v2.json")
+    own = _load("r1_bench_1gpu_final_v4.json")
+    assert d["impl"] == "reference"
+    for k in ("metric", "unit", "higher_is_better"):
+        assert d[k] == own[k], k
+    assert d["config"]["workload"] == own["config"]["workload"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] in ("reference", "port")
