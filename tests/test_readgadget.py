@@ -101,3 +101,46 @@ def test_against_reference_reader_format1(tmp_path, parts, nfiles):
     sub = base if nfiles == 1 else base + ".1"
     np.testing.assert_array_equal(ref.read_field(sub, "POS ", 1), RG.read_field(sub, "POS ", 1))
     np.testing.assert_array_equal(ref.read_field(sub, "VEL ", 4), RG.read_field(sub, "VEL ", 4))
+
+
+# ---- property test: any mix of species / header masses / sub-files / format / byte order round-trips ----------------
+from hypothesis import given, settings, strategies as st, HealthCheck     # noqa: E402
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(counts=st.lists(st.integers(0, 40), min_size=6, max_size=6).filter(lambda c: sum(c) > 0),
+       header_mass=st.lists(st.booleans(), min_size=6, max_size=6),
+       nfiles=st.integers(1, 4), fmt=st.sampled_from([1, 2]), order=st.sampled_from(["<", ">"]),
+       redshift=st.sampled_from([0.0, 2.0]))
+def test_reader_roundtrip_property(tmp_path_factory, counts, header_mass, nfiles, fmt, order, redshift):
+    masstable = np.array([0.37 if h else 0.0 for h in header_mass])
+    parts = GW.make_particles(11, counts, BOX, masstable)
+    base = str(tmp_path_factory.mktemp("snap") / "s")
+    GW.write_snapshot(base, parts, masstable, BOX, redshift, nfiles, fmt, order)
+    h = RG.header(base)
+    assert list(h.nall) == counts and h.filenum == nfiles and h.format == fmt
+    present = [t for t in range(6) if counts[t]]
+    for block in ("POS ", "VEL ", "ID  ", "MASS"):
+        got = RG.read_block(base, block, present)
+        want = np.concatenate([_expect_generic(parts, block, t, h, masstable) for t in present])
+        assert got.dtype == want.dtype and got.shape == want.shape, block
+        np.testing.assert_array_equal(got, want, err_msg=block)
+    # species without particles give empty arrays, not errors
+    empty = [t for t in range(6) if not counts[t]]
+    if empty:
+        assert RG.read_block(base, "POS ", empty[:1]).shape == (0, 3)
+    # per-file reads concatenate to the whole
+    names = [base] if nfiles == 1 else ["%s.%d" % (base, i) for i in range(nfiles)]
+    t = present[0]
+    np.testing.assert_array_equal(np.concatenate([RG.read_field(n, "POS ", t) for n in names]), parts[t][0])
+
+
+def _expect_generic(parts, block, pt, h, masstable):
+    pos, vel, ids, mass = parts[pt]
+    if block == "POS ":
+        return pos
+    if block == "VEL ":
+        return vel * np.float32(np.sqrt(h.time)) if h.redshift != 0 else vel
+    if block == "ID  ":
+        return ids
+    return mass if mass is not None else np.full(len(pos), np.float32(masstable[pt]), np.float32)
