@@ -2,7 +2,10 @@
 box's host cores: snapshot driver (Pk_Gadget on a synthetic multi-file Gadget snapshot), field smoothing, the
 bispectrum and the correlation function.  Writes one JSON line per case.
 
-    python profiles/widen_bench.py [--nside 256] [--out gpurun_out/widen_bench.jsonl]
+    python tests/widen_bench.py [--nside 256] [--out gpurun_out/widen_bench.jsonl]
+
+It lives under tests/ because it runs the compiled reference (oracle/_ref) as the timed CPU baseline, and only tests/,
+smoke() and bench.py's baseline legs may execute anything under oracle/.
 
 GPU times: best of 3 wall-clock runs around the public call with a device synchronise on both sides (these calls
 return host arrays or files, so wall clock is the user-visible time).  Reference: one run (it is slow), all host
@@ -20,7 +23,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))     # gadget_writer
 
 
 def best_of(fn, n=3):
