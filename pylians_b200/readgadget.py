@@ -101,14 +101,15 @@ class SnapFile(object):
             setattr(self, name, np.int32(h[name]))
 
     # ---- where a block lives -------------------------------------------------------------------
-    def _record(self, block):
+    def _record(self, block, ordinal=None):
+        """(payload offset, payload bytes) of a block: by label in format 2, by record number (1 = header) in format 1."""
         if self.format == 2:
             for label, off, n in self.records:
                 if label == block:
                     return off, n
         else:
-            k = _BLOCK_ORDINAL[block] - 1
-            if k < len(self.records):
+            k = (_BLOCK_ORDINAL[block] if ordinal is None else ordinal) - 1
+            if 0 <= k < len(self.records):
                 return self.records[k][1], self.records[k][2]
         raise IOError("Error: block not found (%r in %s)" % (block, self.path))        # readsnap.py:153-155
 

@@ -39,8 +39,9 @@ def make_particles(seed, counts, box_kpc, masstable, clustered=False):
 
 
 def write_snapshot(base, parts, masstable, box_kpc, redshift, nfiles=1, fmt=1, order="<", omega_m=0.3175,
-                   omega_l=0.6825, hubble=0.6711):
-    """Split every species evenly over `nfiles` files named base (nfiles == 1) or base.0 ... base.(nfiles-1)."""
+                   omega_l=0.6825, hubble=0.6711, extra=()):
+    """Split every species evenly over `nfiles` files named base (nfiles == 1) or base.0 ... base.(nfiles-1).
+    extra: further blocks after MASS, [(label, {species: float32 array (n,) or (n,3)}), ...] in file order (U, RHO, ...)."""
     time = 1.0 / (1.0 + redshift)
     nall = np.zeros(6, np.uint32)
     for t, p in parts.items():
@@ -73,4 +74,7 @@ def write_snapshot(base, parts, masstable, box_kpc, redshift, nfiles=1, fmt=1, o
             if with_mass:
                 _record(f, np.concatenate([chunk[t][3] for t in with_mass]).astype(order + "f4").tobytes(), order,
                         "MASS", fmt)
+            for label, per_type in extra:
+                pieces = [np.array_split(per_type[t], nfiles)[i] for t in sorted(per_type)]
+                _record(f, np.concatenate(pieces).astype(order + "f4").tobytes(), order, label, fmt)
     return names
