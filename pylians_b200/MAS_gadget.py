@@ -101,7 +101,9 @@ class StreamedSnapshot(object):
 
 
 def density_field_gadget_device(snapshot_fname, ptypes, dims, MAS="CIC", do_RSD=False, axis=0, verbose=True):
-    """density_field_gadget with the result left in HBM: returns (CUDA float32 (dims,dims,dims) tensor, total)."""
+    """density_field_gadget with the result left in HBM: returns (CUDA float32 (dims,dims,dims) tensor, the part of the
+    deposited total known on the host (counts, header masses), the part summed on the device (MASS blocks; a 1-element
+    float64 tensor, only filled when `verbose`))."""
     snap = StreamedSnapshot(snapshot_fname)
     head = snap.head
     BoxSize = head.boxsize / 1e3                              # Mpc/h
