@@ -58,12 +58,16 @@ const char *pylb_last_error(void);
 /* number of CUDA kernels this library has launched so far in this process (bench accounting) */
 int64_t pylb_launch_count(void);
 
-/* Per-kernel device timing for roofline reports.  When enabled, the two dominant kernels are
- * bracketed by CUDA events on their launching stream: which = 0 the binning ring kernel,
- * 1 the tiled-deposit tile kernel, 2 the direct deposit kernel, 3 the generic binning kernel.
+/* Per-kernel device timing for roofline reports.  When enabled, the dominant kernels / stages are
+ * bracketed by CUDA events on their launching stream: which = 0 the binning ring kernel alone,
+ * 1 the tiled-deposit tile kernel, 2 the direct deposit kernel, 3 the generic binning kernel,
+ * 4 the WHOLE fused binning of one pylb_pk_bin call (bin zeroing, MAS table, self-conjugate columns,
+ * ring kernel, finish pass), 5 the cuFFT execution of one transform call, 6 the sort stage of the tiled
+ * deposit (histogram, scans, both counting-sort passes).
  * pylb_timing_collect synchronises the pending events, returns the summed milliseconds and the
- * number of launches since the last collect, and resets the tally. */
-enum { PYLB_T_RING = 0, PYLB_T_TILE = 1, PYLB_T_DIRECT = 2, PYLB_T_GENERIC = 3, PYLB_T_COUNT = 4 };
+ * number of brackets since the last collect, and resets the tally. */
+enum { PYLB_T_RING = 0, PYLB_T_TILE = 1, PYLB_T_DIRECT = 2, PYLB_T_GENERIC = 3, PYLB_T_BIN = 4, PYLB_T_FFT = 5,
+       PYLB_T_SORT = 6, PYLB_T_COUNT = 7 };
 void pylb_timing_enable(int on);
 int pylb_timing_collect(int which, double *total_ms, int *launches);
 

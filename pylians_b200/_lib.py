@@ -121,7 +121,7 @@ def launch_count():
     return int(load().pylb_launch_count())
 
 
-T_RING, T_TILE, T_DIRECT, T_GENERIC = 0, 1, 2, 3
+T_RING, T_TILE, T_DIRECT, T_GENERIC, T_BIN, T_FFT, T_SORT = 0, 1, 2, 3, 4, 5, 6
 
 
 def timing_enable(on):

@@ -1598,6 +1598,7 @@ extern "C" int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int ax
         fp.p[f] = (float2 *)dk[f];
         g.mas_idx[f] = mas_index[f];
     }
+    timing_begin(PYLB_T_BIN, st);
     if (!accumulate) {
         PYLB_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)L.n_doubles, st));
         PYLB_CHECK(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * (size_t)L.n_counts, st));
@@ -1624,6 +1625,7 @@ extern "C" int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int ax
         rc = launch_generic(g, fp, 0, 1, L.middle + 1, want_phase, write_back, st);
         timing_end(PYLB_T_GENERIC, st);
     }
+    timing_end(PYLB_T_BIN, st);
     cudaFreeAsync(tab, st);
     return rc;
 }

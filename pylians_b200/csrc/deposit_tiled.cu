@@ -3,25 +3,26 @@
 // Particles are first brought into cell-tile order, then every tile is accumulated in shared memory
 // and flushed with red.global.add.v4.f32.  Two ways to get tile order:
 //
-//  BINSORT (ntiles <= 32768; tiles are 16x16x32 cells, or 32x32x32 when that is needed to stay under
-//           the limit) -- a single-pass counting sort that moves the (x,y,z,w) payload itself:
+//  BINSORT (ntiles <= 53248; tiles are 16x16x32 cells, or 32x32x32 when that is needed to stay under
+//           the limit) -- a counting sort that moves the (x,y,z,w) payload itself:
 //     bin_hist_kernel     one CTA per SM builds a histogram over ALL tiles in shared memory (native int
 //                         ATOMS.ADD, 2.6 T/s) and merges it into the global per-tile counts
 //     cub ExclusiveSum    counts -> first output slot of every tile
-//     bin_scatter_kernel  per 32k-particle sub-chunk: count per tile in shared memory, reserve one
-//                         contiguous range per (sub-chunk, tile) with a single atom.global, rank inside
-//                         it with shared atomics, write the payload as float4.  Streaming reads, ~0.4
-//                         global atomics per particle, no random gather (a random 12-byte gather costs
-//                         3.9 ms per 2^27 particles on B200, a streaming read 0.25 ms: profiles/microbench).
+//     bin_pass_kernel x2  two-pass block-local counting sort (hi digit, then lo digit of the tile id); streaming
+//                         reads, one contiguous output run per (chunk, digit), no random gather (a random 12-byte
+//                         gather costs 3.9 ms per 2^27 particles on B200, a streaming read 0.25 ms: profiles/microbench)
 //  RADIX (any ntiles) -- cub radix sort of (tile key, particle index); the tile kernel then gathers
 //     particles through the sorted index.
 //
-//  deposit_tile_kernel   one CTA per work item (tile, chunk of <= CHUNK particles): zero the tile
-//                         (+ halo) in shared memory, accumulate, flush.  Halo cells overlap neighbouring
-//                         tiles, so the flush must add -- and `number` is accumulate-in-place anyway.
+//  deposit_lane_kernel   CIC/TSC/PCS: one CTA per work item (tile, chunk of <= CHUNK particles): zero the tile
+//                         (+ halo) in shared memory, accumulate with the lanes of a warp mapped to the STENCIL POINTS
+//                         of one particle (bank-conflict-free by construction of the tile pitches), flush.  Halo cells
+//                         overlap neighbouring tiles, so the flush must add -- and `number` is accumulate-in-place anyway.
+//  deposit_tile_kernel   NGP (and the A/B baseline): lane per particle.
 //
-// Shared-memory fp32 atomicAdd is an ATOMS.CAST.SPIN loop on sm_100a (2.9 updates/clk/SM measured vs
-// 9.2 for native int atomics); that pipe, not HBM, bounds the accumulation.
+// Shared-memory fp32 atomicAdd is an ATOMS.CAST.SPIN loop on sm_100a (2.9 updates/clk/SM measured for randomly
+// placed cells vs 9.2 for native int atomics); the lane-per-particle kernel is bound by that pipe, which is what the
+// stencil-lane layout removes.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -29,15 +30,15 @@
 
 namespace pylb {
 
-template <int TX_, int TY_, int TZ_, int THREADS_>
+// TX x TY x TZ cells per tile; PB = particles per warp batch of the stencil-lane kernel (bounds its weight staging);
+// CHUNK = particles per work item
+template <int TX_, int TY_, int TZ_, int THREADS_, int PB_, int CHUNK_>
 struct TileCfg {
-    static constexpr int TX = TX_, TY = TY_, TZ = TZ_, THREADS = THREADS_;
+    static constexpr int TX = TX_, TY = TY_, TZ = TZ_, THREADS = THREADS_, PB = PB_, CHUNK = CHUNK_;
 };
-typedef TileCfg<16, 16, 32, 256> TileS;    // 38-51 KB of shared memory per CTA, 4-5 CTAs/SM
-typedef TileCfg<32, 32, 32, 1024> TileL;   // 144-176 KB, 1 CTA/SM of 32 warps, 4x fewer tiles
+typedef TileCfg<16, 16, 32, 256, 32, 8192> TileS;      // 39-75 KB of shared memory per CTA, 3-5 CTAs/SM
+typedef TileCfg<32, 32, 32, 1024, 16, 32768> TileL;    // 144-223 KB, 1 CTA/SM of 32 warps, 4x fewer tiles
 
-constexpr int CHUNK = 8192;              // particles per work item
-constexpr int REGROUP_BATCH = 1024;      // tile kernel: particles regrouped by shared-memory bank at a time
 constexpr int64_t BATCH = 1ll << 28;     // particles binned per pass (bounds the workspace)
 constexpr int BIN_THREADS = 1024;        // binsort CTAs: one per SM, 32 warps
 constexpr int BIN_MAX_TILES = 53248;     // per-CTA histogram must fit shared memory (208 KB of 227 KB); keys are 16-bit
@@ -77,10 +78,6 @@ __device__ __forceinline__ unsigned tile_key(float x, float y, float z, float in
 // ------------------------------------------------------------------------------------------------
 // BINSORT
 // ------------------------------------------------------------------------------------------------
-constexpr int BIN_PER_THREAD = 16;                            // particles per thread per sub-chunk
-constexpr int BIN_SUB = BIN_THREADS * BIN_PER_THREAD;         // 16384 particles per sub-chunk (a round of 148 CTAs must fit L2)
-constexpr int BIN_MLP = 8;                                    // particles whose loads are in flight per thread
-
 // per-tile particle counts: per-CTA shared histogram, merged with one red.global per (CTA, tile)
 template <int MAS, class TC>
 __global__ void __launch_bounds__(BIN_THREADS, 1)
@@ -150,82 +147,6 @@ bin_hist_kernel(const float *__restrict__ pos, int64_t first, int n, int64_t ps0
     for (int t = threadIdx.x; t < tg.ntiles; t += BIN_THREADS) {
         const int c = hist[t];
         if (c) atomicAdd(&counts[t], c);
-    }
-}
-
-// Scatter the (x,y,z,w) payload into tile order.  cursor[t] starts at tile_begin[t].  Per sub-chunk:
-//   sweep A  key every particle, count per tile in shared memory (native ATOMS.ADD);
-//   claim    one atom.global.add per tile present in the sub-chunk reserves a contiguous output range
-//            (ranges of one tile handed to different CTAs are adjacent, so L2 write-combines them);
-//   sweep B  re-read the particles (L1/L2 hits), rank inside the range with a shared atomic, write float4.
-template <int MAS, class TC, bool HASW>
-__global__ void __launch_bounds__(BIN_THREADS, 1)
-bin_scatter_kernel(const float *__restrict__ pos, const float *__restrict__ W, int64_t wst, int64_t first, int n, int64_t ps0,
-                   int64_t ps1, float inv, TileGeom tg, int *__restrict__ cursor, float4 *__restrict__ out) {
-    extern __shared__ int slot[];
-    const int nsub = (n + BIN_SUB - 1) / BIN_SUB;
-    for (int sc = blockIdx.x; sc < nsub; sc += gridDim.x) {
-        const int lo = sc * BIN_SUB;
-        for (int t = threadIdx.x; t < tg.ntiles; t += BIN_THREADS) slot[t] = 0;
-        __syncthreads();
-        // sweep A: BIN_MLP particles' coordinates are loaded before any is used (memory-level parallelism)
-        unsigned short keys[BIN_PER_THREAD];   // ntiles <= 32768, 0xffff = no particle
-#pragma unroll
-        for (int k0 = 0; k0 < BIN_PER_THREAD; k0 += BIN_MLP) {
-            float px[BIN_MLP], py[BIN_MLP], pz[BIN_MLP];
-#pragma unroll
-            for (int u = 0; u < BIN_MLP; u++) {
-                const int i = lo + (k0 + u) * BIN_THREADS + threadIdx.x;
-                if (i < n) {
-                    const float *p = pos + (first + i) * ps0;
-                    px[u] = __ldg(p); py[u] = __ldg(p + ps1); pz[u] = __ldg(p + 2 * ps1);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < BIN_MLP; u++) {
-                const int i = lo + (k0 + u) * BIN_THREADS + threadIdx.x;
-                keys[k0 + u] = 0xffffu;
-                if (i < n) {
-                    keys[k0 + u] = (unsigned short)tile_key<MAS, TC>(px[u], py[u], pz[u], inv, tg);
-                    atomicAdd(&slot[keys[k0 + u]], 1);
-                }
-            }
-        }
-        __syncthreads();
-        // claim: atom.global in groups of 8 issued back to back, results stored afterwards
-        for (int t0 = 0; t0 < tg.ntiles; t0 += 8 * BIN_THREADS) {
-            int base[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int t = t0 + q * BIN_THREADS + threadIdx.x;
-                base[q] = -1;
-                if (t < tg.ntiles) {
-                    const int c = slot[t];
-                    if (c) base[q] = atomicAdd(&cursor[t], c);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 8; q++)
-                if (base[q] >= 0) slot[t0 + q * BIN_THREADS + threadIdx.x] = base[q];
-        }
-        __syncthreads();
-        // sweep B: re-read (L1/L2), rank inside the claimed range, write the payload
-#pragma unroll
-        for (int k0 = 0; k0 < BIN_PER_THREAD; k0 += BIN_MLP) {
-            float4 v[BIN_MLP];
-#pragma unroll
-            for (int u = 0; u < BIN_MLP; u++) {
-                if (keys[k0 + u] != 0xffffu) {
-                    const int i = lo + (k0 + u) * BIN_THREADS + threadIdx.x;
-                    const float *p = pos + (first + i) * ps0;
-                    v[u] = make_float4(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), HASW ? __ldg(W + (first + i) * wst) : 1.0f);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < BIN_MLP; u++)
-                if (keys[k0 + u] != 0xffffu) out[atomicAdd(&slot[keys[k0 + u]], 1)] = v[u];
-        }
-        __syncthreads();
     }
 }
 
@@ -433,22 +354,38 @@ __global__ void tile_begin_kernel(const unsigned *__restrict__ skeys, int n, int
     tile_begin[t] = lo;
 }
 
-__global__ void tile_chunks_kernel(const int *__restrict__ tile_begin, int ntiles, int *nchunks) {
+__global__ void tile_chunks_kernel(const int *__restrict__ tile_begin, int ntiles, int chunk, int *nchunks) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > ntiles) return;
-    nchunks[t] = (t < ntiles) ? (tile_begin[t + 1] - tile_begin[t] + CHUNK - 1) / CHUNK : 0;
+    nchunks[t] = (t < ntiles) ? (tile_begin[t + 1] - tile_begin[t] + chunk - 1) / chunk : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // tile accumulation
 // ------------------------------------------------------------------------------------------------
+constexpr int pad_to(int v, int r) { return v + ((r - v % 32) + 32) % 32; }   // smallest x >= v with x % 32 == r
+
+// Shared-memory tile: SX x SY x SZV cells (tile + S-1 halo cells per axis), z fastest, row pitch PI, plane pitch PL
+// (floats).  The pitches are chosen so that the cells ONE warp instruction of deposit_lane_kernel updates fall into 32
+// distinct banks (lanes = stencil points, see there):
+//   PCS  lane = (a&1, b, c), planes a and a+2   bank = 16 a + 4 b + c          PI = 4, PL = 16 (mod 32)
+//   TSC  lane = (a, b, c), 27 lanes             bank = 9 a + 3 b + c           PI = 3, PL = 9
+//   CIC  lane = (particle q of 4, a, b, c)      bank = base_q + 4 a + 2 b + c  PI = 2, PL = 4
 template <int MAS, class TC>
 struct TileShape {
     static constexpr int S = Support<MAS>::S;
-    static constexpr int SX = TC::TX + S - 1, SY = TC::TY + S - 1;
-    static constexpr int SZ = ((TC::TZ + S - 1) + 3) & ~3;  // padded to a multiple of 4 for the v4 flush
-    static constexpr int CELLS = SX * SY * SZ;
-    static constexpr int HI_WORDS = ((CELLS / 2) + 3) & ~3;   // fixed-point tiles: 16-bit carry counters, two per word
+    static constexpr int SX = TC::TX + S - 1, SY = TC::TY + S - 1, SZV = TC::TZ + S - 1;
+    static constexpr int RI = MAS == PYLB_PCS ? 4 : MAS == PYLB_TSC ? 3 : 2;
+    static constexpr int RL = MAS == PYLB_PCS ? 16 : MAS == PYLB_TSC ? 9 : 4;
+    static constexpr int PI = MAS == PYLB_NGP ? SZV : pad_to(SZV, RI);
+    static constexpr int PL = MAS == PYLB_NGP ? SY * PI : pad_to(SY * PI, RL);
+    static constexpr int CELLS = (SX * PL + 3) & ~3;
+    static constexpr int ZV = (SZV + 3) / 4;                       // float4 groups per z-row in the flush
+    // deposit_lane_kernel: per-warp staging of the factored weights, word-major with pitch PB+1 (bank = word + particle)
+    static constexpr int SW = S * S + S + 1;                       // wxy[S][S], wz[S], W
+    static constexpr int STAGE_WORDS = (MAS == PYLB_PCS || MAS == PYLB_TSC) ? SW * (TC::PB + 1) : 0;
+    static constexpr size_t LANE_SMEM = sizeof(float) * ((size_t)CELLS + (size_t)(TC::THREADS / 32) * STAGE_WORDS);
+    static constexpr size_t PLAIN_SMEM = sizeof(float) * (size_t)CELLS;
 };
 
 __device__ __forceinline__ void red_add_v4(float *p, float4 v) {
@@ -456,243 +393,46 @@ __device__ __forceinline__ void red_add_v4(float *p, float4 v) {
                  : "memory");
 }
 
-// SORTED: particles come as float4 (x,y,z,w) already in tile order.  Otherwise through the sorted index.
-// FIXED (unweighted only): the tile is accumulated as 48-bit fixed point, unit 2^-31, with NATIVE 32-bit shared
-//   atomics: `lo` takes the update (ATOMS.ADD with return), a wrap-around of `lo` adds one to a 16-bit carry counter
-//   packed two per word in `hi`.  A weight is in [0,1], so an update is at most 2^31 and a CTA's <= 8192 particles
-//   can never overflow the 16-bit carry.  Rounding: 2.3e-10 absolute per update (fp32 accumulation rounds every
-//   partial sum to 6e-8 relative), the sum itself is exact and order independent -- the tile result is
-//   deterministic.  Why: atomicAdd(float) on shared memory is an ATOMS.CAST.SPIN loop on sm_100a (2.9
-//   updates/clk/SM measured against 9.2 for native integer atomics).
-template <int MAS, bool HASW, class TC, bool SORTED, bool FIXED, bool REGROUP>
-__global__ void __launch_bounds__(TC::THREADS)
-deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, int64_t ps1,
-                    const float *__restrict__ W, int64_t wst, float inv, TileGeom tg, const unsigned *__restrict__ svals,
-                    const float4 *__restrict__ sorted, const int *__restrict__ tile_begin,
-                    const int *__restrict__ chunk_off, float *__restrict__ grid, int agg) {
-    using TS = TileShape<MAS, TC>;
-    constexpr int S = TS::S;
-    constexpr int TILE_THREADS = TC::THREADS;
-    extern __shared__ __align__(16) float tile[];
-    __shared__ int s_tile, s_lo, s_hi, s_agg;
-
-    if (threadIdx.x == 0) {
-        // find the tile whose chunk range holds blockIdx.x: chunk_off[t] <= b < chunk_off[t+1]
-        const int b = blockIdx.x;
-        const int total = chunk_off[tg.ntiles];
-        if (b >= total) {
-            s_tile = -1;
-        } else {
-            int lo = 0, hi = tg.ntiles;  // invariant: chunk_off[lo] <= b < chunk_off[hi]
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (chunk_off[mid] <= b) lo = mid;
-                else hi = mid;
-            }
-            s_tile = lo;
-            const int begin = tile_begin[lo] + (b - chunk_off[lo]) * CHUNK;
-            s_lo = begin;
-            s_hi = min(begin + CHUNK, tile_begin[lo + 1]);
-            // a tile holding clearly more particles than the average tile is where a halo sits: only its CTAs
-            // pay for looking for lanes that share a cell (agg = that particle count, 0 = never)
-            s_agg = agg > 0 && tile_begin[lo + 1] - tile_begin[lo] >= agg;
-        }
+// work item b -> (tile, particle range); returns false beyond the last item.  Called by thread 0.
+struct WorkItem { int tile, lo, hi; };
+__device__ __forceinline__ bool find_work(int b, const int *__restrict__ chunk_off, const int *__restrict__ tile_begin,
+                                          int ntiles, int chunk, WorkItem &w) {
+    if (b >= chunk_off[ntiles]) return false;
+    int lo = 0, hi = ntiles;                    // invariant: chunk_off[lo] <= b < chunk_off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (chunk_off[mid] <= b) lo = mid; else hi = mid;
     }
-    __syncthreads();
-    const int t = s_tile;
-    if (t < 0) return;  // CTA-uniform: beyond the last work item
-    static_assert(!(FIXED && HASW), "fixed-point accumulation needs weights in [0,1]");
-    unsigned *lo = reinterpret_cast<unsigned *>(tile);
-    unsigned *hi = lo + TS::CELLS;             // HI_WORDS words
-    for (int i = threadIdx.x; i < (FIXED ? (TS::CELLS + TS::HI_WORDS) / 4 : TS::CELLS / 4); i += TILE_THREADS)
-        reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    const int tz = t % tg.ntz, ty = (t / tg.ntz) % tg.nty, tx = t / (tg.ntz * tg.nty);
-    const int ox = tx * TC::TX, oy = ty * TC::TY, oz = tz * TC::TZ;
+    w.tile = lo;
+    w.lo = tile_begin[lo] + (b - chunk_off[lo]) * chunk;
+    w.hi = min(w.lo + chunk, tile_begin[lo + 1]);
+    return true;
+}
 
-    auto load = [&](int i) -> float4 {
-        if (SORTED) return __ldg(sorted + i);
-        const int64_t pi = first + (int64_t)svals[i];
-        const float *p = pos + pi * ps0;
-        return make_float4(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), HASW ? __ldg(W + pi * wst) : 1.0f);
-    };
-    // tile-local cell of the particle's lowest touched grid point, or -1 (mis-routed particle: its updates are dropped)
-    auto base_cell = [&](const float4 q, float (&C)[3][S]) -> int {
-        const int lx = wrap(axis_stencil<MAS>(q.x, inv, C[0]) - tg.x0, tg.dims) - ox;
-        if (lx < 0 || lx >= TC::TX) return -1;
-        const int ly = wrap(axis_stencil<MAS>(q.y, inv, C[1]), tg.dims) - oy;
-        const int lz = wrap(axis_stencil<MAS>(q.z, inv, C[2]), tg.dims) - oz;
-        return (lx * TS::SY + ly) * TS::SZ + lz;
-    };
-    auto put = [&](const int cell0, const float (&C)[3][S], const float w) {
-        float *base = tile + cell0;
-#pragma unroll
-        for (int l = 0; l < S; l++)
-#pragma unroll
-            for (int m = 0; m < S; m++) {
-                const float cxy = C[0][l] * C[1][m];
-#pragma unroll
-                for (int n = 0; n < S; n++) {
-                    float v = cxy * C[2][n];
-                    if (HASW) v *= w;
-                    if (FIXED) {
-                        const int c = cell0 + (l * TS::SY + m) * TS::SZ + n;
-                        const unsigned u = __float2uint_rn(v * 2147483648.0f);
-                        const unsigned old = atomicAdd(lo + c, u);
-                        if (old + u < old) atomicAdd(hi + (c >> 1), 1u << ((c & 1) * 16));
-                    } else {
-                        atomicAdd(base + (l * TS::SY + m) * TS::SZ + n, v);
-                    }
-                }
-            }
-    };
-    if (!REGROUP) {
-        // (hoisting 4 particle loads ahead of the updates changes nothing for CIC and costs PCS 15 % in registers:
-        //  the kernel waits on the shared-memory pipe, not on these loads)
-        if (FIXED || S > 2 || !s_agg) {
-            for (int i = s_lo + threadIdx.x; i < s_hi; i += TILE_THREADS) {
-                const float4 q = load(i);
-                float C[3][S];
-                const int cell0 = base_cell(q, C);
-                if (cell0 >= 0) put(cell0, C, q.w);
-            }
-        } else {
-            // Warp-aggregated updates for clustered inputs.  Lanes whose particles share a base cell update the same
-            // S^3 addresses; a shared atomicAdd(float) is a CAS loop, so n lanes on one address cost ~n rounds each.
-            // When a group of >= AGG_MIN lanes shares its base cell (a halo cell holding a large share of the tile's
-            // particles) the group's S^3 contributions are summed with warp shuffles and its first lane issues ONE
-            // atomic per cell.  Only CTAs of over-populated tiles (s_agg) run this loop, so uniform inputs never pay for it,
-            // and only NGP and CIC do: S^3 x 5 shuffles per group cost more than the contention they remove for TSC / PCS
-            // (measured on a clustered 512^3 set: CIC tile kernel 3.86 -> 2.99 ms, PCS 21.6 -> 25.0 ms).
-            constexpr int AGG_MIN = 4;
-            const unsigned full = 0xffffffffu;
-            const int lane = threadIdx.x & 31;
-            for (int i0 = s_lo + (threadIdx.x & ~31); i0 < s_hi; i0 += TILE_THREADS) {   // warp-uniform trip count
-                const int i = i0 + lane;
-                float C[3][S];
-                int cell0 = -1;
-                float w = 1.0f;
-                if (i < s_hi) {
-                    const float4 q = load(i);
-                    cell0 = base_cell(q, C);
-                    w = q.w;
-                }
-                const unsigned peers = __match_any_sync(full, cell0);
-                const bool heavy = cell0 >= 0 && __popc(peers) >= AGG_MIN;
-                unsigned todo = __ballot_sync(full, heavy);
-                while (todo) {                                   // one round per heavy group: at most 32 / AGG_MIN
-                    const int leader = __ffs(todo) - 1;
-                    const unsigned grp = __shfl_sync(full, peers, leader);
-                    const bool mine = (grp >> lane) & 1u;
-                    const int cell_l = __shfl_sync(full, cell0, leader);
-#pragma unroll
-                    for (int l = 0; l < S; l++)
-#pragma unroll
-                        for (int m = 0; m < S; m++) {
-                            const float cxy = mine ? C[0][l] * C[1][m] : 0.0f;
-#pragma unroll
-                            for (int n = 0; n < S; n++) {
-                                float v = mine ? cxy * C[2][n] : 0.0f;
-                                if (HASW && mine) v *= w;
-#pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
-                                if (lane == leader) atomicAdd(tile + cell_l + (l * TS::SY + m) * TS::SZ + n, v);
-                            }
-                        }
-                    todo &= ~grp;
-                }
-                if (cell0 >= 0 && !heavy) put(cell0, C, w);
-            }
-        }
-    } else {
-        // Regroup by shared-memory bank.  The tile's particles arrive in no particular order, so the 32 cells a warp
-        // updates at once fall into random banks: ~13 shared-memory wavefronts per warp update (LDS + CAS, each
-        // serialised ~3.4x), and that data pipe is what bounds this kernel (95 % busy).  Here a batch of REGROUP_BATCH
-        // particles is first bucketed by the bank of its base cell (one native shared atomic per particle, a 32-entry
-        // scan, one 16-byte shared store); warp r then takes the r-th particle of every bank, lane = bank.  All
-        // lanes of an update hit distinct banks -- every stencil offset shifts all of them alike -- and never the
-        // same address: 2.7x the update rate in profiles/microbench/atomics.cu (830 -> 2200 G updates/s).
-        constexpr int BATCH_P = REGROUP_BATCH;             // 1024 particles: 16 KB of staging
-        constexpr int RG = BATCH_P / TILE_THREADS;
-        float4 *pstage = reinterpret_cast<float4 *>(tile + (FIXED ? TS::CELLS + TS::HI_WORDS : TS::CELLS));
-        __shared__ int bcnt[32], boff[32], s_rows;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int b0 = s_lo; b0 < s_hi; b0 += BATCH_P) {
-            if (threadIdx.x < 32) bcnt[threadIdx.x] = 0;
-            __syncthreads();
-            float4 q[RG];
-            int bank[RG], rk[RG];
-#pragma unroll
-            for (int k = 0; k < RG; k++) {
-                const int i = b0 + k * TILE_THREADS + threadIdx.x;
-                bank[k] = -1;
-                if (i < s_hi) q[k] = load(i);
-            }
-#pragma unroll
-            for (int k = 0; k < RG; k++) {
-                const int i = b0 + k * TILE_THREADS + threadIdx.x;
-                if (i < s_hi) {
-                    float C[3][S];
-                    const int cell0 = base_cell(q[k], C);
-                    if (cell0 >= 0) {
-                        bank[k] = cell0 & 31;
-                        rk[k] = atomicAdd(&bcnt[bank[k]], 1);
-                    }
-                }
-            }
-            __syncthreads();
-            if (threadIdx.x < 32) {            // exclusive scan of the 32 counts, and the longest list
-                const int c = bcnt[lane];
-                int incl = c, mx = c;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int y = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += y;
-                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                }
-                boff[lane] = incl - c;
-                if (lane == 0) s_rows = mx;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < RG; k++)
-                if (bank[k] >= 0) pstage[boff[bank[k]] + rk[k]] = q[k];
-            __syncthreads();
-            const int mycnt = bcnt[lane], myoff = boff[lane], rows = s_rows;
-            for (int r = warp; r < rows; r += TILE_THREADS / 32) {
-                if (r < mycnt) {
-                    const float4 p = pstage[myoff + r];
-                    float C[3][S];
-                    const int cell0 = base_cell(p, C);
-                    put(cell0, C, p.w);
-                }
-            }
-            __syncthreads();                   // the next batch reuses bcnt / pstage
-        }
-    }
-    __syncthreads();
-    // fixed point -> float in place (cell i: carry << 32 | lo, unit 2^-31), then the common flush
-    if (FIXED) {
-        for (int i = threadIdx.x; i < TS::CELLS; i += TILE_THREADS) {
-            const unsigned long long t = ((unsigned long long)((hi[i >> 1] >> ((i & 1) * 16)) & 0xffffu) << 32) | lo[i];
-            tile[i] = (float)t * 4.656612873077393e-10f;
-        }
-        __syncthreads();
-    }
-
-    // flush: local (x,y,z) -> global ((ox+x)%dims, (oy+y)%dims, (oz+z)%dims)
+// flush: tile-local (x,y,z) -> global ((ox+x)%dims, (oy+y)%dims, (oz+z)%dims), added with red.global (halo cells overlap
+// the neighbouring tiles, and `number` is accumulate-in-place anyway); 16-byte vector reds when dims % 4 == 0
+template <class TS, int THREADS>
+__device__ __forceinline__ void flush_tile(const float *tile, float *__restrict__ grid, const TileGeom &tg, int ox, int oy, int oz) {
     const int dims = tg.dims;
     if ((dims & 3) == 0) {
-        constexpr int ZV = TS::SZ / 4;
-        for (int i = threadIdx.x; i < TS::SX * TS::SY * ZV; i += TILE_THREADS) {
-            const int zv = i % ZV, y = (i / ZV) % TS::SY, x = i / (ZV * TS::SY);
-            const float4 v = reinterpret_cast<const float4 *>(tile)[i];
+        for (int i = threadIdx.x; i < TS::SX * TS::SY * TS::ZV; i += THREADS) {
+            const int zv = i % TS::ZV, y = (i / TS::ZV) % TS::SY, x = i / (TS::ZV * TS::SY);
+            const float *row = tile + x * TS::PL + y * TS::PI + zv * 4;
+            float4 v;
+            if constexpr (TS::PI % 4 == 0 && TS::PL % 4 == 0) {
+                v = *reinterpret_cast<const float4 *>(row);        // padding words of a row are never written: zero
+            } else {
+                v.x = row[0];
+                v.y = zv * 4 + 1 < TS::SZV ? row[1] : 0.f;
+                v.z = zv * 4 + 2 < TS::SZV ? row[2] : 0.f;
+                v.w = zv * 4 + 3 < TS::SZV ? row[3] : 0.f;
+            }
             if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
             int gx = ox + x, gy = oy + y, gz = oz + zv * 4;
             if (tg.xext == dims) { if (gx >= dims) gx -= dims; }
             else if (gx >= tg.xext) continue;   // beyond the x window: nothing was deposited there
             if (gy >= dims) gy -= dims;
-            if (gz >= dims) gz -= dims;  // dims%4==0 and gz%4==0: the 4 cells never straddle the wrap
+            if (gz >= dims) gz -= dims;         // dims%4==0 and gz%4==0: the 4 cells never straddle the wrap
             if (gx >= dims || gy >= dims || gz >= dims) {  // only when dims < tile extent: scalar, full modulo
                 const float a[4] = {v.x, v.y, v.z, v.w};
                 for (int q = 0; q < 4; q++)
@@ -703,16 +443,270 @@ deposit_tile_kernel(const float *__restrict__ pos, int64_t first, int64_t ps0, i
             red_add_v4(grid + ((int64_t)gx * dims + gy) * dims + gz, v);
         }
     } else {
-        for (int i = threadIdx.x; i < TS::CELLS; i += TILE_THREADS) {
-            const float v = tile[i];
+        for (int i = threadIdx.x; i < TS::SX * TS::SY * TS::SZV; i += THREADS) {
+            const int z = i % TS::SZV, y = (i / TS::SZV) % TS::SY, x = i / (TS::SZV * TS::SY);
+            const float v = tile[x * TS::PL + y * TS::PI + z];
             if (v == 0.f) continue;
-            const int z = i % TS::SZ, y = (i / TS::SZ) % TS::SY, x = i / (TS::SZ * TS::SY);
             int gx = ox + x;
             if (tg.xext == dims) gx %= dims;
             else if (gx >= tg.xext) continue;
             atomicAdd(grid + ((int64_t)gx * dims + (oy + y) % dims) * dims + (oz + z) % dims, v);
         }
     }
+}
+
+// Particle -> (x,y,z,w).  SORTED: float4 records already in tile order; otherwise through the sorted index (radix path).
+template <bool SORTED, bool HASW>
+struct ParticleSource {
+    const float *pos; int64_t first, ps0, ps1; const float *W; int64_t wst; const unsigned *svals; const float4 *sorted;
+    __device__ __forceinline__ float4 operator()(int i) const {
+        if (SORTED) return __ldg(sorted + i);
+        const int64_t pi = first + (int64_t)svals[i];
+        const float *p = pos + pi * ps0;
+        return make_float4(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), HASW ? __ldg(W + pi * wst) : 1.0f);
+    }
+};
+
+// tile-local cell of the particle's lowest touched grid point, or -1 (particle routed to the wrong x window: dropped)
+template <int MAS, class TC>
+__device__ __forceinline__ int base_cell(const float4 q, float inv, const TileGeom &tg, int ox, int oy, int oz,
+                                         float (&C)[3][Support<MAS>::S]) {
+    using TS = TileShape<MAS, TC>;
+    const int lx = wrap(axis_stencil<MAS>(q.x, inv, C[0]) - tg.x0, tg.dims) - ox;
+    if (lx < 0 || lx >= TC::TX) return -1;
+    const int ly = wrap(axis_stencil<MAS>(q.y, inv, C[1]), tg.dims) - oy;
+    const int lz = wrap(axis_stencil<MAS>(q.z, inv, C[2]), tg.dims) - oz;
+    return lx * TS::PL + ly * TS::PI + lz;
+}
+
+// K independent shared-memory float adds as ONE compare-and-swap loop: the K loads, adds and CAS are issued back to
+// back, so their latencies overlap instead of adding up as in K consecutive atomicAdd(float) loops (ATOMS.CAST.SPIN
+// on sm_100a; there is no native shared fp32 add).  Addresses may repeat: the later CAS fails once and retries.
+template <int K>
+__device__ __forceinline__ void smem_add_joint(float *(&p)[K], const float (&v)[K]) {
+    unsigned o[K];
+    bool done[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { o[k] = *reinterpret_cast<volatile unsigned *>(p[k]); done[k] = false; }
+    bool all;
+    do {
+        all = true;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            if (!done[k]) {
+                const unsigned nv = __float_as_uint(__uint_as_float(o[k]) + v[k]);
+                const unsigned r = atomicCAS(reinterpret_cast<unsigned *>(p[k]), o[k], nv);
+                done[k] = r == o[k];
+                o[k] = r;
+                all = all && done[k];
+            }
+    } while (!all);
+}
+
+// ---- lane-per-particle kernel: NGP (one update per particle) and the A/B baseline for the others ----------------
+// Every lane streams its own particle and issues S^3 shared atomicAdd(float); the 32 cells of one warp instruction
+// fall into random banks (and, for clustered input, onto equal addresses), ~13 shared-memory wavefronts per update.
+template <int MAS, bool HASW, class TC, bool SORTED>
+__global__ void __launch_bounds__(TC::THREADS)
+deposit_tile_kernel(ParticleSource<SORTED, HASW> src, float inv, TileGeom tg, const int *__restrict__ tile_begin,
+                    const int *__restrict__ chunk_off, float *__restrict__ grid) {
+    using TS = TileShape<MAS, TC>;
+    constexpr int S = TS::S;
+    extern __shared__ __align__(16) float tile[];
+    __shared__ WorkItem s_w;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = find_work(blockIdx.x, chunk_off, tile_begin, tg.ntiles, TC::CHUNK, s_w);
+    __syncthreads();
+    if (!s_ok) return;                           // CTA-uniform: beyond the last work item
+    const int t = s_w.tile, lo = s_w.lo, hi = s_w.hi;
+    for (int i = threadIdx.x; i < TS::CELLS / 4; i += TC::THREADS) reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const int tz = t % tg.ntz, ty = (t / tg.ntz) % tg.nty, tx = t / (tg.ntz * tg.nty);
+    const int ox = tx * TC::TX, oy = ty * TC::TY, oz = tz * TC::TZ;
+    for (int i = lo + threadIdx.x; i < hi; i += TC::THREADS) {
+        const float4 q = src(i);
+        float C[3][S];
+        const int cell0 = base_cell<MAS, TC>(q, inv, tg, ox, oy, oz, C);
+        if (cell0 < 0) continue;
+#pragma unroll
+        for (int l = 0; l < S; l++)
+#pragma unroll
+            for (int m = 0; m < S; m++) {
+                const float cxy = C[0][l] * C[1][m];
+#pragma unroll
+                for (int n = 0; n < S; n++) {
+                    float v = cxy * C[2][n];
+                    if (HASW) v *= q.w;
+                    atomicAdd(tile + cell0 + l * TS::PL + m * TS::PI + n, v);
+                }
+            }
+    }
+    __syncthreads();
+    flush_tile<TS, TC::THREADS>(tile, grid, tg, ox, oy, oz);
+}
+
+// ---- stencil-lane kernel: CIC, TSC, PCS ------------------------------------------------------------------------
+// The lanes of a warp are the STENCIL POINTS of one particle (TSC: 27 lanes; PCS: 32 lanes x 2 planes; CIC: 8 lanes x
+// 4 particles), not 32 different particles.  One warp instruction therefore updates cells that are distinct and, thanks
+// to the tile pitches above, lie in distinct banks: a shared float add is a single conflict-free CAS round (~3 wavefronts)
+// instead of ~13, and a particle costs 1-2 warp instructions' worth of atomics instead of 27/64.  Per batch of PB
+// particles, lane p first evaluates particle p's base cell and its S weights per axis exactly like the reference
+// (deposit.cuh) and stages wxy[l][m] = C0[l]*C1[m], wz[n] and W in a per-warp scratch (word-major, pitch PB+1: both the
+// staging stores and the per-particle reads are conflict-free); then the warp walks the batch, every lane forming
+// (wxy * wz) * W for its own stencil point -- the reference's left-to-right fp32 product (MAS_library.pyx:160-166,
+// 400-404, 493-497).  Consecutive particles with the same base cell are summed in registers first (JOINT), and the
+// adds of two particles share one CAS loop so that their latencies overlap.
+template <int MAS, bool HASW, class TC, bool SORTED, bool JOINT>
+__global__ void __launch_bounds__(TC::THREADS)
+deposit_lane_kernel(ParticleSource<SORTED, HASW> src, float inv, TileGeom tg, const int *__restrict__ tile_begin,
+                    const int *__restrict__ chunk_off, float *__restrict__ grid) {
+    using TS = TileShape<MAS, TC>;
+    constexpr int S = TS::S, PB = TC::PB, NW = TC::THREADS / 32, SP = PB + 1;
+    static_assert(MAS != PYLB_NGP, "NGP has one update per particle: lane-per-particle kernel");
+    extern __shared__ __align__(16) float tile[];
+    __shared__ WorkItem s_w;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = find_work(blockIdx.x, chunk_off, tile_begin, tg.ntiles, TC::CHUNK, s_w);
+    __syncthreads();
+    if (!s_ok) return;
+    const int t = s_w.tile, lo = s_w.lo, hi = s_w.hi;
+    for (int i = threadIdx.x; i < TS::CELLS / 4; i += TC::THREADS) reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const int tz = t % tg.ntz, ty = (t / tg.ntz) % tg.nty, tx = t / (tg.ntz * tg.nty);
+    const int ox = tx * TC::TX, oy = ty * TC::TY, oz = tz * TC::TZ;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if constexpr (MAS == PYLB_CIC) {
+        // 4 particles per warp step; lane = (q, a, b, c).  The weights of a CIC stencil point are u or 1-u per axis, so
+        // the three fractions travel by shuffle and every lane rebuilds its own weight with the reference's fp32 ops.
+        const int q = lane >> 3, la = (lane >> 2) & 1, lb = (lane >> 1) & 1, lc = lane & 1;
+        const int loff = la * TS::PL + lb * TS::PI + lc;
+        for (int i0 = lo + warp * 32; i0 < hi; i0 += NW * 32) {      // warp-uniform trip count
+            int cell0 = -1;
+            float ux = 0.f, uy = 0.f, uz = 0.f, w = 1.f;
+            if (i0 + lane < hi) {
+                const float4 p = src(i0 + lane);
+                float C[3][S];
+                cell0 = base_cell<MAS, TC>(p, inv, tg, ox, oy, oz, C);
+                ux = C[0][1]; uy = C[1][1]; uz = C[2][1]; w = p.w;
+            }
+            auto fetch = [&](int s, float *&addr, float &v) {
+                const int from = 4 * s + q;
+                const int b = __shfl_sync(full, cell0, from);
+                const float fx = __shfl_sync(full, ux, from), fy = __shfl_sync(full, uy, from), fz = __shfl_sync(full, uz, from);
+                v = ((la ? fx : __fsub_rn(1.0f, fx)) * (lb ? fy : __fsub_rn(1.0f, fy))) * (lc ? fz : __fsub_rn(1.0f, fz));
+                if (HASW) v *= __shfl_sync(full, w, from);
+                addr = tile + (b < 0 ? 0 : b) + loff;
+                return b >= 0;
+            };
+            if constexpr (JOINT) {
+#pragma unroll
+                for (int s = 0; s < 8; s += 2) {
+                    float *a0, *a1; float v0, v1;
+                    const bool ok0 = fetch(s, a0, v0), ok1 = fetch(s + 1, a1, v1);
+                    if (ok0 && ok1) { float *pp[2] = {a0, a1}; const float vv[2] = {v0, v1}; smem_add_joint<2>(pp, vv); }
+                    else if (ok0) atomicAdd(a0, v0);
+                    else if (ok1) atomicAdd(a1, v1);
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < 8; s++) {
+                    float *a0; float v0;
+                    if (fetch(s, a0, v0)) atomicAdd(a0, v0);
+                }
+            }
+        }
+    } else {
+        constexpr int NP = MAS == PYLB_PCS ? 2 : 1;                 // x-planes per lane
+        int la, lb, lc;
+        bool active = true;
+        if (MAS == PYLB_PCS) { la = lane >> 4; lb = (lane >> 2) & 3; lc = lane & 3; }
+        else { active = lane < 27; la = active ? lane / 9 : 0; lb = active ? (lane / 3) % 3 : 0; lc = active ? lane % 3 : 0; }
+        const int loff = la * TS::PL + lb * TS::PI + lc;
+        float *stage = tile + TS::CELLS + warp * TS::STAGE_WORDS;
+        const float *sxy0 = stage + (la * S + lb) * SP, *sxy1 = stage + ((MAS == PYLB_PCS ? la + 2 : la) * S + lb) * SP;   // second x-plane: PCS only
+        const float *sz = stage + (S * S + lc) * SP, *sw = stage + (S * S + S) * SP;
+        for (int i0 = lo + warp * PB; i0 < hi; i0 += NW * PB) {      // warp-uniform trip count
+            int cell0 = -1;
+            if (lane < PB && i0 + lane < hi) {
+                const float4 p = src(i0 + lane);
+                float C[3][S];
+                cell0 = base_cell<MAS, TC>(p, inv, tg, ox, oy, oz, C);
+                if (cell0 >= 0) {
+#pragma unroll
+                    for (int l = 0; l < S; l++)
+#pragma unroll
+                        for (int m = 0; m < S; m++) stage[(l * S + m) * SP + lane] = C[0][l] * C[1][m];
+#pragma unroll
+                    for (int n = 0; n < S; n++) stage[(S * S + n) * SP + lane] = C[2][n];
+                    if (HASW) stage[(S * S + S) * SP + lane] = p.w;
+                }
+            }
+            __syncwarp();
+            // value(s) of this lane's stencil point(s) for particle p of the batch
+            auto value = [&](int p, float (&v)[NP]) {
+                const float wz = sz[p];
+                v[0] = sxy0[p] * wz;
+                if (NP == 2) v[NP - 1] = sxy1[p] * wz;
+                if (HASW) { const float w = sw[p]; v[0] *= w; if (NP == 2) v[NP - 1] *= w; }
+            };
+            unsigned todo = __ballot_sync(full, cell0 >= 0);
+            if constexpr (JOINT) {
+                // walk the batch two particles at a time; a run of equal base cells is first summed in registers
+                while (todo) {
+                    int p = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int b0 = __shfl_sync(full, cell0, p);
+                    float v0[NP];
+                    if (active) value(p, v0);
+                    int b1 = -1;
+                    float v1[NP];
+                    while (todo) {                                   // warp-uniform
+                        p = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        b1 = __shfl_sync(full, cell0, p);
+                        if (active) value(p, v1);
+                        if (b1 != b0) break;
+#pragma unroll
+                        for (int k = 0; k < NP; k++) v0[k] += v1[k];
+                        b1 = -1;
+                    }
+                    if (active) {
+                        if (b1 >= 0) {
+                            float *pp[2 * NP]; float vv[2 * NP];
+#pragma unroll
+                            for (int k = 0; k < NP; k++) {
+                                pp[k] = tile + b0 + loff + 2 * k * TS::PL; vv[k] = v0[k];
+                                pp[NP + k] = tile + b1 + loff + 2 * k * TS::PL; vv[NP + k] = v1[k];
+                            }
+                            smem_add_joint<2 * NP>(pp, vv);
+                        } else {
+                            float *pp[NP]; float vv[NP];
+#pragma unroll
+                            for (int k = 0; k < NP; k++) { pp[k] = tile + b0 + loff + 2 * k * TS::PL; vv[k] = v0[k]; }
+                            smem_add_joint<NP>(pp, vv);
+                        }
+                    }
+                }
+            } else {
+                while (todo) {
+                    const int p = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int b = __shfl_sync(full, cell0, p);
+                    if (active) {
+                        float v[NP];
+                        value(p, v);
+#pragma unroll
+                        for (int k = 0; k < NP; k++) atomicAdd(tile + b + loff + 2 * k * TS::PL, v[k]);
+                    }
+                }
+            }
+            __syncwarp();                                            // the next batch overwrites the staging
+        }
+    }
+    __syncthreads();
+    flush_tile<TS, TC::THREADS>(tile, grid, tg, ox, oy, oz);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -756,17 +750,15 @@ static int partition_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1,
     PYLB_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tb, counts, offsets, G + 1, st));
     count_launch(2);
     PYLB_CHECK(cudaMemcpyAsync(cursor, offsets, sizeof(int) * (G + 1), cudaMemcpyDeviceToDevice, st));
-    if (G <= PART_MAXBINS) {
+    PYLB_REQUIRE(G <= PART_MAXBINS, "pylb_partition_xslab: at most %d slabs", PART_MAXBINS);
+    {
         // the block-local counting sort of the tiled deposit's pass 0 with the slab as its digit: one coalesced read
-        // of the particles, one contiguous run per (chunk, slab) written out (1.26 ms against 1.74 ms for the two-sweep
-        // scatter at 512^3 particles, G = 8)
+        // of the particles, one contiguous run per (chunk, slab) written out
         constexpr int PT = 256, CH = PT * PART_PER_THREAD;
         const size_t psm = sizeof(PartSmem<PT>);
         if (set_smem(bin_pass_kernel<MAS, TileS, HASW, true, PT>, psm)) return 1;
         bin_pass_kernel<MAS, TileS, HASW, true, PT><<<(unsigned)((n + CH - 1) / CH), PT, psm, st>>>(
             pos, w, wst, 0, n, ps0, ps1, inv, tg, nullptr, out, cursor, nullptr, nullptr, 0, G);
-    } else {
-        bin_scatter_kernel<MAS, TileS, HASW><<<P, BIN_THREADS, hist_smem, st>>>(pos, w, wst, 0, n, ps0, ps1, inv, tg, cursor, out);
     }
     PYLB_LAUNCH_CHECK();
     cudaFreeAsync(counts, st); cudaFreeAsync(cursor, st); cudaFreeAsync(tmp, st);
@@ -791,25 +783,18 @@ int ma_partition(const float *pos, int64_t np, int64_t ps0, int64_t ps1, const f
 }
 
 static int g_force_path = -1;   // tests: exercise every path on small grids (pylb_ma_debug_path)
-static bool g_two_pass = true;  // binsort payload movement: two-pass block-local sort (default) or the one-pass scatter
-static int g_fixed = -1;        // tile accumulation: -1 default (float, or PYLB_MA_FIXED), 0 float, 1 fixed point
+static int g_force_kernel = 0;  // tile kernel: 0 default, 1 lane per particle, 2 stencil lanes (plain atomicAdd), 3 stencil lanes (joint CAS)
 void ma_tiled_force_path(int p) {
-    g_fixed = -1;
-    if (p >= 200) { g_fixed = 1; p -= 200; }          // 2xx: force fixed-point tiles (unweighted deposits)
-    else if (p >= 100) { g_fixed = 0; p -= 100; }     // 1xx: force float tiles
-    g_two_pass = !(p >= 10);
-    g_force_path = p >= 10 ? p - 10 : p;
+    g_force_kernel = 0;
+    if (p >= 100) { g_force_kernel = p / 100; p %= 100; if (p == 99) p = -1; }   // k99: automatic sort path, kernel k
+    g_force_path = p;
 }
-static bool use_fixed(int64_t np, int dims, int xext) {
+// PYLB_TILE_KERNEL = 1 | 2 | 3 overrides the default tile kernel (A/B runs)
+static int tile_kernel_choice() {
     static int env = -2;
-    if (env == -2) { const char *e = getenv("PYLB_MA_FIXED"); env = e ? atoi(e) : -1; }
-    const int f = g_fixed >= 0 ? g_fixed : env;
-    (void)np; (void)dims; (void)xext;
-    // Opt-in (PYLB_MA_FIXED=1 or pylb_ma_debug_path(2xx)): measured 1.68 ms against 1.59 ms for the float CAS loop at
-    // 512^3 CIC -- both saturate the shared-memory data pipe (95 % of LSU wavefronts, ~13 wavefronts per warp
-    // update from bank conflicts of randomly placed cells), so the native atomic buys determinism, not speed.
-    // Its 2.3e-10 absolute rounding per update needs a mean density well above 1e-4 particles per cell.
-    return f > 0;
+    if (env == -2) { const char *e = getenv("PYLB_TILE_KERNEL"); env = e ? atoi(e) : 0; }
+    const int k = g_force_kernel > 0 ? g_force_kernel : env;
+    return (k >= 1 && k <= 3) ? k : 3;
 }
 
 static int choose_path(int dims, int xext) {
@@ -907,51 +892,29 @@ static int run_passes(const float *pos, const float *w, int64_t wst, int64_t fir
     return 0;
 }
 
-// Particle count from which a tile's CTAs use the warp-aggregated branch: 1.25x the mean tile population (Poisson
-// fluctuations of a uniform set at >= 1000 particles per tile stay below 1.1x).  PYLB_MA_AGG=0 switches it off, =2 forces
-// it for every tile (A/B runs).
-static int agg_threshold(int n, int ntiles) {
-    static int env = -2;
-    if (env == -2) { const char *e = getenv("PYLB_MA_AGG"); env = e ? atoi(e) : 1; }
-    if (env == 0) return 0;
-    if (env == 2) return 1;
-    const double mean = (double)n / (double)(ntiles > 0 ? ntiles : 1);
-    const double thr = 1.25 * mean + 64.0;
-    return thr > 2.0e9 ? 2000000000 : (int)thr;
-}
-
-static bool use_regroup() {
-    static int env = -2;
-    // Opt-in (PYLB_MA_REGROUP=1).  Measured at 512^3: CIC 2.31 ms against 1.59 ms in arrival order, PCS 1.50 against
-    // 1.54 ms at 256^3 -- the update rate does go up 2.7x, but three barriers, the 32-counter ranking and the exposed
-    // particle load per 1024-particle batch cost more than the conflicts they remove (profiles/r1_ma_regroup_ab.txt).
-    if (env == -2) { const char *e = getenv("PYLB_MA_REGROUP"); env = e ? atoi(e) : 0; }
-    return env != 0;
-}
-
-template <int MAS, bool HASW, class TC, bool BINSORT, bool FIXED>
+template <int MAS, bool HASW, class TC, bool BINSORT>
 static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv,
                      const float *w, int64_t wst, int x0, int xext, TiledWs &ws, cudaStream_t st) {
     using TS = TileShape<MAS, TC>;
     const TileGeom tg = tile_geom<TC>(dims, x0, xext);
-    // NGP has one update per particle: nothing to gain from regrouping
-    const bool regroup = MAS != PYLB_NGP && use_regroup();
-    const size_t acc_smem = sizeof(float) * (FIXED ? TS::CELLS + TS::HI_WORDS : TS::CELLS);
-    const size_t tile_smem = acc_smem + (regroup ? sizeof(float4) * REGROUP_BATCH : 0);
     const size_t hist_smem = sizeof(int) * (size_t)tg.ntiles;
     const int P = sm_count();
-    if (set_smem(deposit_tile_kernel<MAS, HASW, TC, BINSORT, FIXED, true>, acc_smem + sizeof(float4) * REGROUP_BATCH) ||
-        set_smem(deposit_tile_kernel<MAS, HASW, TC, BINSORT, FIXED, false>, acc_smem)) return 1;
+    const int kern = MAS == PYLB_NGP ? 1 : tile_kernel_choice();
+    // always the maximum these kernels may ever need: the attribute is a limit, and a smaller value set here would make
+    // a later, larger launch of the same instantiation fail
+    if (set_smem(deposit_tile_kernel<MAS, HASW, TC, BINSORT>, TS::PLAIN_SMEM)) return 1;
+    if constexpr (MAS != PYLB_NGP) {
+        if (set_smem(deposit_lane_kernel<MAS, HASW, TC, BINSORT, false>, TS::LANE_SMEM) ||
+            set_smem(deposit_lane_kernel<MAS, HASW, TC, BINSORT, true>, TS::LANE_SMEM)) return 1;
+    }
     if (BINSORT) {
-        // always the maximum these kernels may ever need: the attribute is a limit, and a smaller value set
-        // here would make a later, larger launch of the same instantiation fail
         if (set_smem(bin_hist_kernel<MAS, TC>, sizeof(int) * (size_t)BIN_MAX_TILES)) return 1;
-        if (set_smem(bin_scatter_kernel<MAS, TC, HASW>, sizeof(int) * (size_t)BIN_MAX_TILES)) return 1;
     }
     const int nt1 = tg.ntiles + 1;
     for (int64_t first = 0; first < np; first += BATCH) {
         const int n = (int)((np - first) < BATCH ? (np - first) : BATCH);
         size_t tb = ws.tmp_bytes;
+        timing_begin(PYLB_T_SORT, st);
         if (BINSORT) {
             PYLB_CHECK(cudaMemsetAsync(ws.H, 0, sizeof(int) * (size_t)nt1, st));
             bin_hist_kernel<MAS, TC><<<P, BIN_THREADS, hist_smem, st>>>(pos, first, n, ps0, ps1, inv, tg, ws.H);
@@ -960,21 +923,15 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
             PYLB_CHECK(cub::DeviceScan::ExclusiveSum(ws.tmp, tb, ws.H, ws.tile_begin, nt1, st));
             count_launch(2);
             PYLB_CHECK(cudaMemcpyAsync(ws.S, ws.tile_begin, sizeof(int) * (size_t)nt1, cudaMemcpyDeviceToDevice, st));
-            if (g_two_pass) {
-                int lo_bits = (bits_for((unsigned)(tg.ntiles - 1)) + 1) / 2;
-                if (lo_bits > 8) lo_bits = 8;
-                const int nb0 = (tg.ntiles + (1 << lo_bits) - 1) >> lo_bits;      // <= 256 because ntiles <= 65536
-                if (part_threads() == 256) {
-                    if (run_passes<MAS, TC, HASW, 256>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, lo_bits, nb0, st)) return 1;
-                } else if (part_threads() == 128) {
-                    if (run_passes<MAS, TC, HASW, 128>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, lo_bits, nb0, st)) return 1;
-                } else {
-                    if (run_passes<MAS, TC, HASW, 512>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, lo_bits, nb0, st)) return 1;
-                }
+            int lo_bits = (bits_for((unsigned)(tg.ntiles - 1)) + 1) / 2;
+            if (lo_bits > 8) lo_bits = 8;
+            const int nb0 = (tg.ntiles + (1 << lo_bits) - 1) >> lo_bits;      // <= 256 because ntiles <= 65536
+            if (part_threads() == 256) {
+                if (run_passes<MAS, TC, HASW, 256>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, lo_bits, nb0, st)) return 1;
+            } else if (part_threads() == 128) {
+                if (run_passes<MAS, TC, HASW, 128>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, lo_bits, nb0, st)) return 1;
             } else {
-                bin_scatter_kernel<MAS, TC, HASW><<<P, BIN_THREADS, hist_smem, st>>>(pos, w, wst, first, n, ps0, ps1, inv, tg,
-                                                                                      ws.S, ws.sorted);
-                PYLB_LAUNCH_CHECK();
+                if (run_passes<MAS, TC, HASW, 512>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, lo_bits, nb0, st)) return 1;
             }
         } else {
             tile_key_kernel<MAS, TC><<<(n + 255) / 256, 256, 0, st>>>(pos, first, n, ps0, ps1, inv, tg, ws.k0, ws.v0);
@@ -985,20 +942,27 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
             tile_begin_kernel<<<(nt1 + 255) / 256, 256, 0, st>>>(ws.k1, n, tg.ntiles, ws.tile_begin);
             PYLB_LAUNCH_CHECK();
         }
-        tile_chunks_kernel<<<(nt1 + 255) / 256, 256, 0, st>>>(ws.tile_begin, tg.ntiles, ws.nchunks);
+        tile_chunks_kernel<<<(nt1 + 255) / 256, 256, 0, st>>>(ws.tile_begin, tg.ntiles, TC::CHUNK, ws.nchunks);
         PYLB_LAUNCH_CHECK();
         tb = ws.tmp_bytes;
         PYLB_CHECK(cub::DeviceScan::ExclusiveSum(ws.tmp, tb, ws.nchunks, ws.chunk_off, nt1, st));
         count_launch(2);
         // upper bound on work items: every non-empty tile has at most count/CHUNK + 1 chunks
-        const int64_t max_items = (int64_t)n / CHUNK + tg.ntiles;
+        const unsigned max_items = (unsigned)((int64_t)n / TC::CHUNK + tg.ntiles);
+        const ParticleSource<BINSORT, HASW> src{pos, first, ps0, ps1, w, wst, ws.v1, ws.sorted};
+        timing_end(PYLB_T_SORT, st);
         timing_begin(PYLB_T_TILE, st);
-        if (regroup)
-            deposit_tile_kernel<MAS, HASW, TC, BINSORT, FIXED, true><<<(unsigned)max_items, TC::THREADS, tile_smem, st>>>(
-                pos, first, ps0, ps1, w, wst, inv, tg, ws.v1, ws.sorted, ws.tile_begin, ws.chunk_off, grid, agg_threshold(n, tg.ntiles));
-        else
-            deposit_tile_kernel<MAS, HASW, TC, BINSORT, FIXED, false><<<(unsigned)max_items, TC::THREADS, tile_smem, st>>>(
-                pos, first, ps0, ps1, w, wst, inv, tg, ws.v1, ws.sorted, ws.tile_begin, ws.chunk_off, grid, agg_threshold(n, tg.ntiles));
+        if constexpr (MAS != PYLB_NGP) {
+            if (kern == 3)
+                deposit_lane_kernel<MAS, HASW, TC, BINSORT, true><<<max_items, TC::THREADS, TS::LANE_SMEM, st>>>(
+                    src, inv, tg, ws.tile_begin, ws.chunk_off, grid);
+            else if (kern == 2)
+                deposit_lane_kernel<MAS, HASW, TC, BINSORT, false><<<max_items, TC::THREADS, TS::LANE_SMEM, st>>>(
+                    src, inv, tg, ws.tile_begin, ws.chunk_off, grid);
+        }
+        if (kern == 1)
+            deposit_tile_kernel<MAS, HASW, TC, BINSORT><<<max_items, TC::THREADS, TS::PLAIN_SMEM, st>>>(
+                src, inv, tg, ws.tile_begin, ws.chunk_off, grid);
         timing_end(PYLB_T_TILE, st);
         PYLB_LAUNCH_CHECK();
     }
@@ -1008,16 +972,9 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
 template <int MAS, bool HASW>
 static int tiled_path(int path, const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims,
                       float inv, const float *w, int64_t wst, int x0, int xext, TiledWs &ws, cudaStream_t st) {
-    if constexpr (!HASW) {
-        // TileL + fixed point would need 264 KB of shared memory: fixed point only with the small tile
-        if (path != PATH_BIN_L && use_fixed(np, dims, xext < 0 ? dims : xext)) {
-            if (path == PATH_BIN_S) return tiled_run<MAS, HASW, TileS, true, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
-            return tiled_run<MAS, HASW, TileS, false, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
-        }
-    }
-    if (path == PATH_BIN_S) return tiled_run<MAS, HASW, TileS, true, false>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
-    if (path == PATH_BIN_L) return tiled_run<MAS, HASW, TileL, true, false>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
-    return tiled_run<MAS, HASW, TileS, false, false>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+    if (path == PATH_BIN_S) return tiled_run<MAS, HASW, TileS, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+    if (path == PATH_BIN_L) return tiled_run<MAS, HASW, TileL, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+    return tiled_run<MAS, HASW, TileS, false>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
 }
 
 int ma_tiled(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv, int mas,

@@ -115,7 +115,9 @@ extern "C" int pylb_fft_r2c(const float *in, void *out, int dims, int inplace, v
     Plan *p = nullptr;
     if (get_plan(KIND_R2C_3D, dims, 0, inplace ? 1 : 0, &p)) return 1;
     if (exec_setup(p, work, work_bytes, (cudaStream_t)stream)) return 1;
+    timing_begin(PYLB_T_FFT, (cudaStream_t)stream);
     PYLB_CUFFT(cufftExecR2C(p->h, (cufftReal *)in, (cufftComplex *)out));
+    timing_end(PYLB_T_FFT, (cudaStream_t)stream);
     count_launch();
     return 0;
 }
@@ -135,7 +137,9 @@ extern "C" int pylb_fft_r2c_pitched(const float *in, int64_t in_pitch, void *out
     Plan *p = nullptr;
     if (get_plan(KIND_R2C_3D_PITCHED, dims, in_pitch, out_pitch, &p)) return 1;
     if (exec_setup(p, work, work_bytes, (cudaStream_t)stream)) return 1;
+    timing_begin(PYLB_T_FFT, (cudaStream_t)stream);
     PYLB_CUFFT(cufftExecR2C(p->h, (cufftReal *)in, (cufftComplex *)out));
+    timing_end(PYLB_T_FFT, (cudaStream_t)stream);
     count_launch();
     return 0;
 }
@@ -152,7 +156,9 @@ extern "C" int pylb_fft_slab_yz(const float *in, void *out, int dims, int nx_loc
     Plan *p = nullptr;
     if (get_plan(KIND_SLAB_YZ, dims, nx_local, 0, &p)) return 1;
     if (exec_setup(p, work, work_bytes, (cudaStream_t)stream)) return 1;
+    timing_begin(PYLB_T_FFT, (cudaStream_t)stream);
     PYLB_CUFFT(cufftExecR2C(p->h, (cufftReal *)in, (cufftComplex *)out));
+    timing_end(PYLB_T_FFT, (cudaStream_t)stream);
     count_launch();
     return 0;
 }
@@ -168,7 +174,9 @@ extern "C" int pylb_fft_slab_x(void *data, int dims, int ny_local, void *work, s
     Plan *p = nullptr;
     if (get_plan(KIND_SLAB_X, dims, ny_local, 1, &p)) return 1;
     if (exec_setup(p, work, work_bytes, (cudaStream_t)stream)) return 1;
+    timing_begin(PYLB_T_FFT, (cudaStream_t)stream);
     PYLB_CUFFT(cufftExecC2C(p->h, (cufftComplex *)data, (cufftComplex *)data, CUFFT_FORWARD));
+    timing_end(PYLB_T_FFT, (cudaStream_t)stream);
     count_launch();
     return 0;
 }

@@ -73,6 +73,13 @@ def gold_ma():
     g = np.zeros((dims,) * 3, np.float64); MASL.CICW_d(pos, g, box, W); out["grid_CICW_d"] = g
     # OpenMP C entry points (MAS_c.c) -- same numbers up to summation order
     g = np.zeros((dims,) * 3, np.float32); MASL.PCSWc3D(pos, g, W, box, 2); out["grid_PCSWc3D"] = g
+    # all sixteen MAS_c shims of Test/test_MAS.py:88-238 (3-D and 2-D, plain and weighted): the 2-D C kernels add
+    # every contribution ONCE (n_max = 1, MAS_c.c:21-34) and nothing is renormalised afterwards
+    for mas in ("NGP", "CIC", "TSC", "PCS"):
+        g = np.zeros((dims,) * 3, np.float32); getattr(MASL, mas + "c3D")(pos, g, box, 2); out["c3D_%s" % mas] = g
+        g = np.zeros((dims,) * 3, np.float32); getattr(MASL, mas + "Wc3D")(pos, g, W, box, 3); out["c3D_%sW" % mas] = g
+        g = np.zeros((dims2,) * 2, np.float32); getattr(MASL, mas + "c2D")(pos2, g, box, 2); out["c2D_%s" % mas] = g
+        g = np.zeros((dims2,) * 2, np.float32); getattr(MASL, mas + "Wc2D")(pos2, g, W, box, 1); out["c2D_%sW" % mas] = g
     np.savez_compressed(os.path.join(HERE, "ma.npz"), **out)
 
 

@@ -94,6 +94,49 @@ def test_ma_openmp_shims(MASL, gma):
     parity.assert_grid_close(g, gma["grid_CIC"], "CICc3D")
 
 
+_REF_THREADS = {"CICc3D": 1, "TSCWc3D": 3}          # the thread counts Test/test_MAS.py passes (2 everywhere else)
+
+
+@pytest.mark.parametrize("mas,places", [("NGP", 20), ("CIC", 8), ("TSC", 8), ("PCS", 8)])
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_masc_shims_reference_unit_tests(MASL, mas, places, weighted, ndim):
+    """Test/test_MAS.py:88-238 (test_NGPc3D ... test_PCSWc2D), restated case by case on the product's shims."""
+    particles, BoxSize, dims, seed = 1000, 1.0, 64, 1
+    np.random.seed(seed)
+    pos = np.random.random((particles, ndim)).astype(np.float32)
+    delta = np.zeros((dims,) * ndim, dtype=np.float32)
+    name = "%s%sc%dD" % (mas, "W" if weighted else "", ndim)
+    threads = _REF_THREADS.get(name, 2)
+    if weighted:
+        W = np.ones(particles, dtype=np.float32) * 3.0
+        getattr(MASL, name)(pos, delta, W, BoxSize, threads)
+    else:
+        getattr(MASL, name)(pos, delta, BoxSize, threads)
+    suma = np.sum(delta, dtype=np.float64)
+    assert round(abs(suma / (3.0 * particles if weighted else particles) - 1.0), places) == 0
+
+
+@pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_masc_shims_golden(MASL, gma, mas, weighted, ndim):
+    """All sixteen <MAS>[W]c{2,3}D shims against the grids the reference's own MAS_c kernels produced."""
+    box = float(gma["box"])
+    dims = int(gma["dims"] if ndim == 3 else gma["dims2"])
+    pos = gma["pos"] if ndim == 3 else np.ascontiguousarray(gma["pos"][:, :2])
+    g = np.zeros((dims,) * ndim, np.float32)
+    name = "%s%sc%dD" % (mas, "W" if weighted else "", ndim)
+    if weighted:
+        getattr(MASL, name)(pos, g, gma["W"], box, 2)
+    else:
+        getattr(MASL, name)(pos, g, box, 2)
+    want = gma["c%dD_%s%s" % (ndim, mas, "W" if weighted else "")]
+    if mas == "NGP" and not weighted:
+        parity.assert_exact(g, want, name)
+    parity.assert_grid_close(g, want, name)
+
+
 def test_ma_fortran_order_and_device_tensors(MASL, gma):
     box, dims = float(gma["box"]), int(gma["dims"])
     g = np.zeros((dims,) * 3, np.float32)
@@ -147,17 +190,16 @@ def test_reference_unit_tests_mass_conservation(MASL, mas, places, weighted):
     assert round(abs(suma / (3.0 * particles if weighted else particles) - 1.0), places) == 0
 
 
-# direct; tiled auto; forced two-pass binsort S / L, radix; one-pass scatter S / L; binsort S with float tiles (1xx) and
-# with fixed-point tiles (2xx); radix with fixed-point tiles
-@pytest.mark.parametrize("algo", [1, 2, 20, 21, 22, 30, 31, 120, 220, 222])
+# algo 1: direct kernel.  algo 2 + debug path: -1 automatic; 0 / 1 / 2 = binsort with 16x16x32 tiles, with 32x32x32 tiles,
+# radix sort + gather (default tile kernel); +100 lane-per-particle kernel, +200 stencil lanes with plain atomicAdd,
+# +300 stencil lanes with the joint CAS loop
+@pytest.mark.parametrize("algo,path", [(1, -1), (2, -1), (2, 0), (2, 1), (2, 2), (2, 100), (2, 101), (2, 102),
+                                       (2, 200), (2, 201), (2, 202), (2, 300), (2, 301), (2, 302)])
 @pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
 @pytest.mark.parametrize("dims", [64, 80])
-def test_ma_vs_oracle_both_algorithms(MASL, algo, mas, dims):
-    """Seeded random + clustered particles, direct and tiled kernels (every sort path) against the oracle."""
+def test_ma_vs_oracle_both_algorithms(MASL, algo, path, mas, dims):
+    """Seeded random + clustered particles, direct and tiled kernels (every sort path x every tile kernel) against the oracle."""
     from pylians_b200 import _lib
-    path = -1
-    if algo >= 20:
-        path, algo = algo - 20, 2
     _lib.load().pylb_ma_debug_path(path)
     rng = np.random.default_rng(100 + dims)
     box, n = 1000.0, 300000
@@ -213,6 +255,24 @@ def test_cabi_host_entry_points(gma):
                            pos.shape[0], dims, 3, ctypes.c_float(box), 4)
         assert lib.pylb_last_error() == b"", lib.pylb_last_error()
         parity.assert_grid_close(g, gma[key], "C ABI " + name)
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_cabi_host_entry_points_2d(gma, threads):
+    """axes = 2 through the raw MAS_c.h ABI (MAS_c.c:21-34: one update per cell, no renormalisation), accumulating on
+    top of what `number` already holds."""
+    from pylians_b200 import _lib
+    lib = _lib.load()
+    box, dims = float(gma["box"]), int(gma["dims2"])
+    pos = np.ascontiguousarray(gma["pos"][:, :2]); W = np.ascontiguousarray(gma["W"])
+    for mas in ("NGP", "CIC", "TSC", "PCS"):
+        for w in (None, W):
+            g = np.full((dims,) * 2, 0.25, np.float32)
+            getattr(lib, mas)(pos.ctypes.data, g.ctypes.data, w.ctypes.data if w is not None else None,
+                              pos.shape[0], dims, 2, ctypes.c_float(box), threads)
+            assert lib.pylb_last_error() == b"", lib.pylb_last_error()
+            want = gma["c2D_%s%s" % (mas, "W" if w is not None else "")].astype(np.float64) + 0.25
+            parity.assert_grid_close(g, want, "C ABI 2-D " + mas)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -488,12 +548,15 @@ def test_full_size_1024_tsc_multipoles_and_xpk(MASL, PKL):
     np.testing.assert_allclose(y.Pk[:, :, 1], x.Pk[:, :, 0], rtol=1e-6, atol=1e-7 * shot)
 
 
+@pytest.mark.parametrize("kernel", [199, 299, 399])
 @pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
 @pytest.mark.parametrize("weighted", [False, True])
-def test_ma_clustered_input_warp_aggregation(MASL, mas, weighted):
-    """Half of one tile's particles sit in three cells (a halo): the tile kernel's warp-aggregated branch (groups of
-    lanes sharing a base cell are summed with shuffles, one shared atomic per cell) must give the oracle's grid."""
+def test_ma_clustered_input(MASL, mas, weighted, kernel):
+    """Half of one tile's particles sit in three cells (a halo): many lanes / consecutive particles share a base cell.
+    The stencil-lane kernel sums runs of equal base cells in registers and resolves equal addresses inside its CAS loop;
+    every tile kernel must give the oracle's grid."""
     from oracle import pylians_oracle as O
+    from pylians_b200 import _lib
     import pylians_b200.MAS_library as M
     dims, box = 64, 640.0                                   # 10 length units per cell
     rng = np.random.default_rng(31)
@@ -502,14 +565,17 @@ def test_ma_clustered_input_warp_aggregation(MASL, mas, weighted):
                           (np.array([105.0, 85.0, 155.0]), np.array([104.0, 93.0, 161.0]), np.array([325.0, 325.0, 325.0]))])
     pos = np.mod(np.concatenate([uni, hot]), box).astype(np.float32)
     pos = pos[rng.permutation(len(pos))]
+    pos[:4000] = pos[0]                                     # and a run of identical particles
     W = (rng.random(len(pos)) + 0.5).astype(np.float32) if weighted else None
     ref = np.zeros((dims,) * 3, np.float32)
     O.MA(pos, ref, box, mas, W=W)
     old, M.ALGO = M.ALGO, 2                                 # the tiled (shared-memory) deposit, also on this small grid
+    _lib.load().pylb_ma_debug_path(kernel)                  # k99: automatic sort path, tile kernel k
     try:
         got = np.zeros((dims,) * 3, np.float32)
         MASL.MA(pos, got, box, mas, W=W)
     finally:
         M.ALGO = old
+        _lib.load().pylb_ma_debug_path(-1)
     assert ref.max() > 50 * ref.mean()                      # the halo cells really are hot
     parity.assert_grid_close(got, ref, "clustered " + mas)

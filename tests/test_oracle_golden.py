@@ -66,6 +66,20 @@ def test_ma_matches_openmp_entry(gma):
     parity.assert_grid_close(g, gma["grid_PCSWc3D"], "PCSWc3D")
 
 
+@pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_masc_shims_golden(gma, mas, weighted, ndim):
+    """The sixteen MAS_c shims (Test/test_MAS.py:88-238).  Their 2-D kernels add every contribution once (MAS_c.c:21-34),
+    which equals MA()'s renormalised 2-D grid up to the rounding of S equal fp32 additions."""
+    box = float(gma["box"])
+    dims = int(gma["dims"] if ndim == 3 else gma["dims2"])
+    pos = gma["pos"] if ndim == 3 else np.ascontiguousarray(gma["pos"][:, :2])
+    g = np.zeros((dims,) * ndim, np.float32)
+    O.MA(pos, g, box, mas, W=gma["W"] if weighted else None)
+    parity.assert_grid_close(g, gma["c%dD_%s%s" % (ndim, mas, "W" if weighted else "")], "%s c%dD" % (mas, ndim))
+
+
 def test_ma_fortran_order_pos(gma):
     box, dims = float(gma["box"]), int(gma["dims"])
     g = np.zeros((dims,) * 3, np.float32)
