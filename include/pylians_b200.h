@@ -122,9 +122,10 @@ int pylb_partition_xslab(const float *pos, int64_t np, int64_t pos_stride0, int6
 /* dst[i] += src[i]  (adding received halo planes) */
 int pylb_add_f32(float *dst, const float *src, int64_t n, void *stream);
 
-/* Testing hook: force how the tiled deposit brings particles into tile order.
- * -1 automatic, 0 binsort with 16x16x32 tiles, 1 binsort with 32x32x32 tiles, 2 radix sort + gather;
- * 10 / 11: like 0 / 1 but moving the payload with the one-pass scatter instead of the two-pass block sort. */
+/* Testing hook for the tiled deposit.  path = 100*kernel + sort.
+ * sort:   0 automatic, 2 force the deep sort (second histogram sweep after pass 0), 3 / 4 deep sort with 1024 / 4 lo digits
+ * kernel: 0 automatic, 1 lane-per-particle tile kernel for every scheme, 2 stencil-lane tile kernel where it exists (PCS);
+ * negative = everything automatic. */
 void pylb_ma_debug_path(int path);
 
 /* grid[i] /= divisor  (the `number2 /= 2|3|4` of MAS_library.pyx:90-107; applies to the WHOLE array) */

@@ -1,0 +1,80 @@
+// Shared-memory atomic throughput as a function of the ADDRESS PATTERN of one warp instruction (B200).
+// Round 2 question: the stencil-lane tile kernel updates, per warp instruction, 32 cells in 32 distinct banks that are
+// NOT contiguous (4 consecutive words in each of 8 rows of the tile).  Is that as fast as 32 contiguous words?
+//   pattern 0  32 contiguous words, random row               (what profiles/microbench/atomics.cu case F measured)
+//   pattern 1  PCS stencil: base + a*688 + b*36 + c, a in {0,1}, b,c in 0..3, random base   (distinct banks, 8 rows)
+//   pattern 2  every lane random                               (lane-per-particle kernel)
+//   pattern 3  TSC stencil: base + a*649 + b*35 + c, 27 lanes
+// ops: 0 native int ATOMS.ADD without return, 1 float atomicAdd (CAS loop), 2 plain LDS + FADD + STS (no atomicity)
+// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o atoms_pattern atoms_pattern.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("%s:%d %s\n",__FILE__,__LINE__,cudaGetErrorString(e)); exit(1);} }while(0)
+__device__ __forceinline__ unsigned hash(unsigned x){ x^=x>>16; x*=0x7feb352dU; x^=x>>15; x*=0x846ca68bU; x^=x>>16; return x; }
+constexpr int CELLS = 13072;   // the PCS tile: 19 planes x 688 words
+
+template <int PATTERN, int OP>
+__global__ void k(float *out, int iters) {
+    extern __shared__ int s[];
+    for (int i = threadIdx.x; i < CELLS; i += blockDim.x) s[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned h = hash(warp + 1);
+    int loff; bool active = true;
+    if (PATTERN == 0) loff = lane;
+    else if (PATTERN == 1) loff = (lane >> 4) * 688 + ((lane >> 2) & 3) * 36 + (lane & 3);
+    else if (PATTERN == 3) { active = lane < 27; loff = active ? (lane / 9) * 649 + ((lane / 3) % 3) * 35 + lane % 3 : 0; }
+    else loff = 0;
+    for (int it = 0; it < iters; it++) {
+        h = hash(h + it);                                            // warp-uniform
+        int base;
+        if (PATTERN == 0) base = (h % (CELLS / 32 - 24)) * 32;
+        else if (PATTERN == 1) base = (h % 16) * 688 + ((h >> 4) % 16) * 36 + ((h >> 8) % 32);
+        else if (PATTERN == 3) base = (h % 16) * 649 + ((h >> 4) % 16) * 35 + ((h >> 8) % 32);
+        else base = hash(h ^ (lane * 0x9e3779b9u)) % (CELLS - 1400);
+        int *p0 = s + base + loff, *p1 = p0 + (PATTERN == 1 ? 2 * 688 : 700);
+        if (!active) continue;
+        if (OP == 0) { atomicAdd(p0, it | 1); atomicAdd(p1, it | 3); }
+        else if (OP == 1) { atomicAdd((float *)p0, 1.0f); atomicAdd((float *)p1, 1.0f); }
+        else { float a = ((float *)p0)[0], b = ((float *)p1)[0]; ((float *)p0)[0] = a + 1.0f; ((float *)p1)[0] = b + 1.0f; }
+    }
+    __syncthreads();
+    float acc = 0; for (int i = threadIdx.x; i < CELLS; i += blockDim.x) acc += (float)s[i];
+    if (acc == -1.2345f) out[0] = acc;
+}
+
+template <int PATTERN, int OP>
+void run(const char *name, float *out) {
+    const int sms = 148, iters = 4096;
+    CK(cudaFuncSetAttribute(k<PATTERN, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, CELLS * 4));
+    for (int warps_per_sm : {8, 16, 32}) {
+        const int threads = 256, blocks = sms * warps_per_sm / 8;
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        k<PATTERN, OP><<<blocks, threads, CELLS * 4>>>(out, iters); CK(cudaDeviceSynchronize());
+        float best = 1e30f;
+        for (int r = 0; r < 3; r++) {
+            cudaEventRecord(a); k<PATTERN, OP><<<blocks, threads, CELLS * 4>>>(out, iters); cudaEventRecord(b); CK(cudaEventSynchronize(b));
+            float ms; cudaEventElapsedTime(&ms, a, b); if (ms < best) best = ms;
+        }
+        const double lanes = (PATTERN == 3 ? 27.0 : 32.0);
+        const double ops = (double)blocks * (threads / 32) * iters * 2 * lanes;
+        printf("%-44s warps/SM=%2d: %8.3f ms  %8.1f G lane-updates/s  %6.2f per clk per SM @1.965 GHz\n", name, warps_per_sm, best,
+               ops / best / 1e6, ops / (best * 1e-3) / 148 / 1.965e9);
+    }
+}
+
+int main() {
+    float *out; CK(cudaMalloc(&out, 64));
+    run<0, 0>("int ATOMS.ADD, 32 contiguous words", out);
+    run<1, 0>("int ATOMS.ADD, PCS stencil (8 rows x 4)", out);
+    run<3, 0>("int ATOMS.ADD, TSC stencil (9 rows x 3)", out);
+    run<2, 0>("int ATOMS.ADD, random lanes", out);
+    run<0, 1>("float CAS, 32 contiguous words", out);
+    run<1, 1>("float CAS, PCS stencil", out);
+    run<2, 1>("float CAS, random lanes", out);
+    run<0, 2>("LDS+FADD+STS, 32 contiguous words", out);
+    run<1, 2>("LDS+FADD+STS, PCS stencil", out);
+    run<2, 2>("LDS+FADD+STS, random lanes", out);
+    return 0;
+}

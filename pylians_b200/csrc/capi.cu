@@ -50,7 +50,7 @@ int ma_direct(const float *pos, int64_t np, int ndim, int64_t ps0, int64_t ps1, 
 int ma_tiled(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv,
              int mas, const float *w, int64_t wst, int x0, int xext, void *workspace, size_t workspace_bytes, cudaStream_t st);
 size_t ma_tiled_workspace(int64_t np, int dims, int xext, int mas, int has_w);
-bool ma_tiled_supported(int ndim, int dims, int grid_f64);
+bool ma_tiled_supported(int ndim, int dims, int grid_f64, int xext);
 void ma_tiled_force_path(int p);
 int ma_partition(const float *pos, int64_t np, int64_t ps0, int64_t ps1, const float *w, int64_t wst, int dims, float inv,
                  int mas, int G, float4 *out, int *offsets, cudaStream_t st);
@@ -131,7 +131,7 @@ extern "C" void pylb_ma_debug_path(int path) { ma_tiled_force_path(path); }
 
 extern "C" size_t pylb_ma_workspace_bytes(int64_t np, int ndim, int dims, int mas, int has_w, int grid_f64, int algo) {
     if (algo == PYLB_MA_DIRECT) return 0;
-    if (!ma_tiled_supported(ndim, dims, grid_f64)) return 0;
+    if (!ma_tiled_supported(ndim, dims, grid_f64, dims)) return 0;
     return ma_tiled_workspace(np, dims, dims, mas, has_w);
 }
 
@@ -147,7 +147,7 @@ extern "C" int pylb_ma(const float *pos, int64_t np, int ndim, int64_t ps0, int6
     const float zrep = (ndim == 2 && z_repeat > 1) ? (float)z_repeat : 1.0f;
     cudaStream_t st = (cudaStream_t)stream;
     bool tiled = false;
-    if (algo != PYLB_MA_DIRECT && ma_tiled_supported(ndim, dims, grid_f64)) {
+    if (algo != PYLB_MA_DIRECT && ma_tiled_supported(ndim, dims, grid_f64, dims)) {
         // AUTO: the tiled path pays a binning pass; it wins once the grid no longer lives in L2
         const bool big = (size_t)dims * dims * dims * sizeof(float) > (size_t)48 << 20;
         tiled = (algo == PYLB_MA_TILED) || (big && np >= (int64_t)1 << 20);
@@ -165,7 +165,7 @@ extern "C" int pylb_ma(const float *pos, int64_t np, int ndim, int64_t ps0, int6
 
 // ---- x-window deposit: the grid holds planes x0 .. x0+xext-1 (mod dims) of a dims^3 cube -------------
 extern "C" size_t pylb_ma_window_workspace_bytes(int64_t np, int dims, int xext, int mas, int algo) {
-    if (algo == PYLB_MA_DIRECT || dims < 32) return 0;
+    if (algo == PYLB_MA_DIRECT || !ma_tiled_supported(3, dims, 0, xext)) return 0;
     return ma_tiled_workspace(np, dims, xext, mas, 1);
 }
 
@@ -178,7 +178,7 @@ extern "C" int pylb_ma_window(const float *pos, int64_t np, int64_t ps0, int64_t
     PYLB_REQUIRE(box > 0.0f, "pylb_ma_window: BoxSize must be positive");
     const float inv = (float)dims / box;
     cudaStream_t st = (cudaStream_t)stream;
-    bool tiled = algo != PYLB_MA_DIRECT && dims >= 32 && np >= ((int64_t)1 << 16) &&
+    bool tiled = algo != PYLB_MA_DIRECT && ma_tiled_supported(3, dims, 0, xext) && np >= ((int64_t)1 << 16) &&
                  workspace_bytes >= ma_tiled_workspace(np, dims, xext, mas, 1) && workspace != nullptr;
     PYLB_REQUIRE(tiled || algo != PYLB_MA_TILED, "pylb_ma_window: tiled path unavailable (dims < 32, tiny input or workspace too small)");
     if (tiled) return ma_tiled(pos, np, ps0, ps1, grid, dims, inv, mas, w, w_stride, x0, xext, workspace, workspace_bytes, st);

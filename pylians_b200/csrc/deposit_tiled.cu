@@ -1,47 +1,46 @@
 // Tiled particle deposit for 3-D float32 grids.
 //
-// Particles are first brought into cell-tile order, then every tile is accumulated in shared memory
-// and flushed with red.global.add.v4.f32.  Two ways to get tile order:
+// Particles are first brought into cell-tile order (tiles of 16x16x32 cells), then every tile is accumulated in
+// shared memory and flushed with red.global.add.v4.f32.
 //
-//  BINSORT (ntiles <= 53248; tiles are 16x16x32 cells, or 32x32x32 when that is needed to stay under
-//           the limit) -- a counting sort that moves the (x,y,z,w) payload itself:
-//     bin_hist_kernel     one CTA per SM builds a histogram over ALL tiles in shared memory (native int
-//                         ATOMS.ADD, 2.6 T/s) and merges it into the global per-tile counts
-//     cub ExclusiveSum    counts -> first output slot of every tile
-//     bin_pass_kernel x2  two-pass block-local counting sort (hi digit, then lo digit of the tile id); streaming
+//  SORT -- an MSD counting sort that moves the (x,y,z,w) payload itself, two digits of the tile id:
+//     bin_hist_kernel     one CTA per SM builds a histogram in shared memory (native int ATOMS.ADD) and merges it
+//                         into the global counts.  Up to 53248 tiles ("shallow": every grid up to 768^3, and x-slab
+//                         windows of larger ones) the keys are the tiles themselves and this one sweep over the raw
+//                         particles yields every tile's first output slot.  Beyond that ("deep", up to 2^20 tiles =
+//                         a full 2048^3 grid) the sweep histograms the HI digit only, and the per-tile counts come
+//                         from bin_hist2_kernel, a second sweep over the bucket-ordered payload after pass 0 (a CTA
+//                         then only sees the <= 1024 tiles of one bucket): +16 B per particle, no tile-count limit.
+//     cub ExclusiveSum    counts -> first output slot of every bucket / tile
+//     bin_pass_kernel x2  block-local counting sort by hi digit, then by lo digit inside every bucket; streaming
 //                         reads, one contiguous output run per (chunk, digit), no random gather (a random 12-byte
 //                         gather costs 3.9 ms per 2^27 particles on B200, a streaming read 0.25 ms: profiles/microbench)
-//  RADIX (any ntiles) -- cub radix sort of (tile key, particle index); the tile kernel then gathers
-//     particles through the sorted index.
 //
-//  deposit_lane_kernel   CIC/TSC/PCS: one CTA per work item (tile, chunk of <= CHUNK particles): zero the tile
-//                         (+ halo) in shared memory, accumulate with the lanes of a warp mapped to the STENCIL POINTS
-//                         of one particle (bank-conflict-free by construction of the tile pitches), flush.  Halo cells
-//                         overlap neighbouring tiles, so the flush must add -- and `number` is accumulate-in-place anyway.
-//  deposit_tile_kernel   NGP (and the A/B baseline): lane per particle.
-//
-// Shared-memory fp32 atomicAdd is an ATOMS.CAST.SPIN loop on sm_100a (2.9 updates/clk/SM measured for randomly
-// placed cells vs 9.2 for native int atomics); the lane-per-particle kernel is bound by that pipe, which is what the
-// stencil-lane layout removes.
-#include <cub/device/device_radix_sort.cuh>
+//  ACCUMULATE -- one work item = (tile, chunk of <= 8192 of its particles); persistent CTAs walk the item list:
+//     deposit_tile_kernel   NGP/CIC/TSC: lane per particle, S^3 shared-memory atomicAdd(float) per lane.
+//     deposit_lane_kernel   PCS: the lanes of a warp are the STENCIL POINTS of one particle (32 lanes x 2 x-planes) and the
+//                           tile pitches put those 32 cells into 32 distinct banks, so one warp instruction never touches
+//                           a cell twice and its compare-and-swap only fails when another warp got there first: the
+//                           update is an optimistic load / add / CAS pair with no spin loop on the fast path.
+//   Shared-memory float atomics are what bounds every variant (there is no native fp32 add: atomicAdd is an
+//   ATOMS.CAST.SPIN loop).  Measured on B200 (profiles/r2_atoms_pattern.txt, lane-updates per clock per SM at 32 warps/SM):
+//   float CAS loop 2.8 on randomly placed cells, 5.6 on the stencil pattern; native integer ATOMS.ADD 6.4 / 8.5; plain
+//   LDS+FADD+STS 4.5 / 7.7.  Integer (fixed-point) tiles were built and measured this round -- one word per cell with a
+//   per-item scale from an exact stencil-count bound: PCS 7.3 ms against 8.1 ms at 512^3, but sub-unit contributions
+//   of dense clumps are lost and the 1e-5 contract fails on clustered input; two words per cell are exact but need twice
+//   the atomics (10.7 ms) -- so the tiles stay fp32 (profiles/r2_deposit_variants.txt).
 #include <cub/device/device_scan.cuh>
 
 #include "deposit.cuh"
 
 namespace pylb {
 
-// TX x TY x TZ cells per tile; PB = particles per warp batch of the stencil-lane kernel (bounds its weight staging);
-// CHUNK = particles per work item
-template <int TX_, int TY_, int TZ_, int THREADS_, int PB_, int CHUNK_>
-struct TileCfg {
-    static constexpr int TX = TX_, TY = TY_, TZ = TZ_, THREADS = THREADS_, PB = PB_, CHUNK = CHUNK_;
-};
-typedef TileCfg<16, 16, 32, 256, 32, 8192> TileS;      // 39-75 KB of shared memory per CTA, 3-5 CTAs/SM
-typedef TileCfg<32, 32, 32, 1024, 16, 32768> TileL;    // 144-223 KB, 1 CTA/SM of 32 warps, 4x fewer tiles
-
-constexpr int64_t BATCH = 1ll << 28;     // particles binned per pass (bounds the workspace)
-constexpr int BIN_THREADS = 1024;        // binsort CTAs: one per SM, 32 warps
-constexpr int BIN_MAX_TILES = 53248;     // per-CTA histogram must fit shared memory (208 KB of 227 KB); keys are 16-bit
+constexpr int TX = 16, TY = 16, TZ = 32;     // cells per tile
+constexpr int CHUNK = 8192;                  // particles per work item
+constexpr int64_t BATCH = 1ll << 28;         // particles sorted per round (bounds the workspace)
+constexpr int BIN_THREADS = 1024;            // histogram CTAs: one per SM, 32 warps
+constexpr int BIN_MAX_KEYS = 53248;          // per-CTA histogram must fit shared memory (208 KB of 227 KB)
+constexpr int MAX_TILES = 1 << 20;           // two digits of <= 1024 values
 
 // x0 / xext: x window held by the grid (planes x0 .. x0+xext-1 modulo dims; the whole cube when xext == dims)
 struct TileGeom {
@@ -49,22 +48,21 @@ struct TileGeom {
     int slab_w;   // > 0: partition mode -- the key is the x-slab (of slab_w planes) owning the particle's lowest touched cell
 };
 
-template <class TC>
 static TileGeom tile_geom(int dims, int x0 = 0, int xext = -1) {
     TileGeom t;
     t.dims = dims;
     t.x0 = x0;
     t.slab_w = 0;
     t.xext = xext < 0 ? dims : xext;
-    t.ntx = (t.xext + TC::TX - 1) / TC::TX;
-    t.nty = (dims + TC::TY - 1) / TC::TY;
-    t.ntz = (dims + TC::TZ - 1) / TC::TZ;
+    t.ntx = (t.xext + TX - 1) / TX;
+    t.nty = (dims + TY - 1) / TY;
+    t.ntz = (dims + TZ - 1) / TZ;
     t.ntiles = t.ntx * t.nty * t.ntz;
     return t;
 }
 
 // key of the tile holding the particle's lowest touched cell
-template <int MAS, class TC>
+template <int MAS>
 __device__ __forceinline__ unsigned tile_key(float x, float y, float z, float inv, const TileGeom &tg) {
     float C[Support<MAS>::S];
     int bx = wrap(axis_stencil<MAS>(x, inv, C) - tg.x0, tg.dims);
@@ -72,20 +70,21 @@ __device__ __forceinline__ unsigned tile_key(float x, float y, float z, float in
     if (bx >= tg.xext) bx = tg.xext - 1;   // particle routed to the wrong slab: keep the key in range (its updates are dropped)
     const int by = wrap(axis_stencil<MAS>(y, inv, C), tg.dims);
     const int bz = wrap(axis_stencil<MAS>(z, inv, C), tg.dims);
-    return (unsigned)(((bx / TC::TX) * tg.nty + (by / TC::TY)) * tg.ntz + (bz / TC::TZ));
+    return (unsigned)(((bx / TX) * tg.nty + (by / TY)) * tg.ntz + (bz / TZ));
 }
 
 // ------------------------------------------------------------------------------------------------
-// BINSORT
+// SORT
 // ------------------------------------------------------------------------------------------------
-// per-tile particle counts: per-CTA shared histogram, merged with one red.global per (CTA, tile)
-template <int MAS, class TC>
+// counts[key >> shift] over the raw particles: per-CTA shared histogram, merged with one red.global per (CTA, key)
+template <int MAS>
 __global__ void __launch_bounds__(BIN_THREADS, 1)
 bin_hist_kernel(const float *__restrict__ pos, int64_t first, int n, int64_t ps0, int64_t ps1, float inv,
-                TileGeom tg, int *__restrict__ counts) {
+                TileGeom tg, int shift, int nkeys, int *__restrict__ counts) {
     extern __shared__ int hist[];
-    for (int t = threadIdx.x; t < tg.ntiles; t += BIN_THREADS) hist[t] = 0;
+    for (int t = threadIdx.x; t < nkeys; t += BIN_THREADS) hist[t] = 0;
     __syncthreads();
+    auto key = [&](float x, float y, float z) { return tile_key<MAS>(x, y, z, inv, tg) >> shift; };
     const float *base = pos + first * ps0;
     if (ps0 == 3 && ps1 == 1 && ((uintptr_t)base & 15) == 0) {
         // dense (np,3) array: 4 particles = 3 aligned float4, 8 particles (6 x 16 B) in flight per thread
@@ -102,15 +101,15 @@ bin_hist_kernel(const float *__restrict__ pos, int64_t first, int n, int64_t ps0
 #pragma unroll
             for (int u = 0; u < 2; u++)
                 if (q0 + u * stride < n4) {
-                    atomicAdd(&hist[tile_key<MAS, TC>(a[u].x, a[u].y, a[u].z, inv, tg)], 1);
-                    atomicAdd(&hist[tile_key<MAS, TC>(a[u].w, b[u].x, b[u].y, inv, tg)], 1);
-                    atomicAdd(&hist[tile_key<MAS, TC>(b[u].z, b[u].w, c[u].x, inv, tg)], 1);
-                    atomicAdd(&hist[tile_key<MAS, TC>(c[u].y, c[u].z, c[u].w, inv, tg)], 1);
+                    atomicAdd(&hist[key(a[u].x, a[u].y, a[u].z)], 1);
+                    atomicAdd(&hist[key(a[u].w, b[u].x, b[u].y)], 1);
+                    atomicAdd(&hist[key(b[u].z, b[u].w, c[u].x)], 1);
+                    atomicAdd(&hist[key(c[u].y, c[u].z, c[u].w)], 1);
                 }
         }
         if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
             const float *p = base + 3 * (int64_t)(4 * n4 + threadIdx.x);
-            atomicAdd(&hist[tile_key<MAS, TC>(p[0], p[1], p[2], inv, tg)], 1);
+            atomicAdd(&hist[key(p[0], p[1], p[2])], 1);
         }
     } else if (ps0 == 4 && ps1 == 1 && ((uintptr_t)base & 15) == 0) {
         // packed (x,y,z,w) records (the particle-exchange payload): one 16-byte load per particle, 4 in flight
@@ -123,74 +122,74 @@ bin_hist_kernel(const float *__restrict__ pos, int64_t first, int n, int64_t ps0
                 if (i0 + u * stride < n) q[u] = __ldg(p4 + i0 + u * stride);
 #pragma unroll
             for (int u = 0; u < 4; u++)
-                if (i0 + u * stride < n) atomicAdd(&hist[tile_key<MAS, TC>(q[u].x, q[u].y, q[u].z, inv, tg)], 1);
+                if (i0 + u * stride < n) atomicAdd(&hist[key(q[u].x, q[u].y, q[u].z)], 1);
         }
     } else {
-    // 4 particles per iteration: all 12 loads are issued before the first key is computed
-    const int64_t stride = (int64_t)gridDim.x * BIN_THREADS;
-    for (int64_t i0 = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x; i0 < n; i0 += 4 * stride) {
-        float x[4], y[4], z[4];
+        // 4 particles per iteration: all 12 loads are issued before the first key is computed
+        const int64_t stride = (int64_t)gridDim.x * BIN_THREADS;
+        for (int64_t i0 = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x; i0 < n; i0 += 4 * stride) {
+            float x[4], y[4], z[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int64_t i = i0 + u * stride;
-            if (i < n) {
-                const float *p = pos + (first + i) * ps0;
-                x[u] = __ldg(p); y[u] = __ldg(p + ps1); z[u] = __ldg(p + 2 * ps1);
+            for (int u = 0; u < 4; u++) {
+                const int64_t i = i0 + u * stride;
+                if (i < n) {
+                    const float *p = pos + (first + i) * ps0;
+                    x[u] = __ldg(p); y[u] = __ldg(p + ps1); z[u] = __ldg(p + 2 * ps1);
+                }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (i0 + u * stride < n) atomicAdd(&hist[tile_key<MAS, TC>(x[u], y[u], z[u], inv, tg)], 1);
-    }
+            for (int u = 0; u < 4; u++)
+                if (i0 + u * stride < n) atomicAdd(&hist[key(x[u], y[u], z[u])], 1);
+        }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < tg.ntiles; t += BIN_THREADS) {
+    for (int t = threadIdx.x; t < nkeys; t += BIN_THREADS) {
         const int c = hist[t];
         if (c) atomicAdd(&counts[t], c);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Two-pass block-local counting sort of the payload (default for ntiles <= 65536).
-//   tile id = (hi digit << lo_bits) | lo digit, both digits <= 256 values.
+// Two-pass block-local counting sort of the payload.
+//   tile id = (hi digit << lo_bits) | lo digit, both digits <= MAXB values (256, or 1024 for the deep mode).
 //   pass 0: raw particles  -> buckets of equal hi digit          (cursor = per-bucket write position)
 //   pass 1: bucket by bucket -> tiles (lo digit inside a bucket) (cursor = per-tile write position)
-// One CTA sorts a chunk of PART_CHUNK particles in shared memory (rank by a shared atomic per digit, exclusive
-// scan of the <= 256 counters), reserves ONE contiguous output range per digit present with a single
-// atom.global (<= 256 per 4096 particles), and copies the staged chunk out so that consecutive threads write
-// consecutive addresses inside each run.  ~40 B (pass 0) + 32 B (pass 1) of streaming traffic per particle.
+// One CTA sorts a chunk of PT * 8 particles in shared memory (rank by a shared atomic per digit, exclusive
+// scan of the counters), reserves ONE contiguous output range per digit present with a single atom.global,
+// and copies the staged chunk out so that consecutive threads write consecutive addresses inside each run.
+// ~40 B (pass 0) + 32 B (pass 1) of streaming traffic per particle.
 // ------------------------------------------------------------------------------------------------
 constexpr int PART_PER_THREAD = 8;
-constexpr int PART_CHUNK_MAX = 512 * PART_PER_THREAD;        // 4096 particles, 64 KB of float4 staging (512 threads)
-constexpr int PART_MAXBINS = 256;
 
-template <int PART_THREADS>
+template <int PT, int MAXB>
 struct PartSmem {
-    static constexpr int PART_CHUNK = PART_THREADS * PART_PER_THREAD;
+    static constexpr int PART_CHUNK = PT * PART_PER_THREAD;
     float4 stage[PART_CHUNK];
-    unsigned char dig[PART_CHUNK];
-    int cnt[PART_MAXBINS], start[PART_MAXBINS], gbase[PART_MAXBINS];
+    unsigned short dig[PART_CHUNK];
+    int cnt[MAXB], start[MAXB], gbase[MAXB];
     int lo, hi, bucket;
 };
 
-// chunk list of pass 1: bucket b (tiles [b << lo_bits, (b+1) << lo_bits)) owns ceil(size_b / PART_CHUNK) chunks
-__global__ void __launch_bounds__(PART_MAXBINS)
-part_buckets_kernel(const int *__restrict__ tile_begin, int ntiles, int lo_bits, int nb0, int *bcursor, int *bchunk_off,
-                    int PART_CHUNK) {
-    // one thread per bucket (nb0 <= PART_MAXBINS = blockDim.x) and a shared-memory scan of the chunk counts; the
-    // single-thread loop this replaces took 38 us of dependent global loads per deposit
-    __shared__ int s[PART_MAXBINS];
+// bucket b = entries [b << shift, (b+1) << shift) of `begin` (the tile table in shallow mode, shift = lo_bits; the
+// bucket table itself in deep mode, shift = 0).  Writes bucket_begin[0..nb0], the pass-0 cursors and the chunk list of
+// pass 1: bucket b owns ceil(size_b / chunk) chunks.
+__global__ void __launch_bounds__(1024)
+part_buckets_kernel(const int *__restrict__ begin, int n_entries, int shift, int nb0, int chunk, int *bucket_begin,
+                    int *bcursor, int *bchunk_off) {
+    __shared__ int s[1024];
     const int b = threadIdx.x;
     int c = 0;
     if (b < nb0) {
-        const int t0 = b << lo_bits, t1 = min(ntiles, (b + 1) << lo_bits);
-        const int begin = tile_begin[t0];
-        bcursor[b] = begin;
-        c = (tile_begin[t1] - begin + PART_CHUNK - 1) / PART_CHUNK;
+        const int e0 = b << shift, e1 = min(n_entries, (b + 1) << shift);
+        const int lo = begin[e0], hi = begin[e1];
+        bucket_begin[b] = lo;
+        if (b == nb0 - 1) bucket_begin[nb0] = hi;
+        bcursor[b] = lo;
+        c = (hi - lo + chunk - 1) / chunk;
     }
     s[b] = c;
     __syncthreads();
-    for (int o = 1; o < PART_MAXBINS; o <<= 1) {
+    for (int o = 1; o < 1024; o <<= 1) {
         const int v = b >= o ? s[b - o] : 0;
         __syncthreads();
         s[b] += v;
@@ -200,15 +199,57 @@ part_buckets_kernel(const int *__restrict__ tile_begin, int ntiles, int lo_bits,
     if (b == nb0 - 1) bchunk_off[nb0] = s[b];
 }
 
-template <int MAS, class TC, bool HASW, bool FIRST, int PART_THREADS>
-__global__ void __launch_bounds__(PART_THREADS, 1024 / PART_THREADS)
+// chunk `blk` of the pass-1 chunk list -> (bucket, particle range)
+__device__ __forceinline__ bool bucket_chunk(int blk, const int *__restrict__ bchunk_off, const int *__restrict__ bucket_begin,
+                                             int nb0, int chunk, int &bucket, int &lo, int &hi) {
+    if (blk >= bchunk_off[nb0]) return false;
+    int a = 0, z = nb0;          // bchunk_off[a] <= blk < bchunk_off[z]
+    while (z - a > 1) { const int mid = (a + z) >> 1; if (bchunk_off[mid] <= blk) a = mid; else z = mid; }
+    bucket = a;
+    lo = bucket_begin[a] + (blk - bchunk_off[a]) * chunk;
+    hi = min(bucket_begin[a + 1], lo + chunk);
+    return true;
+}
+
+// deep mode: per-tile counts from the bucket-ordered payload.  A CTA takes one pass-1 chunk (particles of ONE bucket),
+// counts its lo digits in shared memory and adds the non-zero counters to the tiles of that bucket.
+template <int MAS, int PT>
+__global__ void __launch_bounds__(PT)
+bin_hist2_kernel(const float4 *__restrict__ in, float inv, TileGeom tg, const int *__restrict__ bucket_begin,
+                 const int *__restrict__ bchunk_off, int lo_bits, int nb0, int *__restrict__ counts) {
+    __shared__ int cnt[1024];
+    __shared__ int s_lo, s_hi, s_bucket;
+    if (threadIdx.x == 0) {
+        int b = 0, lo = 0, hi = 0;
+        bucket_chunk(blockIdx.x, bchunk_off, bucket_begin, nb0, PT * PART_PER_THREAD, b, lo, hi);
+        s_bucket = b; s_lo = lo; s_hi = hi;
+    }
+    for (int b = threadIdx.x; b < 1024; b += PT) cnt[b] = 0;
+    __syncthreads();
+    const int lo = s_lo, hi = s_hi;
+    if (lo >= hi) return;
+    const unsigned mask = (1u << lo_bits) - 1u;
+    for (int i = lo + threadIdx.x; i < hi; i += PT) {
+        const float4 q = __ldg(in + i);
+        atomicAdd(&cnt[tile_key<MAS>(q.x, q.y, q.z, inv, tg) & mask], 1);
+    }
+    __syncthreads();
+    const int cbase = s_bucket << lo_bits;
+    for (int b = threadIdx.x; b < (1 << lo_bits); b += PT) {
+        const int c = cnt[b];
+        if (c) atomicAdd(&counts[cbase + b], c);
+    }
+}
+
+template <int MAS, bool HASW, bool FIRST, int PT, int MAXB>
+__global__ void __launch_bounds__(PT, 1024 / PT)
 bin_pass_kernel(const float *__restrict__ pos, const float *__restrict__ W, int64_t wst, int64_t first, int n, int64_t ps0,
                 int64_t ps1, float inv, TileGeom tg, const float4 *__restrict__ in, float4 *__restrict__ out,
-                int *__restrict__ cursor, const int *__restrict__ tile_begin, const int *__restrict__ bchunk_off,
+                int *__restrict__ cursor, const int *__restrict__ bucket_begin, const int *__restrict__ bchunk_off,
                 int lo_bits, int nb0) {
     extern __shared__ __align__(16) unsigned char part_raw[];
-    constexpr int PART_CHUNK = PART_THREADS * PART_PER_THREAD;
-    PartSmem<PART_THREADS> &sm = *reinterpret_cast<PartSmem<PART_THREADS> *>(part_raw);
+    constexpr int PART_CHUNK = PT * PART_PER_THREAD;
+    PartSmem<PT, MAXB> &sm = *reinterpret_cast<PartSmem<PT, MAXB> *>(part_raw);
     const int tid = threadIdx.x;
     const int nbins = FIRST ? nb0 : (1 << lo_bits);
     if (tid == 0) {
@@ -217,19 +258,12 @@ bin_pass_kernel(const float *__restrict__ pos, const float *__restrict__ W, int6
             sm.hi = min(n, sm.lo + PART_CHUNK);
             sm.bucket = 0;
         } else {
-            const int blk = blockIdx.x, total = bchunk_off[nb0];
-            if (blk >= total) { sm.lo = sm.hi = 0; sm.bucket = 0; }
-            else {
-                int lo = 0, hi = nb0;          // bchunk_off[lo] <= blk < bchunk_off[hi]
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (bchunk_off[mid] <= blk) lo = mid; else hi = mid; }
-                const int t0 = lo << lo_bits, t1 = min(tg.ntiles, (lo + 1) << lo_bits);
-                sm.bucket = lo;
-                sm.lo = tile_begin[t0] + (blk - bchunk_off[lo]) * PART_CHUNK;
-                sm.hi = min(tile_begin[t1], sm.lo + PART_CHUNK);
-            }
+            int b = 0, lo = 0, hi = 0;
+            bucket_chunk(blockIdx.x, bchunk_off, bucket_begin, nb0, PART_CHUNK, b, lo, hi);
+            sm.bucket = b; sm.lo = lo; sm.hi = hi;
         }
     }
-    for (int b = tid; b < PART_MAXBINS; b += PART_THREADS) sm.cnt[b] = 0;
+    for (int b = tid; b < MAXB; b += PT) sm.cnt[b] = 0;
     __syncthreads();
     const int lo = sm.lo, hi = sm.hi;
     if (lo >= hi) return;                       // CTA-uniform
@@ -237,16 +271,16 @@ bin_pass_kernel(const float *__restrict__ pos, const float *__restrict__ W, int6
 
     float4 v[PART_PER_THREAD];
     int d[PART_PER_THREAD], r[PART_PER_THREAD];
-    // dense (np,3) input: a thread takes 2 x 4 consecutive particles as 3 aligned float4 each (lo is a multiple of 4096)
+    // dense (np,3) input: a thread takes 2 x 4 consecutive particles as 3 aligned float4 each (lo is a multiple of the chunk)
     const float *rawbase = FIRST ? pos + first * ps0 : nullptr;
     const bool vec = FIRST && ps0 == 3 && ps1 == 1 && (((uintptr_t)rawbase) & 15) == 0 && hi - lo == PART_CHUNK;
-    auto index_of = [&](int k) { return vec ? lo + ((k >> 2) * PART_THREADS + tid) * 4 + (k & 3) : lo + k * PART_THREADS + tid; };
+    auto index_of = [&](int k) { return vec ? lo + ((k >> 2) * PT + tid) * 4 + (k & 3) : lo + k * PT + tid; };
     if (vec) {
         const float4 *p4 = reinterpret_cast<const float4 *>(rawbase);
         float4 a[2], b[2], c[2];
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            const int64_t q = ((int64_t)lo >> 2) + u * PART_THREADS + tid;
+            const int64_t q = ((int64_t)lo >> 2) + u * PT + tid;
             a[u] = __ldg(p4 + 3 * q); b[u] = __ldg(p4 + 3 * q + 1); c[u] = __ldg(p4 + 3 * q + 2);
         }
 #pragma unroll
@@ -262,52 +296,53 @@ bin_pass_kernel(const float *__restrict__ pos, const float *__restrict__ W, int6
             v[4 * u + 3] = make_float4(c[u].y, c[u].z, c[u].w, wv[3]);
         }
     } else {
-    // packed (x,y,z,w) records (the particle-exchange payload): one 16-byte load; the weight rides along when W
-    // points at the record's 4th float
-    const bool rec4 = FIRST && ps0 == 4 && ps1 == 1 && (((uintptr_t)rawbase) & 15) == 0;
-    const bool w_in_rec = HASW && rec4 && wst == 4 && W + first * wst == rawbase + 3;
+        // packed (x,y,z,w) records (the particle-exchange payload): one 16-byte load; the weight rides along when W
+        // points at the record's 4th float
+        const bool rec4 = FIRST && ps0 == 4 && ps1 == 1 && (((uintptr_t)rawbase) & 15) == 0;
+        const bool w_in_rec = HASW && rec4 && wst == 4 && W + first * wst == rawbase + 3;
 #pragma unroll
-    for (int k = 0; k < PART_PER_THREAD; k++) {
-        const int i = lo + k * PART_THREADS + tid;
-        if (i < hi) {
-            if (FIRST) {
-                if (rec4) {
-                    const float4 q = __ldg(reinterpret_cast<const float4 *>(rawbase) + i);
-                    v[k] = make_float4(q.x, q.y, q.z, HASW ? (w_in_rec ? q.w : __ldg(W + (first + i) * wst)) : 1.0f);
-                    continue;
+        for (int k = 0; k < PART_PER_THREAD; k++) {
+            const int i = lo + k * PT + tid;
+            if (i < hi) {
+                if (FIRST) {
+                    if (rec4) {
+                        const float4 q = __ldg(reinterpret_cast<const float4 *>(rawbase) + i);
+                        v[k] = make_float4(q.x, q.y, q.z, HASW ? (w_in_rec ? q.w : __ldg(W + (first + i) * wst)) : 1.0f);
+                        continue;
+                    }
+                    const float *p = pos + (first + i) * ps0;
+                    v[k] = make_float4(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), HASW ? __ldg(W + (first + i) * wst) : 1.0f);
+                } else {
+                    v[k] = __ldg(in + i);
                 }
-                const float *p = pos + (first + i) * ps0;
-                v[k] = make_float4(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), HASW ? __ldg(W + (first + i) * wst) : 1.0f);
-            } else {
-                v[k] = __ldg(in + i);
             }
         }
-    }
     }
 #pragma unroll
     for (int k = 0; k < PART_PER_THREAD; k++) {
         const int i = index_of(k);
         d[k] = -1;
         if (i < hi) {
-            const unsigned t = tile_key<MAS, TC>(v[k].x, v[k].y, v[k].z, inv, tg);
+            const unsigned t = tile_key<MAS>(v[k].x, v[k].y, v[k].z, inv, tg);
             d[k] = FIRST ? (int)(t >> lo_bits) : (int)(t & ((1u << lo_bits) - 1u));
             r[k] = atomicAdd(&sm.cnt[d[k]], 1);
         }
     }
     __syncthreads();
-    // exclusive scan of the <= 256 counters by warp 0 (8 per lane) + one global claim per digit present
+    // exclusive scan of the counters by warp 0 (MAXB / 32 per lane) + one global claim per digit present
     if (tid < 32) {
-        int loc[8], sum = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) { loc[q] = sum; sum += sm.cnt[tid * 8 + q]; }
+        constexpr int Q = MAXB / 32;
+        int sum = 0;
+#pragma unroll 8
+        for (int q = 0; q < Q; q++) sum += sm.cnt[tid * Q + q];
         int incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
-        const int excl = incl - sum;
-#pragma unroll
-        for (int q = 0; q < 8; q++) sm.start[tid * 8 + q] = excl + loc[q];
+        int run = incl - sum;
+#pragma unroll 8
+        for (int q = 0; q < Q; q++) { sm.start[tid * Q + q] = run; run += sm.cnt[tid * Q + q]; }
     }
-    for (int b = PART_THREADS - 1 - tid; b < PART_MAXBINS; b += PART_THREADS) {   // last warps first: warp 0 is scanning
+    for (int b = PT - 1 - tid; b < MAXB; b += PT) {   // last warps first: warp 0 is scanning
         const int c = (b < nbins) ? sm.cnt[b] : 0;
         if (c) sm.gbase[b] = atomicAdd(&cursor[cbase + b], c);
     }
@@ -317,41 +352,14 @@ bin_pass_kernel(const float *__restrict__ pos, const float *__restrict__ W, int6
         if (d[k] >= 0) {
             const int p = sm.start[d[k]] + r[k];
             sm.stage[p] = v[k];
-            sm.dig[p] = (unsigned char)d[k];
+            sm.dig[p] = (unsigned short)d[k];
         }
     }
     __syncthreads();
-    for (int i = tid; i < hi - lo; i += PART_THREADS) {
+    for (int i = tid; i < hi - lo; i += PT) {
         const int dd = sm.dig[i];
         out[sm.gbase[dd] + (i - sm.start[dd])] = sm.stage[i];
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// RADIX fallback
-// ------------------------------------------------------------------------------------------------
-template <int MAS, class TC>
-__global__ void __launch_bounds__(256)
-tile_key_kernel(const float *__restrict__ pos, int64_t first, int n, int64_t ps0, int64_t ps1, float inv,
-                TileGeom tg, unsigned *keys, unsigned *vals) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float *p = pos + (first + i) * ps0;
-    keys[i] = tile_key<MAS, TC>(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), inv, tg);
-    vals[i] = (unsigned)i;
-}
-
-// tile_begin[t] = first sorted position whose key >= t  (t = 0..ntiles)
-__global__ void tile_begin_kernel(const unsigned *__restrict__ skeys, int n, int ntiles, int *tile_begin) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > ntiles) return;
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (skeys[mid] < (unsigned)t) lo = mid + 1;
-        else hi = mid;
-    }
-    tile_begin[t] = lo;
 }
 
 __global__ void tile_chunks_kernel(const int *__restrict__ tile_begin, int ntiles, int chunk, int *nchunks) {
@@ -361,31 +369,29 @@ __global__ void tile_chunks_kernel(const int *__restrict__ tile_begin, int ntile
 }
 
 // ------------------------------------------------------------------------------------------------
-// tile accumulation
+// ACCUMULATE
 // ------------------------------------------------------------------------------------------------
 constexpr int pad_to(int v, int r) { return v + ((r - v % 32) + 32) % 32; }   // smallest x >= v with x % 32 == r
 
 // Shared-memory tile: SX x SY x SZV cells (tile + S-1 halo cells per axis), z fastest, row pitch PI, plane pitch PL
-// (floats).  The pitches are chosen so that the cells ONE warp instruction of deposit_lane_kernel updates fall into 32
-// distinct banks (lanes = stencil points, see there):
-//   PCS  lane = (a&1, b, c), planes a and a+2   bank = 16 a + 4 b + c          PI = 4, PL = 16 (mod 32)
-//   TSC  lane = (a, b, c), 27 lanes             bank = 9 a + 3 b + c           PI = 3, PL = 9
-//   CIC  lane = (particle q of 4, a, b, c)      bank = base_q + 4 a + 2 b + c  PI = 2, PL = 4
-template <int MAS, class TC>
+// (floats).  For PCS the pitches are chosen so that the cells ONE warp instruction of deposit_lane_kernel updates --
+// lane = (a&1, b, c), x-planes a and a+2 -- fall into 32 distinct banks: bank = 16 a + 4 b + c, i.e. PI = 4, PL = 16 (mod 32).
+template <int MAS>
 struct TileShape {
     static constexpr int S = Support<MAS>::S;
-    static constexpr int SX = TC::TX + S - 1, SY = TC::TY + S - 1, SZV = TC::TZ + S - 1;
-    static constexpr int RI = MAS == PYLB_PCS ? 4 : MAS == PYLB_TSC ? 3 : 2;
-    static constexpr int RL = MAS == PYLB_PCS ? 16 : MAS == PYLB_TSC ? 9 : 4;
-    static constexpr int PI = MAS == PYLB_NGP ? SZV : pad_to(SZV, RI);
-    static constexpr int PL = MAS == PYLB_NGP ? SY * PI : pad_to(SY * PI, RL);
+    static constexpr int SX = TX + S - 1, SY = TY + S - 1, SZV = TZ + S - 1;
+    static constexpr int PI = MAS == PYLB_PCS ? pad_to(SZV, 4) : ((SZV + 3) & ~3);
+    static constexpr int PL = MAS == PYLB_PCS ? pad_to(SY * PI, 16) : SY * PI;
     static constexpr int CELLS = (SX * PL + 3) & ~3;
     static constexpr int ZV = (SZV + 3) / 4;                       // float4 groups per z-row in the flush
-    // deposit_lane_kernel: per-warp staging of the factored weights, word-major with pitch PB+1 (bank = word + particle)
-    static constexpr int SW = S * S + S + 1;                       // wxy[S][S], wz[S], W
-    static constexpr int STAGE_WORDS = (MAS == PYLB_PCS || MAS == PYLB_TSC) ? SW * (TC::PB + 1) : 0;
-    static constexpr size_t LANE_SMEM = sizeof(float) * ((size_t)CELLS + (size_t)(TC::THREADS / 32) * STAGE_WORDS);
-    static constexpr size_t PLAIN_SMEM = sizeof(float) * (size_t)CELLS;
+    static constexpr int THREADS = 256;
+    static constexpr size_t SMEM = sizeof(float) * (size_t)CELLS;
+    // deposit_lane_kernel: 16 warps per CTA, two CTAs per SM; per-warp staging of the axis weights of 32 particles,
+    // word-major with pitch 33 (bank = word + particle)
+    static constexpr int LANE_THREADS = 512;
+    static constexpr int SW = 3 * S + 1;                           // wx[S], wy[S], wz[S], W
+    static constexpr int STAGE_WORDS = SW * 33;
+    static constexpr size_t LANE_SMEM = sizeof(float) * ((size_t)CELLS + (size_t)(LANE_THREADS / 32) * STAGE_WORDS);
 };
 
 __device__ __forceinline__ void red_add_v4(float *p, float4 v) {
@@ -393,41 +399,33 @@ __device__ __forceinline__ void red_add_v4(float *p, float4 v) {
                  : "memory");
 }
 
-// work item b -> (tile, particle range); returns false beyond the last item.  Called by thread 0.
+// work item b -> (tile, particle range)
 struct WorkItem { int tile, lo, hi; };
-__device__ __forceinline__ bool find_work(int b, const int *__restrict__ chunk_off, const int *__restrict__ tile_begin,
-                                          int ntiles, int chunk, WorkItem &w) {
-    if (b >= chunk_off[ntiles]) return false;
+__device__ __forceinline__ void find_work(int b, const int *__restrict__ chunk_off, const int *__restrict__ tile_begin,
+                                          int ntiles, WorkItem &w) {
     int lo = 0, hi = ntiles;                    // invariant: chunk_off[lo] <= b < chunk_off[hi]
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (chunk_off[mid] <= b) lo = mid; else hi = mid;
     }
     w.tile = lo;
-    w.lo = tile_begin[lo] + (b - chunk_off[lo]) * chunk;
-    w.hi = min(w.lo + chunk, tile_begin[lo + 1]);
-    return true;
+    w.lo = tile_begin[lo] + (b - chunk_off[lo]) * CHUNK;
+    w.hi = min(w.lo + CHUNK, tile_begin[lo + 1]);
 }
 
-// flush: tile-local (x,y,z) -> global ((ox+x)%dims, (oy+y)%dims, (oz+z)%dims), added with red.global (halo cells overlap
-// the neighbouring tiles, and `number` is accumulate-in-place anyway); 16-byte vector reds when dims % 4 == 0
+// Flush and clear: tile-local (x,y,z) -> global ((ox+x)%dims, (oy+y)%dims, (oz+z)%dims), added with red.global (halo
+// cells overlap the neighbouring tiles, and `number` is accumulate-in-place anyway); 16-byte vector reds when
+// dims % 4 == 0.  The tile is left zeroed for the CTA's next work item.
 template <class TS, int THREADS>
-__device__ __forceinline__ void flush_tile(const float *tile, float *__restrict__ grid, const TileGeom &tg, int ox, int oy, int oz) {
+__device__ __forceinline__ void flush_tile(float *tile, float *__restrict__ grid, const TileGeom &tg, int ox, int oy, int oz) {
     const int dims = tg.dims;
     if ((dims & 3) == 0) {
         for (int i = threadIdx.x; i < TS::SX * TS::SY * TS::ZV; i += THREADS) {
             const int zv = i % TS::ZV, y = (i / TS::ZV) % TS::SY, x = i / (TS::ZV * TS::SY);
-            const float *row = tile + x * TS::PL + y * TS::PI + zv * 4;
-            float4 v;
-            if constexpr (TS::PI % 4 == 0 && TS::PL % 4 == 0) {
-                v = *reinterpret_cast<const float4 *>(row);        // padding words of a row are never written: zero
-            } else {
-                v.x = row[0];
-                v.y = zv * 4 + 1 < TS::SZV ? row[1] : 0.f;
-                v.z = zv * 4 + 2 < TS::SZV ? row[2] : 0.f;
-                v.w = zv * 4 + 3 < TS::SZV ? row[3] : 0.f;
-            }
+            float4 *cell = reinterpret_cast<float4 *>(tile + x * TS::PL + y * TS::PI + zv * 4);   // PI, PL are multiples of 4
+            const float4 v = *cell;                                // padding words of a row are never written: zero
             if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+            *cell = make_float4(0.f, 0.f, 0.f, 0.f);
             int gx = ox + x, gy = oy + y, gz = oz + zv * 4;
             if (tg.xext == dims) { if (gx >= dims) gx -= dims; }
             else if (gx >= tg.xext) continue;   // beyond the x window: nothing was deposited there
@@ -445,8 +443,10 @@ __device__ __forceinline__ void flush_tile(const float *tile, float *__restrict_
     } else {
         for (int i = threadIdx.x; i < TS::SX * TS::SY * TS::SZV; i += THREADS) {
             const int z = i % TS::SZV, y = (i / TS::SZV) % TS::SY, x = i / (TS::SZV * TS::SY);
-            const float v = tile[x * TS::PL + y * TS::PI + z];
+            float *cell = tile + x * TS::PL + y * TS::PI + z;
+            const float v = *cell;
             if (v == 0.f) continue;
+            *cell = 0.f;
             int gx = ox + x;
             if (tg.xext == dims) gx %= dims;
             else if (gx >= tg.xext) continue;
@@ -455,258 +455,153 @@ __device__ __forceinline__ void flush_tile(const float *tile, float *__restrict_
     }
 }
 
-// Particle -> (x,y,z,w).  SORTED: float4 records already in tile order; otherwise through the sorted index (radix path).
-template <bool SORTED, bool HASW>
-struct ParticleSource {
-    const float *pos; int64_t first, ps0, ps1; const float *W; int64_t wst; const unsigned *svals; const float4 *sorted;
-    __device__ __forceinline__ float4 operator()(int i) const {
-        if (SORTED) return __ldg(sorted + i);
-        const int64_t pi = first + (int64_t)svals[i];
-        const float *p = pos + pi * ps0;
-        return make_float4(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1), HASW ? __ldg(W + pi * wst) : 1.0f);
-    }
-};
-
-// tile-local cell of the particle's lowest touched grid point, or -1 (particle routed to the wrong x window: dropped)
-template <int MAS, class TC>
+// tile-local word index of the particle's lowest touched grid point, or -1 (particle routed to the wrong x window: dropped)
+template <int MAS>
 __device__ __forceinline__ int base_cell(const float4 q, float inv, const TileGeom &tg, int ox, int oy, int oz,
                                          float (&C)[3][Support<MAS>::S]) {
-    using TS = TileShape<MAS, TC>;
+    using TS = TileShape<MAS>;
     const int lx = wrap(axis_stencil<MAS>(q.x, inv, C[0]) - tg.x0, tg.dims) - ox;
-    if (lx < 0 || lx >= TC::TX) return -1;
+    if (lx < 0 || lx >= TX) return -1;
     const int ly = wrap(axis_stencil<MAS>(q.y, inv, C[1]), tg.dims) - oy;
     const int lz = wrap(axis_stencil<MAS>(q.z, inv, C[2]), tg.dims) - oz;
     return lx * TS::PL + ly * TS::PI + lz;
 }
 
-// K independent shared-memory float adds as ONE compare-and-swap loop: the K loads, adds and CAS are issued back to
-// back, so their latencies overlap instead of adding up as in K consecutive atomicAdd(float) loops (ATOMS.CAST.SPIN
-// on sm_100a; there is no native shared fp32 add).  Addresses may repeat: the later CAS fails once and retries.
-template <int K>
-__device__ __forceinline__ void smem_add_joint(float *(&p)[K], const float (&v)[K]) {
-    unsigned o[K];
-    bool done[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) { o[k] = *reinterpret_cast<volatile unsigned *>(p[k]); done[k] = false; }
-    bool all;
-    do {
-        all = true;
-#pragma unroll
-        for (int k = 0; k < K; k++)
-            if (!done[k]) {
-                const unsigned nv = __float_as_uint(__uint_as_float(o[k]) + v[k]);
-                const unsigned r = atomicCAS(reinterpret_cast<unsigned *>(p[k]), o[k], nv);
-                done[k] = r == o[k];
-                o[k] = r;
-                all = all && done[k];
-            }
-    } while (!all);
-}
-
-// ---- lane-per-particle kernel: NGP (one update per particle) and the A/B baseline for the others ----------------
-// Every lane streams its own particle and issues S^3 shared atomicAdd(float); the 32 cells of one warp instruction
-// fall into random banks (and, for clustered input, onto equal addresses), ~13 shared-memory wavefronts per update.
-template <int MAS, bool HASW, class TC, bool SORTED>
-__global__ void __launch_bounds__(TC::THREADS)
-deposit_tile_kernel(ParticleSource<SORTED, HASW> src, float inv, TileGeom tg, const int *__restrict__ tile_begin,
+// ---- lane per particle: every lane streams its own particle and issues S^3 shared atomicAdd(float) ------------------
+// The 32 cells of one warp instruction fall into random banks (and, for clustered input, onto equal addresses):
+// ~7 shared-memory wavefronts per warp-wide update, which is what bounds this kernel (93 % of the LSU pipe, ncu).
+template <int MAS, bool HASW>
+__global__ void __launch_bounds__(256)
+deposit_tile_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, const int *__restrict__ tile_begin,
                     const int *__restrict__ chunk_off, float *__restrict__ grid) {
-    using TS = TileShape<MAS, TC>;
-    constexpr int S = TS::S;
+    using TS = TileShape<MAS>;
+    constexpr int S = TS::S, THREADS = TS::THREADS;
     extern __shared__ __align__(16) float tile[];
     __shared__ WorkItem s_w;
-    __shared__ int s_ok;
-    if (threadIdx.x == 0) s_ok = find_work(blockIdx.x, chunk_off, tile_begin, tg.ntiles, TC::CHUNK, s_w);
-    __syncthreads();
-    if (!s_ok) return;                           // CTA-uniform: beyond the last work item
-    const int t = s_w.tile, lo = s_w.lo, hi = s_w.hi;
-    for (int i = threadIdx.x; i < TS::CELLS / 4; i += TC::THREADS) reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    const int tz = t % tg.ntz, ty = (t / tg.ntz) % tg.nty, tx = t / (tg.ntz * tg.nty);
-    const int ox = tx * TC::TX, oy = ty * TC::TY, oz = tz * TC::TZ;
-    for (int i = lo + threadIdx.x; i < hi; i += TC::THREADS) {
-        const float4 q = src(i);
-        float C[3][S];
-        const int cell0 = base_cell<MAS, TC>(q, inv, tg, ox, oy, oz, C);
-        if (cell0 < 0) continue;
+    for (int i = threadIdx.x; i < TS::CELLS / 4; i += THREADS) reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nitems = chunk_off[tg.ntiles];
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        __syncthreads();                         // the tile is clear, s_w is free
+        if (threadIdx.x == 0) find_work(item, chunk_off, tile_begin, tg.ntiles, s_w);
+        __syncthreads();
+        const int t = s_w.tile, lo = s_w.lo, hi = s_w.hi;
+        const int tz = t % tg.ntz, ty = (t / tg.ntz) % tg.nty, tx = t / (tg.ntz * tg.nty);
+        const int ox = tx * TX, oy = ty * TY, oz = tz * TZ;
+        for (int i = lo + threadIdx.x; i < hi; i += THREADS) {
+            const float4 q = __ldg(sorted + i);
+            float C[3][S];
+            const int cell0 = base_cell<MAS>(q, inv, tg, ox, oy, oz, C);
+            if (cell0 < 0) continue;
 #pragma unroll
-        for (int l = 0; l < S; l++)
+            for (int l = 0; l < S; l++)
 #pragma unroll
-            for (int m = 0; m < S; m++) {
-                const float cxy = C[0][l] * C[1][m];
+                for (int m = 0; m < S; m++) {
+                    const float cxy = C[0][l] * C[1][m];
 #pragma unroll
-                for (int n = 0; n < S; n++) {
-                    float v = cxy * C[2][n];
-                    if (HASW) v *= q.w;
-                    atomicAdd(tile + cell0 + l * TS::PL + m * TS::PI + n, v);
+                    for (int k = 0; k < S; k++) {
+                        float v = cxy * C[2][k];
+                        if (HASW) v *= q.w;
+                        atomicAdd(tile + cell0 + l * TS::PL + m * TS::PI + k, v);
+                    }
                 }
-            }
+        }
+        __syncthreads();
+        flush_tile<TS, THREADS>(tile, grid, tg, ox, oy, oz);
     }
-    __syncthreads();
-    flush_tile<TS, TC::THREADS>(tile, grid, tg, ox, oy, oz);
 }
 
-// ---- stencil-lane kernel: CIC, TSC, PCS ------------------------------------------------------------------------
-// The lanes of a warp are the STENCIL POINTS of one particle (TSC: 27 lanes; PCS: 32 lanes x 2 planes; CIC: 8 lanes x
-// 4 particles), not 32 different particles.  One warp instruction therefore updates cells that are distinct and, thanks
-// to the tile pitches above, lie in distinct banks: a shared float add is a single conflict-free CAS round (~3 wavefronts)
-// instead of ~13, and a particle costs 1-2 warp instructions' worth of atomics instead of 27/64.  Per batch of PB
-// particles, lane p first evaluates particle p's base cell and its S weights per axis exactly like the reference
-// (deposit.cuh) and stages wxy[l][m] = C0[l]*C1[m], wz[n] and W in a per-warp scratch (word-major, pitch PB+1: both the
-// staging stores and the per-particle reads are conflict-free); then the warp walks the batch, every lane forming
-// (wxy * wz) * W for its own stencil point -- the reference's left-to-right fp32 product (MAS_library.pyx:160-166,
-// 400-404, 493-497).  Consecutive particles with the same base cell are summed in registers first (JOINT), and the
-// adds of two particles share one CAS loop so that their latencies overlap.
-template <int MAS, bool HASW, class TC, bool SORTED, bool JOINT>
-__global__ void __launch_bounds__(TC::THREADS)
-deposit_lane_kernel(ParticleSource<SORTED, HASW> src, float inv, TileGeom tg, const int *__restrict__ tile_begin,
+// ---- stencil lanes: PCS ----------------------------------------------------------------------------------------------
+// Per batch of 32 particles, lane p evaluates particle p's base cell and its 4 weights per axis exactly like the reference
+// (deposit.cuh) and stages them in a per-warp scratch (word-major, pitch 33: the staging stores and the per-particle reads
+// are both conflict-free).  Then the warp walks the batch: lane (a&1, b, c) forms ((wx[a] * wy[b]) * wz[c]) * W -- the
+// reference's left-to-right fp32 product (MAS_library.pyx:493-497) -- for the x-planes a and a+2 and adds both with one
+// optimistic pair of compare-and-swaps: two loads, two adds, two CAS in flight together; a CAS can only fail when another
+// warp updated the same cell in between, and is then repaired with an ordinary atomicAdd.  1.42x the lane-per-particle
+// kernel at 512^3 (8.1 ms against 11.5 ms, profiles/r2_deposit_variants.txt).
+template <bool HASW>
+__global__ void __launch_bounds__(TileShape<PYLB_PCS>::LANE_THREADS, 2)
+deposit_lane_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, const int *__restrict__ tile_begin,
                     const int *__restrict__ chunk_off, float *__restrict__ grid) {
-    using TS = TileShape<MAS, TC>;
-    constexpr int S = TS::S, PB = TC::PB, NW = TC::THREADS / 32, SP = PB + 1;
-    static_assert(MAS != PYLB_NGP, "NGP has one update per particle: lane-per-particle kernel");
+    constexpr int MAS = PYLB_PCS;
+    using TS = TileShape<MAS>;
+    constexpr int S = TS::S, PB = 32, THREADS = TS::LANE_THREADS, NW = THREADS / 32, SP = PB + 1;
     extern __shared__ __align__(16) float tile[];
     __shared__ WorkItem s_w;
-    __shared__ int s_ok;
-    if (threadIdx.x == 0) s_ok = find_work(blockIdx.x, chunk_off, tile_begin, tg.ntiles, TC::CHUNK, s_w);
-    __syncthreads();
-    if (!s_ok) return;
-    const int t = s_w.tile, lo = s_w.lo, hi = s_w.hi;
-    for (int i = threadIdx.x; i < TS::CELLS / 4; i += TC::THREADS) reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    const int tz = t % tg.ntz, ty = (t / tg.ntz) % tg.nty, tx = t / (tg.ntz * tg.nty);
-    const int ox = tx * TC::TX, oy = ty * TC::TY, oz = tz * TC::TZ;
+    for (int i = threadIdx.x; i < TS::CELLS / 4; i += THREADS) reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    if constexpr (MAS == PYLB_CIC) {
-        // 4 particles per warp step; lane = (q, a, b, c).  The weights of a CIC stencil point are u or 1-u per axis, so
-        // the three fractions travel by shuffle and every lane rebuilds its own weight with the reference's fp32 ops.
-        const int q = lane >> 3, la = (lane >> 2) & 1, lb = (lane >> 1) & 1, lc = lane & 1;
-        const int loff = la * TS::PL + lb * TS::PI + lc;
-        for (int i0 = lo + warp * 32; i0 < hi; i0 += NW * 32) {      // warp-uniform trip count
+    const int la = lane >> 4, lb = (lane >> 2) & 3, lc = lane & 3;
+    unsigned *const cell = reinterpret_cast<unsigned *>(tile) + la * TS::PL + lb * TS::PI + lc;
+    float *stage = tile + TS::CELLS + warp * TS::STAGE_WORDS;
+    const float *sx0 = stage + la * SP, *sx1 = stage + (la + 2) * SP;
+    const float *sy = stage + (S + lb) * SP, *sz = stage + (2 * S + lc) * SP, *sw = stage + 3 * S * SP;
+    struct Staged { float x0, x1, y, z, w; int b; };
+    auto fetch = [&](int pp, int b) {
+        Staged q;
+        q.x0 = sx0[pp]; q.x1 = sx1[pp]; q.y = sy[pp]; q.z = sz[pp]; q.w = HASW ? sw[pp] : 1.f; q.b = b;
+        return q;
+    };
+    auto apply = [&](const Staged &q) {
+        float v0 = (q.x0 * q.y) * q.z, v1 = (q.x1 * q.y) * q.z;
+        if (HASW) { v0 *= q.w; v1 *= q.w; }
+        unsigned *p0 = cell + q.b, *p1 = p0 + 2 * TS::PL;
+        const unsigned o0 = *reinterpret_cast<volatile unsigned *>(p0), o1 = *reinterpret_cast<volatile unsigned *>(p1);
+        const unsigned r0 = atomicCAS(p0, o0, __float_as_uint(__uint_as_float(o0) + v0));
+        const unsigned r1 = atomicCAS(p1, o1, __float_as_uint(__uint_as_float(o1) + v1));
+        if (r0 != o0) atomicAdd(reinterpret_cast<float *>(p0), v0);
+        if (r1 != o1) atomicAdd(reinterpret_cast<float *>(p1), v1);
+    };
+    const int nitems = chunk_off[tg.ntiles];
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        __syncthreads();                         // the tile is clear, s_w is free
+        if (threadIdx.x == 0) find_work(item, chunk_off, tile_begin, tg.ntiles, s_w);
+        __syncthreads();
+        const int t = s_w.tile, ilo = s_w.lo, ihi = s_w.hi;
+        const int tz = t % tg.ntz, ty = (t / tg.ntz) % tg.nty, tx = t / (tg.ntz * tg.nty);
+        const int ox = tx * TX, oy = ty * TY, oz = tz * TZ;
+        float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ilo + warp * PB + lane < ihi) nxt = __ldg(sorted + ilo + warp * PB + lane);
+        for (int i0 = ilo + warp * PB; i0 < ihi; i0 += NW * PB) {      // warp-uniform trip count
+            const float4 p = nxt;
+            const bool have = i0 + lane < ihi;
+            if (i0 + NW * PB + lane < ihi) nxt = __ldg(sorted + i0 + NW * PB + lane);   // next batch in flight
             int cell0 = -1;
-            float ux = 0.f, uy = 0.f, uz = 0.f, w = 1.f;
-            if (i0 + lane < hi) {
-                const float4 p = src(i0 + lane);
+            if (have) {
                 float C[3][S];
-                cell0 = base_cell<MAS, TC>(p, inv, tg, ox, oy, oz, C);
-                ux = C[0][1]; uy = C[1][1]; uz = C[2][1]; w = p.w;
-            }
-            auto fetch = [&](int s, float *&addr, float &v) {
-                const int from = 4 * s + q;
-                const int b = __shfl_sync(full, cell0, from);
-                const float fx = __shfl_sync(full, ux, from), fy = __shfl_sync(full, uy, from), fz = __shfl_sync(full, uz, from);
-                v = ((la ? fx : __fsub_rn(1.0f, fx)) * (lb ? fy : __fsub_rn(1.0f, fy))) * (lc ? fz : __fsub_rn(1.0f, fz));
-                if (HASW) v *= __shfl_sync(full, w, from);
-                addr = tile + (b < 0 ? 0 : b) + loff;
-                return b >= 0;
-            };
-            if constexpr (JOINT) {
-#pragma unroll
-                for (int s = 0; s < 8; s += 2) {
-                    float *a0, *a1; float v0, v1;
-                    const bool ok0 = fetch(s, a0, v0), ok1 = fetch(s + 1, a1, v1);
-                    if (ok0 && ok1) { float *pp[2] = {a0, a1}; const float vv[2] = {v0, v1}; smem_add_joint<2>(pp, vv); }
-                    else if (ok0) atomicAdd(a0, v0);
-                    else if (ok1) atomicAdd(a1, v1);
-                }
-            } else {
-#pragma unroll
-                for (int s = 0; s < 8; s++) {
-                    float *a0; float v0;
-                    if (fetch(s, a0, v0)) atomicAdd(a0, v0);
-                }
-            }
-        }
-    } else {
-        constexpr int NP = MAS == PYLB_PCS ? 2 : 1;                 // x-planes per lane
-        int la, lb, lc;
-        bool active = true;
-        if (MAS == PYLB_PCS) { la = lane >> 4; lb = (lane >> 2) & 3; lc = lane & 3; }
-        else { active = lane < 27; la = active ? lane / 9 : 0; lb = active ? (lane / 3) % 3 : 0; lc = active ? lane % 3 : 0; }
-        const int loff = la * TS::PL + lb * TS::PI + lc;
-        float *stage = tile + TS::CELLS + warp * TS::STAGE_WORDS;
-        const float *sxy0 = stage + (la * S + lb) * SP, *sxy1 = stage + ((MAS == PYLB_PCS ? la + 2 : la) * S + lb) * SP;   // second x-plane: PCS only
-        const float *sz = stage + (S * S + lc) * SP, *sw = stage + (S * S + S) * SP;
-        for (int i0 = lo + warp * PB; i0 < hi; i0 += NW * PB) {      // warp-uniform trip count
-            int cell0 = -1;
-            if (lane < PB && i0 + lane < hi) {
-                const float4 p = src(i0 + lane);
-                float C[3][S];
-                cell0 = base_cell<MAS, TC>(p, inv, tg, ox, oy, oz, C);
+                cell0 = base_cell<MAS>(p, inv, tg, ox, oy, oz, C);
                 if (cell0 >= 0) {
 #pragma unroll
-                    for (int l = 0; l < S; l++)
+                    for (int a = 0; a < 3; a++)
 #pragma unroll
-                        for (int m = 0; m < S; m++) stage[(l * S + m) * SP + lane] = C[0][l] * C[1][m];
-#pragma unroll
-                    for (int n = 0; n < S; n++) stage[(S * S + n) * SP + lane] = C[2][n];
-                    if (HASW) stage[(S * S + S) * SP + lane] = p.w;
+                        for (int k = 0; k < S; k++) stage[(a * S + k) * SP + lane] = C[a][k];
+                    if (HASW) stage[3 * S * SP + lane] = p.w;
                 }
             }
             __syncwarp();
-            // value(s) of this lane's stencil point(s) for particle p of the batch
-            auto value = [&](int p, float (&v)[NP]) {
-                const float wz = sz[p];
-                v[0] = sxy0[p] * wz;
-                if (NP == 2) v[NP - 1] = sxy1[p] * wz;
-                if (HASW) { const float w = sw[p]; v[0] *= w; if (NP == 2) v[NP - 1] *= w; }
-            };
             unsigned todo = __ballot_sync(full, cell0 >= 0);
-            if constexpr (JOINT) {
-                // walk the batch two particles at a time; a run of equal base cells is first summed in registers
-                while (todo) {
-                    int p = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int b0 = __shfl_sync(full, cell0, p);
-                    float v0[NP];
-                    if (active) value(p, v0);
-                    int b1 = -1;
-                    float v1[NP];
-                    while (todo) {                                   // warp-uniform
-                        p = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        b1 = __shfl_sync(full, cell0, p);
-                        if (active) value(p, v1);
-                        if (b1 != b0) break;
+            if (todo == full) {
+                // the common case, unrolled: the staging offsets become immediates; the staged values of particle pp+1
+                // are read before particle pp's atomics are issued (the compiler will not move a shared-memory load
+                // above an atomic by itself)
+                Staged nq = fetch(0, __shfl_sync(full, cell0, 0));
 #pragma unroll
-                        for (int k = 0; k < NP; k++) v0[k] += v1[k];
-                        b1 = -1;
-                    }
-                    if (active) {
-                        if (b1 >= 0) {
-                            float *pp[2 * NP]; float vv[2 * NP];
-#pragma unroll
-                            for (int k = 0; k < NP; k++) {
-                                pp[k] = tile + b0 + loff + 2 * k * TS::PL; vv[k] = v0[k];
-                                pp[NP + k] = tile + b1 + loff + 2 * k * TS::PL; vv[NP + k] = v1[k];
-                            }
-                            smem_add_joint<2 * NP>(pp, vv);
-                        } else {
-                            float *pp[NP]; float vv[NP];
-#pragma unroll
-                            for (int k = 0; k < NP; k++) { pp[k] = tile + b0 + loff + 2 * k * TS::PL; vv[k] = v0[k]; }
-                            smem_add_joint<NP>(pp, vv);
-                        }
-                    }
+                for (int pp = 0; pp < PB; pp++) {
+                    const Staged q = nq;
+                    if (pp + 1 < PB) nq = fetch(pp + 1, __shfl_sync(full, cell0, pp + 1));
+                    apply(q);
                 }
             } else {
                 while (todo) {
-                    const int p = __ffs(todo) - 1;
+                    const int pp = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    const int b = __shfl_sync(full, cell0, p);
-                    if (active) {
-                        float v[NP];
-                        value(p, v);
-#pragma unroll
-                        for (int k = 0; k < NP; k++) atomicAdd(tile + b + loff + 2 * k * TS::PL, v[k]);
-                    }
+                    apply(fetch(pp, __shfl_sync(full, cell0, pp)));
                 }
             }
             __syncwarp();                                            // the next batch overwrites the staging
         }
+        __syncthreads();
+        flush_tile<TS, THREADS>(tile, grid, tg, ox, oy, oz);
     }
-    __syncthreads();
-    flush_tile<TS, TC::THREADS>(tile, grid, tg, ox, oy, oz);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -718,20 +613,43 @@ static int bits_for(unsigned v) {
     return b;
 }
 
-enum { PATH_BIN_S = 0, PATH_BIN_L = 1, PATH_RADIX_S = 2 };
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+    PYLB_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+// digits of the tile id for a grid of `ntiles` tiles
+struct SortPlan {
+    bool deep;          // per-tile counts need the second histogram sweep
+    int lo_bits, nb0;   // lo digit = low lo_bits bits (<= 10), nb0 = number of hi digits (<= 1024)
+};
+static SortPlan sort_plan(int ntiles, int force) {
+    SortPlan p;
+    p.deep = force >= 2 || ntiles > BIN_MAX_KEYS;
+    if (ntiles <= BIN_MAX_KEYS) {
+        p.lo_bits = (bits_for((unsigned)(ntiles - 1)) + 1) / 2;
+        if (p.lo_bits > 8) p.lo_bits = 8;
+    } else {
+        p.lo_bits = ntiles <= (1 << 18) ? 8 : 10;
+    }
+    // test hooks: the digit widths of the largest grids on a small one (3: 1024 lo digits; 4: 4 lo digits, many buckets)
+    if (force == 3) p.lo_bits = 10;
+    if (force == 4 && ntiles <= 4096) p.lo_bits = 2;
+    p.nb0 = (ntiles + (1 << p.lo_bits) - 1) >> p.lo_bits;
+    return p;
+}
 
 // ------------------------------------------------------------------------------------------------
-// partition particles by owning x-slab (multi-GPU particle exchange): the binsort kernels with a slab key.
+// partition particles by owning x-slab (multi-GPU particle exchange): the sort's pass 0 with a slab key.
 // out[offsets[g] .. offsets[g+1]) = (x,y,z,w) of the particles whose lowest touched x-plane lies in slab g.
 // ------------------------------------------------------------------------------------------------
-template <class K>
-static int set_smem(K kernel, size_t bytes);
-
 template <int MAS, bool HASW>
 static int partition_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, const float *w, int64_t wst, int dims,
                          float inv, int G, float4 *out, int *offsets, cudaStream_t st) {
     keep_pool_memory();
-    TileGeom tg = tile_geom<TileS>(dims);
+    PYLB_REQUIRE(G <= 256, "pylb_partition_xslab: at most 256 slabs");
+    TileGeom tg = tile_geom(dims);
     tg.slab_w = dims / G;
     tg.ntiles = G;
     const int n = (int)np;
@@ -744,22 +662,16 @@ static int partition_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1,
     PYLB_CHECK(cudaMallocAsync(&cursor, sizeof(int) * (G + 2), st));
     PYLB_CHECK(cudaMallocAsync(&tmp, tb ? tb : 16, st));
     PYLB_CHECK(cudaMemsetAsync(counts, 0, sizeof(int) * (G + 2), st));
-    const int P = sm_count();
-    bin_hist_kernel<MAS, TileS><<<P, BIN_THREADS, hist_smem, st>>>(pos, 0, n, ps0, ps1, inv, tg, counts);
+    bin_hist_kernel<MAS><<<sm_count(), BIN_THREADS, hist_smem, st>>>(pos, 0, n, ps0, ps1, inv, tg, 0, G, counts);
     PYLB_LAUNCH_CHECK();
     PYLB_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tb, counts, offsets, G + 1, st));
     count_launch(2);
     PYLB_CHECK(cudaMemcpyAsync(cursor, offsets, sizeof(int) * (G + 1), cudaMemcpyDeviceToDevice, st));
-    PYLB_REQUIRE(G <= PART_MAXBINS, "pylb_partition_xslab: at most %d slabs", PART_MAXBINS);
-    {
-        // the block-local counting sort of the tiled deposit's pass 0 with the slab as its digit: one coalesced read
-        // of the particles, one contiguous run per (chunk, slab) written out
-        constexpr int PT = 256, CH = PT * PART_PER_THREAD;
-        const size_t psm = sizeof(PartSmem<PT>);
-        if (set_smem(bin_pass_kernel<MAS, TileS, HASW, true, PT>, psm)) return 1;
-        bin_pass_kernel<MAS, TileS, HASW, true, PT><<<(unsigned)((n + CH - 1) / CH), PT, psm, st>>>(
-            pos, w, wst, 0, n, ps0, ps1, inv, tg, nullptr, out, cursor, nullptr, nullptr, 0, G);
-    }
+    constexpr int PT = 256, CH = PT * PART_PER_THREAD;
+    const size_t psm = sizeof(PartSmem<PT, 256>);
+    if (set_smem(bin_pass_kernel<MAS, HASW, true, PT, 256>, psm)) return 1;
+    bin_pass_kernel<MAS, HASW, true, PT, 256><<<(unsigned)((n + CH - 1) / CH), PT, psm, st>>>(
+        pos, w, wst, 0, n, ps0, ps1, inv, tg, nullptr, out, cursor, nullptr, nullptr, 0, G);
     PYLB_LAUNCH_CHECK();
     cudaFreeAsync(counts, st); cudaFreeAsync(cursor, st); cudaFreeAsync(tmp, st);
     return 0;
@@ -782,36 +694,22 @@ int ma_partition(const float *pos, int64_t np, int64_t ps0, int64_t ps1, const f
     return 1;
 }
 
-static int g_force_path = -1;   // tests: exercise every path on small grids (pylb_ma_debug_path)
-static int g_force_kernel = 0;  // tile kernel: 0 default, 1 lane per particle, 2 stencil lanes (plain atomicAdd), 3 stencil lanes (joint CAS)
+// tests / A-B runs (pylb_ma_debug_path): units digit 0 automatic, 2 force the deep sort, 3 / 4 deep with 1024 / 4 lo digits;
+// hundreds digit 0 automatic, 1 lane-per-particle tile kernel for every scheme, 2 stencil-lane kernel where it exists (PCS)
+static int g_force_sort = 0, g_force_kernel = 0;
 void ma_tiled_force_path(int p) {
-    g_force_kernel = 0;
-    if (p >= 100) { g_force_kernel = p / 100; p %= 100; if (p == 99) p = -1; }   // k99: automatic sort path, kernel k
-    g_force_path = p;
+    if (p < 0) p = 0;
+    g_force_kernel = (p / 100) % 10;
+    g_force_sort = p % 100;
 }
-// PYLB_TILE_KERNEL = 1 | 2 | 3 overrides the default tile kernel (A/B runs)
-static int tile_kernel_choice() {
-    static int env = -2;
-    if (env == -2) { const char *e = getenv("PYLB_TILE_KERNEL"); env = e ? atoi(e) : 0; }
-    const int k = g_force_kernel > 0 ? g_force_kernel : env;
-    return (k >= 1 && k <= 3) ? k : 3;
-}
-
-static int choose_path(int dims, int xext) {
-    if (g_force_path >= PATH_BIN_S && g_force_path <= PATH_RADIX_S) return g_force_path;
-    if (tile_geom<TileS>(dims, 0, xext).ntiles <= BIN_MAX_TILES) return PATH_BIN_S;
-    if (tile_geom<TileL>(dims, 0, xext).ntiles <= BIN_MAX_TILES) return PATH_BIN_L;
-    return PATH_RADIX_S;
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
 struct TiledWs {
-    // binsort
-    int *H, *S, *bcursor, *bchunk_off;
+    int *H, *S, *bucket_begin, *bcursor, *bchunk_off, *tile_begin, *nchunks, *chunk_off;
     float4 *sorted, *sorted_tmp;
-    // radix
-    unsigned *k0, *k1, *v0, *v1;
-    // common
-    int *tile_begin, *nchunks, *chunk_off;
     void *tmp;
     size_t tmp_bytes, total;
 };
@@ -819,33 +717,24 @@ struct TiledWs {
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static void plan_ws(int64_t np, int dims, int xext, TiledWs *ws, char *base) {
-    const int path = choose_path(dims, xext);
-    const int ntiles = path == PATH_BIN_L ? tile_geom<TileL>(dims, 0, xext).ntiles : tile_geom<TileS>(dims, 0, xext).ntiles;
+    const int ntiles = tile_geom(dims, 0, xext).ntiles;
     const int64_t nb = np < BATCH ? np : BATCH;
-    size_t o = 0, t1 = 0, t2 = 0, t3 = 0;
+    size_t o = 0, t2 = 0;
     auto take = [&](size_t bytes) { char *p = base ? base + o : nullptr; o += align_up(bytes); return p; };
     memset(ws, 0, sizeof(*ws));
-    if (path == PATH_RADIX_S) {
-        cub::DeviceRadixSort::SortPairs(nullptr, t1, (unsigned *)nullptr, (unsigned *)nullptr, (unsigned *)nullptr,
-                                        (unsigned *)nullptr, (int)nb, 0, 32);
-        ws->k0 = (unsigned *)take(sizeof(unsigned) * nb);
-        ws->k1 = (unsigned *)take(sizeof(unsigned) * nb);
-        ws->v0 = (unsigned *)take(sizeof(unsigned) * nb);
-        ws->v1 = (unsigned *)take(sizeof(unsigned) * nb);
-    } else {
-        ws->H = (int *)take(sizeof(int) * (size_t)(ntiles + 2));   // per-tile counts
-        ws->S = (int *)take(sizeof(int) * (size_t)(ntiles + 2));   // per-tile write cursors
-        ws->sorted = (float4 *)take(sizeof(float4) * nb);
-        ws->sorted_tmp = (float4 *)take(sizeof(float4) * nb);
-        ws->bcursor = (int *)take(sizeof(int) * (PART_MAXBINS + 2));
-        ws->bchunk_off = (int *)take(sizeof(int) * (PART_MAXBINS + 2));
-    }
+    const size_t nt = (size_t)ntiles + 1026;
+    ws->H = (int *)take(sizeof(int) * nt);            // per-key counts
+    ws->S = (int *)take(sizeof(int) * nt);            // per-tile write cursors
+    ws->tile_begin = (int *)take(sizeof(int) * nt);
+    ws->nchunks = (int *)take(sizeof(int) * nt);
+    ws->chunk_off = (int *)take(sizeof(int) * nt);
+    ws->bucket_begin = (int *)take(sizeof(int) * 1026);
+    ws->bcursor = (int *)take(sizeof(int) * 1026);
+    ws->bchunk_off = (int *)take(sizeof(int) * 1026);
+    ws->sorted = (float4 *)take(sizeof(float4) * nb);
+    ws->sorted_tmp = (float4 *)take(sizeof(float4) * nb);
     cub::DeviceScan::ExclusiveSum(nullptr, t2, (int *)nullptr, (int *)nullptr, ntiles + 1);
-    ws->tile_begin = (int *)take(sizeof(int) * (ntiles + 2));
-    ws->nchunks = (int *)take(sizeof(int) * (ntiles + 2));
-    ws->chunk_off = (int *)take(sizeof(int) * (ntiles + 2));
-    ws->tmp_bytes = t1 > t2 ? t1 : t2;
-    if (t3 > ws->tmp_bytes) ws->tmp_bytes = t3;
+    ws->tmp_bytes = t2;
     ws->tmp = take(ws->tmp_bytes ? ws->tmp_bytes : 16);
     ws->total = o;
 }
@@ -858,123 +747,102 @@ size_t ma_tiled_workspace(int64_t np, int dims, int xext, int mas, int has_w) {
     return ws.total;
 }
 
-bool ma_tiled_supported(int ndim, int dims, int grid_f64) { return ndim == 3 && !grid_f64 && dims >= 32; }
-
-template <class K>
-static int set_smem(K kernel, size_t bytes) {
-    PYLB_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return 0;
+bool ma_tiled_supported(int ndim, int dims, int grid_f64, int xext) {
+    return ndim == 3 && !grid_f64 && dims >= 32 && tile_geom(dims, 0, xext).ntiles <= MAX_TILES;
 }
 
-static int part_threads() {
-    static int t = 0;
-    // 256-thread CTAs (2048-particle chunks, 4 CTAs/SM) overlap the load / rank / write-out phases of neighbouring CTAs
-    // better than 512-thread CTAs (4096, 2 CTAs/SM): 3.73 ms against 3.99 ms for the whole 512^3 CIC deposit
-    if (t == 0) { const char *e = getenv("PYLB_PART_THREADS"); const int v = e ? atoi(e) : 256; t = (v == 512 || v == 128) ? v : 256; }
-    return t;
-}
-
-template <int MAS, class TC, bool HASW, int PT>
+template <int MAS, bool HASW, int PT, int MAXB0, int MAXB1>
 static int run_passes(const float *pos, const float *w, int64_t wst, int64_t first, int n, int64_t ps0, int64_t ps1, float inv,
-                      const TileGeom &tg, TiledWs &ws, int lo_bits, int nb0, cudaStream_t st) {
+                      const TileGeom &tg, TiledWs &ws, const SortPlan &sp, cudaStream_t st) {
     constexpr int CH = PT * PART_PER_THREAD;
-    part_buckets_kernel<<<1, PART_MAXBINS, 0, st>>>(ws.tile_begin, tg.ntiles, lo_bits, nb0, ws.bcursor, ws.bchunk_off, CH);
+    const int nt1 = tg.ntiles + 1;
+    size_t tb = ws.tmp_bytes;
+    // bucket table, pass-0 cursors and the chunk list of pass 1 from the (tile or bucket) scan in ws.tile_begin
+    if (!sp.deep)
+        part_buckets_kernel<<<1, 1024, 0, st>>>(ws.tile_begin, tg.ntiles, sp.lo_bits, sp.nb0, CH, ws.bucket_begin, ws.bcursor, ws.bchunk_off);
+    else
+        part_buckets_kernel<<<1, 1024, 0, st>>>(ws.tile_begin, sp.nb0, 0, sp.nb0, CH, ws.bucket_begin, ws.bcursor, ws.bchunk_off);
     PYLB_LAUNCH_CHECK();
-    const size_t psm = sizeof(PartSmem<PT>);
-    if (set_smem(bin_pass_kernel<MAS, TC, HASW, true, PT>, psm) || set_smem(bin_pass_kernel<MAS, TC, HASW, false, PT>, psm)) return 1;
+    const size_t psm0 = sizeof(PartSmem<PT, MAXB0>), psm1 = sizeof(PartSmem<PT, MAXB1>);
+    if (set_smem(bin_pass_kernel<MAS, HASW, true, PT, MAXB0>, psm0) || set_smem(bin_pass_kernel<MAS, HASW, false, PT, MAXB1>, psm1)) return 1;
     const unsigned g0 = (unsigned)((n + CH - 1) / CH);
-    bin_pass_kernel<MAS, TC, HASW, true, PT><<<g0, PT, psm, st>>>(
-        pos, w, wst, first, n, ps0, ps1, inv, tg, nullptr, ws.sorted_tmp, ws.bcursor, ws.tile_begin, ws.bchunk_off, lo_bits, nb0);
+    bin_pass_kernel<MAS, HASW, true, PT, MAXB0><<<g0, PT, psm0, st>>>(
+        pos, w, wst, first, n, ps0, ps1, inv, tg, nullptr, ws.sorted_tmp, ws.bcursor, ws.bucket_begin, ws.bchunk_off, sp.lo_bits, sp.nb0);
     PYLB_LAUNCH_CHECK();
-    bin_pass_kernel<MAS, TC, HASW, false, PT><<<g0 + (unsigned)nb0, PT, psm, st>>>(
-        pos, w, wst, first, n, ps0, ps1, inv, tg, ws.sorted_tmp, ws.sorted, ws.S, ws.tile_begin, ws.bchunk_off, lo_bits, nb0);
+    if (sp.deep) {
+        // per-tile counts from the bucket-ordered payload, then every tile's first slot
+        PYLB_CHECK(cudaMemsetAsync(ws.H, 0, sizeof(int) * (size_t)nt1, st));
+        bin_hist2_kernel<MAS, PT><<<g0 + (unsigned)sp.nb0, PT, 0, st>>>(ws.sorted_tmp, inv, tg, ws.bucket_begin, ws.bchunk_off, sp.lo_bits, sp.nb0, ws.H);
+        PYLB_LAUNCH_CHECK();
+        PYLB_CHECK(cub::DeviceScan::ExclusiveSum(ws.tmp, tb, ws.H, ws.tile_begin, nt1, st));
+        count_launch(2);
+    }
+    PYLB_CHECK(cudaMemcpyAsync(ws.S, ws.tile_begin, sizeof(int) * (size_t)nt1, cudaMemcpyDeviceToDevice, st));
+    bin_pass_kernel<MAS, HASW, false, PT, MAXB1><<<g0 + (unsigned)sp.nb0, PT, psm1, st>>>(
+        pos, w, wst, first, n, ps0, ps1, inv, tg, ws.sorted_tmp, ws.sorted, ws.S, ws.bucket_begin, ws.bchunk_off, sp.lo_bits, sp.nb0);
     PYLB_LAUNCH_CHECK();
     return 0;
 }
 
-template <int MAS, bool HASW, class TC, bool BINSORT>
+template <int MAS, bool HASW>
 static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv,
                      const float *w, int64_t wst, int x0, int xext, TiledWs &ws, cudaStream_t st) {
-    using TS = TileShape<MAS, TC>;
-    const TileGeom tg = tile_geom<TC>(dims, x0, xext);
-    const size_t hist_smem = sizeof(int) * (size_t)tg.ntiles;
+    using TS = TileShape<MAS>;
+    const TileGeom tg = tile_geom(dims, x0, xext);
+    const SortPlan sp = sort_plan(tg.ntiles, g_force_sort);
     const int P = sm_count();
-    const int kern = MAS == PYLB_NGP ? 1 : tile_kernel_choice();
-    // always the maximum these kernels may ever need: the attribute is a limit, and a smaller value set here would make
+    // always the maximum the kernels may ever need: the attribute is a limit, and a smaller value set here would make
     // a later, larger launch of the same instantiation fail
-    if (set_smem(deposit_tile_kernel<MAS, HASW, TC, BINSORT>, TS::PLAIN_SMEM)) return 1;
-    if constexpr (MAS != PYLB_NGP) {
-        if (set_smem(deposit_lane_kernel<MAS, HASW, TC, BINSORT, false>, TS::LANE_SMEM) ||
-            set_smem(deposit_lane_kernel<MAS, HASW, TC, BINSORT, true>, TS::LANE_SMEM)) return 1;
+    if (set_smem(deposit_tile_kernel<MAS, HASW>, TS::SMEM)) return 1;
+    if constexpr (MAS == PYLB_PCS) {
+        if (set_smem(deposit_lane_kernel<HASW>, TS::LANE_SMEM)) return 1;
     }
-    if (BINSORT) {
-        if (set_smem(bin_hist_kernel<MAS, TC>, sizeof(int) * (size_t)BIN_MAX_TILES)) return 1;
-    }
+    if (set_smem(bin_hist_kernel<MAS>, sizeof(int) * (size_t)BIN_MAX_KEYS)) return 1;
+    const int kern = g_force_kernel > 0 ? g_force_kernel : env_int("PYLB_TILE_KERNEL", 0);
     const int nt1 = tg.ntiles + 1;
     for (int64_t first = 0; first < np; first += BATCH) {
         const int n = (int)((np - first) < BATCH ? (np - first) : BATCH);
         size_t tb = ws.tmp_bytes;
         timing_begin(PYLB_T_SORT, st);
-        if (BINSORT) {
-            PYLB_CHECK(cudaMemsetAsync(ws.H, 0, sizeof(int) * (size_t)nt1, st));
-            bin_hist_kernel<MAS, TC><<<P, BIN_THREADS, hist_smem, st>>>(pos, first, n, ps0, ps1, inv, tg, ws.H);
-            PYLB_LAUNCH_CHECK();
-            // tile_begin[0..ntiles] = exclusive scan of the counts (counts[ntiles] = 0)
-            PYLB_CHECK(cub::DeviceScan::ExclusiveSum(ws.tmp, tb, ws.H, ws.tile_begin, nt1, st));
-            count_launch(2);
-            PYLB_CHECK(cudaMemcpyAsync(ws.S, ws.tile_begin, sizeof(int) * (size_t)nt1, cudaMemcpyDeviceToDevice, st));
-            int lo_bits = (bits_for((unsigned)(tg.ntiles - 1)) + 1) / 2;
-            if (lo_bits > 8) lo_bits = 8;
-            const int nb0 = (tg.ntiles + (1 << lo_bits) - 1) >> lo_bits;      // <= 256 because ntiles <= 65536
-            if (part_threads() == 256) {
-                if (run_passes<MAS, TC, HASW, 256>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, lo_bits, nb0, st)) return 1;
-            } else if (part_threads() == 128) {
-                if (run_passes<MAS, TC, HASW, 128>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, lo_bits, nb0, st)) return 1;
-            } else {
-                if (run_passes<MAS, TC, HASW, 512>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, lo_bits, nb0, st)) return 1;
-            }
-        } else {
-            tile_key_kernel<MAS, TC><<<(n + 255) / 256, 256, 0, st>>>(pos, first, n, ps0, ps1, inv, tg, ws.k0, ws.v0);
-            PYLB_LAUNCH_CHECK();
-            const int end_bit = bits_for((unsigned)(tg.ntiles - 1));
-            PYLB_CHECK(cub::DeviceRadixSort::SortPairs(ws.tmp, tb, ws.k0, ws.k1, ws.v0, ws.v1, n, 0, end_bit, st));
-            count_launch(3);
-            tile_begin_kernel<<<(nt1 + 255) / 256, 256, 0, st>>>(ws.k1, n, tg.ntiles, ws.tile_begin);
-            PYLB_LAUNCH_CHECK();
-        }
-        tile_chunks_kernel<<<(nt1 + 255) / 256, 256, 0, st>>>(ws.tile_begin, tg.ntiles, TC::CHUNK, ws.nchunks);
+        // histogram of the tiles (shallow) or of their hi digits (deep), and its exclusive scan (counts[nkeys] = 0)
+        const int shift = sp.deep ? sp.lo_bits : 0, nkeys = sp.deep ? sp.nb0 : tg.ntiles;
+        PYLB_CHECK(cudaMemsetAsync(ws.H, 0, sizeof(int) * (size_t)(nkeys + 1), st));
+        bin_hist_kernel<MAS><<<P, BIN_THREADS, sizeof(int) * (size_t)nkeys, st>>>(pos, first, n, ps0, ps1, inv, tg, shift, nkeys, ws.H);
+        PYLB_LAUNCH_CHECK();
+        PYLB_CHECK(cub::DeviceScan::ExclusiveSum(ws.tmp, tb, ws.H, ws.tile_begin, nkeys + 1, st));
+        count_launch(2);
+        int rc;
+        const bool wide0 = sp.nb0 > 256, wide1 = (1 << sp.lo_bits) > 256;
+        if (!wide0 && !wide1) rc = run_passes<MAS, HASW, 256, 256, 256>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, sp, st);
+        else if (!wide1) rc = run_passes<MAS, HASW, 512, 1024, 256>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, sp, st);
+        else rc = run_passes<MAS, HASW, 512, 1024, 1024>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, sp, st);
+        if (rc) return rc;
+        tile_chunks_kernel<<<(nt1 + 255) / 256, 256, 0, st>>>(ws.tile_begin, tg.ntiles, CHUNK, ws.nchunks);
         PYLB_LAUNCH_CHECK();
         tb = ws.tmp_bytes;
         PYLB_CHECK(cub::DeviceScan::ExclusiveSum(ws.tmp, tb, ws.nchunks, ws.chunk_off, nt1, st));
         count_launch(2);
-        // upper bound on work items: every non-empty tile has at most count/CHUNK + 1 chunks
-        const unsigned max_items = (unsigned)((int64_t)n / TC::CHUNK + tg.ntiles);
-        const ParticleSource<BINSORT, HASW> src{pos, first, ps0, ps1, w, wst, ws.v1, ws.sorted};
         timing_end(PYLB_T_SORT, st);
+        // persistent CTAs walk the work items (tile, chunk) round-robin; every non-empty tile has at most n/CHUNK + 1 chunks
+        const int64_t max_items = (int64_t)n / CHUNK + tg.ntiles;
         timing_begin(PYLB_T_TILE, st);
-        if constexpr (MAS != PYLB_NGP) {
-            if (kern == 3)
-                deposit_lane_kernel<MAS, HASW, TC, BINSORT, true><<<max_items, TC::THREADS, TS::LANE_SMEM, st>>>(
-                    src, inv, tg, ws.tile_begin, ws.chunk_off, grid);
-            else if (kern == 2)
-                deposit_lane_kernel<MAS, HASW, TC, BINSORT, false><<<max_items, TC::THREADS, TS::LANE_SMEM, st>>>(
-                    src, inv, tg, ws.tile_begin, ws.chunk_off, grid);
+        bool lanes = false;
+        if constexpr (MAS == PYLB_PCS) lanes = kern != 1;
+        if (lanes) {
+            if constexpr (MAS == PYLB_PCS) {
+                const int64_t g = (int64_t)P * 2 * 8;
+                deposit_lane_kernel<HASW><<<(unsigned)(max_items < g ? max_items : g), TS::LANE_THREADS, TS::LANE_SMEM, st>>>(
+                    ws.sorted, inv, tg, ws.tile_begin, ws.chunk_off, grid);
+            }
+        } else {
+            const int64_t g = (int64_t)P * 4 * 8;
+            deposit_tile_kernel<MAS, HASW><<<(unsigned)(max_items < g ? max_items : g), TS::THREADS, TS::SMEM, st>>>(
+                ws.sorted, inv, tg, ws.tile_begin, ws.chunk_off, grid);
         }
-        if (kern == 1)
-            deposit_tile_kernel<MAS, HASW, TC, BINSORT><<<max_items, TC::THREADS, TS::PLAIN_SMEM, st>>>(
-                src, inv, tg, ws.tile_begin, ws.chunk_off, grid);
-        timing_end(PYLB_T_TILE, st);
         PYLB_LAUNCH_CHECK();
+        timing_end(PYLB_T_TILE, st);
     }
     return 0;
-}
-
-template <int MAS, bool HASW>
-static int tiled_path(int path, const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims,
-                      float inv, const float *w, int64_t wst, int x0, int xext, TiledWs &ws, cudaStream_t st) {
-    if (path == PATH_BIN_S) return tiled_run<MAS, HASW, TileS, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
-    if (path == PATH_BIN_L) return tiled_run<MAS, HASW, TileL, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
-    return tiled_run<MAS, HASW, TileS, false>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
 }
 
 int ma_tiled(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid, int dims, float inv, int mas,
@@ -985,17 +853,17 @@ int ma_tiled(const float *pos, int64_t np, int64_t ps0, int64_t ps1, float *grid
     PYLB_REQUIRE(workspace != nullptr && workspace_bytes >= ws.total, "pylb_ma: tiled workspace too small (%zu < %zu)",
                  workspace_bytes, ws.total);
     PYLB_REQUIRE(((uintptr_t)grid & 15) == 0, "pylb_ma: grid must be 16-byte aligned");
-    const int path = choose_path(dims, xext);
+    PYLB_REQUIRE(tile_geom(dims, x0, xext).ntiles <= MAX_TILES, "pylb_ma: more than 2^20 tiles in one window; deposit onto x-windows");
     const bool hw = w != nullptr;
     switch (mas) {
-        case PYLB_NGP: return hw ? tiled_path<PYLB_NGP, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st)
-                                 : tiled_path<PYLB_NGP, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
-        case PYLB_CIC: return hw ? tiled_path<PYLB_CIC, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st)
-                                 : tiled_path<PYLB_CIC, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
-        case PYLB_TSC: return hw ? tiled_path<PYLB_TSC, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st)
-                                 : tiled_path<PYLB_TSC, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
-        case PYLB_PCS: return hw ? tiled_path<PYLB_PCS, true>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st)
-                                 : tiled_path<PYLB_PCS, false>(path, pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+        case PYLB_NGP: return hw ? tiled_run<PYLB_NGP, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st)
+                                 : tiled_run<PYLB_NGP, false>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+        case PYLB_CIC: return hw ? tiled_run<PYLB_CIC, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st)
+                                 : tiled_run<PYLB_CIC, false>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+        case PYLB_TSC: return hw ? tiled_run<PYLB_TSC, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st)
+                                 : tiled_run<PYLB_TSC, false>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
+        case PYLB_PCS: return hw ? tiled_run<PYLB_PCS, true>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st)
+                                 : tiled_run<PYLB_PCS, false>(pos, np, ps0, ps1, grid, dims, inv, w, wst, x0, xext, ws, st);
     }
     set_error("pylb_ma: unknown mass-assignment scheme %d", mas);
     return 1;

@@ -49,8 +49,17 @@ def _get(o, n):
     return np.asarray(o[n] if isinstance(o, dict) else getattr(o, n))
 
 
-def check_pk(test, ref, phase=True, rtol=PK_RTOL):
-    """test/ref: objects or dicts with the reference's Pk attribute names."""
+FEW_MODES = 16
+
+
+def check_pk(test, ref, phase=True, rtol=PK_RTOL, few_mode_rtol=None):
+    """test/ref: objects or dicts with the reference's Pk attribute names.
+
+    few_mode_rtol: tolerance for 2-D bins averaging fewer than FEW_MODES modes.  Two fp32 FFTs (cuFFT here, pocketfft in
+    the checker, FFTW in a reference installation) differ by ~1e-7 of the field's rms in every mode; at the Nyquist corner
+    the TSC/PCS window has suppressed the signal to ~1e-2 of that rms before it is deconvolved, so a single mode's
+    |delta_k|^2 differs by ~2e-5 between any two FFT libraries, and a 2-D bin holding 1-4 such modes inherits it.  Only the
+    full-size comparisons pass it (1e-4); everything else keeps 1e-5 for every bin."""
     for n in ("Nmodes3D", "Nmodes1D", "Nmodes2D", "kpar", "kper"):
         assert_exact(_get(test, n), _get(ref, n), n)
     assert_k_close(_get(test, "k3D"), _get(ref, "k3D"), "k3D")
@@ -66,7 +75,13 @@ def check_pk(test, ref, phase=True, rtol=PK_RTOL):
     assert_spec_close(_get(test, "Pk1D"), p1, np.median(np.abs(p1)), "Pk1D", rtol)
     p2 = _get(ref, "Pk2D")
     # bins holding a single (or few) modes carry the FFT's own 1e-7..1e-6 noise; floor at the median
-    assert_spec_close(_get(test, "Pk2D"), p2, np.median(np.abs(p2)), "Pk2D", rtol)
+    if few_mode_rtol is None:
+        assert_spec_close(_get(test, "Pk2D"), p2, np.median(np.abs(p2)), "Pk2D", rtol)
+    else:
+        few = _get(ref, "Nmodes2D") < FEW_MODES
+        t2 = _get(test, "Pk2D")
+        assert_spec_close(t2[~few], p2[~few], np.median(np.abs(p2)), "Pk2D", rtol)
+        assert_spec_close(t2[few], p2[few], np.median(np.abs(p2)), "Pk2D (bins of < %d modes)" % FEW_MODES, few_mode_rtol)
 
 
 def check_xpk(test, ref, rtol=PK_RTOL):

@@ -190,11 +190,11 @@ def test_reference_unit_tests_mass_conservation(MASL, mas, places, weighted):
     assert round(abs(suma / (3.0 * particles if weighted else particles) - 1.0), places) == 0
 
 
-# algo 1: direct kernel.  algo 2 + debug path: -1 automatic; 0 / 1 / 2 = binsort with 16x16x32 tiles, with 32x32x32 tiles,
-# radix sort + gather (default tile kernel); +100 lane-per-particle kernel, +200 stencil lanes with plain atomicAdd,
-# +300 stencil lanes with the joint CAS loop
-@pytest.mark.parametrize("algo,path", [(1, -1), (2, -1), (2, 0), (2, 1), (2, 2), (2, 100), (2, 101), (2, 102),
-                                       (2, 200), (2, 201), (2, 202), (2, 300), (2, 301), (2, 302)])
+# algo 1: direct kernel.  algo 2 + debug path = 100 * kernel + sort: sort 0 automatic, 2 deep (second histogram sweep),
+# 3 / 4 deep with 1024 / 4 lo digits (the digit widths of the largest grids); kernel 0 automatic, 1 lane per particle for
+# every scheme, 2 stencil lanes where they exist (PCS)
+@pytest.mark.parametrize("algo,path", [(1, 0), (2, 0), (2, 2), (2, 3), (2, 4), (2, 100), (2, 102), (2, 200), (2, 202), (2, 203),
+                                       (2, 204)])
 @pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
 @pytest.mark.parametrize("dims", [64, 80])
 def test_ma_vs_oracle_both_algorithms(MASL, algo, path, mas, dims):
@@ -220,6 +220,52 @@ def test_ma_vs_oracle_both_algorithms(MASL, algo, path, mas, dims):
     finally:
         M.ALGO = old
         _lib.load().pylb_ma_debug_path(-1)
+
+
+@pytest.mark.parametrize("dims,n", [(800, 6000000), (832, 3000000)])
+def test_ma_deep_sort_large_grid(MASL, dims, n):
+    """Grids with more than 53248 tiles take the deep sort by themselves (800^3: 62500 tiles; 832^3: 70304 tiles, more
+    than 256 buckets)."""
+    import pylians_b200.MAS_library as M
+    rng = np.random.default_rng(dims)
+    box = 1000.0
+    pos = (rng.random((n, 3)) * box).astype(np.float32)
+    pos[: n // 8] = (np.float32(box) * 0.5 + rng.standard_normal((n // 8, 3)) * 20.0).astype(np.float32) % np.float32(box)
+    old, M.ALGO = M.ALGO, 2
+    try:
+        for mas in ("NGP", "PCS"):
+            a = np.zeros((dims,) * 3, np.float32); MASL.MA(pos, a, box, mas)
+            b = np.zeros((dims,) * 3, np.float32); O.MA(pos, b, box, mas)
+            if mas == "NGP":
+                parity.assert_exact(a, b, "NGP deep")
+            parity.assert_grid_close(a, b, "%s deep %d" % (mas, dims))
+            del a, b
+    finally:
+        M.ALGO = old
+
+
+@pytest.mark.parametrize("mas", ["CIC", "TSC", "PCS"])
+@pytest.mark.parametrize("kind", ["wide", "negative", "zero", "sparse"])
+def test_ma_weights(MASL, mas, kind):
+    """Weights spanning orders of magnitude, negative weights, all-zero weights and a very sparse deposit through the tiled path."""
+    import pylians_b200.MAS_library as M
+    rng = np.random.default_rng(5)
+    dims, box = 96, 1000.0
+    n = 3000 if kind == "sparse" else 400000
+    pos = (rng.random((n, 3)) * box).astype(np.float32)
+    W = {"wide": np.exp(rng.standard_normal(n) * 4.0), "negative": rng.standard_normal(n) + 0.25,
+         "zero": np.zeros(n), "sparse": rng.random(n) + 0.5}[kind].astype(np.float32)
+    old, M.ALGO = M.ALGO, 2
+    try:
+        a = np.full((dims,) * 3, 0.125, np.float32); MASL.MA(pos, a, box, mas, W=W)
+    finally:
+        M.ALGO = old
+    b = np.full((dims,) * 3, 0.125, np.float32); O.MA(pos, b, box, mas, W=W)
+    if kind == "negative":          # cancellations: compare against the scale of |W| deposited, not of the net field
+        c = np.zeros((dims,) * 3, np.float32); O.MA(pos, c, box, mas, W=np.abs(W))
+        assert np.all(np.abs(a.astype(np.float64) - b) <= 1e-5 * (c + np.mean(c)))
+    else:
+        parity.assert_grid_close(a, b, "%s weights %s" % (mas, kind))
 
 
 @pytest.mark.parametrize("mas", ["CIC", "TSC", "PCS"])
@@ -548,13 +594,13 @@ def test_full_size_1024_tsc_multipoles_and_xpk(MASL, PKL):
     np.testing.assert_allclose(y.Pk[:, :, 1], x.Pk[:, :, 0], rtol=1e-6, atol=1e-7 * shot)
 
 
-@pytest.mark.parametrize("kernel", [199, 299, 399])
+@pytest.mark.parametrize("kernel", [100, 200])
 @pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
 @pytest.mark.parametrize("weighted", [False, True])
 def test_ma_clustered_input(MASL, mas, weighted, kernel):
-    """Half of one tile's particles sit in three cells (a halo): many lanes / consecutive particles share a base cell.
-    The stencil-lane kernel sums runs of equal base cells in registers and resolves equal addresses inside its CAS loop;
-    every tile kernel must give the oracle's grid."""
+    """Half of one tile's particles sit in three cells (a halo): many lanes / consecutive particles share a base cell and
+    every warp of the CTA hammers the same few words -- the CAS loops of the lane-per-particle kernel and the optimistic
+    CAS + repair of the stencil-lane kernel must both give the oracle's grid."""
     from oracle import pylians_oracle as O
     from pylians_b200 import _lib
     import pylians_b200.MAS_library as M
@@ -565,12 +611,12 @@ def test_ma_clustered_input(MASL, mas, weighted, kernel):
                           (np.array([105.0, 85.0, 155.0]), np.array([104.0, 93.0, 161.0]), np.array([325.0, 325.0, 325.0]))])
     pos = np.mod(np.concatenate([uni, hot]), box).astype(np.float32)
     pos = pos[rng.permutation(len(pos))]
-    pos[:4000] = pos[0]                                     # and a run of identical particles
+    pos[:300] = pos[0]                                      # and a run of identical particles
     W = (rng.random(len(pos)) + 0.5).astype(np.float32) if weighted else None
     ref = np.zeros((dims,) * 3, np.float32)
     O.MA(pos, ref, box, mas, W=W)
     old, M.ALGO = M.ALGO, 2                                 # the tiled (shared-memory) deposit, also on this small grid
-    _lib.load().pylb_ma_debug_path(kernel)                  # k99: automatic sort path, tile kernel k
+    _lib.load().pylb_ma_debug_path(kernel)                  # automatic sort; 1 lane per particle, 2 stencil lanes (PCS)
     try:
         got = np.zeros((dims,) * 3, np.float32)
         MASL.MA(pos, got, box, mas, W=W)
