@@ -59,7 +59,8 @@ def _to_device(a, dev):
     return t.to(dev, non_blocking=True)
 
 
-HOST_CHUNK = 1 << 24      # particles per H2D chunk when `pos` lives on the host (201 MB of float32 x 3)
+HOST_CHUNK = 1 << 26      # particles per H2D chunk when `pos` lives on the host (805 MB of float32 x 3): few enough chunks that the
+                          # fixed costs of a deposit (scans, tile flush) stay small, small enough to double-buffer
 _COPY_STREAMS = {}
 
 

@@ -52,8 +52,15 @@ def _get(o, n):
 FEW_MODES = 16
 
 
-def check_pk(test, ref, phase=True, rtol=PK_RTOL, few_mode_rtol=None):
+def check_pk(test, ref, phase=True, rtol=PK_RTOL, few_mode_rtol=None, corner_rtol=None):
     """test/ref: objects or dicts with the reference's Pk attribute names.
+
+    corner_rtol: tolerance for 3-D bins beyond the Nyquist frequency k_N (the corners of the k-space cube) when the two
+    spectra come from two DIFFERENT fp32 grids (the whole chain deposit -> Pk on either side).  Two deposits of the same
+    particles differ by their fp32 summation order (~1e-7 per cell, white); the TSC/PCS deconvolution amplifies that by
+    up to 58x / 226x in amplitude at the corner, where the signal itself is suppressed, so bins there agree to ~3e-5, not
+    1e-5 -- the reference's own serial and OpenMP deposits already differ by 4e-6 there at 128^3 (1e-8 below k_N).  Spectra of
+    one and the same field keep 1e-5.
 
     few_mode_rtol: tolerance for 2-D bins averaging fewer than FEW_MODES modes.  Two fp32 FFTs (cuFFT here, pocketfft in
     the checker, FFTW in a reference installation) differ by ~1e-7 of the field's rms in every mode; at the Nyquist corner
@@ -67,7 +74,15 @@ def check_pk(test, ref, phase=True, rtol=PK_RTOL, few_mode_rtol=None):
     P = _get(ref, "Pk")
     p0 = np.abs(P[:, 0])
     floor3 = p0 + np.median(p0)               # multipoles may cancel; floor at the monopole level
-    assert_spec_close(_get(test, "Pk"), P, floor3[:, None] * np.array([1.0, 5.0, 9.0])[None, :], "Pk3D", rtol)
+    ell = np.array([1.0, 5.0, 9.0])[None, :]
+    if corner_rtol is None:
+        assert_spec_close(_get(test, "Pk"), P, floor3[:, None] * ell, "Pk3D", rtol)
+    else:
+        kN = _get(ref, "k1D")[-1]                       # k1D runs up to k_N = middle * kF
+        corner = _get(ref, "k3D") > kN * (1 + 1e-9)
+        T = _get(test, "Pk")
+        assert_spec_close(T[~corner], P[~corner], floor3[~corner, None] * ell, "Pk3D (k <= k_N)", rtol)
+        assert_spec_close(T[corner], P[corner], floor3[corner, None] * ell, "Pk3D (k > k_N)", corner_rtol)
     if phase:
         ph = _get(ref, "Pkphase")
         assert_spec_close(_get(test, "Pkphase"), ph, np.median(np.abs(ph)), "Pkphase", rtol=2 * rtol)

@@ -101,7 +101,7 @@ def run_case(nside, mas, weighted, data, axis, fast_ref):
     few = 1e-4 if mas in ("TSC", "PCS") else None          # Nyquist-corner 2-D bins of 1-4 modes: see parity.check_pk
     parity.check_pk(mine, ref_pk(got, mas, axis), few_mode_rtol=few)
     # ---- the whole chain: the reference's spectrum of the reference's own field ---------------------------
-    parity.check_pk(mine, ref_pk(ref, mas, axis), few_mode_rtol=few)
+    parity.check_pk(mine, ref_pk(ref, mas, axis), few_mode_rtol=few, corner_rtol=few)
 
 
 @pytest.mark.parametrize("data", ["uniform", "zeldovich"])
