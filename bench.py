@@ -34,6 +34,10 @@ WORKLOADS = {
     "cfg1_128_cic": dict(nside=128, fields=[("CIC", False)], axis=2),
     "cfg3_1024_tsc": dict(nside=1024, fields=[("TSC", False)], axis=2),
     "cfg5_1024_xpk": dict(nside=1024, fields=[("CIC", False), ("PCS", True)], axis=2),   # CDM + weighted gas
+    # BASELINE configs[3] as written: 2048^3 particles in TOTAL onto a 2048^3 grid at 1 / 2 / 4 / 8 GPUs (strong scaling);
+    # a rank whose share does not fit next to its grid generates and deposits it in batches of 2^28 particles
+    "cfg4_2048_strong": dict(nside=2048, fields=[("PCS", False)], axis=2, strong=True),
+    "512_strong": dict(nside=512, fields=[("PCS", False)], axis=2, strong=True, batch=1 << 24),     # the same code path, small
     "512_pcs": dict(nside=512, fields=[("PCS", False)], axis=2),
     "256_pcs": dict(nside=256, fields=[("PCS", False)], axis=2),
     "256_xpk": dict(nside=256, fields=[("CIC", False), ("PCS", True)], axis=2),
@@ -193,14 +197,27 @@ def cpu_measure(nside, wl, repeats, parts=None):
     return dict(times=times, kind=kind, threads=threads, deposit=deposit, variants=variants, result=res, parts=parts)
 
 
+def grid_side(wl, world):
+    return wl["nside"] if wl.get("strong") else int(round(wl["nside"] * GRID_FOR_GPUS.get(world, 1.0)))
+
+
+def rank_particles(wl, world, rank):
+    """particles of one field held by `rank`: nside^3 each (weak scaling), or an even share of nside^3 (strong scaling)"""
+    n = wl["nside"] ** 3
+    if not wl.get("strong"):
+        return n
+    return n // world + (1 if rank < n % world else 0)
+
+
 def workload_config(args, wl, world=None, sample_nside=None):
     n = world or args.gpus
-    gside = int(round(wl["nside"] * GRID_FOR_GPUS.get(n, 1.0)))
+    gside = grid_side(wl, n)
     nf = len(wl["fields"])
-    desc = "%s: %s%d^3 particles per GPU x %d GPU(s), %s onto %d^3 grid, BoxSize=%g, %s axis=%d (l=0,2,4)" % (
-        args.workload, "%d x " % nf if nf > 1 else "", wl["nside"], n, "+".join(m + ("W" if w else "") for m, w in wl["fields"]),
-        gside, BOX, "XPk" if nf > 1 else "Pk", wl["axis"])
-    cfg = {"workload": desc, "particles_total": wl["nside"] ** 3 * n * nf, "grid": gside, "mas": mas_names(wl),
+    strong = bool(wl.get("strong"))
+    desc = "%s: %s%d^3 particles %s %d GPU(s), %s onto %d^3 grid, BoxSize=%g, %s axis=%d (l=0,2,4)" % (
+        args.workload, "%d x " % nf if nf > 1 else "", wl["nside"], "in total over" if strong else "per GPU x", n,
+        "+".join(m + ("W" if w else "") for m, w in wl["fields"]), gside, BOX, "XPk" if nf > 1 else "Pk", wl["axis"])
+    cfg = {"workload": desc, "particles_total": wl["nside"] ** 3 * (1 if strong else n) * nf, "grid": gside, "mas": mas_names(wl),
            "axis": wl["axis"], "fields": nf,
            "l2": "inputs exceed L2 (pos %.2f GB per field, grid %.2f GB per GPU vs 126 MB L2)" % (
                wl["nside"] ** 3 * 12 / 1e9, gside ** 3 * 4 / 1e9 / n)}
@@ -313,8 +330,13 @@ class Pipeline(object):
         self.wl, self.world, self.dev, self.dist = wl, world, dev, dist
         self.MASL, self.PKL, self.torch = MASL, PKL, torch
         self.nf = len(wl["fields"])
-        self.gside = int(round(wl["nside"] * GRID_FOR_GPUS.get(world, 1.0)))
+        self.gside = grid_side(wl, world)
         self.axis = wl["axis"]
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.npart = rank_particles(wl, world, self.rank)
+        # a share that does not fit next to the grid is generated and deposited batch by batch
+        self.batch = int(wl.get("batch", 1 << 28))
+        self.streamed = bool(wl.get("strong")) and (self.npart * 12 > 24e9 or "batch" in wl)
         if world > 1:
             from pylians_b200 import dist as pdist
             self.engine = pdist.SlabPk(self.gside, BOX, wl["fields"][0][0], self.axis)
@@ -327,13 +349,32 @@ class Pipeline(object):
         n = self.wl["nside"]
         parts = []
         for _, weighted in self.wl["fields"]:
-            if data == "uniform":
-                pos = torch.rand((n ** 3, 3), device=self.dev, dtype=torch.float32, generator=gen) * BOX
+            if self.streamed:
+                parts.append(self.batches(gen, weighted))
+                continue
+            if data == "uniform" or self.npart != n ** 3:
+                pos = torch.rand((self.npart, 3), device=self.dev, dtype=torch.float32, generator=gen) * BOX
             else:
                 pos = zeldovich_particles(n, BOX, gen, self.dev)
-            W = (torch.rand(n ** 3, device=self.dev, dtype=torch.float32, generator=gen) + 0.5) if weighted else None
+            W = (torch.rand(self.npart, device=self.dev, dtype=torch.float32, generator=gen) + 0.5) if weighted else None
             parts.append((pos, W))
         return parts
+
+    def batches(self, gen, weighted, host=None):
+        """This rank's share as ParticleBatches: batch i is drawn on the device when asked for (uniform random), or is
+        the pinned host buffer `host` again (the end-to-end arm: every batch crosses PCIe, the bytes are what counts)."""
+        from pylians_b200.dist import ParticleBatches
+        torch, B, n = self.torch, self.batch, self.npart
+        nb = (n + B - 1) // B
+
+        def make(i):
+            m = min(B, n - i * B)
+            if host is not None:
+                return host[0][:m], (host[1][:m] if weighted else None)
+            pos = torch.rand((m, 3), device=self.dev, dtype=torch.float32, generator=gen) * BOX
+            W = (torch.rand(m, device=self.dev, dtype=torch.float32, generator=gen) + 0.5) if weighted else None
+            return pos, W
+        return ParticleBatches(make, nb, n)
 
     def snapshot(self, parts, hook=None):
         """parts: list of (pos, W) per field, device or pinned-host tensors."""
@@ -341,17 +382,19 @@ class Pipeline(object):
         if self.world > 1:
             eng = self.engine
             if self.nf == 1:
-                (pos, W), (mas, _) = parts[0], self.wl["fields"][0]
+                (mas, _) = self.wl["fields"][0]
+                pos, W = (parts[0], None) if self.streamed else parts[0]
                 slab = eng.density_slab(pos, W, mas)
                 if hook is not None:
                     hook()                               # GPU busy with the deposit / exchange just queued
                 return eng.pk_from_slab(slab, mas)
             return eng.run_x([p for p, _ in parts], [w for _, w in parts], mas_names(self.wl))
-        for g, (pos, W), (mas, _) in zip(self.grids, parts, self.wl["fields"]):
+        for g, part, (mas, _) in zip(self.grids, parts, self.wl["fields"]):
             g.zero_()
-            MASL.MA(pos, g, BOX, mas, W=W)               # host tensors: the H2D copy happens inside MA
-            if hook is not None:
-                hook(); hook = None                      # GPU busy with the deposit kernels just queued
+            for pos, W in (part if self.streamed else [part]):
+                MASL.MA(pos, g, BOX, mas, W=W)           # host tensors: the H2D copy happens inside MA
+                if hook is not None:
+                    hook(); hook = None                  # GPU busy with the deposit kernels just queued
             MASL.overdensity(g)
         if self.nf == 1:
             return PKL.Pk(self.grids[0], BOX, self.axis, self.wl["fields"][0][0], 1)     # D2H of the bins inside Pk
@@ -400,7 +443,8 @@ def run_ours(args, wl):
     def measure(wl_, data, steps, warm, full):
         """Device-resident timing of one workload; `full` adds the e2e arm, the stage breakdown and the kernel brackets."""
         pipe = Pipeline(wl_, world, dev, dist)
-        nf, npart, gside = pipe.nf, wl_["nside"] ** 3, pipe.gside
+        nf, gside = pipe.nf, pipe.gside
+        npart = wl_["nside"] ** 3 / (world if wl_.get("strong") else 1)      # particles per field per rank (average)
         parts = pipe.make_particles(data, 1 + rank)
         for _ in range(max(warm, 3)):
             pipe.snapshot(parts)
@@ -434,8 +478,9 @@ def run_ours(args, wl):
                 for g in pipe.grids:
                     g.zero_()
                 e0 = ev()
-                for g, (pos, W), (mas, _) in zip(pipe.grids, parts, wl_["fields"]):
-                    MASL.MA(pos, g, BOX, mas, W=W)
+                for g, part, (mas, _) in zip(pipe.grids, parts, wl_["fields"]):
+                    for pos, W in (part if pipe.streamed else [part]):
+                        MASL.MA(pos, g, BOX, mas, W=W)
                 e1 = ev()
                 for g in pipe.grids:
                     MASL.overdensity(g)
@@ -453,17 +498,28 @@ def run_ours(args, wl):
             res["stages"] = st
         # ---- end-to-end arm: particles in pinned host memory, spectra read back ------------------------
         host = []
-        for pos, W in parts:
-            hp = torch.empty(pos.shape, dtype=torch.float32, pin_memory=True); hp.copy_(pos)
-            hw = None
-            if W is not None:
-                hw = torch.empty(W.shape, dtype=torch.float32, pin_memory=True); hw.copy_(W)
-            host.append((hp, hw))
+        if pipe.streamed:
+            # one pinned batch buffer per field, sent again for every batch: each batch crosses PCIe inside the timed region
+            gen = torch.Generator(device=dev); gen.manual_seed(99 + rank)
+            for _, weighted in wl_["fields"]:
+                m = min(pipe.batch, pipe.npart)
+                hp = torch.empty((m, 3), dtype=torch.float32, pin_memory=True)
+                hp.copy_(torch.rand((m, 3), device=dev, dtype=torch.float32, generator=gen) * BOX)
+                hw = torch.empty(m, dtype=torch.float32, pin_memory=True); hw.fill_(1.0)
+                host.append(pipe.batches(None, weighted, host=(hp, hw)))
+            h2d = sum((16 if weighted else 12) * pipe.npart for _, weighted in wl_["fields"])
+        else:
+            for pos, W in parts:
+                hp = torch.empty(pos.shape, dtype=torch.float32, pin_memory=True); hp.copy_(pos)
+                hw = None
+                if W is not None:
+                    hw = torch.empty(W.shape, dtype=torch.float32, pin_memory=True); hw.copy_(W)
+                host.append((hp, hw))
+            h2d = sum(p.numel() * 4 + (w.numel() * 4 if w is not None else 0) for p, w in host)
         torch.cuda.synchronize()
-        h2d = sum(p.numel() * 4 + (w.numel() * 4 if w is not None else 0) for p, w in host)
 
         def e2e_step():
-            if world > 1:
+            if world > 1 and not pipe.streamed:
                 return pipe.snapshot([(p.to(dev, non_blocking=True), w.to(dev, non_blocking=True) if w is not None else None)
                                       for p, w in host])
             return pipe.snapshot(host)
@@ -474,7 +530,7 @@ def run_ours(args, wl):
         ms_e2e, _ = timed_loop(e2e_step, e2e_steps)
         L = PKL.get_layout(gside, nf)
         res["e2e"] = {"value": nf * npart * world / (ms_e2e / e2e_steps * 1e-3), "unit": "particles/s",
-                      "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int((L.n_doubles + L.n_counts) * 8 * world),
+                      "h2d_bytes_per_step": int(h2d * world) if not wl_.get("strong") else int(sum((16 if w_ else 12) for _, w_ in wl_["fields"]) * wl_["nside"] ** 3), "d2h_bytes_per_step": int((L.n_doubles + L.n_counts) * 8 * world),
                       "ms_per_step": ms_e2e / e2e_steps,
                       "note": "particle arrays in pinned host memory on every rank -> MASL.MA (chunked H2D overlapped with the deposit at "
                               "N=1) -> overdensity -> PKL.Pk/XPk -> bins on host; byte counts are totals over all ranks"}
@@ -483,7 +539,8 @@ def run_ours(args, wl):
         return res
 
     main = measure(wl, args.data, args.steps, args.warmup, True)
-    nf, npart, gside, spec = len(wl["fields"]), wl["nside"] ** 3, main["grid"], main["spec"]
+    nf, gside, spec = len(wl["fields"]), main["grid"], main["spec"]
+    npart = wl["nside"] ** 3 / (world if wl.get("strong") else 1)
     steps = args.steps
     K = main["kernels_ms_per_step"]
 
@@ -575,7 +632,7 @@ def run_ours(args, wl):
         ms_step = main["ms_per_step"]
         line = {"metric": "MA+Pk snapshot throughput", "value": main["value"], "unit": "particles/s", "n_gpus": world,
                 "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-                "s_per_snapshot": ms_step * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "s_per_snapshot": ms_step * 1e-3, "higher_is_better": True, "scaling": "strong" if wl.get("strong") else "weak", "vs_baseline": None,
                 "dtype": "f32", "data": ("synthetic uniform random particles" if args.data == "uniform" else
                                          "synthetic Zel'dovich-displaced lattice (rms 2 cells, lattice order)") + " generated on device, seed 1+rank",
                 "config": workload_config(args, wl, world), "clocks": main["clocks"], "gpu_launches": main["launches"],

@@ -211,10 +211,6 @@ int pylb_fft_slab_x(void *data, int dims, int ny_local, void *work, size_t work_
 /* Slab transpose pack: src complex [nx_local][dims][nz] -> dst [G][nx_local][dims/G][nz], i.e. the
  * send buffer of the all-to-all, block g going to rank g.  nz = dims/2+1. */
 int pylb_slab_pack(const void *src, void *dst, int dims, int nx_local, int G, void *stream);
-/* Same transpose, but written straight into each peer's receive buffer over NVLink (peer-mapped
- * pointers): block g goes to peer_recv[g] + my_rank*nx_local*(dims/G)*nz complex elements. */
-int pylb_slab_pack_push(const void *src, void *const *peer_recv, int dims, int nx_local, int G,
-                        int my_rank, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Power-spectrum binning

@@ -69,7 +69,6 @@ SIGNATURES = {
     "pylb_fft_slab_x_work_bytes": (c_size_t, [c_int, c_int]),
     "pylb_fft_slab_x": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pylb_slab_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "pylb_slab_pack_push": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p]),
     "pylb_pk_finish_tables": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p]),
     "pylb_scale_f32": (c_int, [c_void_p, c_int64, c_float, c_void_p]),
     "pylb_overdensity_mean": (c_int, [c_void_p, c_int64, c_float, c_void_p]),

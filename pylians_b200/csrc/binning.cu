@@ -20,6 +20,9 @@
 //  generic_kernel (any axis, any F <= 8, any subset of kz columns)
 //     One thread per mode, red.global for everything.  Used for the two special columns above and
 //     as the any-axis path.
+#include <map>
+#include <mutex>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include <vector>
@@ -1039,7 +1042,9 @@ static int launch_ring2(const BinGeom &g, const float2 *dk, const Row2 *tab, int
     double *t3 = nullptr;
     const int t3_kz = (kz_hi + 1 + 3) & ~3;                     // kz = 0 .. kz_hi, rows padded to 32 bytes
     const size_t t3_bytes = sizeof(double) * (size_t)nbins3 * R2_T3_VALS * t3_kz;
+    ScratchGuard guard(st);
     PYLB_CHECK(cudaMallocAsync(&t3, t3_bytes, st));
+    guard.add(t3);
     PYLB_CHECK(cudaMemsetAsync(t3, 0, t3_bytes, st));
     long long *trace = nullptr;
     const char *trace_path = getenv("PYLB_RING2_TRACE");
@@ -1054,7 +1059,6 @@ static int launch_ring2(const BinGeom &g, const float2 *dk, const Row2 *tab, int
     PYLB_LAUNCH_CHECK();
     ring2_finish_kernel<<<(unsigned)(((long long)nbins3 * R2_T3_VALS * 32 + 255) / 256), 256, 0, st>>>(g, t3, t3_kz, nbins3, PHASE ? 1 : 0);
     PYLB_LAUNCH_CHECK();
-    cudaFreeAsync(t3, st);
     if (trace) {                                // debugging aid: dump the per-span timeline (synchronises)
         std::vector<long long> h(5 * (size_t)nitems);
         PYLB_CHECK(cudaStreamSynchronize(st));
@@ -1423,7 +1427,15 @@ struct Ring2Cache {
     Row2 *tab = nullptr;
     cudaEvent_t ready = nullptr;
 };
-static Ring2Cache g_ring2_cache[16];
+// A few tables per device (a caller alternating between two grid sizes, or Pk and a slab engine, no longer rebuilds one
+// every call), replaced round-robin; guarded by a mutex because host threads may share a device.
+constexpr int R2_CACHE_WAYS = 4;
+struct Ring2DeviceCache {
+    Ring2Cache way[R2_CACHE_WAYS];
+    int next = 0;
+};
+static std::mutex g_ring2_mutex;
+static std::map<int, Ring2DeviceCache> g_ring2_cache;      // keyed by the full device ordinal
 
 // one field, even dims, default arithmetic, no write-back: parity-split row table + ring2_kernel
 static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cudaStream_t st) {
@@ -1441,12 +1453,18 @@ static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cuda
     // keep the last one per device (24 B per row; rebuilding costs a radix sort of N^2 keys and ~8 launches).
     int dev = 0;
     PYLB_CHECK(cudaGetDevice(&dev));
-    Ring2Cache &c = g_ring2_cache[dev & 15];
     Ring2Key key;
     memset(&key, 0, sizeof(key));               // the struct has padding and is compared with memcmp
     key.dims = g.dims; key.x0 = g.x0; key.nx = g.nx; key.y0 = g.y0; key.ny = g.ny;
     key.stride_x = g.stride_x; key.stride_y = g.stride_y; key.bp = bp; key.mas = g.mas_idx[0];
-    if (!c.tab || memcmp(&c.key, &key, sizeof(key)) != 0) {
+    std::lock_guard<std::mutex> lock(g_ring2_mutex);       // held until the kernels using the table are queued on `st`
+    Ring2DeviceCache &dc = g_ring2_cache[dev];
+    Ring2Cache *hit = nullptr;
+    for (auto &w : dc.way)
+        if (w.tab && memcmp(&w.key, &key, sizeof(key)) == 0) hit = &w;
+    if (!hit) {
+        Ring2Cache &c = dc.way[dc.next];
+        dc.next = (dc.next + 1) % R2_CACHE_WAYS;
         if (c.tab) { cudaFree(c.tab); c.tab = nullptr; }          // synchronises: nobody is reading it any more
         if (!c.ready) PYLB_CHECK(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
         unsigned *buf = nullptr;
@@ -1457,8 +1475,11 @@ static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cuda
         PYLB_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned *)nullptr, (unsigned *)nullptr,
                                                    (unsigned *)nullptr, (unsigned *)nullptr, nrows, 0, par_bit + 1, st));
         PYLB_CHECK(cudaMalloc(&c.tab, sizeof(Row2) * (size_t)nrows));
+        ScratchGuard guard(st);
         PYLB_CHECK(cudaMallocAsync(&buf, sizeof(unsigned) * 4 * (size_t)nrows, st));
+        guard.add(buf);
         PYLB_CHECK(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st));
+        guard.add(tmp);
         unsigned *k_in = buf, *v_in = buf + nrows, *k_out = buf + 2 * (size_t)nrows, *v_out = buf + 3 * (size_t)nrows;
         const unsigned blocks = (unsigned)((nrows + 255) / 256);
         row_keys2_kernel<<<blocks, 256, 0, st>>>(k_in, v_in, nrows, g, bp, par_bit);
@@ -1467,16 +1488,18 @@ static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cuda
         count_launch(3);
         row_table2_kernel<<<blocks, 256, 0, st>>>(k_out, v_out, c.tab, nrows, g, par_bit);
         PYLB_LAUNCH_CHECK();
-        cudaFreeAsync(buf, st);
-        cudaFreeAsync(tmp, st);
         PYLB_CHECK(cudaEventRecord(c.ready, st));
         c.key = key;
+        hit = &c;
     } else {
-        PYLB_CHECK(cudaStreamWaitEvent(st, c.ready, 0));           // built on another stream, perhaps
+        PYLB_CHECK(cudaStreamWaitEvent(st, hit->ready, 0));        // built on another stream, perhaps
     }
+    Ring2Cache &c = *hit;
     Row2 *tab = c.tab;
     int *counter = nullptr;
+    ScratchGuard guard(st);
     PYLB_CHECK(cudaMallocAsync(&counter, 16, st));
+    guard.add(counter);
 
     special2_kernel<<<dim3((unsigned)((nrows + 255) / 256), (g.middle > 0) ? 2 : 1), 256, 0, st>>>(g, dk.p[0], tab, nrows, want_phase);
     PYLB_LAUNCH_CHECK();
@@ -1486,7 +1509,6 @@ static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cuda
         rc = want_phase ? launch_ring2<true>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, st)
                         : launch_ring2<false>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, st);
     }
-    cudaFreeAsync(counter, st);
     return rc;
 }
 
@@ -1506,9 +1528,13 @@ static int run_ring(const BinGeom &g, const FieldPtrs &dk, int want_phase, int w
     const int end_bit = bits_for((unsigned)kmaxsq);
     PYLB_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned *)nullptr, (unsigned *)nullptr,
                                                (unsigned *)nullptr, (unsigned *)nullptr, nrows, 0, end_bit, st));
+    ScratchGuard guard(st);
     PYLB_CHECK(cudaMallocAsync(&buf, sizeof(unsigned) * 4 * (size_t)nrows, st));
+    guard.add(buf);
     PYLB_CHECK(cudaMallocAsync(&tab, sizeof(RowEnt) * (size_t)nrows, st));
+    guard.add(tab);
     PYLB_CHECK(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st));
+    guard.add(tmp);
     unsigned *k_in = buf, *v_in = buf + nrows, *k_out = buf + 2 * (size_t)nrows, *v_out = buf + 3 * (size_t)nrows;
     const unsigned blocks = (unsigned)((nrows + 255) / 256);
     row_keys_kernel<<<blocks, 256, 0, st>>>(k_in, v_in, nrows, g);
@@ -1529,9 +1555,6 @@ static int run_ring(const BinGeom &g, const FieldPtrs &dk, int want_phase, int w
                      (kz_hi >= 1 && launch_ring_f<3>(g, dk, tab, nrows, kz_hi, want_phase, write_back, precise, st)); break;
         default: set_error("ring binning supports 1..3 fields, got %d", g.F);
     }
-    cudaFreeAsync(buf, st);
-    cudaFreeAsync(tab, st);
-    cudaFreeAsync(tmp, st);
     return rc;
 }
 
@@ -1605,7 +1628,9 @@ extern "C" int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int ax
     }
     double *tab = nullptr;
     const int ntab = F * (L.middle + 1);
+    ScratchGuard guard(st);
     PYLB_CHECK(cudaMallocAsync(&tab, sizeof(double) * (size_t)ntab, st));
+    guard.add(tab);
     g.mas_tab = tab;
     mas_table_kernel<<<(ntab + 127) / 128, 128, 0, st>>>(tab, L.middle, ks->dims, F, g);
     PYLB_LAUNCH_CHECK();
@@ -1626,6 +1651,5 @@ extern "C" int pylb_pk_bin(void *const *dk, int F, const pylb_kspace *ks, int ax
         timing_end(PYLB_T_GENERIC, st);
     }
     timing_end(PYLB_T_BIN, st);
-    cudaFreeAsync(tab, st);
     return rc;
 }

@@ -66,39 +66,28 @@ __global__ void add_f32_kernel(float *__restrict__ dst, const float *__restrict_
 // ------------------------------------------------------------------------------------------------
 template <typename V>
 __global__ void __launch_bounds__(256)
-slab_pack_kernel(const V *__restrict__ src, V *__restrict__ dst, V *const *peer, long long blk,
-                 int nx, int G, int my_rank) {
+slab_pack_kernel(const V *__restrict__ src, V *__restrict__ dst, long long blk, int nx, int G) {
     // blk = ny_loc*nz in units of V
     const int ix = blockIdx.y, gq = blockIdx.z;
     const V *s = src + ((long long)ix * G + gq) * blk;
-    V *d = peer ? peer[gq] + ((long long)my_rank * nx + ix) * blk : dst + ((long long)gq * nx + ix) * blk;
+    V *d = dst + ((long long)gq * nx + ix) * blk;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < blk; i += (long long)gridDim.x * blockDim.x)
         d[i] = s[i];
 }
 
-static int slab_pack_impl(const void *src, void *dst, void *const *peer, int dims, int nx, int G, int my_rank,
-                          cudaStream_t st) {
+static int slab_pack_impl(const void *src, void *dst, int dims, int nx, int G, cudaStream_t st) {
     PYLB_REQUIRE(G >= 1 && dims % G == 0 && nx >= 1, "pylb_slab_pack: dims must be divisible by G");
     const long long nz = dims / 2 + 1, blk = (long long)(dims / G) * nz;  // complex elements per block
     int bx = (int)((blk + 256 * 8 - 1) / (256 * 8));
     if (bx < 1) bx = 1;
     if (bx > 64) bx = 64;
     dim3 grid(bx, nx, G);
-    void *const *dpeer = nullptr;
-    void **dtmp = nullptr;
-    if (peer) {
-        PYLB_CHECK(cudaMallocAsync(&dtmp, sizeof(void *) * G, st));
-        PYLB_CHECK(cudaMemcpyAsync(dtmp, peer, sizeof(void *) * G, cudaMemcpyHostToDevice, st));
-        dpeer = dtmp;
-    }
-    bool v16 = (blk % 2 == 0) && (((uintptr_t)src & 15) == 0) && (peer || ((uintptr_t)dst & 15) == 0);
-    if (peer) for (int i = 0; i < G; i++) v16 = v16 && (((uintptr_t)peer[i] & 15) == 0);
+    const bool v16 = (blk % 2 == 0) && (((uintptr_t)src & 15) == 0) && (((uintptr_t)dst & 15) == 0);
     if (v16)
-        slab_pack_kernel<float4><<<grid, 256, 0, st>>>((const float4 *)src, (float4 *)dst, (float4 *const *)dpeer, blk / 2, nx, G, my_rank);
+        slab_pack_kernel<float4><<<grid, 256, 0, st>>>((const float4 *)src, (float4 *)dst, blk / 2, nx, G);
     else
-        slab_pack_kernel<float2><<<grid, 256, 0, st>>>((const float2 *)src, (float2 *)dst, (float2 *const *)dpeer, blk, nx, G, my_rank);
+        slab_pack_kernel<float2><<<grid, 256, 0, st>>>((const float2 *)src, (float2 *)dst, blk, nx, G);
     PYLB_LAUNCH_CHECK();
-    if (dtmp) cudaFreeAsync(dtmp, st);
     return 0;
 }
 
@@ -251,11 +240,6 @@ extern "C" int pylb_add_f32(float *dst, const float *src, int64_t n, void *strea
 
 extern "C" int pylb_slab_pack(const void *src, void *dst, int dims, int nx_local, int G, void *stream) {
     PYLB_REQUIRE(src && dst, "pylb_slab_pack: NULL pointer");
-    return slab_pack_impl(src, dst, nullptr, dims, nx_local, G, 0, (cudaStream_t)stream);
+    return slab_pack_impl(src, dst, dims, nx_local, G, (cudaStream_t)stream);
 }
 
-extern "C" int pylb_slab_pack_push(const void *src, void *const *peer_recv, int dims, int nx_local, int G,
-                                   int my_rank, void *stream) {
-    PYLB_REQUIRE(src && peer_recv && my_rank >= 0 && my_rank < G, "pylb_slab_pack_push: bad arguments");
-    return slab_pack_impl(src, nullptr, peer_recv, dims, nx_local, G, my_rank, (cudaStream_t)stream);
-}

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/pylians_b200.h"
@@ -45,10 +46,16 @@ void timing_end(int which, cudaStream_t st);
 // The library's scratch comes from the stream-ordered allocator.  Its default pool hands unused memory back to
 // the driver at every synchronisation (release threshold 0), and Pk() synchronises once per call to read the bins:
 // without this the next call's cudaMallocAsync goes back to the driver (sporadic 30-700 ms stalls were measured).
+// This raises the release threshold of the DEVICE'S DEFAULT POOL, i.e. for the whole process: memory that this
+// library (or the host application) frees with cudaFreeAsync stays cached in the pool instead of going back to the
+// driver.  Set PYLB_KEEP_POOL=0 to leave the pool's threshold alone.
 inline void keep_pool_memory() {
     static bool done[64] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    done[dev] = true;
+    const char *e = getenv("PYLB_KEEP_POOL");
+    if (e && e[0] == '0') return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         unsigned long long keep = ~0ull;
@@ -56,6 +63,18 @@ inline void keep_pool_memory() {
     }
     done[dev] = true;
 }
+
+// Stream-ordered scratch that is released on every way out of a function, error returns included.
+struct ScratchGuard {
+    cudaStream_t st;
+    void *p[8];
+    int n = 0;
+    explicit ScratchGuard(cudaStream_t s) : st(s) {}
+    void add(void *q) { if (q && n < 8) p[n++] = q; }
+    ~ScratchGuard() { for (int i = 0; i < n; i++) cudaFreeAsync(p[i], st); }
+    ScratchGuard(const ScratchGuard &) = delete;
+    ScratchGuard &operator=(const ScratchGuard &) = delete;
+};
 
 inline int sm_count() {
     static int n = 0;

@@ -139,6 +139,19 @@ class CudaOps(object):
         return out
 
 
+class ParticleBatches(object):
+    """A rank's particles as a sequence of (pos, W) batches produced on demand (a snapshot read file by file, a synthetic
+    set generated in pieces): what `SlabPk.density_slab` takes when the shard does not fit in HBM next to the grid.
+    make(i) -> (pos (n_i, 3) float32, W (n_i,) float32 or None); total = particles of this rank over all batches."""
+
+    def __init__(self, make, nbatches, total):
+        self.make, self.nbatches, self.total = make, int(nbatches), int(total)
+
+    def __iter__(self):
+        for i in range(self.nbatches):
+            yield self.make(i)
+
+
 def _group_info(group):
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
@@ -175,7 +188,7 @@ class SlabPk(object):
              overlaps the transfer of the next; must be the same on every rank."""
         self.exchange = exchange
         self.exchange_chunks = max(1, int(exchange_chunks))
-        self._auto_mode = None
+        self._auto_mode = {}
         self.rank, self.G = _group_info(group)
         self.group = group
         if dims % self.G != 0:
@@ -186,30 +199,35 @@ class SlabPk(object):
 
     # ---- stage 1: particles -> overdensity slab --------------------------------------------------
     def density_slab(self, pos, W=None, MAS=None, overdensity=True):
-        """Deposit this rank's particles and return the x-slab this rank owns (optionally as overdensity)."""
+        """Deposit this rank's particles and return the x-slab this rank owns (optionally as overdensity).
+        `pos` is an (n, 3) array / tensor, or a ParticleBatches whose batches are deposited one after the other."""
         ops, N, G = self.ops, self.dims, self.G
         MAS = MAS or self.MAS
         halo = {"NGP": 0, "CIC": 1, "TSC": 2, "PCS": 3}[MAS]
+        batched = isinstance(pos, ParticleBatches)
+        count = pos.total if batched else int(pos.shape[0])
         mode = self.exchange
         if mode == "auto":
             # Whichever moves fewer bytes per rank: 4 N^3 (reduce-scatter of the partial grids, which also have to be
             # zeroed and flushed in full) against 16 B per particle (all-to-all of the routed payload).  Measured on
             # 8xB200, 512^3 particles per GPU (profiles/r1_dist_stages_8gpu.txt): N=1024, G=8: particles 14.4 ms vs grid
             # 20.8 ms per snapshot; N=640, G=2: grid 9.7 vs particles 13.7 ms; 2048^3 PCS, G=8: particles 219 vs 295 ms.
-            # Every rank must take the same branch, so the particle count is agreed on once (max over ranks) and the
-            # choice is kept for the engine's lifetime.
-            if self._auto_mode is None:
-                npmax = int(pos.shape[0])
+            # Every rank must take the same branch, so the particle count is agreed on (max over ranks); the choice is
+            # kept per (scheme, particle-count magnitude), and a stencil wider than a rank's slab always takes "grid".
+            key = (MAS, count.bit_length())
+            if key not in self._auto_mode:
+                npmax = count
                 if G > 1:
                     t = torch.tensor([npmax], dtype=torch.int64, device=getattr(ops, "dev", torch.device("cpu")))
                     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-                    npmax = int(t.item())
+                    npmax = int(t[0].item())
                 ok = G > 1 and self.nxl >= max(halo, 1)
-                self._auto_mode = "particles" if (ok and 4 * N ** 3 > 16 * npmax) else "grid"
-            mode = self._auto_mode
+                self._auto_mode[key] = "particles" if (ok and 4 * N ** 3 > 16 * npmax) else "grid"
+            mode = self._auto_mode[key]
         if mode == "particles" and self.nxl < halo:
             raise ValueError("particle exchange needs at least %d planes per rank for %s" % (halo, MAS))
-        slab = self._slab_from_particles(pos, W, MAS, halo) if mode == "particles" else self._slab_from_grids(pos, W, MAS)
+        batches = pos if batched else [(pos, W)]
+        slab = self._slab_from_particles(batches, MAS, halo) if mode == "particles" else self._slab_from_grids(batches, MAS)
         if overdensity:
             total = ops.grid_sum(slab)
             if G > 1:
@@ -217,10 +235,11 @@ class SlabPk(object):
             ops.overdensity_apply(slab, total, N ** 3)
         return slab
 
-    def _slab_from_grids(self, pos, W, MAS):
+    def _slab_from_grids(self, batches, MAS):
         ops, N, G = self.ops, self.dims, self.G
         partial = ops.zeros((N, N, N))
-        ops.deposit(pos, W, partial, self.BoxSize, MAS)
+        for pos, W in batches:
+            ops.deposit(pos, W, partial, self.BoxSize, MAS)
         slab = ops.empty((self.nxl, N, N))
         _reduce_scatter_sum(slab, partial, self.group, G)
         return slab
@@ -228,25 +247,49 @@ class SlabPk(object):
     def _peer(self, g):
         return dist.get_global_rank(self.group, g) if self.group is not None else g
 
-    def _slab_from_particles(self, pos, W, MAS, halo):
+    def _slab_from_particles(self, batches, MAS, halo):
         """Route every particle to the rank owning its lowest touched x-plane and deposit there.
 
         The routed payload moves in `exchange_chunks` pieces: all pieces are queued on NCCL's stream at once (grouped
         send/recv = all-to-all), and the windowed deposit of piece c runs on the compute stream as soon as piece c has
         arrived, i.e. while piece c+1 is still crossing NVLink.  MA only ever adds into the grid, so depositing in
-        pieces changes nothing but the fp32 summation order."""
+        pieces (and in batches) changes nothing but the fp32 summation order."""
         ops, N, G, r = self.ops, self.dims, self.G, self.rank
-        send, offsets = ops.partition(pos, W, self.BoxSize, MAS, G, N)
         if G == 1:
             grid = ops.zeros((self.nxl, N, N))                    # the window is the whole periodic cube
-            ops.deposit_window(send, grid, 0, self.BoxSize, MAS, W is not None, N)
+            for pos, W in batches:
+                send, _ = ops.partition(pos, W, self.BoxSize, MAS, G, N)
+                ops.deposit_window(send, grid, 0, self.BoxSize, MAS, W is not None, N)
             return grid
-        off = offsets.to("cpu").tolist()                          # G+1 ints: the split sizes must be known on the host
-        send_tot = [off[g + 1] - off[g] for g in range(G)]
-        t_send = torch.tensor(send_tot, dtype=torch.int64, device=send.device)
-        t_recv = torch.empty_like(t_send)
-        dist.all_to_all_single(t_recv, t_send, group=self.group)
-        recv_tot = t_recv.to("cpu").tolist()
+        grid = ops.zeros((self.nxl + halo, N, N))
+        for pos, W in batches:
+            self._route_and_deposit(pos, W, MAS, grid)
+        if halo:
+            mine = grid[self.nxl:]                                # planes that belong to the next rank
+            got = torch.empty_like(mine)
+            nxt, prv = self._peer((r + 1) % G), self._peer((r - 1) % G)
+            reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, mine, nxt, group=self.group),
+                                           dist.P2POp(dist.irecv, got, prv, group=self.group)])
+            for q in reqs:
+                q.wait()
+            ops.add(grid[:halo], got)
+        return grid[: self.nxl]
+
+    def _route_and_deposit(self, pos, W, MAS, grid):
+        """One batch: partition by owner, exchange in pieces, deposit every piece onto this rank's window `grid`."""
+        ops, N, G, r = self.ops, self.dims, self.G, self.rank
+        send, offsets = ops.partition(pos, W, self.BoxSize, MAS, G, N)
+        # the split sizes must be known on the host: every rank's G counts are gathered on the device and read back with
+        # ONE device-to-host copy (row s = what rank s sends to each destination)
+        counts = (offsets[1:] - offsets[:-1]).to(torch.int64)
+        table = torch.empty(G * G, dtype=torch.int64, device=counts.device)          # flat: gloo wants a 1-D output
+        dist.all_gather_into_tensor(table, counts.contiguous(), group=self.group)
+        table = table.view(G, G).to("cpu").tolist()
+        send_tot = table[r]
+        recv_tot = [table[s_][r] for s_ in range(G)]
+        off = [0]
+        for g in range(G):
+            off.append(off[-1] + send_tot[g])
         K = self.exchange_chunks
 
         def part(c, total):                                       # rows [lo, hi) of a `total`-row range that travel in piece c
@@ -271,23 +314,12 @@ class SlabPk(object):
                 if hi > lo and g != r:
                     p2p.append(dist.P2POp(dist.isend, send[off[g] + lo:off[g] + hi], self._peer(g), group=self.group))
             pieces.append((buf, dist.batch_isend_irecv(p2p) if p2p else []))
-        grid = ops.zeros((self.nxl + halo, N, N))
         for buf, reqs in pieces:
             for q in reqs:
                 q.wait()
             if buf.shape[0]:
                 ops.deposit_window(buf, grid, r * self.nxl, self.BoxSize, MAS, W is not None, N)
         del pieces, send
-        if halo:
-            mine = grid[self.nxl:]                                # planes that belong to the next rank
-            got = torch.empty_like(mine)
-            nxt, prv = self._peer((r + 1) % G), self._peer((r - 1) % G)
-            reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, mine, nxt, group=self.group),
-                                           dist.P2POp(dist.irecv, got, prv, group=self.group)])
-            for q in reqs:
-                q.wait()
-            ops.add(grid[:halo], got)
-        return grid[: self.nxl]
 
     # ---- stage 2: x-slab (real) -> ky-slab (k-space, transposed) --------------------------------
     def fft_slab(self, slab):

@@ -9,7 +9,8 @@ Built differently from the reference: every file is indexed ONCE (`SnapFile`: re
 markers, either byte order, format-2 labels), blocks are read with `readinto` straight into a caller-supplied
 buffer (the snapshot drivers pass pinned host tensors, so a block goes disk -> pinned memory -> HBM with no
 intermediate copy), and particle totals are taken from the per-file counts, so snapshots with more than 2^32
-particles of a type (2048^3, the north-star size; header `nall` is 32-bit) need no manual override.
+particles of a type (2048^3, the north-star size; header `nall` is 32-bit) need no manual override; records of
+4 GiB or more, whose Fortran markers wrap modulo 2^32, are indexed by trying the wrapped lengths.
 
 This is host-side I/O: no arithmetic beyond the reference's unit conversions.  HDF5 snapshots need `h5py`, which
 this image does not have; those paths raise ImportError instead of guessing.
@@ -51,6 +52,7 @@ def fname_format(snapshot):
 
 class SnapFile(object):
     """One binary Gadget file, indexed once: byte order, format (1|2), header, and the table of data records."""
+    _MARKER_MOD = 1 << 32            # Fortran record markers are 32-bit: lengths wrap modulo this (a test shrinks it)
 
     def __init__(self, path):
         self.path = path
@@ -78,9 +80,17 @@ class SnapFile(object):
                     label = f.read(4).decode("ascii", "replace")
                     pos += 16
                     continue
-                f.seek(pos + 4 + n)
-                tail = f.read(4)
-                if len(tail) < 4 or int(np.frombuffer(tail, u4)[0]) != n:      # readsnap.py:146-148
+                # a record of 4 GiB or more (the POS block of one 2048^3 file is 103 GB) carries its length modulo 2^32
+                # in both markers: the true length is the first n + k 2^32 whose trailing marker repeats the leading one
+                low, ok = n, False
+                while pos + 8 + n <= size:
+                    f.seek(pos + 4 + n)
+                    tail = f.read(4)
+                    if len(tail) == 4 and int(np.frombuffer(tail, u4)[0]) == low:
+                        ok = True
+                        break
+                    n += self._MARKER_MOD
+                if not ok:                                                     # readsnap.py:146-148
                     raise IOError("something wrong: record markers of %s disagree at byte %d" % (path, pos))
                 self.records.append((label, pos + 4, n))
                 label = None

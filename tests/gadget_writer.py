@@ -5,6 +5,9 @@ by 4-byte Fortran record markers; format 2 adds a 16-byte label record in front 
 import numpy as np
 
 
+MARKER_MOD = 1 << 32      # record markers hold the length modulo this (tests of >= 4 GiB records shrink it)
+
+
 def _record(f, payload, order, label=None, fmt=1):
     u4 = np.dtype(order + "u4")
     if fmt == 2:
@@ -12,9 +15,9 @@ def _record(f, payload, order, label=None, fmt=1):
         f.write(label.encode("ascii"))
         f.write(np.array([len(payload) + 8], u4).tobytes())
         f.write(np.array([8], u4).tobytes())
-    f.write(np.array([len(payload)], u4).tobytes())
+    f.write(np.array([len(payload) % MARKER_MOD], u4).tobytes())
     f.write(payload)
-    f.write(np.array([len(payload)], u4).tobytes())
+    f.write(np.array([len(payload) % MARKER_MOD], u4).tobytes())
 
 
 def make_particles(seed, counts, box_kpc, masstable, clustered=False):

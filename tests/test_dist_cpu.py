@@ -119,6 +119,49 @@ def _worker_uneven(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_batches(rank, world, port, q):
+    """A rank's particles handed over as ParticleBatches (deposited batch after batch into one window / partial grid)
+    give the slab of a single call, in both exchange modes."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import parity
+        from cpu_slab_ops import CpuOps
+        from pylians_b200.dist import SlabPk, ParticleBatches
+        dims, box, mas = 16, 500.0, "TSC"
+        rng = np.random.default_rng(23)
+        pos = (rng.random((4 * dims ** 3, 3)) * box).astype(np.float32)[rank::world]
+        W = (rng.random(len(pos)) + 0.5).astype(np.float32)
+        cuts = [0, 1000, 1001, len(pos) // 2, len(pos)]           # uneven batches, one of a single particle
+        for mode in ("grid", "particles", "auto"):
+            eng = SlabPk(dims, box, mas, 2, ops=CpuOps(), exchange=mode)
+            one = eng.density_slab(pos, W, overdensity=False)
+            pb = ParticleBatches(lambda i: (pos[cuts[i]:cuts[i + 1]], W[cuts[i]:cuts[i + 1]]), len(cuts) - 1, len(pos))
+            many = eng.density_slab(pb, None, overdensity=False)
+            parity.assert_grid_close(many.numpy(), one.numpy(), "batched vs single deposit, %s" % mode, rtol=1e-5)
+        q.put((rank, "ok"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_particle_batches_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_batches, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == "ok", "rank %d failed:\n%s" % (rank, msg)
+
+
 def test_particle_exchange_pieces_world4_uneven_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -58,6 +58,18 @@ def test_reader_returns_what_was_written(tmp_path, parts, fmt, order, nfiles):
     assert RG.read_field(names[0], "MASS", 1).dtype == np.float32
 
 
+def test_records_longer_than_the_marker_range(tmp_path, parts, monkeypatch):
+    """A block of 4 GiB or more wraps its 32-bit Fortran markers (the POS block of one 2048^3 file is 103 GB).  Same
+    logic with the modulus shrunk to 4096 bytes, so that every particle block of a small file wraps several times."""
+    monkeypatch.setattr(GW, "MARKER_MOD", 4096)
+    monkeypatch.setattr(RG.SnapFile, "_MARKER_MOD", 4096)
+    base = str(tmp_path / "snap_wrap")
+    GW.write_snapshot(base, parts, MASSTABLE, BOX, Z, 1, 1, "<")
+    for pt in (0, 1, 4):
+        for block in ("POS ", "VEL ", "ID  "):
+            np.testing.assert_array_equal(RG.read_block(base, block, [pt]), _expect(parts, block, pt, 1 / (1 + Z)))
+
+
 def test_errors(tmp_path, parts):
     with pytest.raises(Exception, match="File not found"):
         RG.header(str(tmp_path / "nothing_here"))
