@@ -201,16 +201,19 @@ int pylb_xi_bin(const float *xi, int dims, int axis, double *sums, void *stream)
 int pylb_swap_axes(const float *in, float *out, int dims, int axis, int64_t out_pitch, void *stream);
 
 /* Slab-decomposed pieces (multi-GPU).  Real slab [nx_local][dims][dims] -> batched 2-D R2C over
- * (y,z) -> complex [nx_local][dims][dims/2+1]; then, after the all-to-all, 1-D C2C along x on the
- * transposed layout [dims][ny_local][dims/2+1] (in place). */
-size_t pylb_fft_slab_yz_work_bytes(int dims, int nx_local);
-int pylb_fft_slab_yz(const float *in, void *out, int dims, int nx_local, void *work, size_t work_bytes, void *stream);
-size_t pylb_fft_slab_x_work_bytes(int dims, int ny_local);
-int pylb_fft_slab_x(void *data, int dims, int ny_local, void *work, size_t work_bytes, void *stream);
+ * (y,z) -> complex [nx_local][dims][pitch]; then, after the all-to-all, 1-D C2C along x on the
+ * transposed layout [dims][ny_local][pitch] (in place).  `pitch` = complex elements per kz-row, >= dims/2+1; the slab
+ * engine uses the next even number, so that every row starts on a 16-byte boundary for the binning kernel (the padding
+ * column travels with its row and is never read as a mode). */
+size_t pylb_fft_slab_yz_work_bytes(int dims, int nx_local, int64_t out_pitch);
+int pylb_fft_slab_yz(const float *in, void *out, int dims, int nx_local, int64_t out_pitch, void *work, size_t work_bytes,
+                     void *stream);
+size_t pylb_fft_slab_x_work_bytes(int dims, int ny_local, int64_t pitch);
+int pylb_fft_slab_x(void *data, int dims, int ny_local, int64_t pitch, void *work, size_t work_bytes, void *stream);
 
-/* Slab transpose pack: src complex [nx_local][dims][nz] -> dst [G][nx_local][dims/G][nz], i.e. the
- * send buffer of the all-to-all, block g going to rank g.  nz = dims/2+1. */
-int pylb_slab_pack(const void *src, void *dst, int dims, int nx_local, int G, void *stream);
+/* Slab transpose pack: src complex [nx_local][dims][pitch] -> dst [G][nx_local][dims/G][pitch], i.e. the
+ * send buffer of the all-to-all, block g going to rank g. */
+int pylb_slab_pack(const void *src, void *dst, int dims, int nx_local, int G, int64_t pitch, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Power-spectrum binning

@@ -64,11 +64,11 @@ SIGNATURES = {
     "pylb_theta_bin": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "pylb_plane_bin": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pylb_xi_bin": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    "pylb_fft_slab_yz_work_bytes": (c_size_t, [c_int, c_int]),
-    "pylb_fft_slab_yz": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "pylb_fft_slab_x_work_bytes": (c_size_t, [c_int, c_int]),
-    "pylb_fft_slab_x": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "pylb_slab_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pylb_fft_slab_yz_work_bytes": (c_size_t, [c_int, c_int, c_int64]),
+    "pylb_fft_slab_yz": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_size_t, c_void_p]),
+    "pylb_fft_slab_x_work_bytes": (c_size_t, [c_int, c_int, c_int64]),
+    "pylb_fft_slab_x": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_size_t, c_void_p]),
+    "pylb_slab_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_void_p]),
     "pylb_pk_finish_tables": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p]),
     "pylb_scale_f32": (c_int, [c_void_p, c_int64, c_float, c_void_p]),
     "pylb_overdensity_mean": (c_int, [c_void_p, c_int64, c_float, c_void_p]),

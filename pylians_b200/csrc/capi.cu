@@ -75,9 +75,9 @@ slab_pack_kernel(const V *__restrict__ src, V *__restrict__ dst, long long blk, 
         d[i] = s[i];
 }
 
-static int slab_pack_impl(const void *src, void *dst, int dims, int nx, int G, cudaStream_t st) {
-    PYLB_REQUIRE(G >= 1 && dims % G == 0 && nx >= 1, "pylb_slab_pack: dims must be divisible by G");
-    const long long nz = dims / 2 + 1, blk = (long long)(dims / G) * nz;  // complex elements per block
+static int slab_pack_impl(const void *src, void *dst, int dims, int nx, int G, long long pitch, cudaStream_t st) {
+    PYLB_REQUIRE(G >= 1 && dims % G == 0 && nx >= 1 && pitch >= dims / 2 + 1, "pylb_slab_pack: dims must be divisible by G");
+    const long long blk = (long long)(dims / G) * pitch;   // complex elements per block (rows keep their pitch)
     int bx = (int)((blk + 256 * 8 - 1) / (256 * 8));
     if (bx < 1) bx = 1;
     if (bx > 64) bx = 64;
@@ -238,8 +238,8 @@ extern "C" int pylb_add_f32(float *dst, const float *src, int64_t n, void *strea
     return 0;
 }
 
-extern "C" int pylb_slab_pack(const void *src, void *dst, int dims, int nx_local, int G, void *stream) {
+extern "C" int pylb_slab_pack(const void *src, void *dst, int dims, int nx_local, int G, int64_t pitch, void *stream) {
     PYLB_REQUIRE(src && dst, "pylb_slab_pack: NULL pointer");
-    return slab_pack_impl(src, dst, dims, nx_local, G, (cudaStream_t)stream);
+    return slab_pack_impl(src, dst, dims, nx_local, G, pitch, (cudaStream_t)stream);
 }
 

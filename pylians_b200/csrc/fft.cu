@@ -75,13 +75,13 @@ static int get_plan(int kind, int dims, long long nloc, long long inplace, Plan 
         long long n[3] = {N, N, N};
         long long inembed[3] = {N, N, nloc}, onembed[3] = {N, N, inplace};
         PYLB_CUFFT(cufftMakePlanMany64(p.h, 3, n, inembed, 1, N * N * nloc, onembed, 1, N * N * inplace, CUFFT_R2C, 1, &p.work));
-    } else if (kind == KIND_SLAB_YZ) {
+    } else if (kind == KIND_SLAB_YZ) {           // inplace = output row pitch in complex elements (>= nz)
         long long n[2] = {N, N};
-        long long inembed[2] = {N, N}, onembed[2] = {N, nz};
-        PYLB_CUFFT(cufftMakePlanMany64(p.h, 2, n, inembed, 1, N * N, onembed, 1, N * nz, CUFFT_R2C, nloc, &p.work));
-    } else {
+        long long inembed[2] = {N, N}, onembed[2] = {N, inplace};
+        PYLB_CUFFT(cufftMakePlanMany64(p.h, 2, n, inembed, 1, N * N, onembed, 1, N * inplace, CUFFT_R2C, nloc, &p.work));
+    } else {                                     // KIND_SLAB_X: inplace = row pitch; the padding column rides along
         long long n[1] = {N};
-        const long long batch = (long long)nloc * nz;
+        const long long batch = (long long)nloc * inplace;
         long long embed[1] = {N};
         PYLB_CUFFT(cufftMakePlanMany64(p.h, 1, n, embed, batch, 1, embed, batch, 1, CUFFT_C2C, batch, &p.work));
     }
@@ -144,17 +144,17 @@ extern "C" int pylb_fft_r2c_pitched(const float *in, int64_t in_pitch, void *out
     return 0;
 }
 
-extern "C" size_t pylb_fft_slab_yz_work_bytes(int dims, int nx_local) {
+extern "C" size_t pylb_fft_slab_yz_work_bytes(int dims, int nx_local, int64_t out_pitch) {
     Plan *p = nullptr;
-    if (dims < 2 || nx_local < 1 || get_plan(KIND_SLAB_YZ, dims, nx_local, 0, &p)) return (size_t)-1;
+    if (dims < 2 || nx_local < 1 || out_pitch < dims / 2 + 1 || get_plan(KIND_SLAB_YZ, dims, nx_local, out_pitch, &p)) return (size_t)-1;
     return p->work;
 }
 
-extern "C" int pylb_fft_slab_yz(const float *in, void *out, int dims, int nx_local, void *work, size_t work_bytes,
-                                void *stream) {
-    PYLB_REQUIRE(dims >= 2 && nx_local >= 1, "pylb_fft_slab_yz: bad shape");
+extern "C" int pylb_fft_slab_yz(const float *in, void *out, int dims, int nx_local, int64_t out_pitch, void *work,
+                                size_t work_bytes, void *stream) {
+    PYLB_REQUIRE(dims >= 2 && nx_local >= 1 && out_pitch >= dims / 2 + 1, "pylb_fft_slab_yz: bad shape");
     Plan *p = nullptr;
-    if (get_plan(KIND_SLAB_YZ, dims, nx_local, 0, &p)) return 1;
+    if (get_plan(KIND_SLAB_YZ, dims, nx_local, out_pitch, &p)) return 1;
     if (exec_setup(p, work, work_bytes, (cudaStream_t)stream)) return 1;
     timing_begin(PYLB_T_FFT, (cudaStream_t)stream);
     PYLB_CUFFT(cufftExecR2C(p->h, (cufftReal *)in, (cufftComplex *)out));
@@ -163,16 +163,16 @@ extern "C" int pylb_fft_slab_yz(const float *in, void *out, int dims, int nx_loc
     return 0;
 }
 
-extern "C" size_t pylb_fft_slab_x_work_bytes(int dims, int ny_local) {
+extern "C" size_t pylb_fft_slab_x_work_bytes(int dims, int ny_local, int64_t pitch) {
     Plan *p = nullptr;
-    if (dims < 2 || ny_local < 1 || get_plan(KIND_SLAB_X, dims, ny_local, 1, &p)) return (size_t)-1;
+    if (dims < 2 || ny_local < 1 || pitch < dims / 2 + 1 || get_plan(KIND_SLAB_X, dims, ny_local, pitch, &p)) return (size_t)-1;
     return p->work;
 }
 
-extern "C" int pylb_fft_slab_x(void *data, int dims, int ny_local, void *work, size_t work_bytes, void *stream) {
-    PYLB_REQUIRE(dims >= 2 && ny_local >= 1, "pylb_fft_slab_x: bad shape");
+extern "C" int pylb_fft_slab_x(void *data, int dims, int ny_local, int64_t pitch, void *work, size_t work_bytes, void *stream) {
+    PYLB_REQUIRE(dims >= 2 && ny_local >= 1 && pitch >= dims / 2 + 1, "pylb_fft_slab_x: bad shape");
     Plan *p = nullptr;
-    if (get_plan(KIND_SLAB_X, dims, ny_local, 1, &p)) return 1;
+    if (get_plan(KIND_SLAB_X, dims, ny_local, pitch, &p)) return 1;
     if (exec_setup(p, work, work_bytes, (cudaStream_t)stream)) return 1;
     timing_begin(PYLB_T_FFT, (cudaStream_t)stream);
     PYLB_CUFFT(cufftExecC2C(p->h, (cufftComplex *)data, (cufftComplex *)data, CUFFT_FORWARD));

@@ -90,31 +90,36 @@ class CudaOps(object):
         _lib.check(self.lib.pylb_overdensity_apply(slab.data_ptr(), slab.numel(), total.data_ptr(), int(n_total),
                                                    self._stream()), "pylb_overdensity_apply")
 
+    def kpitch(self, dims):
+        """complex elements per kz-row of this engine's k-space buffers: even, so that every row is 16-byte aligned"""
+        nz = dims // 2 + 1
+        return nz + (nz & 1)
+
     def fft_yz(self, slab, dims):
-        nxl, nz = slab.shape[0], dims // 2 + 1
-        out = torch.empty((nxl, dims, nz), dtype=torch.complex64, device=self.dev)
-        wb = self.lib.pylb_fft_slab_yz_work_bytes(dims, nxl)
+        nxl, pitch = slab.shape[0], self.kpitch(dims)
+        out = torch.empty((nxl, dims, pitch), dtype=torch.complex64, device=self.dev)
+        wb = self.lib.pylb_fft_slab_yz_work_bytes(dims, nxl, pitch)
         work = torch.empty(max(int(wb), 1), dtype=torch.uint8, device=self.dev)
-        _lib.check(self.lib.pylb_fft_slab_yz(slab.data_ptr(), out.data_ptr(), dims, nxl, work.data_ptr(), int(wb),
+        _lib.check(self.lib.pylb_fft_slab_yz(slab.data_ptr(), out.data_ptr(), dims, nxl, pitch, work.data_ptr(), int(wb),
                                              self._stream()), "pylb_fft_slab_yz")
         return out
 
     def pack(self, cplx, dims, G):
-        nxl, nz = cplx.shape[0], dims // 2 + 1
-        send = torch.empty((G, nxl, dims // G, nz), dtype=torch.complex64, device=self.dev)
-        _lib.check(self.lib.pylb_slab_pack(cplx.data_ptr(), send.data_ptr(), dims, nxl, G, self._stream()), "pylb_slab_pack")
+        nxl, pitch = cplx.shape[0], cplx.shape[2]
+        send = torch.empty((G, nxl, dims // G, pitch), dtype=torch.complex64, device=self.dev)
+        _lib.check(self.lib.pylb_slab_pack(cplx.data_ptr(), send.data_ptr(), dims, nxl, G, pitch, self._stream()), "pylb_slab_pack")
         return send
 
     def fft_x(self, recv, dims):
-        nyl = recv.shape[1]
-        wb = self.lib.pylb_fft_slab_x_work_bytes(dims, nyl)
+        nyl, pitch = recv.shape[1], recv.shape[2]
+        wb = self.lib.pylb_fft_slab_x_work_bytes(dims, nyl, pitch)
         work = torch.empty(max(int(wb), 1), dtype=torch.uint8, device=self.dev)
-        _lib.check(self.lib.pylb_fft_slab_x(recv.data_ptr(), dims, nyl, work.data_ptr(), int(wb), self._stream()),
+        _lib.check(self.lib.pylb_fft_slab_x(recv.data_ptr(), dims, nyl, pitch, work.data_ptr(), int(wb), self._stream()),
                    "pylb_fft_slab_x")
 
     def bin(self, fields, dims, axis, mas_index, want_phase, y0, nyl):
-        nz = dims // 2 + 1
-        ks = _lib.KSpace(dims, 0, dims, int(y0), int(nyl), nyl * nz, nz)
+        pitch = fields[0].shape[2]
+        ks = _lib.KSpace(dims, 0, dims, int(y0), int(nyl), nyl * pitch, pitch)
         return PKL.bin_modes(fields, dims, axis, mas_index, want_phase, False, ks=ks)
 
     def overdensity_mean(self, slab, mean):
@@ -333,7 +338,7 @@ class SlabPk(object):
             dist.all_to_all_single(recv, send, group=self.group)
         else:
             recv = send
-        recv = recv.view(N, self.nyl, N // 2 + 1)          # block g holds x in [g N/G, (g+1) N/G)
+        recv = recv.view(N, self.nyl, recv.shape[-1])      # block g holds x in [g N/G, (g+1) N/G); rows keep their pitch
         ops.fft_x(recv, N)
         return recv
 
