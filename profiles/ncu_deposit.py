@@ -8,7 +8,7 @@ dev = torch.device('cuda', 0)
 gen = torch.Generator(device=dev); gen.manual_seed(1)
 pos = torch.rand((N ** 3, 3), device=dev, generator=gen) * 1000.0
 grid = torch.zeros((N,) * 3, device=dev)
-_lib.load().pylb_ma_debug_path(100 * k)
+_lib.load().pylb_ma_debug_path(100 * k if k else -1)
 for _ in range(2):
     MASL.MA(pos, grid, 1000.0, mas)
 torch.cuda.synchronize()
