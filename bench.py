@@ -35,7 +35,7 @@ WORKLOADS = {
     "cfg3_1024_tsc": dict(nside=1024, fields=[("TSC", False)], axis=2),
     "cfg5_1024_xpk": dict(nside=1024, fields=[("CIC", False), ("PCS", True)], axis=2),   # CDM + weighted gas
     # BASELINE configs[3] as written: 2048^3 particles in TOTAL onto a 2048^3 grid at 1 / 2 / 4 / 8 GPUs (strong scaling);
-    # a rank whose share does not fit next to its grid generates and deposits it in batches of 2^28 particles
+    # a rank whose share does not fit next to its grid generates and deposits it in batches of 2^30 particles
     "cfg4_2048_strong": dict(nside=2048, fields=[("PCS", False)], axis=2, strong=True),
     "512_strong": dict(nside=512, fields=[("PCS", False)], axis=2, strong=True, batch=1 << 24),     # the same code path, small
     "512_pcs": dict(nside=512, fields=[("PCS", False)], axis=2),
@@ -335,7 +335,7 @@ class Pipeline(object):
         self.rank = dist.get_rank() if dist is not None else 0
         self.npart = rank_particles(wl, world, self.rank)
         # a share that does not fit next to the grid is generated and deposited batch by batch
-        self.batch = int(wl.get("batch", 1 << 28))
+        self.batch = int(wl.get("batch", 1 << 30))
         self.streamed = bool(wl.get("strong")) and (self.npart * 12 > 24e9 or "batch" in wl)
         if world > 1:
             from pylians_b200 import dist as pdist

@@ -59,8 +59,18 @@ def _to_device(a, dev):
     return t.to(dev, non_blocking=True)
 
 
-HOST_CHUNK = 1 << 26      # particles per H2D chunk when `pos` lives on the host (805 MB of float32 x 3): few enough chunks that the
-                          # fixed costs of a deposit (scans, tile flush) stay small, small enough to double-buffer
+HOST_CHUNK = None         # tests: force a (small) chunk size
+
+
+def _host_chunk(dims, ndim):
+    """Particles per H2D chunk when `pos` lives on the host.  Every chunk is one deposit, and a deposit flushes every tile
+    it touches, so a chunk should not be sparse on the grid (a quarter of a particle per cell at least); 2^26 (805 MB of
+    positions) is enough to hide the fixed costs on small grids, 2^28 (3.2 GB, double-buffered) bounds the staging."""
+    if HOST_CHUNK is not None:
+        return int(HOST_CHUNK)
+    return int(min(max(dims ** ndim // 4, 1 << 26), 1 << 28))
+
+
 _COPY_STREAMS = {}
 
 
@@ -108,7 +118,8 @@ def _deposit(pos, number, BoxSize, mas, W, z_repeat, grid_f64=False, algo=None):
     algo = ALGO if algo is None else algo
     d_grid = _to_device(number, dev) if host_grid else number
     pos_on_dev = _is_torch(pos) and pos.is_cuda
-    if pos_on_dev or npart <= HOST_CHUNK:
+    chunk = _host_chunk(dims, ndim)
+    if pos_on_dev or npart <= chunk:
         d_pos = _to_device(pos, dev)
         d_w = None
         if W is not None:
@@ -127,16 +138,16 @@ def _deposit(pos, number, BoxSize, mas, W, z_repeat, grid_f64=False, algo=None):
         h_w = _as_cpu_tensor(W) if not (_is_torch(W) and W.is_cuda) else None
         d_w_full = W if h_w is None else None
     cs = _copy_stream(dev)
-    bufs = [torch.empty((HOST_CHUNK, ndim), dtype=torch.float32, device=dev) for _ in range(2)]
-    wbufs = [torch.empty(HOST_CHUNK, dtype=torch.float32, device=dev) for _ in range(2)] if h_w is not None else None
+    bufs = [torch.empty((chunk, ndim), dtype=torch.float32, device=dev) for _ in range(2)]
+    wbufs = [torch.empty(chunk, dtype=torch.float32, device=dev) for _ in range(2)] if h_w is not None else None
     copied = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     cs.wait_stream(stream)
-    nchunks = (npart + HOST_CHUNK - 1) // HOST_CHUNK
+    nchunks = (npart + chunk - 1) // chunk
 
     def issue_copy(i):
         b = i % 2
-        lo, hi = i * HOST_CHUNK, min(npart, (i + 1) * HOST_CHUNK)
+        lo, hi = i * chunk, min(npart, (i + 1) * chunk)
         with torch.cuda.stream(cs):
             if i >= 2:
                 cs.wait_event(consumed[b])
@@ -148,7 +159,7 @@ def _deposit(pos, number, BoxSize, mas, W, z_repeat, grid_f64=False, algo=None):
     issue_copy(0)
     for i in range(nchunks):
         b = i % 2
-        lo, hi = i * HOST_CHUNK, min(npart, (i + 1) * HOST_CHUNK)
+        lo, hi = i * chunk, min(npart, (i + 1) * chunk)
         if i + 1 < nchunks:
             issue_copy(i + 1)
         stream.wait_event(copied[b])

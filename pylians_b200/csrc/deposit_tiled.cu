@@ -37,7 +37,18 @@ namespace pylb {
 
 constexpr int TX = 16, TY = 16, TZ = 32;     // cells per tile
 constexpr int CHUNK = 8192;                  // particles per work item
-constexpr int64_t BATCH = 1ll << 28;         // particles sorted per round (bounds the workspace)
+// Particles sorted and deposited per round.  A round flushes every tile it touches (the whole grid plus halo for a
+// space-filling input: ~3 x 4 B per cell of red.global traffic), so it should hold about one particle per cell; the
+// workspace (two float4 payload buffers, 32 B per particle of a round) bounds it from above.  2^28 particles (8.6 GB) up
+// to 640^3 cells, 2^30 (34 GB) from 1024^3 on: 2048^3 particles onto 2048^3 cells went from 47 to 19 ms per 2^28
+// particles of tile kernel when the rounds grew from 2^28 to 2^30 (profiles/r2_bench_2048_strong_1gpu*.json).
+static int64_t round_particles(int dims, int xext) {
+    const int64_t cells = (int64_t)(xext < 0 ? dims : xext) * dims * dims, q = 1ll << 28;
+    int64_t r = (cells + q - 1) / q * q;
+    if (r < q) r = q;
+    if (r > 4 * q) r = 4 * q;
+    return r;
+}
 constexpr int BIN_THREADS = 1024;            // histogram CTAs: one per SM, 32 warps
 constexpr int BIN_MAX_KEYS = 53248;          // per-CTA histogram must fit shared memory (208 KB of 227 KB)
 constexpr int MAX_TILES = 1 << 20;           // two digits of <= 1024 values
@@ -718,6 +729,7 @@ static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static void plan_ws(int64_t np, int dims, int xext, TiledWs *ws, char *base) {
     const int ntiles = tile_geom(dims, 0, xext).ntiles;
+    const int64_t BATCH = round_particles(dims, xext);
     const int64_t nb = np < BATCH ? np : BATCH;
     size_t o = 0, t2 = 0;
     auto take = [&](size_t bytes) { char *p = base ? base + o : nullptr; o += align_up(bytes); return p; };
@@ -800,6 +812,7 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
     if (set_smem(bin_hist_kernel<MAS>, sizeof(int) * (size_t)BIN_MAX_KEYS)) return 1;
     const int kern = g_force_kernel > 0 ? g_force_kernel : env_int("PYLB_TILE_KERNEL", 0);
     const int nt1 = tg.ntiles + 1;
+    const int64_t BATCH = round_particles(dims, xext);
     for (int64_t first = 0; first < np; first += BATCH) {
         const int n = (int)((np - first) < BATCH ? (np - first) : BATCH);
         size_t tb = ws.tmp_bytes;

@@ -183,7 +183,7 @@ class _Result(object):
 class SlabPk(object):
     """Distributed MA + Pk / XPk.  Every rank calls the same methods with its own particle shard."""
 
-    def __init__(self, dims, BoxSize, MAS="CIC", axis=2, group=None, ops=None, exchange="auto", exchange_chunks=2):
+    def __init__(self, dims, BoxSize, MAS="CIC", axis=2, group=None, ops=None, exchange="auto", exchange_chunks=4):
         """exchange: how per-rank deposits become x-slabs --
              "grid"      every rank deposits onto a full partial grid, then reduce-scatter (4 N^3 bytes per rank);
              "particles" particles are routed to the rank owning their lowest touched x-plane (16 B per particle),
@@ -348,8 +348,17 @@ class SlabPk(object):
         mas_index = [PKL.MAS_function(m) for m in mas_list]
         L, sums, counts = ops.bin(fields_k, N, self.axis, mas_index, want_phase, self.rank * self.nyl, self.nyl)
         if G > 1:
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
+            raw = getattr(sums, "_pylb_raw", None)
+            if raw is not None and raw.is_cuda and raw.numel() == L.n_doubles + L.n_counts:
+                # sums and counts share one buffer: ONE all-reduce.  The mode counts travel as float64 (exact below
+                # 2^53) in the words they occupy as int64, and are converted back afterwards.
+                tail = raw[L.n_doubles:]
+                tail.copy_(counts.to(torch.float64))
+                dist.all_reduce(raw, op=dist.ReduceOp.SUM, group=self.group)
+                counts.copy_(tail.clone().round_().to(torch.int64))
+            else:
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+                dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
         return PKL._Bins(L, sums, counts, (self.BoxSize / N ** 2) ** 3 if getattr(sums, "is_cuda", False) else None)
 
     # ---- whole pipelines -------------------------------------------------------------------------
