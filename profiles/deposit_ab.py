@@ -34,7 +34,7 @@ for N in sizes:
     W = torch.rand(N ** 3, device=dev, generator=gen) + 0.5
     grid = torch.zeros((N,) * 3, device=dev)
     for mas in ('NGP', 'CIC', 'TSC', 'PCS'):
-        for k in ((1, 2) if mas == 'PCS' else (1,)):
+        for k in ((1, 2) if mas in ('PCS', 'TSC') else (1,)):
             for w in ((None, W) if mas in ('CIC', 'PCS') else (None,)):
                 lib.pylb_ma_debug_path(100 * k)
                 ma, sort, tile = run(pos, grid, mas, w)

@@ -385,21 +385,25 @@ __global__ void tile_chunks_kernel(const int *__restrict__ tile_begin, int ntile
 constexpr int pad_to(int v, int r) { return v + ((r - v % 32) + 32) % 32; }   // smallest x >= v with x % 32 == r
 
 // Shared-memory tile: SX x SY x SZV cells (tile + S-1 halo cells per axis), z fastest, row pitch PI, plane pitch PL
-// (floats).  For PCS the pitches are chosen so that the cells ONE warp instruction of deposit_lane_kernel updates --
-// lane = (a&1, b, c), x-planes a and a+2 -- fall into 32 distinct banks: bank = 16 a + 4 b + c, i.e. PI = 4, PL = 16 (mod 32).
-template <int MAS>
+// (floats).  For deposit_lane_kernel (LANES) the pitches are chosen so that the cells ONE warp instruction updates fall
+// into distinct banks:
+//   PCS  lane = (a&1, b, c), x-planes a and a+2   bank = 16 a + 4 b + c   PI = 4, PL = 16 (mod 32)
+//   TSC  lane = (a, b, c), 27 lanes               bank = 9 a + 3 b + c    PI = 3, PL = 9
+template <int MAS, bool LANES = false>
 struct TileShape {
     static constexpr int S = Support<MAS>::S;
     static constexpr int SX = TX + S - 1, SY = TY + S - 1, SZV = TZ + S - 1;
-    static constexpr int PI = MAS == PYLB_PCS ? pad_to(SZV, 4) : ((SZV + 3) & ~3);
-    static constexpr int PL = MAS == PYLB_PCS ? pad_to(SY * PI, 16) : SY * PI;
+    static constexpr int RI = MAS == PYLB_PCS ? 4 : 3, RL = MAS == PYLB_PCS ? 16 : 9;
+    static constexpr int PI = LANES ? pad_to(SZV, RI) : ((SZV + 3) & ~3);
+    static constexpr int PL = LANES ? pad_to(SY * PI, RL) : SY * PI;
     static constexpr int CELLS = (SX * PL + 3) & ~3;
     static constexpr int ZV = (SZV + 3) / 4;                       // float4 groups per z-row in the flush
     static constexpr int THREADS = 256;
     static constexpr size_t SMEM = sizeof(float) * (size_t)CELLS;
-    // deposit_lane_kernel: 16 warps per CTA, two CTAs per SM; per-warp staging of the axis weights of 32 particles,
-    // word-major with pitch 33 (bank = word + particle)
+    // deposit_lane_kernel: 16 warps per CTA; per-warp staging of the axis weights of 32 particles, word-major with
+    // pitch 33 (bank = word + particle)
     static constexpr int LANE_THREADS = 512;
+    static constexpr int LANE_CTAS = MAS == PYLB_PCS ? 2 : 3;      // CTAs per SM that fit shared memory
     static constexpr int SW = 3 * S + 1;                           // wx[S], wy[S], wz[S], W
     static constexpr int STAGE_WORDS = SW * 33;
     static constexpr size_t LANE_SMEM = sizeof(float) * ((size_t)CELLS + (size_t)(LANE_THREADS / 32) * STAGE_WORDS);
@@ -433,10 +437,21 @@ __device__ __forceinline__ void flush_tile(float *tile, float *__restrict__ grid
     if ((dims & 3) == 0) {
         for (int i = threadIdx.x; i < TS::SX * TS::SY * TS::ZV; i += THREADS) {
             const int zv = i % TS::ZV, y = (i / TS::ZV) % TS::SY, x = i / (TS::ZV * TS::SY);
-            float4 *cell = reinterpret_cast<float4 *>(tile + x * TS::PL + y * TS::PI + zv * 4);   // PI, PL are multiples of 4
-            const float4 v = *cell;                                // padding words of a row are never written: zero
-            if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
-            *cell = make_float4(0.f, 0.f, 0.f, 0.f);
+            float *row = tile + x * TS::PL + y * TS::PI + zv * 4;
+            float4 v;
+            if constexpr (TS::PI % 4 == 0 && TS::PL % 4 == 0) {
+                v = *reinterpret_cast<float4 *>(row);              // padding words of a row are never written: zero
+                if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+                *reinterpret_cast<float4 *>(row) = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {                                               // rows of odd pitch: scalar loads, masked at the row's end
+                const bool h1 = zv * 4 + 1 < TS::SZV, h2 = zv * 4 + 2 < TS::SZV, h3 = zv * 4 + 3 < TS::SZV;
+                v.x = row[0]; v.y = h1 ? row[1] : 0.f; v.z = h2 ? row[2] : 0.f; v.w = h3 ? row[3] : 0.f;
+                if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+                row[0] = 0.f;
+                if (h1) row[1] = 0.f;
+                if (h2) row[2] = 0.f;
+                if (h3) row[3] = 0.f;
+            }
             int gx = ox + x, gy = oy + y, gz = oz + zv * 4;
             if (tg.xext == dims) { if (gx >= dims) gx -= dims; }
             else if (gx >= tg.xext) continue;   // beyond the x window: nothing was deposited there
@@ -467,10 +482,10 @@ __device__ __forceinline__ void flush_tile(float *tile, float *__restrict__ grid
 }
 
 // tile-local word index of the particle's lowest touched grid point, or -1 (particle routed to the wrong x window: dropped)
-template <int MAS>
+template <int MAS, bool LANES = false>
 __device__ __forceinline__ int base_cell(const float4 q, float inv, const TileGeom &tg, int ox, int oy, int oz,
                                          float (&C)[3][Support<MAS>::S]) {
-    using TS = TileShape<MAS>;
+    using TS = TileShape<MAS, LANES>;
     const int lx = wrap(axis_stencil<MAS>(q.x, inv, C[0]) - tg.x0, tg.dims) - ox;
     if (lx < 0 || lx >= TX) return -1;
     const int ly = wrap(axis_stencil<MAS>(q.y, inv, C[1]), tg.dims) - oy;
@@ -521,47 +536,76 @@ deposit_tile_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, c
     }
 }
 
-// ---- stencil lanes: PCS ----------------------------------------------------------------------------------------------
-// Per batch of 32 particles, lane p evaluates particle p's base cell and its 4 weights per axis exactly like the reference
+// ---- stencil lanes: TSC and PCS --------------------------------------------------------------------------------------
+// Per batch of 32 particles, lane p evaluates particle p's base cell and its S weights per axis exactly like the reference
 // (deposit.cuh) and stages them in a per-warp scratch (word-major, pitch 33: the staging stores and the per-particle reads
-// are both conflict-free).  Then the warp walks the batch: lane (a&1, b, c) forms ((wx[a] * wy[b]) * wz[c]) * W -- the
-// reference's left-to-right fp32 product (MAS_library.pyx:493-497) -- for the x-planes a and a+2 and adds both with one
-// optimistic pair of compare-and-swaps: two loads, two adds, two CAS in flight together; a CAS can only fail when another
-// warp updated the same cell in between, and is then repaired with an ordinary atomicAdd.  1.42x the lane-per-particle
-// kernel at 512^3 (8.1 ms against 11.5 ms, profiles/r2_deposit_variants.txt).
-template <bool HASW>
-__global__ void __launch_bounds__(TileShape<PYLB_PCS>::LANE_THREADS, 2)
+// are both conflict-free).  Then the warp walks the batch: every lane forms ((wx[a] * wy[b]) * wz[c]) * W -- the
+// reference's left-to-right fp32 product (MAS_library.pyx:400-404, 493-497) -- for its own stencil point(s): PCS lane
+// (a&1, b, c) serves the x-planes a and a+2 of one particle, TSC lane (a, b, c) (27 of 32 lanes) one point of two
+// consecutive particles.  Either way a lane has two independent cells per step and adds both with one optimistic pair of
+// compare-and-swaps: two loads, two adds, two CAS in flight together; since one instruction never touches a cell twice, a
+// CAS can only fail when another warp updated the same cell in between (or, for TSC, when the two particles share the
+// cell), and is then repaired with an ordinary atomicAdd.  PCS: 1.42x the lane-per-particle kernel at 512^3 (8.1 ms against
+// 11.5 ms, profiles/r2_deposit_variants.txt).
+template <int MAS, bool HASW>
+__global__ void __launch_bounds__(TileShape<MAS, true>::LANE_THREADS, TileShape<MAS, true>::LANE_CTAS)
 deposit_lane_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, const int *__restrict__ tile_begin,
                     const int *__restrict__ chunk_off, float *__restrict__ grid) {
-    constexpr int MAS = PYLB_PCS;
-    using TS = TileShape<MAS>;
+    static_assert(MAS == PYLB_PCS || MAS == PYLB_TSC, "stencil lanes: TSC and PCS");
+    using TS = TileShape<MAS, true>;
     constexpr int S = TS::S, PB = 32, THREADS = TS::LANE_THREADS, NW = THREADS / 32, SP = PB + 1;
+    constexpr bool PCS = MAS == PYLB_PCS;
     extern __shared__ __align__(16) float tile[];
     __shared__ WorkItem s_w;
     for (int i = threadIdx.x; i < TS::CELLS / 4; i += THREADS) reinterpret_cast<float4 *>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int la = lane >> 4, lb = (lane >> 2) & 3, lc = lane & 3;
+    const bool active = PCS || lane < 27;
+    const int la = PCS ? lane >> 4 : (active ? lane / 9 : 0);
+    const int lb = PCS ? (lane >> 2) & 3 : (active ? (lane / 3) % 3 : 0);
+    const int lc = PCS ? lane & 3 : (active ? lane % 3 : 0);
     unsigned *const cell = reinterpret_cast<unsigned *>(tile) + la * TS::PL + lb * TS::PI + lc;
     float *stage = tile + TS::CELLS + warp * TS::STAGE_WORDS;
-    const float *sx0 = stage + la * SP, *sx1 = stage + (la + 2) * SP;
+    const float *sx0 = stage + la * SP, *sx1 = stage + (PCS ? la + 2 : la) * SP;
     const float *sy = stage + (S + lb) * SP, *sz = stage + (2 * S + lc) * SP, *sw = stage + 3 * S * SP;
-    struct Staged { float x0, x1, y, z, w; int b; };
-    auto fetch = [&](int pp, int b) {
-        Staged q;
-        q.x0 = sx0[pp]; q.x1 = sx1[pp]; q.y = sy[pp]; q.z = sz[pp]; q.w = HASW ? sw[pp] : 1.f; q.b = b;
+    // the two cells of one step: (word offset, value) twice
+    struct Step { int b0, b1; float v0, v1; };
+    auto fetch = [&](int pp, int cell0) {                 // PCS: particle pp, planes a and a+2.  TSC: particles pp and pp+1.
+        Step q;
+        if (PCS) {
+            const float y = sy[pp], z = sz[pp];
+            q.b0 = __shfl_sync(full, cell0, pp); q.b1 = q.b0 + 2 * TS::PL;
+            q.v0 = (sx0[pp] * y) * z; q.v1 = (sx1[pp] * y) * z;
+            if (HASW) { const float w = sw[pp]; q.v0 *= w; q.v1 *= w; }
+        } else {
+            q.b0 = __shfl_sync(full, cell0, pp); q.b1 = __shfl_sync(full, cell0, pp + 1);
+            q.v0 = (sx0[pp] * sy[pp]) * sz[pp]; q.v1 = (sx0[pp + 1] * sy[pp + 1]) * sz[pp + 1];
+            if (HASW) { q.v0 *= sw[pp]; q.v1 *= sw[pp + 1]; }
+        }
         return q;
     };
-    auto apply = [&](const Staged &q) {
-        float v0 = (q.x0 * q.y) * q.z, v1 = (q.x1 * q.y) * q.z;
-        if (HASW) { v0 *= q.w; v1 *= q.w; }
-        unsigned *p0 = cell + q.b, *p1 = p0 + 2 * TS::PL;
+    auto apply = [&](const Step &q) {
+        unsigned *p0 = cell + q.b0, *p1 = cell + q.b1;
         const unsigned o0 = *reinterpret_cast<volatile unsigned *>(p0), o1 = *reinterpret_cast<volatile unsigned *>(p1);
-        const unsigned r0 = atomicCAS(p0, o0, __float_as_uint(__uint_as_float(o0) + v0));
-        const unsigned r1 = atomicCAS(p1, o1, __float_as_uint(__uint_as_float(o1) + v1));
-        if (r0 != o0) atomicAdd(reinterpret_cast<float *>(p0), v0);
-        if (r1 != o1) atomicAdd(reinterpret_cast<float *>(p1), v1);
+        const unsigned r0 = atomicCAS(p0, o0, __float_as_uint(__uint_as_float(o0) + q.v0));
+        // TSC: the two particles may share their base cell; the second CAS then sees a stale value and is repaired below
+        const unsigned r1 = atomicCAS(p1, o1, __float_as_uint(__uint_as_float(o1) + q.v1));
+        if (r0 != o0) atomicAdd(reinterpret_cast<float *>(p0), q.v0);
+        if (r1 != o1) atomicAdd(reinterpret_cast<float *>(p1), q.v1);
     };
+    auto single = [&](int pp, int cell0) {                // one particle (TSC tail / partial batches)
+        const int b = __shfl_sync(full, cell0, pp);
+        if (!active) return;
+        float v = (sx0[pp] * sy[pp]) * sz[pp];
+        if (HASW) v *= sw[pp];
+        atomicAdd(reinterpret_cast<float *>(cell + b), v);
+        if (PCS) {
+            float v1 = (sx1[pp] * sy[pp]) * sz[pp];
+            if (HASW) v1 *= sw[pp];
+            atomicAdd(reinterpret_cast<float *>(cell + b + 2 * TS::PL), v1);
+        }
+    };
+    constexpr int STEP = PCS ? 1 : 2;                      // particles per step
     const int nitems = chunk_off[tg.ntiles];
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         __syncthreads();                         // the tile is clear, s_w is free
@@ -579,7 +623,7 @@ deposit_lane_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, c
             int cell0 = -1;
             if (have) {
                 float C[3][S];
-                cell0 = base_cell<MAS>(p, inv, tg, ox, oy, oz, C);
+                cell0 = base_cell<MAS, true>(p, inv, tg, ox, oy, oz, C);
                 if (cell0 >= 0) {
 #pragma unroll
                     for (int a = 0; a < 3; a++)
@@ -591,21 +635,21 @@ deposit_lane_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, c
             __syncwarp();
             unsigned todo = __ballot_sync(full, cell0 >= 0);
             if (todo == full) {
-                // the common case, unrolled: the staging offsets become immediates; the staged values of particle pp+1
-                // are read before particle pp's atomics are issued (the compiler will not move a shared-memory load
-                // above an atomic by itself)
-                Staged nq = fetch(0, __shfl_sync(full, cell0, 0));
+                // the common case, unrolled: the staging offsets become immediates; the staged values of the next step
+                // are read before this step's atomics are issued (the compiler will not move a shared-memory load above
+                // an atomic by itself)
+                Step nq = fetch(0, cell0);
 #pragma unroll
-                for (int pp = 0; pp < PB; pp++) {
-                    const Staged q = nq;
-                    if (pp + 1 < PB) nq = fetch(pp + 1, __shfl_sync(full, cell0, pp + 1));
-                    apply(q);
+                for (int pp = 0; pp < PB; pp += STEP) {
+                    const Step q = nq;
+                    if (pp + STEP < PB) nq = fetch(pp + STEP, cell0);
+                    if (active) apply(q);
                 }
             } else {
                 while (todo) {
                     const int pp = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    apply(fetch(pp, __shfl_sync(full, cell0, pp)));
+                    single(pp, cell0);
                 }
             }
             __syncwarp();                                            // the next batch overwrites the staging
@@ -806,8 +850,10 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
     // always the maximum the kernels may ever need: the attribute is a limit, and a smaller value set here would make
     // a later, larger launch of the same instantiation fail
     if (set_smem(deposit_tile_kernel<MAS, HASW>, TS::SMEM)) return 1;
-    if constexpr (MAS == PYLB_PCS) {
-        if (set_smem(deposit_lane_kernel<HASW>, TS::LANE_SMEM)) return 1;
+    using TL = TileShape<MAS, true>;
+    constexpr bool HAS_LANES = MAS == PYLB_PCS || MAS == PYLB_TSC;
+    if constexpr (HAS_LANES) {
+        if (set_smem(deposit_lane_kernel<MAS, HASW>, TL::LANE_SMEM)) return 1;
     }
     if (set_smem(bin_hist_kernel<MAS>, sizeof(int) * (size_t)BIN_MAX_KEYS)) return 1;
     const int kern = g_force_kernel > 0 ? g_force_kernel : env_int("PYLB_TILE_KERNEL", 0);
@@ -840,11 +886,11 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
         const int64_t max_items = (int64_t)n / CHUNK + tg.ntiles;
         timing_begin(PYLB_T_TILE, st);
         bool lanes = false;
-        if constexpr (MAS == PYLB_PCS) lanes = kern != 1;
+        if constexpr (HAS_LANES) lanes = kern != 1;
         if (lanes) {
-            if constexpr (MAS == PYLB_PCS) {
-                const int64_t g = (int64_t)P * 2 * 8;
-                deposit_lane_kernel<HASW><<<(unsigned)(max_items < g ? max_items : g), TS::LANE_THREADS, TS::LANE_SMEM, st>>>(
+            if constexpr (HAS_LANES) {
+                const int64_t g = (int64_t)P * TL::LANE_CTAS * 8;
+                deposit_lane_kernel<MAS, HASW><<<(unsigned)(max_items < g ? max_items : g), TL::LANE_THREADS, TL::LANE_SMEM, st>>>(
                     ws.sorted, inv, tg, ws.tile_begin, ws.chunk_off, grid);
             }
         } else {
