@@ -350,7 +350,7 @@ class XPk(object):
         stream = torch.cuda.current_stream(dev)
         swap = int(axis) if (int(axis) in (0, 1) and fields <= 3 and (ALGO & 3) != _lib.BIN_GENERIC and SWAP_AXES
                              and not self._ALGO_FLAGS) else 2
-        delta_k = [_fft_field(lib, d, dims, dev, stream, swap) for d in delta]
+        delta_k = [_fft_field(lib, d, dims, dev, stream, swap, pad=True) for d in delta]   # even row pitch: one aligned row table
         _say("Time FFTS = %.2f" % (time.time() - start))
         start2 = time.time()
         L, sums, counts = bin_modes(delta_k, dims, 2 if swap != 2 else int(axis), mas_index[:fields], False, False,

@@ -700,12 +700,20 @@ __global__ void row_keys2_kernel(unsigned *keys, unsigned *vals, int nrows, BinG
     vals[r] = (unsigned)r;
 }
 
-__global__ void row_table2_kernel(const unsigned *keys, const unsigned *vals, Row2 *tab, int nrows, BinGeom g, int par_bit) {
+// cext[(f-1) * nrows + i] = the same split of Cx*Cy for field f = 1 .. F-1 (XPk: per-field MAS), in table order
+__global__ void row_table2_kernel(const unsigned *keys, const unsigned *vals, Row2 *tab, int nrows, BinGeom g, int par_bit,
+                                  float2 *cext) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrows) return;
     const int r = (int)vals[i];
     const int ix = r / g.ny, iy = r - ix * g.ny;
     const int kx = wavenumber(g.x0 + ix, g.dims, g.middle), ky = wavenumber(g.y0 + iy, g.dims, g.middle);
+    for (int f = 1; f < g.F && cext != nullptr; f++) {
+        const int m1 = g.middle + 1;
+        const double cf = g.mas_tab[f * m1 + (kx < 0 ? -kx : kx)] * g.mas_tab[f * m1 + (ky < 0 ? -ky : ky)];
+        const float hi = (float)cf;
+        cext[(size_t)(f - 1) * nrows + i] = make_float2(hi, (float)(cf - (double)hi));
+    }
     const double c = g.mas_tab[kx < 0 ? -kx : kx] * g.mas_tab[ky < 0 ? -ky : ky];   // field 0
     Row2 e;
     e.off = 8ll * ((long long)ix * g.stride_x + (long long)iy * g.stride_y);
@@ -975,6 +983,286 @@ ring2_finish_kernel(BinGeom g, const double *__restrict__ t3, int t3_kz, int nbi
     else red_add(g.sums + g.o_phase + b, acc);
 }
 
+// ------------------------------------------------------------------------------------------------
+// ring2x kernel: ring2 for F = 2 or 3 fields (class XPk): auto spectra of every field and the cross spectra of every
+// pair, per-field MAS factors, no phase term, no write-back.  Same row tables, span schedule, two kz per thread, 16-byte
+// cp.async loads (one per field and row) and kz-private flush table as ring2_kernel; every accumulator exists Q = F + X
+// times (X = F(F-1)/2 pairs in the reference's order (0,1),(0,2),(1,2), Pk_library.pyx:628-737).  |delta_k|^2 and the
+// cross terms Re(d_a conj d_b) are formed in fp32 from the fp32-deconvolved modes -- the reference's operands -- summed
+// over the rows of one r2-group in fp32 and in fp64 from there on.
+// ------------------------------------------------------------------------------------------------
+constexpr int R2X_D = 8;            // rows in flight per thread and field
+
+template <int F>
+struct Ring2xSmem {
+    float4 z[F][R2X_D][R2_T];
+    long long off[R2_SPAN_MAX];
+    int r2[R2_SPAN_MAX + 4];
+    float2 c[F][R2_SPAN_MAX];
+    int item;
+};
+
+template <int F>
+__global__ void __launch_bounds__(R2_T, 2)
+ring2x_kernel(BinGeom g, FieldPtrs dk, const Row2 *__restrict__ tab_all, const float2 *__restrict__ cext, int nrows_all, int n0,
+              int kz_hi, int nseg, int npar, Ring2Sched sc, int *__restrict__ counter, double *__restrict__ t3, int t3_kz) {
+    constexpr int X = F * (F - 1) / 2, Q = F + X, NV = 3 * Q + 2;
+    extern __shared__ __align__(128) unsigned char ring2x_raw[];
+    Ring2xSmem<F> &sm = *reinterpret_cast<Ring2xSmem<F> *>(ring2x_raw);
+    const int tid = threadIdx.x;
+    const int groups = nseg * npar;
+    const int nitems = sc.nlevels * sc.per_level * groups;
+    const int mid2 = g.middle * g.middle, m1i = g.middle + 1;
+    const unsigned long long m1 = pack2(-1.0f, -1.0f);
+
+    for (;;) {
+        __syncthreads();                        // everyone is done with the previous span's tables
+        if (tid == 0) sm.item = atomicAdd(counter, 1);
+        __syncthreads();
+        const int item = sm.item;
+        if (item >= nitems) break;
+        const int lev = item / (sc.per_level * groups), w = item - lev * (sc.per_level * groups);
+        const int grp = w % groups, k = w / groups;
+        const int seg = grp % nseg;
+        const int P = npar == 2 ? grp / nseg : (sc.base[0][sc.nlevels] > 0 ? 0 : 1);   // parity table of this span
+        const int i0 = sc.base[P][lev] + k * sc.size[P][lev];
+        const int total = min(sc.size[P][lev], sc.base[P][lev + 1] - i0);
+        if (total <= 0) continue;
+        const int npairs = P ? (kz_hi - 1) / 2 + 1 : kz_hi / 2 + 1;
+        const int first_pair = seg * R2_T;
+        const int cnt = min(R2_T, npairs - first_pair);            // kz pairs served by this span
+        if (cnt <= 0) continue;
+        const int t0 = (P ? n0 : 0) + i0;                          // first table row of this span
+        for (int j = tid; j < total; j += R2_T) {
+            const Row2 e = tab_all[t0 + j];
+            sm.off[j] = e.off; sm.r2[j] = e.r2; sm.c[0][j] = make_float2(e.chi, e.clo);
+#pragma unroll
+            for (int f = 1; f < F; f++) sm.c[f][j] = cext[(size_t)(f - 1) * nrows_all + t0 + j];
+        }
+        __syncthreads();
+
+        const long long coloff = 8ll * (2 * (first_pair + tid) + P);   // this thread's 16 bytes inside a row
+        const bool loader = tid < cnt;
+        auto prefetch = [&](int j) {
+            if (j < total && loader) {
+#pragma unroll
+                for (int f = 0; f < F; f++)
+                    cp_async16(&sm.z[f][j & (R2X_D - 1)][tid], reinterpret_cast<const char *>(dk.p[f]) + coloff + sm.off[j]);
+            }
+            cp_async_commit();                  // one group per row, even when empty, so wait_group<N> counts rows
+        };
+        for (int j = 0; j < R2X_D; j++) prefetch(j);
+
+        // ---- per-kz constants (s = 0: kzA, s = 1: kzB = kzA + 1), per field
+        const int kzA = 2 * (first_pair + tid) + P;
+        int kz[2], kz2[2];
+        bool act[2];
+        float kz2f[2];
+        unsigned long long czh2[F], nczh2[F], nczl2[F];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            kz[s] = kzA + s;
+            act[s] = loader && kz[s] >= 1 && kz[s] <= kz_hi;
+            const int kc = min(kz[s], g.middle);
+            kz2[s] = kc * kc;
+            kz2f[s] = (float)kz2[s];
+        }
+#pragma unroll
+        for (int f = 0; f < F; f++) {
+            float h[2], l[2];
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const double czd = g.mas_tab[f * m1i + min(kz[s], g.middle)];
+                h[s] = (float)czd;
+                l[s] = (float)(czd - (double)h[s]);
+            }
+            czh2[f] = pack2(h[0], h[1]); nczh2[f] = pack2(-h[0], -h[1]); nczl2[f] = pack2(-l[0], -l[1]);
+        }
+
+        // ---- accumulators
+        double s3[2][Q][3], a2[2][Q], a1[2][Q], ks[2], kk[2];
+        float gq[2][Q], w2f[2], w4f[2];
+        int cn[2], c1[2], bin[2], thr[2];
+        bool in1d[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+#pragma unroll
+            for (int q = 0; q < Q; q++) { s3[s][q][0] = s3[s][q][1] = s3[s][q][2] = 0; a2[s][q] = a1[s][q] = 0; gq[s][q] = 0; }
+            ks[s] = 0; kk[s] = 0; cn[s] = c1[s] = 0; bin[s] = 0; thr[s] = 0; w2f[s] = w4f[s] = 0; in1d[s] = false;
+        }
+        int gcnt = 0, c2 = 0, cur_r2 = -1, ring_p = 0, ring_hi = 0;
+
+        auto apply_group = [&]() {
+            if (gcnt == 0) return;
+            const double dg = (double)gcnt;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    const double v0 = (double)gq[s][q];
+                    s3[s][q][0] += v0;
+                    s3[s][q][1] += (double)(gq[s][q] * w2f[s]);
+                    s3[s][q][2] += (double)(gq[s][q] * w4f[s]);
+                    a2[s][q] += v0;
+                    if (in1d[s]) a1[s][q] += v0;
+                    gq[s][q] = 0;
+                }
+                ks[s] = fma(dg, kk[s], ks[s]);
+                cn[s] += gcnt;
+                if (in1d[s]) c1[s] += gcnt;
+            }
+            c2 += gcnt;
+            gcnt = 0;
+        };
+        auto flush3 = [&](int s) {
+            if (act[s] && cn[s] > 0) {
+                double *t = t3 + ((long long)bin[s] * NV) * t3_kz + kz[s];
+#pragma unroll
+                for (int q = 0; q < Q; q++)
+#pragma unroll
+                    for (int l = 0; l < 3; l++) red_add(t + (long long)(q * 3 + l) * t3_kz, s3[s][q][l]);
+                red_add(t + (long long)(3 * Q) * t3_kz, ks[s]);
+                red_add(t + (long long)(3 * Q + 1) * t3_kz, (double)cn[s]);     // exact: counts < 2^53
+            }
+#pragma unroll
+            for (int q = 0; q < Q; q++) s3[s][q][0] = s3[s][q][1] = s3[s][q][2] = 0;
+            ks[s] = 0; cn[s] = 0;
+        };
+        auto flush2 = [&]() {
+            if (c2 > 0) {
+#pragma unroll
+                for (int s = 0; s < 2; s++)
+                    if (act[s]) {
+                        const long long i2 = (long long)g.kmax_par1 * ring_p + kz[s];   // (kmax_par+1)*k_per + k_par
+                        red_add_u64(g.counts + g.o_n2d + i2, (uint64_t)c2);
+#pragma unroll
+                        for (int f = 0; f < F; f++) red_add(g.sums + g.o_p2d + i2 * F + f, a2[s][f]);
+#pragma unroll
+                        for (int x = 0; x < X; x++) red_add(g.sums + g.o_x2d + i2 * X + x, a2[s][F + x]);
+                    }
+            }
+#pragma unroll
+            for (int s = 0; s < 2; s++)
+#pragma unroll
+                for (int q = 0; q < Q; q++) a2[s][q] = 0;
+            c2 = 0;
+        };
+        auto new_group = [&](int r2) {
+            apply_group();
+            cur_r2 = r2;
+            if (r2 >= ring_hi) {                   // k_per = floor(sqrt(r2)) changes, uniform
+                flush2();
+                ring_p = isqrt_exact(r2);
+                ring_hi = (ring_p + 1) * (ring_p + 1);
+            }
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const int n = r2 + kz2[s];
+                if (n >= thr[s]) {
+                    flush3(s);
+                    bin[s] = isqrt_exact(n);
+                    thr[s] = (bin[s] + 1) * (bin[s] + 1);
+                }
+                in1d[s] = n <= mid2;
+                const float nf = (float)n;
+                float rs;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(nf, 1.0f)));
+                const float h = nf * rs;
+                const double k0 = (double)h;
+                kk[s] = fma(fma(-k0, k0, (double)n), (double)(0.5f * rs), k0);
+                const float rs2 = rs * rs;
+                const float rn = fmaf(rs2, fmaf(-h, rs, 1.0f), rs2);
+                const float mu2f = fminf(kz2f[s] * rn, 1.0f);
+                w2f[s] = fmaf(1.5f, mu2f, -0.5f);
+                w4f[s] = fmaf(fmaf(4.375f, mu2f, -3.75f), mu2f, 0.375f);
+            }
+        };
+        // one row: deconvolve every field's element pair, then the Q products for kzA (s = 0) and kzB (s = 1)
+        auto row = [&](int j) {
+            unsigned long long dA[F], dB[F];
+#pragma unroll
+            for (int f = 0; f < F; f++) {
+                const float4 z = sm.z[f][j & (R2X_D - 1)][tid];
+                const float2 c = sm.c[f][j];
+                const unsigned long long chi2 = pack2(c.x, c.x), clo2 = pack2(c.y, c.y);
+                const unsigned long long p = mul2(chi2, czh2[f]);
+                unsigned long long t = fma2(chi2, nczh2[f], p);
+                t = fma2(chi2, nczl2[f], t);
+                t = fma2(clo2, nczh2[f], t);
+                const float2 mf = unpack2(fma2(t, m1, p));              // (float)(Cx*Cy*Cz) of field f for kzA, kzB
+                dA[f] = mul2(pack2(z.x, z.y), pack2(mf.x, mf.x));       // complex64 *= float
+                dB[f] = mul2(pack2(z.z, z.w), pack2(mf.y, mf.y));
+            }
+            const int r2 = sm.r2[j];
+            if (r2 != cur_r2) new_group(r2);       // CTA-uniform
+#pragma unroll
+            for (int f = 0; f < F; f++) {
+                const float2 sA = unpack2(mul2(dA[f], dA[f])), sB = unpack2(mul2(dB[f], dB[f]));
+                gq[0][f] += sA.x + sA.y;
+                gq[1][f] += sB.x + sB.y;
+            }
+            int ix = 0;
+#pragma unroll
+            for (int a = 0; a < F; a++)
+#pragma unroll
+                for (int b = a + 1; b < F; b++) {
+                    const float2 xA = unpack2(mul2(dA[a], dA[b])), xB = unpack2(mul2(dB[a], dB[b]));   // (re re, im im)
+                    gq[0][F + ix] += xA.x + xA.y;
+                    gq[1][F + ix] += xB.x + xB.y;
+                    ix++;
+                }
+            gcnt++;
+        };
+
+        int j = 0;
+        for (; j + 2 <= total; j += 2) {
+            cp_async_wait<R2X_D - 2>();           // rows complete in order: rows j, j+1 have landed
+            row(j);
+            row(j + 1);
+            prefetch(j + R2X_D);
+            prefetch(j + R2X_D + 1);
+        }
+        cp_async_wait<0>();
+        for (; j < total; j++) row(j);
+        apply_group();
+        flush3(0);
+        flush3(1);
+        flush2();
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+            if (act[s] && c1[s] > 0) {
+                red_add_u64(g.counts + g.o_n1d + kz[s], (uint64_t)c1[s]);
+#pragma unroll
+                for (int f = 0; f < F; f++) red_add(g.sums + g.o_p1d + (long long)kz[s] * F + f, a1[s][f]);
+#pragma unroll
+                for (int x = 0; x < X; x++) red_add(g.sums + g.o_x1d + (long long)kz[s] * X + x, a1[s][F + x]);
+            }
+    }
+}
+
+// t3[bin][value][kz] -> the 3-D bins of ring2x.  One warp per (bin, value); values: Q x 3 multipole sums, sum |k|, count.
+template <int F>
+__global__ void __launch_bounds__(256)
+ring2x_finish_kernel(BinGeom g, const double *__restrict__ t3, int t3_kz, int nbins) {
+    constexpr int X = F * (F - 1) / 2, Q = F + X, NV = 3 * Q + 2;
+    const int wid = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (wid >= nbins * NV) return;
+    const int b = wid / NV, v = wid - b * NV;
+    const double *rowp = t3 + (long long)wid * t3_kz;
+    double acc = 0;
+    const int kz_end = min(t3_kz, b + 1);          // n = r2 + kz^2 >= kz^2: bin b only ever holds kz <= b
+    for (int k = lane; k < kz_end; k += 32) acc += rowp[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane != 0 || acc == 0.0) return;
+    if (v < 3 * Q) {
+        const int q = v / 3, l = v - 3 * q;
+        if (q < F) red_add(g.sums + g.o_p3d + ((long long)b * 3 + l) * F + q, acc);
+        else red_add(g.sums + g.o_x3d + ((long long)b * 3 + l) * X + (q - F), acc);
+    } else if (v == 3 * Q) red_add(g.sums + g.o_k3d + b, acc);
+    else red_add_u64(g.counts + g.o_n3d + b, (uint64_t)(acc + 0.5));
+}
+
 static double ring2_first_share() {
     static double f = 0;
     if (f == 0) {
@@ -1075,6 +1363,50 @@ static int launch_ring2(const BinGeom &g, const float2 *dk, const Row2 *tab, int
             fclose(f);
         }
     }
+    return 0;
+}
+
+template <int F>
+static int launch_ring2x(const BinGeom &g, const FieldPtrs &dk, const Row2 *tab, const float2 *cext, int nrows, int n0, int n1,
+                         int kz_hi, int *counter, int nbins3, cudaStream_t st) {
+    constexpr int NV = 3 * (F + F * (F - 1) / 2) + 2;
+    const size_t smem = sizeof(Ring2xSmem<F>);
+    PYLB_CHECK(cudaFuncSetAttribute(ring2x_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring2x_kernel<F>, R2_T, smem);
+    if (occ < 1) occ = 1;
+    const int npairs = kz_hi / 2 + 1;                           // parity 0 (never fewer than parity 1)
+    const int nseg = (npairs + R2_T - 1) / R2_T;
+    const int npar = (n0 > 0) + (n1 > 0);
+    const int ctas = sm_count() * occ;                          // persistent: one resident wave
+    int per_level = ctas / (nseg * npar);
+    if (per_level < 1) per_level = 1;
+    {
+        const long long need = (long long)(ring2_first_share() * (n0 > n1 ? n0 : n1) / R2_SPAN_MAX) + 1;
+        if (need > per_level) per_level = (int)need;
+    }
+    Ring2Sched sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.per_level = per_level;
+    int nlev = 0;
+    ring2_levels(n0, per_level, 0, sc, nlev);
+    ring2_levels(n1, per_level, 1, sc, nlev);
+    sc.nlevels = nlev;
+    PYLB_REQUIRE(sc.base[0][nlev] == n0 && sc.base[1][nlev] == n1, "ring2x: row table too large for the span schedule");
+    PYLB_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    double *t3 = nullptr;
+    const int t3_kz = (kz_hi + 1 + 3) & ~3;
+    const size_t t3_bytes = sizeof(double) * (size_t)nbins3 * NV * t3_kz;
+    ScratchGuard guard(st);
+    PYLB_CHECK(cudaMallocAsync(&t3, t3_bytes, st));
+    guard.add(t3);
+    PYLB_CHECK(cudaMemsetAsync(t3, 0, t3_bytes, st));
+    timing_begin(PYLB_T_RING, st);
+    ring2x_kernel<F><<<ctas, R2_T, smem, st>>>(g, dk, tab, cext, nrows, n0, kz_hi, nseg, npar, sc, counter, t3, t3_kz);
+    timing_end(PYLB_T_RING, st);
+    PYLB_LAUNCH_CHECK();
+    ring2x_finish_kernel<F><<<(unsigned)(((long long)nbins3 * NV * 32 + 255) / 256), 256, 0, st>>>(g, t3, t3_kz, nbins3);
+    PYLB_LAUNCH_CHECK();
     return 0;
 }
 
@@ -1420,11 +1752,12 @@ static bool g_allow_ring2 = true;
 struct Ring2Key {
     int dims, x0, nx, y0, ny;
     long long stride_x, stride_y;
-    int bp, mas;
+    int bp, F, mas[3];
 };
 struct Ring2Cache {
     Ring2Key key = {};
     Row2 *tab = nullptr;
+    float2 *cext = nullptr;          // [(F-1)][nrows]: Cx*Cy splits of fields 1 .. F-1, in table order
     cudaEvent_t ready = nullptr;
 };
 // A few tables per device (a caller alternating between two grid sizes, or Pk and a slab engine, no longer rebuilds one
@@ -1456,7 +1789,8 @@ static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cuda
     Ring2Key key;
     memset(&key, 0, sizeof(key));               // the struct has padding and is compared with memcmp
     key.dims = g.dims; key.x0 = g.x0; key.nx = g.nx; key.y0 = g.y0; key.ny = g.ny;
-    key.stride_x = g.stride_x; key.stride_y = g.stride_y; key.bp = bp; key.mas = g.mas_idx[0];
+    key.stride_x = g.stride_x; key.stride_y = g.stride_y; key.bp = bp; key.F = g.F;
+    for (int f = 0; f < g.F && f < 3; f++) key.mas[f] = g.mas_idx[f];
     std::lock_guard<std::mutex> lock(g_ring2_mutex);       // held until the kernels using the table are queued on `st`
     Ring2DeviceCache &dc = g_ring2_cache[dev];
     Ring2Cache *hit = nullptr;
@@ -1466,6 +1800,7 @@ static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cuda
         Ring2Cache &c = dc.way[dc.next];
         dc.next = (dc.next + 1) % R2_CACHE_WAYS;
         if (c.tab) { cudaFree(c.tab); c.tab = nullptr; }          // synchronises: nobody is reading it any more
+        if (c.cext) { cudaFree(c.cext); c.cext = nullptr; }
         if (!c.ready) PYLB_CHECK(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
         unsigned *buf = nullptr;
         void *tmp = nullptr;
@@ -1475,6 +1810,7 @@ static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cuda
         PYLB_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned *)nullptr, (unsigned *)nullptr,
                                                    (unsigned *)nullptr, (unsigned *)nullptr, nrows, 0, par_bit + 1, st));
         PYLB_CHECK(cudaMalloc(&c.tab, sizeof(Row2) * (size_t)nrows));
+        if (g.F > 1) PYLB_CHECK(cudaMalloc(&c.cext, sizeof(float2) * (size_t)(g.F - 1) * nrows));
         ScratchGuard guard(st);
         PYLB_CHECK(cudaMallocAsync(&buf, sizeof(unsigned) * 4 * (size_t)nrows, st));
         guard.add(buf);
@@ -1486,7 +1822,7 @@ static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cuda
         PYLB_LAUNCH_CHECK();
         PYLB_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, nrows, 0, par_bit + 1, st));
         count_launch(3);
-        row_table2_kernel<<<blocks, 256, 0, st>>>(k_out, v_out, c.tab, nrows, g, par_bit);
+        row_table2_kernel<<<blocks, 256, 0, st>>>(k_out, v_out, c.tab, nrows, g, par_bit, c.cext);
         PYLB_LAUNCH_CHECK();
         PYLB_CHECK(cudaEventRecord(c.ready, st));
         c.key = key;
@@ -1501,23 +1837,33 @@ static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cuda
     PYLB_CHECK(cudaMallocAsync(&counter, 16, st));
     guard.add(counter);
 
-    special2_kernel<<<dim3((unsigned)((nrows + 255) / 256), (g.middle > 0) ? 2 : 1), 256, 0, st>>>(g, dk.p[0], tab, nrows, want_phase);
-    PYLB_LAUNCH_CHECK();
-    int rc = 0;
-    if (!rc && kz_hi >= 1) {
-        const int nbins3 = isqrt_exact(3 * g.middle * g.middle) + 1;     // kmax + 1
-        rc = want_phase ? launch_ring2<true>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, st)
-                        : launch_ring2<false>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, st);
+    const int nbins3 = isqrt_exact(3 * g.middle * g.middle) + 1;     // kmax + 1
+    if (g.F == 1) {
+        special2_kernel<<<dim3((unsigned)((nrows + 255) / 256), (g.middle > 0) ? 2 : 1), 256, 0, st>>>(g, dk.p[0], tab, nrows, want_phase);
+        PYLB_LAUNCH_CHECK();
+        if (kz_hi < 1) return 0;
+        return want_phase ? launch_ring2<true>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, st)
+                          : launch_ring2<false>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, st);
     }
-    return rc;
+    // XPk: the self-conjugate columns through the F-field special kernel (it only needs r2, kx, ky, off of a row)
+    if (g.F == 2) {
+        if (launch_special<2, Row2>(g, dk, tab, nrows, 0, 0, st)) return 1;
+        return kz_hi < 1 ? 0 : launch_ring2x<2>(g, dk, tab, c.cext, nrows, n0, (int)n1, kz_hi, counter, nbins3, st);
+    }
+    if (launch_special<3, Row2>(g, dk, tab, nrows, 0, 0, st)) return 1;
+    return kz_hi < 1 ? 0 : launch_ring2x<3>(g, dk, tab, c.cext, nrows, n0, (int)n1, kz_hi, counter, nbins3, st);
 }
 
 static int run_ring(const BinGeom &g, const FieldPtrs &dk, int want_phase, int write_back, int precise, cudaStream_t st) {
     const int nrows = g.nx * g.ny;
     const int kz_hi = g.even ? g.middle - 1 : g.middle;  // columns 1..kz_hi carry no skip rule
     if (nrows == 0) return 0;
-    if (g_allow_ring2 && g.F == 1 && !write_back && !precise && g.even && g.middle >= 2 && ((uintptr_t)dk.p[0] & 7) == 0)
-        return run_ring2(g, dk, want_phase, st);
+    if (g_allow_ring2 && g.F <= 3 && !write_back && !precise && !g.ximag && g.even && g.middle >= 2) {
+        // one row table serves every field: they must agree in the parity of their base pointers (in units of 8 bytes)
+        bool ok = ((uintptr_t)dk.p[0] & 7) == 0 && (g.F == 1 || !want_phase);
+        for (int f = 1; f < g.F; f++) ok = ok && ((((uintptr_t)dk.p[f] ^ (uintptr_t)dk.p[0]) & 15) == 0);
+        if (ok) return run_ring2(g, dk, want_phase, st);
+    }
 
     // scratch: keys/vals (double-buffered for the radix sort), row table, cub temp
     unsigned *buf = nullptr;

@@ -52,6 +52,7 @@ static int64_t round_particles(int dims, int xext) {
 constexpr int BIN_THREADS = 1024;            // histogram CTAs: one per SM, 32 warps
 constexpr int BIN_MAX_KEYS = 53248;          // per-CTA histogram must fit shared memory (208 KB of 227 KB)
 constexpr int MAX_TILES = 1 << 20;           // two digits of <= 1024 values
+constexpr int FEW_KEYS = 32;                 // at most this many sort keys: count and rank per warp first (match.any)
 
 // x0 / xext: x window held by the grid (planes x0 .. x0+xext-1 modulo dims; the whole cube when xext == dims)
 struct TileGeom {
@@ -96,6 +97,28 @@ bin_hist_kernel(const float *__restrict__ pos, int64_t first, int n, int64_t ps0
     for (int t = threadIdx.x; t < nkeys; t += BIN_THREADS) hist[t] = 0;
     __syncthreads();
     auto key = [&](float x, float y, float z) { return tile_key<MAS>(x, y, z, inv, tg) >> shift; };
+    if (nkeys <= FEW_KEYS) {
+        // a handful of keys (the x-slab partition of the multi-GPU exchange): 1024 threads on 8 counters serialise on
+        // the address, so every warp first counts its lanes per key (match.any) and adds once per key present
+        const int64_t stride = (int64_t)gridDim.x * BIN_THREADS;
+        const int lane = threadIdx.x & 31;
+        for (int64_t i0 = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x - lane; i0 < n; i0 += stride) {   // warp-uniform
+            const int64_t i = i0 + lane;
+            int k = -1;
+            if (i < n) {
+                const float *p = pos + (first + i) * ps0;
+                k = (int)key(__ldg(p), __ldg(p + ps1), __ldg(p + 2 * ps1));
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, k);
+            if (k >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[k], __popc(peers));
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < nkeys; t += BIN_THREADS) {
+            const int c = hist[t];
+            if (c) atomicAdd(&counts[t], c);
+        }
+        return;
+    }
     const float *base = pos + first * ps0;
     if (ps0 == 3 && ps1 == 1 && ((uintptr_t)base & 15) == 0) {
         // dense (np,3) array: 4 particles = 3 aligned float4, 8 particles (6 x 16 B) in flight per thread
@@ -329,6 +352,7 @@ bin_pass_kernel(const float *__restrict__ pos, const float *__restrict__ W, int6
             }
         }
     }
+    const bool few = nbins <= FEW_KEYS;          // CTA-uniform: rank per warp first, one shared atomic per digit present
 #pragma unroll
     for (int k = 0; k < PART_PER_THREAD; k++) {
         const int i = index_of(k);
@@ -336,7 +360,16 @@ bin_pass_kernel(const float *__restrict__ pos, const float *__restrict__ W, int6
         if (i < hi) {
             const unsigned t = tile_key<MAS>(v[k].x, v[k].y, v[k].z, inv, tg);
             d[k] = FIRST ? (int)(t >> lo_bits) : (int)(t & ((1u << lo_bits) - 1u));
-            r[k] = atomicAdd(&sm.cnt[d[k]], 1);
+            if (!few) r[k] = atomicAdd(&sm.cnt[d[k]], 1);
+        }
+        if (few) {                               // every lane of the warp takes part (hi - lo may cut a warp)
+            const int lane = tid & 31;
+            const unsigned peers = __match_any_sync(0xffffffffu, d[k]);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (d[k] >= 0 && lane == leader) base = atomicAdd(&sm.cnt[d[k]], __popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            r[k] = base + __popc(peers & ((1u << lane) - 1u));
         }
     }
     __syncthreads();

@@ -384,7 +384,8 @@ def test_pk_vs_oracle(PKL, algo, dims):
         P.ALGO = old
 
 
-@pytest.mark.parametrize("algo", [1, 2, 2 | 16, 2 | 32])
+# 1 generic; 2 ring2x (two kz per thread, F = 2 / 3); 2|64 the one-kz ring kernel; 2|16 its fp64 option; 2|32 its bulk-copy loads
+@pytest.mark.parametrize("algo", [1, 2, 2 | 64, 2 | 16, 2 | 32 | 64])
 def test_xpk_vs_oracle(PKL, algo):
     import pylians_b200.Pk_library as P
     box, dims = 500.0, 40
@@ -421,6 +422,38 @@ def test_ring2_segments_and_unaligned_rows(PKL, dims):
         ws, wc = ws.cpu().numpy(), wc.cpu().numpy()
         for algo in (2, 2 | 64):
             _, gs, gc = P.bin_modes([dk], dims, 2, [2], True, False, algo=algo)
+            assert np.array_equal(gc.cpu().numpy(), wc)              # mode counts: bit-exact
+            np.testing.assert_allclose(gs.cpu().numpy(), ws, rtol=2e-6, atol=1e-7 * float(np.abs(ws).max()))
+    finally:
+        P.ALGO = old
+
+
+@pytest.mark.parametrize("dims,F", [(520, 2), (264, 3)])
+def test_ring2x_segments_and_unaligned_rows(PKL, dims, F):
+    """The multi-field ring2x kernel (class XPk, F = 2 and 3) against the one-thread-per-mode kernel at sizes the oracle is
+    too slow for: 520 -> two kz segments and several spans per level; 264 -> N/2+1 odd; through XPk (padded, aligned rows)
+    and straight from dense k-space fields whose odd row pitch splits the row table by parity (8-byte aligned base)."""
+    import pylians_b200.Pk_library as P
+    gen = torch.Generator(device="cuda"); gen.manual_seed(dims + F)
+    fields = [torch.randn((dims,) * 3, device="cuda", dtype=torch.float32, generator=gen) for _ in range(F)]
+    fields[1] += 0.5 * fields[0]                                    # a real cross-correlation
+    mas = ["CIC", "PCS", "None"][:F]
+    old = P.ALGO
+    try:
+        P.ALGO = 1
+        ref = PKL.XPk(fields, 1000.0, 2, mas, 1)
+        for algo in (2, 2 | 64):
+            P.ALGO = algo
+            parity.check_xpk(PKL.XPk(fields, 1000.0, 2, mas, 1), ref)
+        m = dims // 2 + 1
+        bufs = [torch.randn((dims * dims * m + 1, 2), device="cuda", dtype=torch.float32, generator=gen) for _ in range(F)]
+        dks = [torch.view_as_complex(b[1:]).reshape(dims, dims, m) for b in bufs]
+        assert all(dk.data_ptr() % 16 == 8 for dk in dks)
+        mi = [2, 4, 0][:F]
+        _, ws, wc = P.bin_modes(dks, dims, 2, mi, False, False, algo=1)
+        ws, wc = ws.cpu().numpy(), wc.cpu().numpy()
+        for algo in (2, 2 | 64):
+            _, gs, gc = P.bin_modes(dks, dims, 2, mi, False, False, algo=algo)
             assert np.array_equal(gc.cpu().numpy(), wc)              # mode counts: bit-exact
             np.testing.assert_allclose(gs.cpu().numpy(), ws, rtol=2e-6, atol=1e-7 * float(np.abs(ws).max()))
     finally:
