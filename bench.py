@@ -519,10 +519,7 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
         def e2e_step():
-            if world > 1 and not pipe.streamed:
-                return pipe.snapshot([(p.to(dev, non_blocking=True), w.to(dev, non_blocking=True) if w is not None else None)
-                                      for p, w in host])
-            return pipe.snapshot(host)
+            return pipe.snapshot(host)           # host tensors: MASL.MA / SlabPk stream them in chunks, H2D overlapped with the deposit
 
         for _ in range(2):
             e2e_step()
@@ -532,8 +529,9 @@ def run_ours(args, wl):
         res["e2e"] = {"value": nf * npart * world / (ms_e2e / e2e_steps * 1e-3), "unit": "particles/s",
                       "h2d_bytes_per_step": int(h2d * world) if not wl_.get("strong") else int(sum((16 if w_ else 12) for _, w_ in wl_["fields"]) * wl_["nside"] ** 3), "d2h_bytes_per_step": int((L.n_doubles + L.n_counts) * 8 * world),
                       "ms_per_step": ms_e2e / e2e_steps,
-                      "note": "particle arrays in pinned host memory on every rank -> MASL.MA (chunked H2D overlapped with the deposit at "
-                              "N=1) -> overdensity -> PKL.Pk/XPk -> bins on host; byte counts are totals over all ranks"}
+                      "note": "particle arrays in pinned host memory on every rank -> MASL.MA / SlabPk (H2D in chunks on a side stream, "
+                              "overlapped with the deposit of the previous chunk) -> overdensity -> PKL.Pk/XPk -> bins on host; byte "
+                              "counts are totals over all ranks"}
         del parts, host, pipe
         torch.cuda.empty_cache()
         return res

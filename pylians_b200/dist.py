@@ -231,7 +231,7 @@ class SlabPk(object):
             mode = self._auto_mode[key]
         if mode == "particles" and self.nxl < halo:
             raise ValueError("particle exchange needs at least %d planes per rank for %s" % (halo, MAS))
-        batches = pos if batched else [(pos, W)]
+        batches = pos if batched else self._batches_of(pos, W)
         slab = self._slab_from_particles(batches, MAS, halo) if mode == "particles" else self._slab_from_grids(batches, MAS)
         if overdensity:
             total = ops.grid_sum(slab)
@@ -239,6 +239,53 @@ class SlabPk(object):
                 dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
             ops.overdensity_apply(slab, total, N ** 3)
         return slab
+
+    def _batches_of(self, pos, W):
+        """One (pos, W) batch -- or, for a HOST array feeding a CUDA engine, a stream of device chunks: the H2D copy of
+        chunk i+1 runs on a side stream while chunk i is partitioned, exchanged and deposited (double-buffered, pinned
+        host memory makes the copies truly asynchronous).  Chunking changes nothing but the fp32 summation order."""
+        dev = getattr(self.ops, "dev", None)
+        on_host = not (isinstance(pos, torch.Tensor) and pos.is_cuda)
+        if dev is None or not on_host:
+            return [(pos, W)]
+        chunk = MASL._host_chunk(self.dims, 3)
+        n = int(pos.shape[0])
+        if n <= chunk:
+            return [(pos, W)]
+        return self._stream_host_chunks(MASL._as_cpu_tensor(pos), None if W is None else MASL._as_cpu_tensor(W), n, chunk, dev)
+
+    def _stream_host_chunks(self, h_pos, h_w, n, chunk, dev):
+        cs = MASL._copy_stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        bufs = [torch.empty((chunk, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+        wbufs = [torch.empty(chunk, dtype=torch.float32, device=dev) for _ in range(2)] if h_w is not None else None
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        nchunks = (n + chunk - 1) // chunk
+        cs.wait_stream(cur)
+
+        def issue(i):
+            b = i % 2
+            lo, hi = i * chunk, min(n, (i + 1) * chunk)
+            with torch.cuda.stream(cs):
+                if i >= 2:
+                    cs.wait_event(consumed[b])
+                bufs[b][: hi - lo].copy_(h_pos[lo:hi], non_blocking=True)
+                if wbufs is not None:
+                    wbufs[b][: hi - lo].copy_(h_w[lo:hi], non_blocking=True)
+                copied[b].record(cs)
+
+        issue(0)
+        for i in range(nchunks):
+            b = i % 2
+            m = min(n, (i + 1) * chunk) - i * chunk
+            if i + 1 < nchunks:
+                issue(i + 1)
+            cur.wait_event(copied[b])
+            yield bufs[b][:m], (wbufs[b][:m] if wbufs is not None else None)
+            consumed[b].record(cur)              # runs when the consumer asks for the next chunk: chunk i is fully queued
+        for t in bufs + (wbufs or []):
+            t.record_stream(cur)
 
     def _slab_from_grids(self, batches, MAS):
         ops, N, G = self.ops, self.dims, self.G
