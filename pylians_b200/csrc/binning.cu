@@ -1263,6 +1263,88 @@ ring2x_finish_kernel(BinGeom g, const double *__restrict__ t3, int t3_kz, int nb
     else red_add_u64(g.counts + g.o_n3d + b, (uint64_t)(acc + 0.5));
 }
 
+// special columns of the ring2x path: special2_kernel for F = 2 or 3 fields (no phase term)
+template <int F>
+__global__ void __launch_bounds__(256)
+special2x_kernel(BinGeom g, FieldPtrs dk, const Row2 *__restrict__ tab, int nrows) {
+    constexpr int X = F * (F - 1) / 2, Q = F + X;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // whole warps stay alive: shuffles below use the full mask
+    const int kz = blockIdx.y == 0 ? 0 : g.middle;
+    bool valid = i < nrows;
+    Row2 e;
+    e.off = 0; e.r2 = 0; e.chi = e.clo = 0.f; e.kx = e.ky = 0;
+    if (valid) e = tab[i];
+    const int kx = e.kx, ky = e.ky;
+    // keep one of each conjugate pair, Pk_library.pyx:326-330 / :640-644
+    if (kx < 0) valid = false;
+    if ((kx == 0 || (kx == g.middle && g.even)) && ky < 0) valid = false;
+    const int n = e.r2 + kz * kz, m1 = g.middle + 1;
+    const int b3 = isqrt_exact(n), b2 = isqrt_exact(e.r2);
+    double v3[3 * Q + 2], v2[Q + 1], v1[Q + 1];
+#pragma unroll
+    for (int q = 0; q < 3 * Q + 2; q++) v3[q] = 0;
+#pragma unroll
+    for (int q = 0; q < Q + 1; q++) { v2[q] = 0; v1[q] = 0; }
+    if (valid) {
+        const double k = sqrt((double)n);
+        const double mu = (n == 0) ? 0.0 : (double)kz / k;
+        const double mu2 = mu * mu;
+        const double w2 = (3.0 * mu2 - 1.0) / 2.0, w4 = (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0;
+        const int ax = kx, ay = ky < 0 ? -ky : ky;
+        double re[F], im[F], d[Q];
+#pragma unroll
+        for (int f = 0; f < F; f++) {
+            const float mf = (float)(g.mas_tab[f * m1 + ax] * g.mas_tab[f * m1 + ay] * g.mas_tab[f * m1 + kz]);
+            const float2 z = *(reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(dk.p[f]) + e.off) + kz);
+            re[f] = (double)__fmul_rn(z.x, mf); im[f] = (double)__fmul_rn(z.y, mf);
+            d[f] = re[f] * re[f] + im[f] * im[f];
+        }
+        int ix = 0;
+#pragma unroll
+        for (int a = 0; a < F; a++)
+#pragma unroll
+            for (int b = a + 1; b < F; b++) { d[F + ix] = re[a] * re[b] + im[a] * im[b]; ix++; }
+        const bool in1d = n <= g.middle * g.middle;
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            v3[3 * q] = d[q]; v3[3 * q + 1] = d[q] * w2; v3[3 * q + 2] = d[q] * w4;
+            v2[q] = d[q];
+            if (in1d) v1[q] = d[q];
+        }
+        v3[3 * Q] = k; v3[3 * Q + 1] = 1.0;
+        v2[Q] = 1.0;
+        if (in1d) v1[Q] = 1.0;
+    }
+    warp_reduce_by_key<3 * Q + 2>(b3, valid, v3, [&](int b, const double (&s)[3 * Q + 2]) {
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+#pragma unroll
+            for (int f = 0; f < F; f++) red_add(g.sums + g.o_p3d + ((long long)b * 3 + l) * F + f, s[3 * f + l]);
+#pragma unroll
+            for (int x = 0; x < X; x++) red_add(g.sums + g.o_x3d + ((long long)b * 3 + l) * X + x, s[3 * (F + x) + l]);
+        }
+        red_add(g.sums + g.o_k3d + b, s[3 * Q]);
+        red_add_u64(g.counts + g.o_n3d + b, (uint64_t)(s[3 * Q + 1] + 0.5));
+    });
+    warp_reduce_by_key<Q + 1>(b2, valid, v2, [&](int b, const double (&s)[Q + 1]) {
+        const long long i2 = (long long)g.kmax_par1 * b + kz;
+#pragma unroll
+        for (int f = 0; f < F; f++) red_add(g.sums + g.o_p2d + i2 * F + f, s[f]);
+#pragma unroll
+        for (int x = 0; x < X; x++) red_add(g.sums + g.o_x2d + i2 * X + x, s[F + x]);
+        red_add_u64(g.counts + g.o_n2d + i2, (uint64_t)(s[Q] + 0.5));
+    });
+    warp_reduce_by_key<Q + 1>(0, valid, v1, [&](int, const double (&s)[Q + 1]) {
+        if (s[Q] > 0.5) {
+#pragma unroll
+            for (int f = 0; f < F; f++) red_add(g.sums + g.o_p1d + (long long)kz * F + f, s[f]);
+#pragma unroll
+            for (int x = 0; x < X; x++) red_add(g.sums + g.o_x1d + (long long)kz * X + x, s[F + x]);
+            red_add_u64(g.counts + g.o_n1d + kz, (uint64_t)(s[Q] + 0.5));
+        }
+    });
+}
+
 static double ring2_first_share() {
     static double f = 0;
     if (f == 0) {
@@ -1845,12 +1927,15 @@ static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cuda
         return want_phase ? launch_ring2<true>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, st)
                           : launch_ring2<false>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, st);
     }
-    // XPk: the self-conjugate columns through the F-field special kernel (it only needs r2, kx, ky, off of a row)
+    // XPk: the self-conjugate columns through the F-field version of special2_kernel
+    const dim3 sgrid((unsigned)((nrows + 255) / 256), (g.middle > 0) ? 2 : 1);
     if (g.F == 2) {
-        if (launch_special<2, Row2>(g, dk, tab, nrows, 0, 0, st)) return 1;
+        special2x_kernel<2><<<sgrid, 256, 0, st>>>(g, dk, tab, nrows);
+        PYLB_LAUNCH_CHECK();
         return kz_hi < 1 ? 0 : launch_ring2x<2>(g, dk, tab, c.cext, nrows, n0, (int)n1, kz_hi, counter, nbins3, st);
     }
-    if (launch_special<3, Row2>(g, dk, tab, nrows, 0, 0, st)) return 1;
+    special2x_kernel<3><<<sgrid, 256, 0, st>>>(g, dk, tab, nrows);
+    PYLB_LAUNCH_CHECK();
     return kz_hi < 1 ? 0 : launch_ring2x<3>(g, dk, tab, c.cext, nrows, n0, (int)n1, kz_hi, counter, nbins3, st);
 }
 

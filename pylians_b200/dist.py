@@ -183,7 +183,8 @@ class _Result(object):
 class SlabPk(object):
     """Distributed MA + Pk / XPk.  Every rank calls the same methods with its own particle shard."""
 
-    def __init__(self, dims, BoxSize, MAS="CIC", axis=2, group=None, ops=None, exchange="auto", exchange_chunks=4):
+    def __init__(self, dims, BoxSize, MAS="CIC", axis=2, group=None, ops=None, exchange="auto", exchange_chunks=4,
+                 fft_chunks=4):
         """exchange: how per-rank deposits become x-slabs --
              "grid"      every rank deposits onto a full partial grid, then reduce-scatter (4 N^3 bytes per rank);
              "particles" particles are routed to the rank owning their lowest touched x-plane (16 B per particle),
@@ -193,6 +194,7 @@ class SlabPk(object):
              overlaps the transfer of the next; must be the same on every rank."""
         self.exchange = exchange
         self.exchange_chunks = max(1, int(exchange_chunks))
+        self.fft_chunks = max(1, int(fft_chunks))         # x-plane groups of the slab FFT (transform of one overlaps the transpose of the previous)
         self._auto_mode = {}
         self.rank, self.G = _group_info(group)
         self.group = group
@@ -375,16 +377,42 @@ class SlabPk(object):
 
     # ---- stage 2: x-slab (real) -> ky-slab (k-space, transposed) --------------------------------
     def fft_slab(self, slab):
-        """(N/G, N, N) real x-slab -> (N, N/G, N/2+1) complex: all kx, this rank's ky, kz >= 0."""
-        ops, N, G = self.ops, self.dims, self.G
-        cplx = ops.fft_yz(slab, N)
-        send = ops.pack(cplx, N, G)
-        del cplx
-        if G > 1:
-            recv = torch.empty_like(send)
-            dist.all_to_all_single(recv, send, group=self.group)
+        """(N/G, N, N) real x-slab -> (N, N/G, P) complex: all kx, this rank's ky, kz >= 0 (P = the row pitch of `ops`).
+
+        The x-planes go through in `fft_chunks` groups: while the transposed blocks of one group cross NVLink (grouped
+        send/recv straight into their place in the receive buffer -- a source's planes are contiguous there), the 2-D
+        transforms and the pack of the next group run on the compute stream."""
+        ops, N, G, r = self.ops, self.dims, self.G, self.rank
+        nxl = slab.shape[0]
+        C = min(self.fft_chunks, nxl) if G > 1 else 1
+        if C <= 1:
+            cplx = ops.fft_yz(slab, N)
+            send = ops.pack(cplx, N, G)
+            del cplx
+            if G > 1:
+                recv = torch.empty_like(send)
+                dist.all_to_all_single(recv, send, group=self.group)
+            else:
+                recv = send
         else:
-            recv = send
+            recv, pending, keep = None, [], []
+            for c in range(C):
+                lo, hi = (c * nxl) // C, ((c + 1) * nxl) // C
+                send = ops.pack(ops.fft_yz(slab[lo:hi], N), N, G)             # (G, hi-lo, N/G, P)
+                if recv is None:
+                    recv = send.new_empty((G, nxl) + tuple(send.shape[2:]))
+                recv[r, lo:hi].copy_(send[r])                                  # my own block stays on the device
+                p2p = []
+                for g in range(G):
+                    if g != r:
+                        p2p.append(dist.P2POp(dist.irecv, recv[g, lo:hi], self._peer(g), group=self.group))
+                        p2p.append(dist.P2POp(dist.isend, send[g], self._peer(g), group=self.group))
+                pending.append(dist.batch_isend_irecv(p2p))
+                keep.append(send)
+            for reqs in pending:
+                for q in reqs:
+                    q.wait()
+            del keep
         recv = recv.view(N, self.nyl, recv.shape[-1])      # block g holds x in [g N/G, (g+1) N/G); rows keep their pitch
         ops.fft_x(recv, N)
         return recv
