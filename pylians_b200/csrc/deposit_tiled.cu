@@ -263,10 +263,13 @@ bin_hist2_kernel(const float4 *__restrict__ in, float inv, TileGeom tg, const in
     const int lo = s_lo, hi = s_hi;
     if (lo >= hi) return;
     const unsigned mask = (1u << lo_bits) - 1u;
-    for (int i = lo + threadIdx.x; i < hi; i += PT) {
-        const float4 q = __ldg(in + i);
-        atomicAdd(&cnt[tile_key<MAS>(q.x, q.y, q.z, inv, tg) & mask], 1);
-    }
+    float4 q[PART_PER_THREAD];                    // the chunk holds at most PT * PART_PER_THREAD particles: all loads in flight
+#pragma unroll
+    for (int k = 0; k < PART_PER_THREAD; k++)
+        if (lo + k * PT + (int)threadIdx.x < hi) q[k] = __ldg(in + lo + k * PT + threadIdx.x);
+#pragma unroll
+    for (int k = 0; k < PART_PER_THREAD; k++)
+        if (lo + k * PT + (int)threadIdx.x < hi) atomicAdd(&cnt[tile_key<MAS>(q[k].x, q[k].y, q[k].z, inv, tg) & mask], 1);
     __syncthreads();
     const int cbase = s_bucket << lo_bits;
     for (int b = threadIdx.x; b < (1 << lo_bits); b += PT) {
