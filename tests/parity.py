@@ -90,13 +90,18 @@ def check_pk(test, ref, phase=True, rtol=PK_RTOL, few_mode_rtol=None, corner_rto
     assert_spec_close(_get(test, "Pk1D"), p1, np.median(np.abs(p1)), "Pk1D", rtol)
     p2 = _get(ref, "Pk2D")
     # bins holding a single (or few) modes carry the FFT's own 1e-7..1e-6 noise; floor at the median
-    if few_mode_rtol is None:
+    if few_mode_rtol is None and corner_rtol is None:
         assert_spec_close(_get(test, "Pk2D"), p2, np.median(np.abs(p2)), "Pk2D", rtol)
     else:
-        few = _get(ref, "Nmodes2D") < FEW_MODES
+        loose = np.zeros(p2.shape, bool)
+        if few_mode_rtol is not None:
+            loose |= _get(ref, "Nmodes2D") < FEW_MODES
+        if corner_rtol is not None:                    # the same corners of the cube, in the (k_par, k_per) table
+            loose |= np.hypot(_get(ref, "kpar"), _get(ref, "kper")) > _get(ref, "k1D")[-1]
         t2 = _get(test, "Pk2D")
-        assert_spec_close(t2[~few], p2[~few], np.median(np.abs(p2)), "Pk2D", rtol)
-        assert_spec_close(t2[few], p2[few], np.median(np.abs(p2)), "Pk2D (bins of < %d modes)" % FEW_MODES, few_mode_rtol)
+        assert_spec_close(t2[~loose], p2[~loose], np.median(np.abs(p2)), "Pk2D", rtol)
+        assert_spec_close(t2[loose], p2[loose], np.median(np.abs(p2)), "Pk2D (few-mode / corner bins)",
+                          max(few_mode_rtol or 0.0, corner_rtol or 0.0))
 
 
 def check_xpk(test, ref, rtol=PK_RTOL):
