@@ -106,6 +106,18 @@ def _worker(rank, world, port, q):
             eng = SlabPk(dims, box, "CIC", 2, exchange=exchange)
             got = eng.run(torch.from_numpy(pos[rank::world]).cuda())
             parity.check_pk(got, PKL.Pk(d, box, 2, "CIC", 1), rtol=1e-4)
+            # the same shard as a HOST array, streamed in chunks (H2D on a side stream), and as ParticleBatches
+            import pylians_b200.MAS_library as M
+            from pylians_b200.dist import ParticleBatches
+            shard = np.ascontiguousarray(pos[rank::world])
+            old, M.HOST_CHUNK = M.HOST_CHUNK, 300001
+            try:
+                parity.check_pk(eng.run(shard), PKL.Pk(d, box, 2, "CIC", 1), rtol=1e-4)
+            finally:
+                M.HOST_CHUNK = old
+            cuts = [0, 7, len(shard) // 3, len(shard)]
+            pb = ParticleBatches(lambda i: (torch.from_numpy(shard[cuts[i]:cuts[i + 1]]).cuda(), None), 3, len(shard))
+            parity.check_pk(eng.run(pb), PKL.Pk(d, box, 2, "CIC", 1), rtol=1e-4)
         gx = eng.run_x([torch.from_numpy(pos[rank::world]).cuda(), torch.from_numpy(pos2[rank::world]).cuda()],
                        [None, torch.from_numpy(W2[rank::world]).cuda()], ["CIC", "TSC"])
         d2 = np.zeros((dims,) * 3, np.float32); MASL.MA(pos2, d2, box, "TSC", W=W2); MASL.overdensity(d2)
