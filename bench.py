@@ -596,9 +596,14 @@ def run_ours(args, wl):
                     "sort_achieved_GBs": sort_bytes / (K["sort"] * 1e-3) / 1e9 if K["sort"] > 0 else None,
                     "tile_kernel_ms_per_step": K["tile"], "tile_kernel_launches_per_step": main["kernel_launches_per_step"]["tile"],
                     "tile_updates_per_s": updates / (K["tile"] * 1e-3)}
+        # atomic / L2 / LSU-pipe figures of the deposit kernels from the committed `ncu --set full` captures (512^3 launches)
         try:
             with open(os.path.join(ROOT, "profiles", "r2_ncu_deposit.json")) as f:
-                roof_dep["ncu"] = json.load(f)
+                keep = ("duration", "duration_unit", "l1tex__data_pipe_lsu_wavefronts_pct", "shared_atomic_instructions",
+                        "shared_atomic_wavefronts", "shared_bank_conflicts", "l2_throughput_pct", "dram_throughput_pct",
+                        "issue_active_pct", "warp_instructions", "achieved_occupancy_pct")
+                roof_dep["ncu"] = {name: [{k: l[k] for k in keep if k in l} for l in launches]
+                                   for name, launches in json.load(f).items() if not name.startswith("dropped")}
         except (OSError, ValueError):
             pass
 
