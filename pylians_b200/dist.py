@@ -183,7 +183,7 @@ class _Result(object):
 class SlabPk(object):
     """Distributed MA + Pk / XPk.  Every rank calls the same methods with its own particle shard."""
 
-    def __init__(self, dims, BoxSize, MAS="CIC", axis=2, group=None, ops=None, exchange="auto", exchange_chunks=4,
+    def __init__(self, dims, BoxSize, MAS="CIC", axis=2, group=None, ops=None, exchange="auto", exchange_chunks=2,
                  fft_chunks=4):
         """exchange: how per-rank deposits become x-slabs --
              "grid"      every rank deposits onto a full partial grid, then reduce-scatter (4 N^3 bytes per rank);
