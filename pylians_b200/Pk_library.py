@@ -178,18 +178,6 @@ def bin_modes(delta_k, dims, axis, mas_index, want_phase, write_back, ks=None, s
     return L, sums, counts
 
 
-_PINNED = {}
-
-
-def _pinned(n):
-    t = _PINNED.get(n)
-    if t is None:
-        t = torch.empty(n, dtype=torch.float64, pin_memory=True)
-        _PINNED.clear()
-        _PINNED[n] = t
-    return t
-
-
 _KGRID = {}
 
 
@@ -224,16 +212,17 @@ class _Bins(object):
                                                              float(fact), torch.cuda.current_stream(raw.device).cuda_stream),
                            "pylb_pk_finish_tables")
                 self.tables_done = True
-            # single async copy into a cached pinned buffer + one stream sync
-            host = _pinned(raw.numel())
+            # single async copy into a pinned buffer of this call's own + one stream sync.  The buffer comes from torch's
+            # caching host allocator (no cudaHostAlloc after the first calls) and IS the result: every attribute below is a
+            # view of it, so the 24 MB of a 2048^3 bin table are not copied a second time on the host.
+            host = torch.empty(raw.numel(), dtype=torch.float64, pin_memory=True)
             host.copy_(raw, non_blocking=True)
             torch.cuda.current_stream(raw.device).synchronize()
+            h = host.numpy()
             if self.tables_done:
-                h = host.numpy().copy()  # the caller's private copy: the pinned buffer is reused by the next call
                 s, c = h[:L.n_doubles], h[L.n_doubles:]
             else:
-                h = host.numpy()
-                s = h[:L.n_doubles]          # view of the pinned buffer: _finish only derives new arrays from it
+                s = h[:L.n_doubles]
                 c = h[L.n_doubles:].view(np.int64).astype(np.float64)   # counts < 2^53: exact in float64
         else:
             s = sums.cpu().numpy()
