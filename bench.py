@@ -417,6 +417,8 @@ def run_ours(args, wl):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # stdout carries ONE JSON line: whatever NCCL logs (its version banner under NCCL_DEBUG=VERSION) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     peaks, peak_src = read_peaks()
 

@@ -49,3 +49,24 @@ def test_reference_arm_line():
     assert d["config"]["mas"] == own["config"]["mas"] and d["config"]["axis"] == own["config"]["axis"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] in ("reference", "port")
+
+
+@pytest.mark.parametrize("name,gpus", [("r2_bench_2gpu.json", 2), ("r2_bench_4gpu.json", 4), ("r2_bench_8gpu.json", 8)])
+def test_multi_gpu_lines(name, gpus):
+    """The weak-scaling lines recorded under torchrun: whole-job value, NCCL-vs-single-GPU parity printed and green."""
+    d = _load(name)
+    assert d["n_gpus"] == gpus and d["scaling"] == "weak" and d["config"]["particles_total"] == gpus * 1024 ** 3
+    assert abs(d["value"] - d["config"]["particles_total"] / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    p = d["check"]["parity"]
+    assert p["ok"] is True and p["nmodes_exact"] is True and p["grid_max_rel"] <= 1e-5 and p["pk_max_rel"] <= 1e-5
+    assert {c["exchange"] for c in p["cases"]} == {"grid", "particles"}
+    assert d["e2e"]["h2d_bytes_per_step"] == 12 * d["config"]["particles_total"]        # totals over all ranks
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_north_star_line():
+    """BASELINE.json's target: 2048^3 particles, PCS, 2048^3 grid, l = 0, 2, 4, 8 GPUs, under 1 s per snapshot."""
+    d = _load("r2_bench_8gpu.json")
+    assert d["config"]["grid"] == 2048 and d["config"]["mas"] == ["PCS"] and d["config"]["particles_total"] == 2048 ** 3
+    assert d["s_per_snapshot"] < 1.0
+    assert d["roofline"]["ring_kernel_only"]["frac"] >= 0.60        # the binning kernel on the slab layout
