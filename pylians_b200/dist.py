@@ -215,10 +215,11 @@ class SlabPk(object):
         count = pos.total if batched else int(pos.shape[0])
         mode = self.exchange
         if mode == "auto":
-            # Whichever moves fewer bytes per rank: 4 N^3 (reduce-scatter of the partial grids, which also have to be
-            # zeroed and flushed in full) against 16 B per particle (all-to-all of the routed payload).  Measured on
-            # 8xB200, 512^3 particles per GPU (profiles/r1_dist_stages_8gpu.txt): N=1024, G=8: particles 14.4 ms vs grid
-            # 20.8 ms per snapshot; N=640, G=2: grid 9.7 vs particles 13.7 ms; 2048^3 PCS, G=8: particles 219 vs 295 ms.
+            # The reduce-scatter of the partial grids moves 4 N^3 bytes per rank and nothing hides it; the routed particles
+            # move 16 B each, but in pieces that cross NVLink while the previous piece is being deposited, and the deposit
+            # then only covers (and flushes) a slab instead of the whole cube.  Measured with 1024^3 PCS particles per GPU
+            # (profiles/r2_dist_stages_{2,4,8}gpu*.txt, ms per density_slab, grid / particles): G=2, 1280^3: 122.8 / 125.4;
+            # G=4, 1600^3: 141.3 / 122.3; G=8, 2048^3: 184.7 / 131.9 -- i.e. particles win once 8 N^3 > 16 B x particles.
             # Every rank must take the same branch, so the particle count is agreed on (max over ranks); the choice is
             # kept per (scheme, particle-count magnitude), and a stencil wider than a rank's slab always takes "grid".
             key = (MAS, count.bit_length())
@@ -229,7 +230,7 @@ class SlabPk(object):
                     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
                     npmax = int(t[0].item())
                 ok = G > 1 and self.nxl >= max(halo, 1)
-                self._auto_mode[key] = "particles" if (ok and 4 * N ** 3 > 16 * npmax) else "grid"
+                self._auto_mode[key] = "particles" if (ok and 8 * N ** 3 > 16 * npmax) else "grid"
             mode = self._auto_mode[key]
         if mode == "particles" and self.nxl < halo:
             raise ValueError("particle exchange needs at least %d planes per rank for %s" % (halo, MAS))
