@@ -175,32 +175,43 @@ extern "C" int pylb_ma_window(const float *pos, int64_t np, int64_t ps0, int64_t
 }
 
 // ---- reference-compatible host entry points (MAS_c.h:3-10) -------------------------------------
+// One stream per host thread, created on first use and kept; all device buffers of a call come from the stream-ordered
+// pool (no cudaMalloc / cudaFree, no stream creation per call: a caller looping over many small deposits used to pay four
+// synchronising allocations each time).
+static cudaStream_t masc_stream() {
+    static thread_local cudaStream_t st = nullptr;
+    if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) st = nullptr;
+    return st;
+}
+
 static void masc_host(int mas, float *pos, float *number, float *W, long particles, int dims, int axes, float box) {
     g_err[0] = 0;
     if (axes != 2 && axes != 3) { set_error("MAS_c entry: axes must be 2 or 3"); return; }
-    size_t cells = (size_t)dims * dims * (axes == 3 ? dims : 1);
+    keep_pool_memory();
+    const size_t cells = (size_t)dims * dims * (axes == 3 ? dims : 1);
     float *dpos = nullptr, *dgrid = nullptr, *dw = nullptr;
     void *ws = nullptr;
-    cudaStream_t st = nullptr;
-    bool ok = cudaStreamCreate(&st) == cudaSuccess;
-    ok = ok && cudaMalloc(&dpos, sizeof(float) * (size_t)particles * axes + 16) == cudaSuccess;
-    ok = ok && cudaMalloc(&dgrid, sizeof(float) * cells) == cudaSuccess;
-    if (ok && W) ok = cudaMalloc(&dw, sizeof(float) * (size_t)particles + 16) == cudaSuccess;
-    size_t wsb = pylb_ma_workspace_bytes(particles, axes, dims, mas, W != nullptr, 0, PYLB_MA_AUTO);
-    if (ok && wsb) ok = cudaMalloc(&ws, wsb) == cudaSuccess;
-    if (!ok) set_error("MAS_c entry: CUDA allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
-    if (ok) {
-        cudaMemcpyAsync(dpos, pos, sizeof(float) * (size_t)particles * axes, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dgrid, number, sizeof(float) * cells, cudaMemcpyHostToDevice, st);
-        if (W) cudaMemcpyAsync(dw, W, sizeof(float) * (size_t)particles, cudaMemcpyHostToDevice, st);
-        if (pylb_ma(dpos, particles, axes, axes, 1, dgrid, 0, dims, box, mas, dw, 1, PYLB_MA_AUTO, ws, wsb, st) == 0) {
-            cudaMemcpyAsync(number, dgrid, sizeof(float) * cells, cudaMemcpyDeviceToHost, st);
-            if (cudaStreamSynchronize(st) != cudaSuccess)
-                set_error("MAS_c entry: execution failed: %s", cudaGetErrorString(cudaGetLastError()));
-        }
+    cudaStream_t st = masc_stream();
+    bool ok = st != nullptr;
+    ScratchGuard guard(st);
+    ok = ok && cudaMallocAsync(&dpos, sizeof(float) * (size_t)particles * axes + 16, st) == cudaSuccess;
+    guard.add(dpos);
+    ok = ok && cudaMallocAsync(&dgrid, sizeof(float) * cells, st) == cudaSuccess;
+    guard.add(dgrid);
+    if (ok && W) { ok = cudaMallocAsync(&dw, sizeof(float) * (size_t)particles + 16, st) == cudaSuccess; guard.add(dw); }
+    const size_t wsb = pylb_ma_workspace_bytes(particles, axes, dims, mas, W != nullptr, 0, PYLB_MA_AUTO);
+    if (ok && wsb) { ok = cudaMallocAsync(&ws, wsb, st) == cudaSuccess; guard.add(ws); }
+    if (!ok) { set_error("MAS_c entry: CUDA allocation failed: %s", cudaGetErrorString(cudaGetLastError())); return; }
+    cudaMemcpyAsync(dpos, pos, sizeof(float) * (size_t)particles * axes, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dgrid, number, sizeof(float) * cells, cudaMemcpyHostToDevice, st);
+    if (W) cudaMemcpyAsync(dw, W, sizeof(float) * (size_t)particles, cudaMemcpyHostToDevice, st);
+    if (pylb_ma(dpos, particles, axes, axes, 1, dgrid, 0, dims, box, mas, dw, 1, PYLB_MA_AUTO, ws, wsb, st) == 0) {
+        cudaMemcpyAsync(number, dgrid, sizeof(float) * cells, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess)
+            set_error("MAS_c entry: execution failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } else {
+        cudaStreamSynchronize(st);               // the host arrays must not be in use by a pending copy when we return
     }
-    cudaFree(dpos); cudaFree(dgrid); cudaFree(dw); cudaFree(ws);
-    if (st) cudaStreamDestroy(st);
 }
 
 extern "C" void NGP(float *pos, float *number, float *W, long particles, int dims, int axes, float BoxSize, int threads) {
