@@ -1,5 +1,5 @@
 """A/B of the tile kernels of the tiled deposit (round 2): lane per particle (k=1) against stencil lanes with the
-optimistic CAS pair (k=2, PCS only).  CUDA events around MASL.MA and the library's own brackets around the sort stage
+optimistic CAS pair (k=2, TSC and PCS).  CUDA events around MASL.MA and the library's own brackets around the sort stage
 and the tile kernel.
 
     python profiles/deposit_ab.py [sizes...]      # default 512 1024

@@ -71,6 +71,28 @@ def _host_chunk(dims, ndim):
     return int(min(max(dims ** ndim // 4, 1 << 26), 1 << 28))
 
 
+def _chunk_bounds(npart, chunk, taper_floor=1 << 24):
+    """(lo, hi) ranges of the H2D chunks.  The copies run back to back and the deposit of a chunk is faster than its
+    copy, so what the caller waits for after the LAST copy has landed is the deposit of the last chunk: the final full
+    chunk is therefore cut into 1/2, 1/4, 1/4 (never below `taper_floor` particles)."""
+    bounds, lo = [], 0
+    while lo < npart:
+        hi = min(npart, lo + chunk)
+        bounds.append((lo, hi))
+        lo = hi
+    if len(bounds) >= 2:
+        lo, hi = bounds.pop()
+        n = hi - lo
+        cuts = [lo]
+        if n // 4 >= taper_floor:
+            cuts += [lo + n // 2, lo + n // 2 + n // 4]
+        elif n // 2 >= taper_floor:
+            cuts += [lo + n // 2]
+        cuts.append(hi)
+        bounds += [(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    return bounds
+
+
 _COPY_STREAMS = {}
 
 
@@ -143,11 +165,12 @@ def _deposit(pos, number, BoxSize, mas, W, z_repeat, grid_f64=False, algo=None):
     copied = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     cs.wait_stream(stream)
-    nchunks = (npart + chunk - 1) // chunk
+    bounds = _chunk_bounds(npart, chunk)
+    nchunks = len(bounds)
 
     def issue_copy(i):
         b = i % 2
-        lo, hi = i * chunk, min(npart, (i + 1) * chunk)
+        lo, hi = bounds[i]
         with torch.cuda.stream(cs):
             if i >= 2:
                 cs.wait_event(consumed[b])
@@ -159,7 +182,7 @@ def _deposit(pos, number, BoxSize, mas, W, z_repeat, grid_f64=False, algo=None):
     issue_copy(0)
     for i in range(nchunks):
         b = i % 2
-        lo, hi = i * chunk, min(npart, (i + 1) * chunk)
+        lo, hi = bounds[i]
         if i + 1 < nchunks:
             issue_copy(i + 1)
         stream.wait_event(copied[b])

@@ -32,10 +32,23 @@ __device__ __forceinline__ int axis_stencil(float p, float inv, float (&C)[Suppo
         return id;
     } else if constexpr (MAS == PYLB_TSC) {
         const int m = __double2int_rd((double)dist - 1.5);  // <int>floor(dist-1.5), :393
+        // `diff` is a float; the literals are doubles, so the polynomial is evaluated in double and
+        // rounded once to float (:396-399).  Keeps sum(weights) == 1 to ~1e-8 like the reference.
+        if (fabsf(dist) < 4194304.0f) {
+            // m + 1 <= dist - 0.5 < m + 2 exactly, fp32 subtraction is monotone and 0.5 / 1.5 are representable, so
+            // the three distances fall into [0.5, 1.5], [0, 0.5], [0.5, 1.5] and the reference's branches are known
+            // in advance (where two branches meet they give the same value): no compares, no divergence.
+            const float f1 = (float)(m + 1);
+            const float d0 = fabsf(__fsub_rn(f1, dist)), d1 = fabsf(__fsub_rn(__fadd_rn(f1, 1.0f), dist)),
+                        d2 = fabsf(__fsub_rn(__fadd_rn(f1, 2.0f), dist));
+            const double e0 = 1.5 - (double)d0, e2 = 1.5 - (double)d2;
+            C[0] = (float)(0.5 * e0 * e0);
+            C[1] = (float)(0.75 - (double)__fmul_rn(d1, d1));
+            C[2] = (float)(0.5 * e2 * e2);
+            return m + 1;
+        }
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-            // `diff` is a float; the literals are doubles, so the polynomial is evaluated in double and
-            // rounded once to float (:396-399).  Keeps sum(weights) == 1 to ~1e-8 like the reference.
+        for (int j = 0; j < 3; j++) {      // positions far outside the box (or not finite): the reference's branches as written
             const float diff = fabsf(__fsub_rn((float)(m + j + 1), dist));
             const double dd = (double)diff;
             float c;
@@ -47,13 +60,29 @@ __device__ __forceinline__ int axis_stencil(float p, float inv, float (&C)[Suppo
         return m + 1;
     } else {
         const int m = __double2int_rd((double)dist - 2.0);  // <int>floor(dist-2.0), :486
+        // double evaluation, one rounding to float (:489-492).  x / 6.0 is formed as x * (1.0 / 6.0): the two differ by
+        // at most one ulp of the double, i.e. in the rounded float for about one weight in 2^29.
+        constexpr double SIXTH = 1.0 / 6.0;
+        if (fabsf(dist) < 4194304.0f) {
+            // m + 2 = floor(dist): the four distances fall into [1, 2], [0, 1), (0, 1], (1, 2] -- outer, inner, inner,
+            // outer branch of the reference; where branches meet (1 and 2) they give the same value
+            const float f1 = (float)(m + 1);
+            const float d0 = fabsf(__fsub_rn(f1, dist)), d1 = fabsf(__fsub_rn(__fadd_rn(f1, 1.0f), dist)),
+                        d2 = fabsf(__fsub_rn(__fadd_rn(f1, 2.0f), dist)), d3 = fabsf(__fsub_rn(__fadd_rn(f1, 3.0f), dist));
+            const double u0 = 2.0 - (double)d0, u3 = 2.0 - (double)d3, a1 = (double)d1, a2 = (double)d2;
+            C[0] = (float)(u0 * u0 * u0 * SIXTH);
+            C[1] = (float)(fma(fma(3.0, a1, -6.0), a1 * a1, 4.0) * SIXTH);
+            C[2] = (float)(fma(fma(3.0, a2, -6.0), a2 * a2, 4.0) * SIXTH);
+            C[3] = (float)(u3 * u3 * u3 * SIXTH);
+            return m + 1;
+        }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 4; j++) {      // positions far outside the box (or not finite): the reference's branches as written
             const float diff = fabsf(__fsub_rn((float)(m + j + 1), dist));
-            const double dd = (double)diff;   // double evaluation, one rounding to float (:489-492)
+            const double dd = (double)diff;
             float c;
-            if (diff < 1.0f) c = (float)((4.0 - 6.0 * dd * dd + 3.0 * dd * dd * dd) / 6.0);
-            else if (diff < 2.0f) c = (float)((2.0 - dd) * (2.0 - dd) * (2.0 - dd) / 6.0);
+            if (diff < 1.0f) c = (float)((4.0 - 6.0 * dd * dd + 3.0 * dd * dd * dd) * SIXTH);
+            else if (diff < 2.0f) c = (float)((2.0 - dd) * (2.0 - dd) * (2.0 - dd) * SIXTH);
             else c = 0.0f;
             C[j] = c;
         }

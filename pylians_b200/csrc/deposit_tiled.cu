@@ -437,11 +437,13 @@ struct TileShape {
     static constexpr int THREADS = 256;
     static constexpr size_t SMEM = sizeof(float) * (size_t)CELLS;
     // deposit_lane_kernel: 16 warps per CTA; per-warp staging of the axis weights of 32 particles, word-major with
-    // pitch 33 (bank = word + particle)
+    // an even pitch of 34 words: a word row of two consecutive particles is one aligned 8-byte load, and both the
+    // staging stores (32 consecutive words) and the per-lane row reads (rows 2 banks apart) stay conflict-free
     static constexpr int LANE_THREADS = 512;
     static constexpr int LANE_CTAS = MAS == PYLB_PCS ? 2 : 3;      // CTAs per SM that fit shared memory
     static constexpr int SW = 3 * S + 1;                           // wx[S], wy[S], wz[S], W
-    static constexpr int STAGE_WORDS = SW * 33;
+    static constexpr int SP = 34;
+    static constexpr int STAGE_WORDS = SW * SP;
     static constexpr size_t LANE_SMEM = sizeof(float) * ((size_t)CELLS + (size_t)(LANE_THREADS / 32) * STAGE_WORDS);
 };
 
@@ -589,7 +591,7 @@ deposit_lane_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, c
                     const int *__restrict__ chunk_off, float *__restrict__ grid) {
     static_assert(MAS == PYLB_PCS || MAS == PYLB_TSC, "stencil lanes: TSC and PCS");
     using TS = TileShape<MAS, true>;
-    constexpr int S = TS::S, PB = 32, THREADS = TS::LANE_THREADS, NW = THREADS / 32, SP = PB + 1;
+    constexpr int S = TS::S, PB = 32, THREADS = TS::LANE_THREADS, NW = THREADS / 32, SP = TS::SP;
     constexpr bool PCS = MAS == PYLB_PCS;
     extern __shared__ __align__(16) float tile[];
     __shared__ WorkItem s_w;
@@ -606,19 +608,31 @@ deposit_lane_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, c
     const float *sy = stage + (S + lb) * SP, *sz = stage + (2 * S + lc) * SP, *sw = stage + 3 * S * SP;
     // the two cells of one step: (word offset, value) twice
     struct Step { int b0, b1; float v0, v1; };
-    auto fetch = [&](int pp, int cell0) {                 // PCS: particle pp, planes a and a+2.  TSC: particles pp and pp+1.
-        Step q;
-        if (PCS) {
-            const float y = sy[pp], z = sz[pp];
-            q.b0 = __shfl_sync(full, cell0, pp); q.b1 = q.b0 + 2 * TS::PL;
-            q.v0 = (sx0[pp] * y) * z; q.v1 = (sx1[pp] * y) * z;
-            if (HASW) { const float w = sw[pp]; q.v0 *= w; q.v1 *= w; }
+    // the steps of the particle pair (pp, pp + 1), pp even: every staged row is read as one 8-byte pair.
+    // PCS: two steps (one particle each: planes a and a+2).  TSC: one step (the two particles).
+    constexpr int NSTEP = PCS ? 2 : 1;
+    auto fetch2 = [&](int pp, int cell0, Step (&q)[NSTEP]) {
+        const float2 x0 = *reinterpret_cast<const float2 *>(sx0 + pp), y = *reinterpret_cast<const float2 *>(sy + pp),
+                     z = *reinterpret_cast<const float2 *>(sz + pp);
+        const int c0 = __shfl_sync(full, cell0, pp), c1 = __shfl_sync(full, cell0, pp + 1);
+        if constexpr (PCS) {
+            const float2 x1 = *reinterpret_cast<const float2 *>(sx1 + pp);
+            q[0].b0 = c0; q[0].b1 = c0 + 2 * TS::PL;
+            q[1].b0 = c1; q[1].b1 = c1 + 2 * TS::PL;
+            q[0].v0 = (x0.x * y.x) * z.x; q[0].v1 = (x1.x * y.x) * z.x;
+            q[1].v0 = (x0.y * y.y) * z.y; q[1].v1 = (x1.y * y.y) * z.y;
+            if (HASW) {
+                const float2 w = *reinterpret_cast<const float2 *>(sw + pp);
+                q[0].v0 *= w.x; q[0].v1 *= w.x; q[1].v0 *= w.y; q[1].v1 *= w.y;
+            }
         } else {
-            q.b0 = __shfl_sync(full, cell0, pp); q.b1 = __shfl_sync(full, cell0, pp + 1);
-            q.v0 = (sx0[pp] * sy[pp]) * sz[pp]; q.v1 = (sx0[pp + 1] * sy[pp + 1]) * sz[pp + 1];
-            if (HASW) { q.v0 *= sw[pp]; q.v1 *= sw[pp + 1]; }
+            q[0].b0 = c0; q[0].b1 = c1;
+            q[0].v0 = (x0.x * y.x) * z.x; q[0].v1 = (x0.y * y.y) * z.y;
+            if (HASW) {
+                const float2 w = *reinterpret_cast<const float2 *>(sw + pp);
+                q[0].v0 *= w.x; q[0].v1 *= w.y;
+            }
         }
-        return q;
     };
     auto apply = [&](const Step &q) {
         unsigned *p0 = cell + q.b0, *p1 = cell + q.b1;
@@ -641,7 +655,6 @@ deposit_lane_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, c
             atomicAdd(reinterpret_cast<float *>(cell + b + 2 * TS::PL), v1);
         }
     };
-    constexpr int STEP = PCS ? 1 : 2;                      // particles per step
     const int nitems = chunk_off[tg.ntiles];
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         __syncthreads();                         // the tile is clear, s_w is free
@@ -676,12 +689,18 @@ deposit_lane_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, c
                 // an atomic by itself)
                 // (fully unrolled on purpose: unrolling by 8 steps only -- a loop body that fits the instruction cache -- was
                 // measured slower, 8.5 against 7.9 ms at 512^3 PCS)
-                Step nq = fetch(0, cell0);
+                Step nq[NSTEP];
+                fetch2(0, cell0, nq);
 #pragma unroll
-                for (int pp = 0; pp < PB; pp += STEP) {
-                    const Step q = nq;
-                    if (pp + STEP < PB) nq = fetch(pp + STEP, cell0);
-                    if (active) apply(q);
+                for (int pp = 0; pp < PB; pp += 2) {
+                    Step q[NSTEP];
+#pragma unroll
+                    for (int u = 0; u < NSTEP; u++) q[u] = nq[u];
+                    if (pp + 2 < PB) fetch2(pp + 2, cell0, nq);
+                    if (active) {
+#pragma unroll
+                        for (int u = 0; u < NSTEP; u++) apply(q[u]);
+                    }
                 }
             } else {
                 while (todo) {
@@ -788,7 +807,7 @@ int ma_partition(const float *pos, int64_t np, int64_t ps0, int64_t ps1, const f
 }
 
 // tests / A-B runs (pylb_ma_debug_path): units digit 0 automatic, 2 force the deep sort, 3 / 4 deep with 1024 / 4 lo digits;
-// hundreds digit 0 automatic, 1 lane-per-particle tile kernel for every scheme, 2 stencil-lane kernel where it exists (PCS)
+// hundreds digit 0 automatic, 1 lane-per-particle tile kernel for every scheme, 2 stencil-lane kernel where it exists (TSC, PCS)
 static int g_force_sort = 0, g_force_kernel = 0;
 void ma_tiled_force_path(int p) {
     if (p < 0) p = 0;
@@ -923,6 +942,7 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
         // persistent CTAs walk the work items (tile, chunk) round-robin; every non-empty tile has at most n/CHUNK + 1 chunks
         const int64_t max_items = (int64_t)n / CHUNK + tg.ntiles;
         timing_begin(PYLB_T_TILE, st);
+        // TSC, PCS: stencil lanes with optimistic CAS pairs unless the lane-per-particle kernel is forced (A/B, tests)
         bool lanes = false;
         if constexpr (HAS_LANES) lanes = kern != 1;
         if (lanes) {

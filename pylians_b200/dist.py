@@ -264,12 +264,13 @@ class SlabPk(object):
         wbufs = [torch.empty(chunk, dtype=torch.float32, device=dev) for _ in range(2)] if h_w is not None else None
         copied = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
-        nchunks = (n + chunk - 1) // chunk
+        bounds = MASL._chunk_bounds(n, chunk)         # the last full chunk tapers: less work left after the last copy
+        nchunks = len(bounds)
         cs.wait_stream(cur)
 
         def issue(i):
             b = i % 2
-            lo, hi = i * chunk, min(n, (i + 1) * chunk)
+            lo, hi = bounds[i]
             with torch.cuda.stream(cs):
                 if i >= 2:
                     cs.wait_event(consumed[b])
@@ -281,7 +282,7 @@ class SlabPk(object):
         issue(0)
         for i in range(nchunks):
             b = i % 2
-            m = min(n, (i + 1) * chunk) - i * chunk
+            m = bounds[i][1] - bounds[i][0]
             if i + 1 < nchunks:
                 issue(i + 1)
             cur.wait_event(copied[b])

@@ -192,7 +192,7 @@ def test_reference_unit_tests_mass_conservation(MASL, mas, places, weighted):
 
 # algo 1: direct kernel.  algo 2 + debug path = 100 * kernel + sort: sort 0 automatic, 2 deep (second histogram sweep),
 # 3 / 4 deep with 1024 / 4 lo digits (the digit widths of the largest grids); kernel 0 automatic, 1 lane per particle for
-# every scheme, 2 stencil lanes where they exist (PCS)
+# every scheme, 2 stencil lanes where they exist (TSC, PCS)
 @pytest.mark.parametrize("algo,path", [(1, 0), (2, 0), (2, 2), (2, 3), (2, 4), (2, 100), (2, 102), (2, 200), (2, 202), (2, 203),
                                        (2, 204)])
 @pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
