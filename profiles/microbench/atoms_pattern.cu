@@ -5,7 +5,9 @@
 //   pattern 1  PCS stencil: base + a*688 + b*36 + c, a in {0,1}, b,c in 0..3, random base   (distinct banks, 8 rows)
 //   pattern 2  every lane random                               (lane-per-particle kernel)
 //   pattern 3  TSC stencil: base + a*649 + b*35 + c, 27 lanes
-// ops: 0 native int ATOMS.ADD without return, 1 float atomicAdd (CAS loop), 2 plain LDS + FADD + STS (no atomicity)
+// ops: 0 native int ATOMS.ADD without return, 1 float atomicAdd (CAS loop), 2 plain LDS + FADD + STS (no atomicity),
+//      3 optimistic 32-bit pair (2 LDS, 2 FADD, 2 CAS in flight, atomicAdd on failure: what deposit_lane_kernel issues),
+//      4 optimistic 64-bit CAS on two adjacent cells (pattern 4: lane = (a, b, z-pair), 32 lanes x 2 cells per instruction)
 // Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o atoms_pattern atoms_pattern.cu
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +26,7 @@ __global__ void k(float *out, int iters) {
     int loff; bool active = true;
     if (PATTERN == 0) loff = lane;
     else if (PATTERN == 1) loff = (lane >> 4) * 688 + ((lane >> 2) & 3) * 36 + (lane & 3);
+    else if (PATTERN == 4) loff = (lane >> 3) * 688 + ((lane >> 1) & 3) * 36 + (lane & 1) * 2;
     else if (PATTERN == 3) { active = lane < 27; loff = active ? (lane / 9) * 649 + ((lane / 3) % 3) * 35 + lane % 3 : 0; }
     else loff = 0;
     for (int it = 0; it < iters; it++) {
@@ -31,12 +34,28 @@ __global__ void k(float *out, int iters) {
         int base;
         if (PATTERN == 0) base = (h % (CELLS / 32 - 24)) * 32;
         else if (PATTERN == 1) base = (h % 16) * 688 + ((h >> 4) % 16) * 36 + ((h >> 8) % 32);
+        else if (PATTERN == 4) base = (h % 16) * 688 + ((h >> 4) % 16) * 36 + ((h >> 8) % 16) * 2;
         else if (PATTERN == 3) base = (h % 16) * 649 + ((h >> 4) % 16) * 35 + ((h >> 8) % 32);
         else base = hash(h ^ (lane * 0x9e3779b9u)) % (CELLS - 1400);
         int *p0 = s + base + loff, *p1 = p0 + (PATTERN == 1 ? 2 * 688 : 700);
         if (!active) continue;
         if (OP == 0) { atomicAdd(p0, it | 1); atomicAdd(p1, it | 3); }
         else if (OP == 1) { atomicAdd((float *)p0, 1.0f); atomicAdd((float *)p1, 1.0f); }
+        else if (OP == 3) {
+            unsigned *q0 = (unsigned *)p0, *q1 = (unsigned *)p1;
+            const unsigned o0 = *(volatile unsigned *)q0, o1 = *(volatile unsigned *)q1;
+            const unsigned r0 = atomicCAS(q0, o0, __float_as_uint(__uint_as_float(o0) + 1.0f));
+            const unsigned r1 = atomicCAS(q1, o1, __float_as_uint(__uint_as_float(o1) + 1.0f));
+            if (r0 != o0) atomicAdd((float *)p0, 1.0f);
+            if (r1 != o1) atomicAdd((float *)p1, 1.0f);
+        } else if (OP == 4) {
+            unsigned long long *q0 = (unsigned long long *)p0;
+            const unsigned long long o = *(volatile unsigned long long *)q0;
+            const float lo = __uint_as_float((unsigned)o) + 1.0f, hi = __uint_as_float((unsigned)(o >> 32)) + 1.0f;
+            const unsigned long long nv = (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+            const unsigned long long r = atomicCAS(q0, o, nv);
+            if (r != o) { atomicAdd((float *)p0, 1.0f); atomicAdd((float *)p0 + 1, 1.0f); }
+        }
         else { float a = ((float *)p0)[0], b = ((float *)p1)[0]; ((float *)p0)[0] = a + 1.0f; ((float *)p1)[0] = b + 1.0f; }
     }
     __syncthreads();
@@ -58,7 +77,7 @@ void run(const char *name, float *out) {
             float ms; cudaEventElapsedTime(&ms, a, b); if (ms < best) best = ms;
         }
         const double lanes = (PATTERN == 3 ? 27.0 : 32.0);
-        const double ops = (double)blocks * (threads / 32) * iters * 2 * lanes;
+        const double ops = (double)blocks * (threads / 32) * iters * 2 * lanes;   // OP 4: one instruction, two cells per lane
         printf("%-44s warps/SM=%2d: %8.3f ms  %8.1f G lane-updates/s  %6.2f per clk per SM @1.965 GHz\n", name, warps_per_sm, best,
                ops / best / 1e6, ops / (best * 1e-3) / 148 / 1.965e9);
     }
@@ -70,6 +89,8 @@ int main() {
     run<1, 0>("int ATOMS.ADD, PCS stencil (8 rows x 4)", out);
     run<3, 0>("int ATOMS.ADD, TSC stencil (9 rows x 3)", out);
     run<2, 0>("int ATOMS.ADD, random lanes", out);
+    run<1, 3>("optimistic 32-bit CAS pair, PCS stencil", out);
+    run<4, 4>("optimistic 64-bit CAS (2 cells), PCS z-pairs", out);
     run<0, 1>("float CAS, 32 contiguous words", out);
     run<1, 1>("float CAS, PCS stencil", out);
     run<2, 1>("float CAS, random lanes", out);

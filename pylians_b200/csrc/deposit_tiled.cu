@@ -37,6 +37,9 @@ namespace pylb {
 
 constexpr int TX = 16, TY = 16, TZ = 32;     // cells per tile
 constexpr int CHUNK = 8192;                  // particles per work item
+#ifndef PYLB_LANE_DEPTH
+#define PYLB_LANE_DEPTH 2                     // stencil-lane kernel: steps (compare-and-swap pairs) in flight together
+#endif
 // Particles sorted and deposited per round.  A round flushes every tile it touches (the whole grid plus halo for a
 // space-filling input: ~3 x 4 B per cell of red.global traffic), so it should hold about one particle per cell; the
 // workspace (two float4 payload buffers, 32 B per particle of a round) bounds it from above.  2^28 particles (8.6 GB) up
@@ -440,7 +443,10 @@ struct TileShape {
     // an even pitch of 34 words: a word row of two consecutive particles is one aligned 8-byte load, and both the
     // staging stores (32 consecutive words) and the per-lane row reads (rows 2 banks apart) stay conflict-free
     static constexpr int LANE_THREADS = 512;
-    static constexpr int LANE_CTAS = MAS == PYLB_PCS ? 2 : 3;      // CTAs per SM that fit shared memory
+#ifndef PYLB_TSC_LANE_CTAS
+#define PYLB_TSC_LANE_CTAS 3
+#endif
+    static constexpr int LANE_CTAS = MAS == PYLB_PCS ? 2 : PYLB_TSC_LANE_CTAS;      // CTAs per SM (PCS: what fits shared memory)
     static constexpr int SW = 3 * S + 1;                           // wx[S], wy[S], wz[S], W
     static constexpr int SP = 34;
     static constexpr int STAGE_WORDS = SW * SP;
@@ -611,7 +617,7 @@ deposit_lane_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, c
     // the steps of the particle pair (pp, pp + 1), pp even: every staged row is read as one 8-byte pair.
     // PCS: two steps (one particle each: planes a and a+2).  TSC: one step (the two particles).
     constexpr int NSTEP = PCS ? 2 : 1;
-    auto fetch2 = [&](int pp, int cell0, Step (&q)[NSTEP]) {
+    auto fetch2 = [&](int pp, int cell0, Step *q) {
         const float2 x0 = *reinterpret_cast<const float2 *>(sx0 + pp), y = *reinterpret_cast<const float2 *>(sy + pp),
                      z = *reinterpret_cast<const float2 *>(sz + pp);
         const int c0 = __shfl_sync(full, cell0, pp), c1 = __shfl_sync(full, cell0, pp + 1);
@@ -634,14 +640,46 @@ deposit_lane_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, c
             }
         }
     };
-    auto apply = [&](const Step &q) {
-        unsigned *p0 = cell + q.b0, *p1 = cell + q.b1;
-        const unsigned o0 = *reinterpret_cast<volatile unsigned *>(p0), o1 = *reinterpret_cast<volatile unsigned *>(p1);
-        const unsigned r0 = atomicCAS(p0, o0, __float_as_uint(__uint_as_float(o0) + q.v0));
-        // TSC: the two particles may share their base cell; the second CAS then sees a stale value and is repaired below
-        const unsigned r1 = atomicCAS(p1, o1, __float_as_uint(__uint_as_float(o1) + q.v1));
-        if (r0 != o0) atomicAdd(reinterpret_cast<float *>(p0), q.v0);
-        if (r1 != o1) atomicAdd(reinterpret_cast<float *>(p1), q.v1);
+    // NQ steps at a time: all 2 NQ loads, then all 2 NQ compare-and-swaps are in flight together before the first result
+    // is looked at (the float CAS rate on shared memory is latency-bound: it doubles from 16 to 32 warps per SM,
+    // profiles/r2_atoms_pattern.txt).  Two steps of a group may meet in a cell (equal particles): the later CAS then fails
+    // on its stale value and is repaired like a collision with another warp.
+    constexpr int NQ = PCS ? PYLB_LANE_DEPTH : 1, GP = NQ * (PCS ? 1 : 2);   // steps / particles per group (TSC: deeper groups spill at 3 CTAs per SM and measured slower)
+    static_assert(PB % GP == 0 && GP % 2 == 0, "groups are whole particle pairs");
+    auto fetch_group = [&](int pp, int cell0, Step (&q)[NQ]) {
+#pragma unroll
+        for (int u = 0; u < GP; u += 2) fetch2(pp + u, cell0, &q[(u / 2) * NSTEP]);
+    };
+    auto apply_group = [&](const Step (&q)[NQ]) {
+        unsigned *p0[NQ], *p1[NQ], o0[NQ], o1[NQ], r0[NQ], r1[NQ];
+#pragma unroll
+        for (int u = 0; u < NQ; u++) {
+            p0[u] = cell + q[u].b0;
+            p1[u] = PCS ? p0[u] + 2 * TS::PL : cell + q[u].b1;
+            o0[u] = *reinterpret_cast<volatile unsigned *>(p0[u]);
+            o1[u] = *reinterpret_cast<volatile unsigned *>(p1[u]);
+        }
+        bool bad = false;
+#pragma unroll
+        for (int u = 0; u < NQ; u++) {
+            r0[u] = atomicCAS(p0[u], o0[u], __float_as_uint(__uint_as_float(o0[u]) + q[u].v0));
+            // TSC: the two particles of a step may share their base cell; the second CAS then sees a stale value
+            r1[u] = atomicCAS(p1[u], o1[u], __float_as_uint(__uint_as_float(o1[u]) + q[u].v1));
+        }
+#pragma unroll
+        for (int u = 0; u < NQ; u++) bad = bad || r0[u] != o0[u] || r1[u] != o1[u];
+        // ~7 % of the CAS lose against another warp of the CTA (ncu: 0.29 repairs per particle).  One branch for the group;
+        // a failed CAS has returned the cell's current value, so the repair is a second optimistic CAS on that value
+        // (2 shared-memory wavefronts) and only its rare failure takes the spin loop of atomicAdd (8 wavefronts measured).
+        if (bad) {
+#pragma unroll
+            for (int u = 0; u < NQ; u++) {
+                if (r0[u] != o0[u] && atomicCAS(p0[u], r0[u], __float_as_uint(__uint_as_float(r0[u]) + q[u].v0)) != r0[u])
+                    atomicAdd(reinterpret_cast<float *>(p0[u]), q[u].v0);
+                if (r1[u] != o1[u] && atomicCAS(p1[u], r1[u], __float_as_uint(__uint_as_float(r1[u]) + q[u].v1)) != r1[u])
+                    atomicAdd(reinterpret_cast<float *>(p1[u]), q[u].v1);
+            }
+        }
     };
     auto single = [&](int pp, int cell0) {                // one particle (TSC tail / partial batches)
         const int b = __shfl_sync(full, cell0, pp);
@@ -689,18 +727,15 @@ deposit_lane_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, c
                 // an atomic by itself)
                 // (fully unrolled on purpose: unrolling by 8 steps only -- a loop body that fits the instruction cache -- was
                 // measured slower, 8.5 against 7.9 ms at 512^3 PCS)
-                Step nq[NSTEP];
-                fetch2(0, cell0, nq);
+                Step nq[NQ];
+                fetch_group(0, cell0, nq);
 #pragma unroll
-                for (int pp = 0; pp < PB; pp += 2) {
-                    Step q[NSTEP];
+                for (int pp = 0; pp < PB; pp += GP) {
+                    Step q[NQ];
 #pragma unroll
-                    for (int u = 0; u < NSTEP; u++) q[u] = nq[u];
-                    if (pp + 2 < PB) fetch2(pp + 2, cell0, nq);
-                    if (active) {
-#pragma unroll
-                        for (int u = 0; u < NSTEP; u++) apply(q[u]);
-                    }
+                    for (int u = 0; u < NQ; u++) q[u] = nq[u];
+                    if (pp + GP < PB) fetch_group(pp + GP, cell0, nq);
+                    if (active) apply_group(q);
                 }
             } else {
                 while (todo) {
