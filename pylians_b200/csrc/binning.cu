@@ -1263,84 +1263,160 @@ ring2x_finish_kernel(BinGeom g, const double *__restrict__ t3, int t3_kz, int nb
     else red_add_u64(g.counts + g.o_n3d + b, (uint64_t)(acc + 0.5));
 }
 
+// Running per-lane sums for the special-column kernels.  A warp walks a CONTIGUOUS range of the r2-sorted row table, 32 rows
+// per step; with kz fixed both k_index = floor(sqrt(r2 + kz^2)) and k_per = floor(sqrt(r2)) are non-decreasing along the
+// table and the 32 rows of a step hardly ever span more than two bins.  Every lane therefore keeps sums for the bin of the
+// step's first row (`cur`) and for the next one; only when `cur` moves are both summed over the warp and added to the bins
+// (one red.global per value) -- a handful of times per warp instead of once per 32 rows and distinct bin, which is what
+// bounded these kernels: red.global on the same few hot bins from every warp serialises.
+template <int NV>
+struct RunSums {
+    int cur;
+    double a[NV], b[NV];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int q = 0; q < NV; q++) { a[q] = 0; b[q] = 0; }
+    }
+    __device__ __forceinline__ void init() { cur = -2; clear(); }
+    // all lanes; flush(key, sums) runs on lane 0 for every key with a non-zero LAST value (the mode count)
+    template <class FLUSH>
+    __device__ __forceinline__ void flush_all(FLUSH flush) {
+        const unsigned full = 0xffffffffu;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            double t[NV];
+#pragma unroll
+            for (int q = 0; q < NV; q++) {
+                t[q] = half ? b[q] : a[q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t[q] += __shfl_xor_sync(full, t[q], o);
+            }
+            if ((threadIdx.x & 31) == 0 && t[NV - 1] > 0.5) flush(cur + half, t);
+        }
+        clear();
+    }
+    // kmin: the key of the step's first row (warp-uniform)
+    template <class FLUSH>
+    __device__ __forceinline__ void step(int kmin, bool valid, int key, const double (&v)[NV], FLUSH flush) {
+        if (kmin != cur) {
+            if (cur >= 0) flush_all(flush);
+            cur = kmin;
+        }
+        if (valid) {
+            if (key == cur) {
+#pragma unroll
+                for (int q = 0; q < NV; q++) a[q] += v[q];
+            } else if (key == cur + 1) {
+#pragma unroll
+                for (int q = 0; q < NV; q++) b[q] += v[q];
+            } else {
+                flush(key, v);                  // more than two bins in one step: only among the first few hundred rows
+            }
+        }
+    }
+};
+
+// rows [lo, hi) of warp `w` of `nw`: equal contiguous shares, whole steps of 32 rows
+__device__ __forceinline__ void warp_rows(int nrows, int &lo, int &hi) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long steps = (nrows + 31) / 32, per = (steps + nw - 1) / nw;
+    lo = (int)min((long long)nrows, w * per * 32);
+    hi = (int)min((long long)nrows, (w + 1) * per * 32);
+}
+
 // special columns of the ring2x path: special2_kernel for F = 2 or 3 fields (no phase term)
 template <int F>
 __global__ void __launch_bounds__(256)
 special2x_kernel(BinGeom g, FieldPtrs dk, const Row2 *__restrict__ tab, int nrows) {
-    constexpr int X = F * (F - 1) / 2, Q = F + X;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // whole warps stay alive: shuffles below use the full mask
-    const int kz = blockIdx.y == 0 ? 0 : g.middle;
-    bool valid = i < nrows;
-    Row2 e;
-    e.off = 0; e.r2 = 0; e.chi = e.clo = 0.f; e.kx = e.ky = 0;
-    if (valid) e = tab[i];
-    const int kx = e.kx, ky = e.ky;
-    // keep one of each conjugate pair, Pk_library.pyx:326-330 / :640-644
-    if (kx < 0) valid = false;
-    if ((kx == 0 || (kx == g.middle && g.even)) && ky < 0) valid = false;
-    const int n = e.r2 + kz * kz, m1 = g.middle + 1;
-    const int b3 = isqrt_exact(n), b2 = isqrt_exact(e.r2);
-    double v3[3 * Q + 2], v2[Q + 1], v1[Q + 1];
+    constexpr int X = F * (F - 1) / 2, Q = F + X, N3 = 3 * Q + 2, N2 = Q + 1;
+    const int kz = blockIdx.y == 0 ? 0 : g.middle, m1 = g.middle + 1;
+    const int lane = threadIdx.x & 31;
+    double v1[N2];                                             // the 1-D bin is kz itself: one running sum per thread
 #pragma unroll
-    for (int q = 0; q < 3 * Q + 2; q++) v3[q] = 0;
-#pragma unroll
-    for (int q = 0; q < Q + 1; q++) { v2[q] = 0; v1[q] = 0; }
-    if (valid) {
-        const double k = sqrt((double)n);
-        const double mu = (n == 0) ? 0.0 : (double)kz / k;
-        const double mu2 = mu * mu;
-        const double w2 = (3.0 * mu2 - 1.0) / 2.0, w4 = (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0;
-        const int ax = kx, ay = ky < 0 ? -ky : ky;
-        double re[F], im[F], d[Q];
-#pragma unroll
-        for (int f = 0; f < F; f++) {
-            const float mf = (float)(g.mas_tab[f * m1 + ax] * g.mas_tab[f * m1 + ay] * g.mas_tab[f * m1 + kz]);
-            const float2 z = *(reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(dk.p[f]) + e.off) + kz);
-            re[f] = (double)__fmul_rn(z.x, mf); im[f] = (double)__fmul_rn(z.y, mf);
-            d[f] = re[f] * re[f] + im[f] * im[f];
-        }
-        int ix = 0;
-#pragma unroll
-        for (int a = 0; a < F; a++)
-#pragma unroll
-            for (int b = a + 1; b < F; b++) { d[F + ix] = re[a] * re[b] + im[a] * im[b]; ix++; }
-        const bool in1d = n <= g.middle * g.middle;
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-            v3[3 * q] = d[q]; v3[3 * q + 1] = d[q] * w2; v3[3 * q + 2] = d[q] * w4;
-            v2[q] = d[q];
-            if (in1d) v1[q] = d[q];
-        }
-        v3[3 * Q] = k; v3[3 * Q + 1] = 1.0;
-        v2[Q] = 1.0;
-        if (in1d) v1[Q] = 1.0;
-    }
-    warp_reduce_by_key<3 * Q + 2>(b3, valid, v3, [&](int b, const double (&s)[3 * Q + 2]) {
+    for (int q = 0; q < N2; q++) v1[q] = 0;
+    RunSums<N3> r3;
+    RunSums<N2> r2s;
+    r3.init(); r2s.init();
+    auto flush3 = [&](int b, const double (&t)[N3]) {
 #pragma unroll
         for (int l = 0; l < 3; l++) {
 #pragma unroll
-            for (int f = 0; f < F; f++) red_add(g.sums + g.o_p3d + ((long long)b * 3 + l) * F + f, s[3 * f + l]);
+            for (int f = 0; f < F; f++) red_add(g.sums + g.o_p3d + ((long long)b * 3 + l) * F + f, t[3 * f + l]);
 #pragma unroll
-            for (int x = 0; x < X; x++) red_add(g.sums + g.o_x3d + ((long long)b * 3 + l) * X + x, s[3 * (F + x) + l]);
+            for (int x = 0; x < X; x++) red_add(g.sums + g.o_x3d + ((long long)b * 3 + l) * X + x, t[3 * (F + x) + l]);
         }
-        red_add(g.sums + g.o_k3d + b, s[3 * Q]);
-        red_add_u64(g.counts + g.o_n3d + b, (uint64_t)(s[3 * Q + 1] + 0.5));
-    });
-    warp_reduce_by_key<Q + 1>(b2, valid, v2, [&](int b, const double (&s)[Q + 1]) {
+        red_add(g.sums + g.o_k3d + b, t[3 * Q]);
+        red_add_u64(g.counts + g.o_n3d + b, (uint64_t)(t[3 * Q + 1] + 0.5));
+    };
+    auto flush2 = [&](int b, const double (&t)[N2]) {
         const long long i2 = (long long)g.kmax_par1 * b + kz;
 #pragma unroll
-        for (int f = 0; f < F; f++) red_add(g.sums + g.o_p2d + i2 * F + f, s[f]);
+        for (int f = 0; f < F; f++) red_add(g.sums + g.o_p2d + i2 * F + f, t[f]);
 #pragma unroll
-        for (int x = 0; x < X; x++) red_add(g.sums + g.o_x2d + i2 * X + x, s[F + x]);
-        red_add_u64(g.counts + g.o_n2d + i2, (uint64_t)(s[Q] + 0.5));
-    });
-    warp_reduce_by_key<Q + 1>(0, valid, v1, [&](int, const double (&s)[Q + 1]) {
-        if (s[Q] > 0.5) {
+        for (int x = 0; x < X; x++) red_add(g.sums + g.o_x2d + i2 * X + x, t[F + x]);
+        red_add_u64(g.counts + g.o_n2d + i2, (uint64_t)(t[Q] + 0.5));
+    };
+    int lo, hi;
+    warp_rows(nrows, lo, hi);
+    for (int i0 = lo; i0 < hi; i0 += 32) {                     // warp-uniform
+        const int i = i0 + lane;
+        bool valid = i < hi;
+        Row2 e;
+        e.off = 0; e.r2 = 0; e.chi = e.clo = 0.f; e.kx = e.ky = 0;
+        if (valid) e = tab[i];
+        const int kx = e.kx, ky = e.ky;
+        // keep one of each conjugate pair, Pk_library.pyx:326-330 / :640-644
+        if (kx < 0) valid = false;
+        if ((kx == 0 || (kx == g.middle && g.even)) && ky < 0) valid = false;
+        const int n = e.r2 + kz * kz;
+        const int b3 = isqrt_exact(n), b2 = isqrt_exact(e.r2);
+        double v3[N3], v2[N2];
 #pragma unroll
-            for (int f = 0; f < F; f++) red_add(g.sums + g.o_p1d + (long long)kz * F + f, s[f]);
+        for (int q = 0; q < N3; q++) v3[q] = 0;
 #pragma unroll
-            for (int x = 0; x < X; x++) red_add(g.sums + g.o_x1d + (long long)kz * X + x, s[F + x]);
-            red_add_u64(g.counts + g.o_n1d + kz, (uint64_t)(s[Q] + 0.5));
+        for (int q = 0; q < N2; q++) v2[q] = 0;
+        if (valid) {
+            const double k = sqrt((double)n);
+            const double mu = (n == 0) ? 0.0 : (double)kz / k;
+            const double mu2 = mu * mu;
+            const double w2 = (3.0 * mu2 - 1.0) / 2.0, w4 = (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0;
+            const int ax = kx, ay = ky < 0 ? -ky : ky;
+            double re[F], im[F], d[Q];
+#pragma unroll
+            for (int f = 0; f < F; f++) {
+                const float mf = (float)(g.mas_tab[f * m1 + ax] * g.mas_tab[f * m1 + ay] * g.mas_tab[f * m1 + kz]);
+                const float2 z = *(reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(dk.p[f]) + e.off) + kz);
+                re[f] = (double)__fmul_rn(z.x, mf); im[f] = (double)__fmul_rn(z.y, mf);
+                d[f] = re[f] * re[f] + im[f] * im[f];
+            }
+            int ix = 0;
+#pragma unroll
+            for (int a = 0; a < F; a++)
+#pragma unroll
+                for (int b = a + 1; b < F; b++) { d[F + ix] = re[a] * re[b] + im[a] * im[b]; ix++; }
+            const bool in1d = n <= g.middle * g.middle;
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                v3[3 * q] = d[q]; v3[3 * q + 1] = d[q] * w2; v3[3 * q + 2] = d[q] * w4;
+                v2[q] = d[q];
+                if (in1d) v1[q] += d[q];
+            }
+            v3[3 * Q] = k; v3[3 * Q + 1] = 1.0;
+            v2[Q] = 1.0;
+            if (in1d) v1[Q] += 1.0;
+        }
+        r3.step(__shfl_sync(0xffffffffu, b3, 0), valid, b3, v3, flush3);
+        r2s.step(__shfl_sync(0xffffffffu, b2, 0), valid, b2, v2, flush2);
+    }
+    if (r3.cur >= 0) r3.flush_all(flush3);
+    if (r2s.cur >= 0) r2s.flush_all(flush2);
+    warp_reduce_by_key<N2>(0, true, v1, [&](int, const double (&t)[N2]) {
+        if (t[Q] > 0.5) {
+#pragma unroll
+            for (int f = 0; f < F; f++) red_add(g.sums + g.o_p1d + (long long)kz * F + f, t[f]);
+#pragma unroll
+            for (int x = 0; x < X; x++) red_add(g.sums + g.o_x1d + (long long)kz * X + x, t[F + x]);
+            red_add_u64(g.counts + g.o_n1d + kz, (uint64_t)(t[Q] + 0.5));
         }
     });
 }
@@ -1380,7 +1456,8 @@ static void ring2_levels(int rows, int per_level, int P, Ring2Sched &sc, int &nl
 }
 
 template <bool PHASE>
-static int launch_ring2(const BinGeom &g, const float2 *dk, const Row2 *tab, int n0, int n1, int kz_hi, int *counter, int nbins3, cudaStream_t st) {
+static int launch_ring2(const BinGeom &g, const float2 *dk, const Row2 *tab, int n0, int n1, int kz_hi, int *counter, int nbins3,
+                       double *t3, cudaStream_t st) {
     const size_t smem = sizeof(Ring2Smem);
     static bool attr_set = false;
     if (!attr_set) {
@@ -1409,13 +1486,7 @@ static int launch_ring2(const BinGeom &g, const float2 *dk, const Row2 *tab, int
     sc.nlevels = nlev;
     PYLB_REQUIRE(sc.base[0][nlev] == n0 && sc.base[1][nlev] == n1, "ring2: row table too large for the span schedule");
     PYLB_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), st));
-    double *t3 = nullptr;
-    const int t3_kz = (kz_hi + 1 + 3) & ~3;                     // kz = 0 .. kz_hi, rows padded to 32 bytes
-    const size_t t3_bytes = sizeof(double) * (size_t)nbins3 * R2_T3_VALS * t3_kz;
-    ScratchGuard guard(st);
-    PYLB_CHECK(cudaMallocAsync(&t3, t3_bytes, st));
-    guard.add(t3);
-    PYLB_CHECK(cudaMemsetAsync(t3, 0, t3_bytes, st));
+    const int t3_kz = (kz_hi + 1 + 3) & ~3;                     // kz = 0 .. kz_hi, rows padded to 32 bytes; t3 comes zeroed
     long long *trace = nullptr;
     const char *trace_path = getenv("PYLB_RING2_TRACE");
     const int nitems = sc.nlevels * sc.per_level * nseg * npar;
@@ -1450,7 +1521,7 @@ static int launch_ring2(const BinGeom &g, const float2 *dk, const Row2 *tab, int
 
 template <int F>
 static int launch_ring2x(const BinGeom &g, const FieldPtrs &dk, const Row2 *tab, const float2 *cext, int nrows, int n0, int n1,
-                         int kz_hi, int *counter, int nbins3, cudaStream_t st) {
+                         int kz_hi, int *counter, int nbins3, double *t3, cudaStream_t st) {
     constexpr int NV = 3 * (F + F * (F - 1) / 2) + 2;
     const size_t smem = sizeof(Ring2xSmem<F>);
     PYLB_CHECK(cudaFuncSetAttribute(ring2x_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1476,13 +1547,7 @@ static int launch_ring2x(const BinGeom &g, const FieldPtrs &dk, const Row2 *tab,
     sc.nlevels = nlev;
     PYLB_REQUIRE(sc.base[0][nlev] == n0 && sc.base[1][nlev] == n1, "ring2x: row table too large for the span schedule");
     PYLB_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), st));
-    double *t3 = nullptr;
-    const int t3_kz = (kz_hi + 1 + 3) & ~3;
-    const size_t t3_bytes = sizeof(double) * (size_t)nbins3 * NV * t3_kz;
-    ScratchGuard guard(st);
-    PYLB_CHECK(cudaMallocAsync(&t3, t3_bytes, st));
-    guard.add(t3);
-    PYLB_CHECK(cudaMemsetAsync(t3, 0, t3_bytes, st));
+    const int t3_kz = (kz_hi + 1 + 3) & ~3;                     // t3 comes zeroed
     timing_begin(PYLB_T_RING, st);
     ring2x_kernel<F><<<ctas, R2_T, smem, st>>>(g, dk, tab, cext, nrows, n0, kz_hi, nseg, npar, sc, counter, t3, t3_kz);
     timing_end(PYLB_T_RING, st);
@@ -1608,61 +1673,74 @@ special_kernel(BinGeom g, FieldPtrs dk, const ROW *__restrict__ tab, int nrows, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// special columns for the ring2 path (one field, no write-back): one thread per (row, plane), then a warp-level
-// reduce-by-key -- neighbouring rows of the r2-sorted table share their bins, so a warp issues one red.global
-// per value for each of its 1-2 distinct bins instead of one per thread (red.global on the hot 3-D bins
-// serialises; the 16-rows-per-thread kernel above spends 50-75 us there at 512^3).
+// special columns for the ring2 path (one field, no write-back): a warp walks a contiguous range of the r2-sorted table,
+// one thread per row and step, with running sums for the current and the next bin (RunSums above) -- red.global on the
+// hot bins serialises: the 16-rows-per-thread kernel above spends 50-75 us there at 512^3, a warp-level reduce-by-key
+// per 32 rows 84 us at 1024^3.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 special2_kernel(BinGeom g, const float2 *__restrict__ dk, const Row2 *__restrict__ tab, int nrows, int want_phase) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // whole warps stay alive: shuffles below use the full mask
     const int kz = blockIdx.y == 0 ? 0 : g.middle;
-    bool valid = i < nrows;
-    Row2 e;
-    e.off = 0; e.r2 = 0; e.chi = e.clo = 0.f; e.kx = e.ky = 0;
-    if (valid) e = tab[i];
-    const int kx = e.kx, ky = e.ky;
-    // keep one of each conjugate pair, :326-330
-    if (kx < 0) valid = false;
-    if ((kx == 0 || (kx == g.middle && g.even)) && ky < 0) valid = false;
-    const int n = e.r2 + kz * kz;
-    const int b3 = isqrt_exact(n), b2 = isqrt_exact(e.r2);
-    double v3[6] = {0, 0, 0, 0, 0, 0}, v2[2] = {0, 0}, v1[2] = {0, 0};
-    if (valid) {
-        const double k = sqrt((double)n);
-        const double mu = (n == 0) ? 0.0 : (double)kz / k;
-        const double mu2 = mu * mu;
-        const int ax = kx, ay = ky < 0 ? -ky : ky;
-        const float mf = (float)(g.mas_tab[ax] * g.mas_tab[ay] * g.mas_tab[kz]);   // :354
-        const float2 z = *(reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(dk) + e.off) + kz);
-        const float r = __fmul_rn(z.x, mf), q = __fmul_rn(z.y, mf);                // :355
-        const double d2 = (double)r * (double)r + (double)q * (double)q;           // :358-360
-        v3[0] = d2;
-        v3[1] = d2 * ((3.0 * mu2 - 1.0) / 2.0);
-        v3[2] = d2 * ((35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0);
-        v3[3] = k;
-        v3[4] = 1.0;
-        v3[5] = want_phase ? (double)phase_sq(r, (float)d2) : 0.0;                 // atan2(re, |delta_k|)^2, :361
-        v2[0] = d2; v2[1] = 1.0;
-        if (n <= g.middle * g.middle) { v1[0] = d2; v1[1] = 1.0; }
-    }
-    warp_reduce_by_key<6>(b3, valid, v3, [&](int b, const double (&s)[6]) {
-        red_add(g.sums + g.o_p3d + (long long)b * 3 + 0, s[0]);
-        red_add(g.sums + g.o_p3d + (long long)b * 3 + 1, s[1]);
-        red_add(g.sums + g.o_p3d + (long long)b * 3 + 2, s[2]);
-        red_add(g.sums + g.o_k3d + b, s[3]);
-        red_add_u64(g.counts + g.o_n3d + b, (uint64_t)(s[4] + 0.5));
-        if (want_phase) red_add(g.sums + g.o_phase + b, s[5]);
-    });
-    warp_reduce_by_key<2>(b2, valid, v2, [&](int b, const double (&s)[2]) {
+    const int lane = threadIdx.x & 31;
+    double v1[2] = {0, 0};                                     // the 1-D bin is kz itself: one running sum per thread
+    RunSums<6> r3;                                             // P0, P2, P4 sums, phase^2, |k|, count (count last)
+    RunSums<2> r2s;
+    r3.init(); r2s.init();
+    auto flush3 = [&](int b, const double (&t)[6]) {
+        red_add(g.sums + g.o_p3d + (long long)b * 3 + 0, t[0]);
+        red_add(g.sums + g.o_p3d + (long long)b * 3 + 1, t[1]);
+        red_add(g.sums + g.o_p3d + (long long)b * 3 + 2, t[2]);
+        if (want_phase) red_add(g.sums + g.o_phase + b, t[3]);
+        red_add(g.sums + g.o_k3d + b, t[4]);
+        red_add_u64(g.counts + g.o_n3d + b, (uint64_t)(t[5] + 0.5));
+    };
+    auto flush2 = [&](int b, const double (&t)[2]) {
         const long long i2 = (long long)g.kmax_par1 * b + kz;
-        red_add(g.sums + g.o_p2d + i2, s[0]);
-        red_add_u64(g.counts + g.o_n2d + i2, (uint64_t)(s[1] + 0.5));
-    });
-    warp_reduce_by_key<2>(0, valid, v1, [&](int, const double (&s)[2]) {
-        if (s[1] > 0.5) {
-            red_add(g.sums + g.o_p1d + kz, s[0]);
-            red_add_u64(g.counts + g.o_n1d + kz, (uint64_t)(s[1] + 0.5));
+        red_add(g.sums + g.o_p2d + i2, t[0]);
+        red_add_u64(g.counts + g.o_n2d + i2, (uint64_t)(t[1] + 0.5));
+    };
+    int lo, hi;
+    warp_rows(nrows, lo, hi);
+    for (int i0 = lo; i0 < hi; i0 += 32) {                     // warp-uniform
+        const int i = i0 + lane;
+        bool valid = i < hi;
+        Row2 e;
+        e.off = 0; e.r2 = 0; e.chi = e.clo = 0.f; e.kx = e.ky = 0;
+        if (valid) e = tab[i];
+        const int kx = e.kx, ky = e.ky;
+        // keep one of each conjugate pair, :326-330
+        if (kx < 0) valid = false;
+        if ((kx == 0 || (kx == g.middle && g.even)) && ky < 0) valid = false;
+        const int n = e.r2 + kz * kz;
+        const int b3 = isqrt_exact(n), b2 = isqrt_exact(e.r2);
+        double v3[6] = {0, 0, 0, 0, 0, 0}, v2[2] = {0, 0};
+        if (valid) {
+            const double k = sqrt((double)n);
+            const double mu = (n == 0) ? 0.0 : (double)kz / k;
+            const double mu2 = mu * mu;
+            const int ax = kx, ay = ky < 0 ? -ky : ky;
+            const float mf = (float)(g.mas_tab[ax] * g.mas_tab[ay] * g.mas_tab[kz]);   // :354
+            const float2 z = *(reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(dk) + e.off) + kz);
+            const float r = __fmul_rn(z.x, mf), q = __fmul_rn(z.y, mf);                // :355
+            const double d2 = (double)r * (double)r + (double)q * (double)q;           // :358-360
+            v3[0] = d2;
+            v3[1] = d2 * ((3.0 * mu2 - 1.0) / 2.0);
+            v3[2] = d2 * ((35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0);
+            v3[3] = want_phase ? (double)phase_sq(r, (float)d2) : 0.0;                 // atan2(re, |delta_k|)^2, :361
+            v3[4] = k;
+            v3[5] = 1.0;
+            v2[0] = d2; v2[1] = 1.0;
+            if (n <= g.middle * g.middle) { v1[0] += d2; v1[1] += 1.0; }
+        }
+        r3.step(__shfl_sync(0xffffffffu, b3, 0), valid, b3, v3, flush3);
+        r2s.step(__shfl_sync(0xffffffffu, b2, 0), valid, b2, v2, flush2);
+    }
+    if (r3.cur >= 0) r3.flush_all(flush3);
+    if (r2s.cur >= 0) r2s.flush_all(flush2);
+    warp_reduce_by_key<2>(0, true, v1, [&](int, const double (&t)[2]) {
+        if (t[1] > 0.5) {
+            red_add(g.sums + g.o_p1d + kz, t[0]);
+            red_add_u64(g.counts + g.o_n1d + kz, (uint64_t)(t[1] + 0.5));
         }
     });
 }
@@ -1920,23 +1998,31 @@ static int run_ring2(const BinGeom &g, const FieldPtrs &dk, int want_phase, cuda
     guard.add(counter);
 
     const int nbins3 = isqrt_exact(3 * g.middle * g.middle) + 1;     // kmax + 1
-    if (g.F == 1) {
-        special2_kernel<<<dim3((unsigned)((nrows + 255) / 256), (g.middle > 0) ? 2 : 1), 256, 0, st>>>(g, dk.p[0], tab, nrows, want_phase);
-        PYLB_LAUNCH_CHECK();
-        if (kz_hi < 1) return 0;
-        return want_phase ? launch_ring2<true>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, st)
-                          : launch_ring2<false>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, st);
+    // the ring kernel's kz-private flush table t3[bin][value][kz] (22 MB at 1024^3, 87 MB at 2048^3)
+    const int nvals = g.F == 1 ? R2_T3_VALS : 3 * (g.F + g.F * (g.F - 1) / 2) + 2;
+    const int t3_kz = (kz_hi + 1 + 3) & ~3;
+    const size_t t3_bytes = kz_hi >= 1 ? sizeof(double) * (size_t)nbins3 * nvals * t3_kz : 0;
+    double *t3 = nullptr;
+    if (t3_bytes) {
+        PYLB_CHECK(cudaMallocAsync(&t3, t3_bytes, st));
+        guard.add(t3);
+        PYLB_CHECK(cudaMemsetAsync(t3, 0, t3_bytes, st));
     }
-    // XPk: the self-conjugate columns through the F-field version of special2_kernel
-    const dim3 sgrid((unsigned)((nrows + 255) / 256), (g.middle > 0) ? 2 : 1);
-    if (g.F == 2) {
-        special2x_kernel<2><<<sgrid, 256, 0, st>>>(g, dk, tab, nrows);
-        PYLB_LAUNCH_CHECK();
-        return kz_hi < 1 ? 0 : launch_ring2x<2>(g, dk, tab, c.cext, nrows, n0, (int)n1, kz_hi, counter, nbins3, st);
-    }
-    special2x_kernel<3><<<sgrid, 256, 0, st>>>(g, dk, tab, nrows);
+    // The self-conjugate columns first, on the same stream.  Measured and dropped: (i) a side stream next to the ring kernel
+    // (the ring kernel slows down by more than the special kernel takes: 0.885 against 0.771 ms at 1024^3); (ii) clearing t3
+    // with an extra row of CTAs of the special kernel instead of the memset (no gain at 2048^3, 13 us slower at 1024^3).
+    // What bounds the special kernel is its 2 N^2 / G column gathers, one 32-byte sector per 8 KB row: ~35 G per second.
+    const unsigned sblocks = (unsigned)((nrows + 255) / 256), scap = 4u * (unsigned)sm_count();
+    const dim3 sgrid(sblocks < scap ? sblocks : scap, (g.middle > 0) ? 2 : 1);
+    if (g.F == 1) special2_kernel<<<sgrid, 256, 0, st>>>(g, dk.p[0], tab, nrows, want_phase);
+    else if (g.F == 2) special2x_kernel<2><<<sgrid, 256, 0, st>>>(g, dk, tab, nrows);
+    else special2x_kernel<3><<<sgrid, 256, 0, st>>>(g, dk, tab, nrows);
     PYLB_LAUNCH_CHECK();
-    return kz_hi < 1 ? 0 : launch_ring2x<3>(g, dk, tab, c.cext, nrows, n0, (int)n1, kz_hi, counter, nbins3, st);
+    if (kz_hi < 1) return 0;
+    if (g.F == 1) return want_phase ? launch_ring2<true>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, t3, st)
+                                    : launch_ring2<false>(g, dk.p[0], tab, n0, (int)n1, kz_hi, counter, nbins3, t3, st);
+    if (g.F == 2) return launch_ring2x<2>(g, dk, tab, c.cext, nrows, n0, (int)n1, kz_hi, counter, nbins3, t3, st);
+    return launch_ring2x<3>(g, dk, tab, c.cext, nrows, n0, (int)n1, kz_hi, counter, nbins3, t3, st);
 }
 
 static int run_ring(const BinGeom &g, const FieldPtrs &dk, int want_phase, int write_back, int precise, cudaStream_t st) {
