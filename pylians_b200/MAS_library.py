@@ -60,6 +60,7 @@ def _to_device(a, dev):
 
 
 HOST_CHUNK = None         # tests: force a (small) chunk size
+HOST_TAPER_FLOOR = 1 << 24  # smallest piece the last H2D chunk is cut into (tests lower it)
 
 
 def _host_chunk(dims, ndim):
@@ -71,10 +72,12 @@ def _host_chunk(dims, ndim):
     return int(min(max(dims ** ndim // 4, 1 << 26), 1 << 28))
 
 
-def _chunk_bounds(npart, chunk, taper_floor=1 << 24):
+def _chunk_bounds(npart, chunk, taper_floor=None):
     """(lo, hi) ranges of the H2D chunks.  The copies run back to back and the deposit of a chunk is faster than its
     copy, so what the caller waits for after the LAST copy has landed is the deposit of the last chunk: the final full
     chunk is therefore cut into 1/2, 1/4, 1/4 (never below `taper_floor` particles)."""
+    if taper_floor is None:
+        taper_floor = HOST_TAPER_FLOOR
     bounds, lo = [], 0
     while lo < npart:
         hi = min(npart, lo + chunk)

@@ -226,3 +226,20 @@ def test_distributed_pk_comp_matches_reference_driver(tmp_path, golden_dir):
         p0 = np.abs(want[:, 1])
         floor = (p0 + np.median(p0))[:, None] * np.array([1.0, 5.0, 9.0])[None, :]
         parity.assert_spec_close(got[:, 1:4], want[:, 1:4], floor, fname, rtol=1e-3)
+
+
+def test_host_chunk_schedule_covers_every_particle_once():
+    """The H2D chunk schedule (MAS_library._chunk_bounds): contiguous, complete, at most `chunk` long, and the last full
+    chunk tapers into pieces no smaller than the floor."""
+    from pylians_b200.MAS_library import _chunk_bounds
+    for npart, chunk, floor in [(0, 10, 2), (5, 10, 2), (10, 10, 2), (100, 30, 4), (96, 32, 4), (96, 32, 100), (2 ** 30, 2 ** 28, 2 ** 24),
+                                (2 ** 30 + 12345, 2 ** 28, 2 ** 24), (1000, 7, 1)]:
+        b = _chunk_bounds(npart, chunk, floor)
+        assert (b[0][0] == 0 and b[-1][1] == npart) if npart else b == []
+        assert all(x[1] == y[0] for x, y in zip(b[:-1], b[1:]))
+        assert all(0 < hi - lo <= chunk for lo, hi in b)
+        full = [hi - lo for lo, hi in b if hi - lo == chunk]
+        if len(b) >= 2 and chunk // 4 >= floor and npart % chunk == 0:
+            assert [hi - lo for lo, hi in b[-3:]] == [chunk // 2, chunk // 4, chunk - chunk // 2 - chunk // 4] and len(full) == npart // chunk - 1
+    assert _chunk_bounds(2 ** 30, 2 ** 28, 2 ** 24)[-3:] == [(3 * 2 ** 28, 3 * 2 ** 28 + 2 ** 27), (3 * 2 ** 28 + 2 ** 27, 3 * 2 ** 28 + 3 * 2 ** 26),
+                                                           (3 * 2 ** 28 + 3 * 2 ** 26, 2 ** 30)]

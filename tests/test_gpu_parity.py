@@ -153,6 +153,7 @@ def test_ma_host_chunked_streaming(MASL, gma):
     import pylians_b200.MAS_library as M
     box, dims = float(gma["box"]), int(gma["dims"])
     old, M.HOST_CHUNK = M.HOST_CHUNK, 1700
+    oldf, M.HOST_TAPER_FLOOR = M.HOST_TAPER_FLOOR, 200          # the last full chunk is cut into 1/2, 1/4, 1/4
     try:
         g = np.zeros((dims,) * 3, np.float32); MASL.MA(gma["pos"], g, box, "TSC", W=gma["W"])
         parity.assert_grid_close(g, gma["grid_TSCW"], "chunked host TSCW")
@@ -161,6 +162,7 @@ def test_ma_host_chunked_streaming(MASL, gma):
         parity.assert_grid_close(gt.cpu().numpy(), gma["grid_CIC"], "chunked host CIC -> device grid")
     finally:
         M.HOST_CHUNK = old
+        M.HOST_TAPER_FLOOR = oldf
 
 
 def test_ma_errors(MASL):
