@@ -899,34 +899,37 @@ bool ma_tiled_supported(int ndim, int dims, int grid_f64, int xext) {
     return ndim == 3 && !grid_f64 && dims >= 32 && tile_geom(dims, 0, xext).ntiles <= MAX_TILES;
 }
 
-template <int MAS, bool HASW, int PT, int MAXB0, int MAXB1>
+// PT0 / PT1: CTA sizes of pass 0 and of pass 1 (and the second histogram sweep, which walks the same chunk list).  More
+// than 256 digits need the 512-thread CTA (4096-particle chunks, 2 CTAs per SM); a pass with <= 256 digits runs faster with
+// 256 threads and 4 CTAs per SM (4.4 against 3.7 TB/s of traffic measured), also in the deep mode.
+template <int MAS, bool HASW, int PT0, int PT1, int MAXB0, int MAXB1>
 static int run_passes(const float *pos, const float *w, int64_t wst, int64_t first, int n, int64_t ps0, int64_t ps1, float inv,
                       const TileGeom &tg, TiledWs &ws, const SortPlan &sp, cudaStream_t st) {
-    constexpr int CH = PT * PART_PER_THREAD;
+    constexpr int CH0 = PT0 * PART_PER_THREAD, CH1 = PT1 * PART_PER_THREAD;
     const int nt1 = tg.ntiles + 1;
     size_t tb = ws.tmp_bytes;
     // bucket table, pass-0 cursors and the chunk list of pass 1 from the (tile or bucket) scan in ws.tile_begin
     if (!sp.deep)
-        part_buckets_kernel<<<1, 1024, 0, st>>>(ws.tile_begin, tg.ntiles, sp.lo_bits, sp.nb0, CH, ws.bucket_begin, ws.bcursor, ws.bchunk_off);
+        part_buckets_kernel<<<1, 1024, 0, st>>>(ws.tile_begin, tg.ntiles, sp.lo_bits, sp.nb0, CH1, ws.bucket_begin, ws.bcursor, ws.bchunk_off);
     else
-        part_buckets_kernel<<<1, 1024, 0, st>>>(ws.tile_begin, sp.nb0, 0, sp.nb0, CH, ws.bucket_begin, ws.bcursor, ws.bchunk_off);
+        part_buckets_kernel<<<1, 1024, 0, st>>>(ws.tile_begin, sp.nb0, 0, sp.nb0, CH1, ws.bucket_begin, ws.bcursor, ws.bchunk_off);
     PYLB_LAUNCH_CHECK();
-    const size_t psm0 = sizeof(PartSmem<PT, MAXB0>), psm1 = sizeof(PartSmem<PT, MAXB1>);
-    if (set_smem(bin_pass_kernel<MAS, HASW, true, PT, MAXB0>, psm0) || set_smem(bin_pass_kernel<MAS, HASW, false, PT, MAXB1>, psm1)) return 1;
-    const unsigned g0 = (unsigned)((n + CH - 1) / CH);
-    bin_pass_kernel<MAS, HASW, true, PT, MAXB0><<<g0, PT, psm0, st>>>(
+    const size_t psm0 = sizeof(PartSmem<PT0, MAXB0>), psm1 = sizeof(PartSmem<PT1, MAXB1>);
+    if (set_smem(bin_pass_kernel<MAS, HASW, true, PT0, MAXB0>, psm0) || set_smem(bin_pass_kernel<MAS, HASW, false, PT1, MAXB1>, psm1)) return 1;
+    const unsigned g0 = (unsigned)((n + CH0 - 1) / CH0), g1 = (unsigned)((n + CH1 - 1) / CH1) + (unsigned)sp.nb0;
+    bin_pass_kernel<MAS, HASW, true, PT0, MAXB0><<<g0, PT0, psm0, st>>>(
         pos, w, wst, first, n, ps0, ps1, inv, tg, nullptr, ws.sorted_tmp, ws.bcursor, ws.bucket_begin, ws.bchunk_off, sp.lo_bits, sp.nb0);
     PYLB_LAUNCH_CHECK();
     if (sp.deep) {
         // per-tile counts from the bucket-ordered payload, then every tile's first slot
         PYLB_CHECK(cudaMemsetAsync(ws.H, 0, sizeof(int) * (size_t)nt1, st));
-        bin_hist2_kernel<MAS, PT><<<g0 + (unsigned)sp.nb0, PT, 0, st>>>(ws.sorted_tmp, inv, tg, ws.bucket_begin, ws.bchunk_off, sp.lo_bits, sp.nb0, ws.H);
+        bin_hist2_kernel<MAS, PT1><<<g1, PT1, 0, st>>>(ws.sorted_tmp, inv, tg, ws.bucket_begin, ws.bchunk_off, sp.lo_bits, sp.nb0, ws.H);
         PYLB_LAUNCH_CHECK();
         PYLB_CHECK(cub::DeviceScan::ExclusiveSum(ws.tmp, tb, ws.H, ws.tile_begin, nt1, st));
         count_launch(2);
     }
     PYLB_CHECK(cudaMemcpyAsync(ws.S, ws.tile_begin, sizeof(int) * (size_t)nt1, cudaMemcpyDeviceToDevice, st));
-    bin_pass_kernel<MAS, HASW, false, PT, MAXB1><<<g0 + (unsigned)sp.nb0, PT, psm1, st>>>(
+    bin_pass_kernel<MAS, HASW, false, PT1, MAXB1><<<g1, PT1, psm1, st>>>(
         pos, w, wst, first, n, ps0, ps1, inv, tg, ws.sorted_tmp, ws.sorted, ws.S, ws.bucket_begin, ws.bchunk_off, sp.lo_bits, sp.nb0);
     PYLB_LAUNCH_CHECK();
     return 0;
@@ -964,9 +967,9 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
         count_launch(2);
         int rc;
         const bool wide0 = sp.nb0 > 256, wide1 = (1 << sp.lo_bits) > 256;
-        if (!wide0 && !wide1) rc = run_passes<MAS, HASW, 256, 256, 256>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, sp, st);
-        else if (!wide1) rc = run_passes<MAS, HASW, 512, 1024, 256>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, sp, st);
-        else rc = run_passes<MAS, HASW, 512, 1024, 1024>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, sp, st);
+        if (!wide0 && !wide1) rc = run_passes<MAS, HASW, 256, 256, 256, 256>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, sp, st);
+        else if (!wide1) rc = run_passes<MAS, HASW, 512, 256, 1024, 256>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, sp, st);
+        else rc = run_passes<MAS, HASW, 512, 512, 1024, 1024>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, sp, st);
         if (rc) return rc;
         tile_chunks_kernel<<<(nt1 + 255) / 256, 256, 0, st>>>(ws.tile_begin, tg.ntiles, CHUNK, ws.nchunks);
         PYLB_LAUNCH_CHECK();
