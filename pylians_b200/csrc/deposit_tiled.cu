@@ -37,6 +37,9 @@ namespace pylb {
 
 constexpr int TX = 16, TY = 16, TZ = 32;     // cells per tile
 constexpr int CHUNK = 8192;                  // particles per work item
+#ifndef PYLB_WIDE_PT0
+#define PYLB_WIDE_PT0 512                      // CTA size of a sort pass with more than 256 digits
+#endif
 #ifndef PYLB_LANE_DEPTH
 #define PYLB_LANE_DEPTH 2                     // stencil-lane kernel: steps (compare-and-swap pairs) in flight together
 #endif
@@ -968,7 +971,7 @@ static int tiled_run(const float *pos, int64_t np, int64_t ps0, int64_t ps1, flo
         int rc;
         const bool wide0 = sp.nb0 > 256, wide1 = (1 << sp.lo_bits) > 256;
         if (!wide0 && !wide1) rc = run_passes<MAS, HASW, 256, 256, 256, 256>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, sp, st);
-        else if (!wide1) rc = run_passes<MAS, HASW, 512, 256, 1024, 256>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, sp, st);
+        else if (!wide1) rc = run_passes<MAS, HASW, PYLB_WIDE_PT0, 256, 1024, 256>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, sp, st);
         else rc = run_passes<MAS, HASW, 512, 512, 1024, 1024>(pos, w, wst, first, n, ps0, ps1, inv, tg, ws, sp, st);
         if (rc) return rc;
         tile_chunks_kernel<<<(nt1 + 255) / 256, 256, 0, st>>>(ws.tile_begin, tg.ntiles, CHUNK, ws.nchunks);
