@@ -17,18 +17,22 @@
 //                         gather costs 3.9 ms per 2^27 particles on B200, a streaming read 0.25 ms: profiles/microbench)
 //
 //  ACCUMULATE -- one work item = (tile, chunk of <= 8192 of its particles); persistent CTAs walk the item list:
-//     deposit_tile_kernel   NGP/CIC/TSC: lane per particle, S^3 shared-memory atomicAdd(float) per lane.
-//     deposit_lane_kernel   PCS: the lanes of a warp are the STENCIL POINTS of one particle (32 lanes x 2 x-planes) and the
-//                           tile pitches put those 32 cells into 32 distinct banks, so one warp instruction never touches
-//                           a cell twice and its compare-and-swap only fails when another warp got there first: the
-//                           update is an optimistic load / add / CAS pair with no spin loop on the fast path.
-//   Shared-memory float atomics are what bounds every variant (there is no native fp32 add: atomicAdd is an
-//   ATOMS.CAST.SPIN loop).  Measured on B200 (profiles/r2_atoms_pattern.txt, lane-updates per clock per SM at 32 warps/SM):
-//   float CAS loop 2.8 on randomly placed cells, 5.6 on the stencil pattern; native integer ATOMS.ADD 6.4 / 8.5; plain
-//   LDS+FADD+STS 4.5 / 7.7.  Integer (fixed-point) tiles were built and measured this round -- one word per cell with a
-//   per-item scale from an exact stencil-count bound: PCS 7.3 ms against 8.1 ms at 512^3, but sub-unit contributions
-//   of dense clumps are lost and the 1e-5 contract fails on clustered input; two words per cell are exact but need twice
-//   the atomics (10.7 ms) -- so the tiles stay fp32 (profiles/r2_deposit_variants.txt).
+//     deposit_tile_kernel   NGP/CIC: lane per particle, S^3 shared-memory atomicAdd(float) per lane.
+//     deposit_lane_kernel   TSC/PCS: the lanes of a warp are the STENCIL POINTS of a particle (PCS: 32 lanes x 2 x-planes of
+//                           one particle; TSC: 27 lanes x 2 consecutive particles) and the tile pitches put the cells of one
+//                           instruction into distinct banks, so a warp instruction never touches a cell twice and its
+//                           compare-and-swap only fails when another warp got there first: the update is an optimistic
+//                           load / add / CAS with no spin loop on the fast path, and a second optimistic CAS on the value the
+//                           failed one returned on the slow path.
+//   Shared-memory float updates are what bounds every variant (there is no native fp32 add: atomicAdd is an
+//   ATOMS.CAST.SPIN loop).  Measured on B200 (profiles/r2_atoms_pattern*.txt, cell updates per clock per SM at 32 warps/SM):
+//   float CAS loop 2.8 on randomly placed cells, 5.6 on the stencil pattern (the optimistic pair 5.4, a 64-bit CAS on two
+//   adjacent cells 5.8); native integer ATOMS.ADD 6.4 / 8.5; plain LDS+FADD+STS 4.5 / 7.7.  The PCS lane kernel reaches 4.9.
+//   Built, measured and dropped this round (profiles/r2_deposit_variants.txt, profiles/variants/): integer (fixed-point)
+//   tiles -- one word per cell with a per-item scale loses the sub-unit contributions of dense clumps (the 1e-5 contract
+//   fails on clustered input), two words per cell are exact but need twice the atomics (10.7 ms against 8.1 ms then); and
+//   column accumulators in registers (lanes = z cells, S^2 FMAs per particle and lane, one add to the tile per column
+//   visit) -- no longer bound by shared memory but by its 65 warp instructions per particle (10.9 ms against 5.95 ms).
 #include <cub/device/device_scan.cuh>
 
 #include "deposit.cuh"
@@ -585,15 +589,15 @@ deposit_tile_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, c
 
 // ---- stencil lanes: TSC and PCS --------------------------------------------------------------------------------------
 // Per batch of 32 particles, lane p evaluates particle p's base cell and its S weights per axis exactly like the reference
-// (deposit.cuh) and stages them in a per-warp scratch (word-major, pitch 33: the staging stores and the per-particle reads
-// are both conflict-free).  Then the warp walks the batch: every lane forms ((wx[a] * wy[b]) * wz[c]) * W -- the
-// reference's left-to-right fp32 product (MAS_library.pyx:400-404, 493-497) -- for its own stencil point(s): PCS lane
-// (a&1, b, c) serves the x-planes a and a+2 of one particle, TSC lane (a, b, c) (27 of 32 lanes) one point of two
-// consecutive particles.  Either way a lane has two independent cells per step and adds both with one optimistic pair of
-// compare-and-swaps: two loads, two adds, two CAS in flight together; since one instruction never touches a cell twice, a
-// CAS can only fail when another warp updated the same cell in between (or, for TSC, when the two particles share the
-// cell), and is then repaired with an ordinary atomicAdd.  PCS: 1.42x the lane-per-particle kernel at 512^3 (8.1 ms against
-// 11.5 ms, profiles/r2_deposit_variants.txt).
+// (deposit.cuh) and stages them in a per-warp scratch (word-major, even pitch 34: the staging stores are conflict-free and
+// the rows of two consecutive particles are one aligned 8-byte load).  Then the warp walks the batch: every lane forms
+// ((wx[a] * wy[b]) * wz[c]) * W -- the reference's left-to-right fp32 product (MAS_library.pyx:400-404, 493-497) -- for its
+// own stencil point(s): PCS lane (a&1, b, c) serves the x-planes a and a+2 of one particle, TSC lane (a, b, c) (27 of 32
+// lanes) one point of two consecutive particles.  Either way a lane has two independent cells per step and adds both with
+// an optimistic pair of compare-and-swaps (PCS: the pairs of two particles in flight together); since one instruction never
+// touches a cell twice, a CAS can only fail when another warp updated the same cell in between (or when two particles of a
+// group share the cell), and is then repaired.  PCS 5.95 ms at 512^3 against 11.2 ms for the lane-per-particle kernel,
+// TSC 4.15 against 4.94 ms (profiles/r2_deposit_ab_v2.txt); ncu: 0.9 of the float-update rate of shared memory.
 template <int MAS, bool HASW>
 __global__ void __launch_bounds__(TileShape<MAS, true>::LANE_THREADS, TileShape<MAS, true>::LANE_CTAS)
 deposit_lane_kernel(const float4 *__restrict__ sorted, float inv, TileGeom tg, const int *__restrict__ tile_begin,
