@@ -255,7 +255,7 @@ def run_reference(args, wl):
                                      "and its OpenMP C kernel (MAS_c, all threads), see `deposit`; Pk: threads feed the FFT, its mode loop is serial"},
             "e2e": {"value": val, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "s_per_snapshot_sample": sec}
-    print(json.dumps(line))
+    emit(line)
 
 
 def zeldovich_particles(nside, box, gen, dev, sigma_cells=2.0, n_s=-1.0):
@@ -649,7 +649,7 @@ def run_ours(args, wl):
                           "Nmodes_sum_ok": bool(spec.Nmodes3D.sum() + 1 == (gside ** 3 - 8) // 2 + 8) if gside % 2 == 0 else None,
                           "parity": parity},
                 "extra": extra}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -742,7 +742,32 @@ def parity_multi(args, wl, dev, rank, world, dist):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+    version banner there under NCCL_DEBUG=VERSION, whatever NCCL_DEBUG_FILE says; the compiled reference prints its timings),
+    so fd 1 is pointed at stderr for the whole run and the JSON line goes to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+        return
+    while data:
+        data = data[os.write(_REAL_STDOUT, data):]
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
