@@ -83,3 +83,15 @@ def test_north_star_line(name):
     assert d["config"]["grid"] == 2048 and d["config"]["mas"] == ["PCS"] and d["config"]["particles_total"] == 2048 ** 3
     assert d["s_per_snapshot"] < 1.0
     assert d["roofline"]["ring_kernel_only"]["frac"] >= 0.60        # the binning kernel on the slab layout
+
+
+def test_stdout_carries_only_the_json_line():
+    """Whatever libraries write to file descriptor 1 (NCCL's banner, the compiled reference's prints) must not reach stdout."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench._claim_stdout(); os.write(1, b'noise from a C library\\n'); "
+            "print('noise from python'); bench.emit({'a': 1})" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"a": 1}\n'
+    assert "noise from a C library" in r.stderr and "noise from python" in r.stderr
