@@ -586,8 +586,12 @@ def run_ours(args, wl):
     # shared-memory atomics / issue slots, not HBM -- so `frac` states the distance to an ideal one-pass deposit.
     roof_dep = None
     st = main.get("stages")
+    if st is None and world > 1 and K["tile"] > 0:
+        # N > 1: no separate stage pass; rank 0's sort + tile brackets of the windowed deposits (the partition pass and the
+        # exchange are outside these brackets)
+        st = {"deposit_ms": K["sort"] + K["tile"], "note": "rank 0: sort + tile-kernel brackets of the windowed deposits only"}
     if st and K["tile"] > 0:
-        dep_bytes = sum((16.0 if w else 12.0) for _, w in wl["fields"]) * npart + 8.0 * nf * gside ** 3
+        dep_bytes = sum((16.0 if w else 12.0) for _, w in wl["fields"]) * npart + 8.0 * nf * gside ** 3 / world
         dep_gbs = dep_bytes / (st["deposit_ms"] * 1e-3) / 1e9
         updates = sum(STENCIL[m] for m in mas_names(wl)) * npart
         sort_bytes = sum((12.0 + (16.0 if w else 12.0) + 16.0 + 16.0 + 16.0 + (4.0 if w else 0.0)) for _, w in wl["fields"]) * npart
@@ -598,6 +602,8 @@ def run_ours(args, wl):
                     "sort_achieved_GBs": sort_bytes / (K["sort"] * 1e-3) / 1e9 if K["sort"] > 0 else None,
                     "tile_kernel_ms_per_step": K["tile"], "tile_kernel_launches_per_step": main["kernel_launches_per_step"]["tile"],
                     "tile_updates_per_s": updates / (K["tile"] * 1e-3)}
+        if "note" in st:
+            roof_dep["note"] = st["note"]
         # atomic / L2 / LSU-pipe figures of the deposit kernels from the committed `ncu --set full` captures (512^3 launches)
         try:
             with open(os.path.join(ROOT, "profiles", "r2_ncu_deposit.json")) as f:
@@ -605,7 +611,7 @@ def run_ours(args, wl):
                         "shared_atomic_wavefronts", "shared_bank_conflicts", "l2_throughput_pct", "dram_throughput_pct",
                         "issue_active_pct", "warp_instructions", "achieved_occupancy_pct")
                 roof_dep["ncu"] = {name: [{k: l[k] for k in keep if k in l} for l in launches]
-                                   for name, launches in json.load(f).items() if not name.startswith("dropped")}
+                                   for name, launches in json.load(f).items() if not name.startswith(("dropped", "earlier"))}
         except (OSError, ValueError):
             pass
 
