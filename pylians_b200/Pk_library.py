@@ -300,12 +300,26 @@ class Pk(object):
         stream = torch.cuda.current_stream(dev)
         # line of sight along x or y: swap that axis with z in real space and bin along z (same bins, same
         # mode counts; which member of each conjugate pair is kept differs, its |delta_k|^2 does not).
-        # keep_deltak must return the reference's (kx,ky,kz>=0) layout, so it keeps the original axes.
-        swap = int(axis) if (int(axis) in (0, 1) and not keep_deltak and (ALGO & 3) != _lib.BIN_GENERIC and SWAP_AXES) else 2
-        delta_k = _fft_field(lib, delta, dims, dev, stream, swap, pad=not keep_deltak)
-        start2 = time.time()
-        L, sums, counts = bin_modes([delta_k], dims, 2 if swap != 2 else int(axis), [MAS_function(MAS)], True,
-                                    bool(keep_deltak))
+        # keep_deltak must return the reference's (kx,ky,kz>=0) layout: see below.
+        can_swap = int(axis) in (0, 1) and (ALGO & 3) != _lib.BIN_GENERIC and SWAP_AXES
+        if can_swap and keep_deltak:
+            # The spectra come from the swapped field like without keep_deltak.  The array handed back is the transform of
+            # the ORIGINAL field with every independent mode deconvolved: neither the MAS factor Cx*Cy*Cz nor the rule
+            # which member of a conjugate pair is kept (Pk_library.pyx:326-330, in terms of the array axes) depends on the
+            # line of sight, so a second transform plus the ring kernel's write-back pass along z produces it (its bins are
+            # discarded).  14 ms instead of the 186 ms of the one-thread-per-mode kernel at 512^3.
+            dk_s = _fft_field(lib, delta, dims, dev, stream, int(axis), pad=True)
+            start2 = time.time()
+            L, sums, counts = bin_modes([dk_s], dims, 2, [MAS_function(MAS)], True, False)
+            del dk_s
+            delta_k = _fft_field(lib, delta, dims, dev, stream, 2, pad=False)
+            bin_modes([delta_k], dims, 2, [MAS_function(MAS)], False, True)
+        else:
+            swap = int(axis) if (can_swap and not keep_deltak) else 2
+            delta_k = _fft_field(lib, delta, dims, dev, stream, swap, pad=not keep_deltak)
+            start2 = time.time()
+            L, sums, counts = bin_modes([delta_k], dims, 2 if swap != 2 else int(axis), [MAS_function(MAS)], True,
+                                        bool(keep_deltak))
         bins = _Bins(L, sums, counts, (BoxSize / dims ** 2) ** 3)       # one D2H of the bins; synchronises the stream
         _say("Time to complete loop = %.2f" % (time.time() - start2))
         _finish(self, bins, dims, BoxSize, False)

@@ -494,6 +494,25 @@ def test_pk_axis_keep_deltak_keeps_reference_layout(PKL, gpk):
     parity.check_pk(p, {n: gpk["pk_16_a0_TSC_%s" % n] for n in PK_NAMES})
 
 
+@pytest.mark.parametrize("dims", [48, 33])
+@pytest.mark.parametrize("axis", [0, 1])
+def test_pk_axis_keep_deltak_fast_path_vs_generic(PKL, dims, axis):
+    """Pk(axis=0|1, keep_deltak=True): spectra from the swapped field + delta_k from a write-back pass along z, against the
+    one-thread-per-mode kernel binning along the requested axis."""
+    import pylians_b200.Pk_library as P
+    rng = np.random.default_rng(dims + axis)
+    delta = rng.standard_normal((dims,) * 3).astype(np.float32)
+    fast = PKL.Pk(delta, 1000.0, axis, "PCS", 1, keep_deltak=True)
+    old, P.ALGO = P.ALGO, 1                                      # BIN_GENERIC: no swap, write-back in the generic kernel
+    try:
+        slow = PKL.Pk(delta, 1000.0, axis, "PCS", 1, keep_deltak=True)
+    finally:
+        P.ALGO = old
+    assert fast.delta_k.shape == slow.delta_k.shape == (dims, dims, dims // 2 + 1)
+    np.testing.assert_allclose(fast.delta_k, slow.delta_k, rtol=2e-5, atol=2e-5 * np.abs(slow.delta_k).max())
+    parity.check_pk(fast, slow)
+
+
 def test_pk_errors(PKL):
     with pytest.raises(ValueError):
         PKL.Pk(np.zeros((8, 8, 8), np.float64), 1.0, 2, "CIC", 1)
