@@ -178,6 +178,63 @@ def bin_modes(delta_k, dims, axis, mas_index, want_phase, write_back, ks=None, s
     return L, sums, counts
 
 
+def _field_subsets(F, width=3):
+    """Field subsets of `width` covering every pair (i, j), i < j < F, at least once (greedy)."""
+    import itertools
+    need = {(i, j) for i in range(F) for j in range(i + 1, F)}
+    subsets = []
+    while need:
+        best = max(itertools.combinations(range(F), width), key=lambda c: len(need & set(itertools.combinations(c, 2))))
+        subsets.append(best)
+        need -= set(itertools.combinations(best, 2))
+    return subsets
+
+
+def bin_modes_by_subsets(delta_k, dims, axis, mas_index, width=3):
+    """The bins of F > 3 fields from the two- / three-field ring kernel: every auto and cross spectrum of F fields is an
+    auto or cross spectrum of some subset of three of them, so the fields are binned three at a time (F = 4: three passes,
+    F = 5: four) and the sums are copied into the F-field layout on the device.  The mode counts, sum |k| and the bin
+    geometry do not depend on the fields.  Replaces the one-thread-per-mode kernel for XPk with more than three fields
+    (Pk_Gadget on four particle types): it reads 8 B x 3 per mode and pass instead of taking a global atomic per mode."""
+    F = len(delta_k)
+    dev = delta_k[0].device
+    L = get_layout(dims, F)
+    raw = torch.zeros(L.n_doubles + L.n_counts, dtype=torch.float64, device=dev)
+    sums, counts = raw[:L.n_doubles], raw[L.n_doubles:].view(torch.int64)
+    sums._pylb_raw = raw
+    n3, n1, B2 = L.kmax + 1, L.kmax_par + 1, L.B2
+    pair = lambda i, j, nf: i * nf - i * (i + 1) // 2 + (j - i - 1)
+    done_f, done_x, first = set(), set(), True
+    for sub in _field_subsets(F, width):
+        Ls, ss, cs = bin_modes([delta_k[f] for f in sub], dims, axis, [mas_index[f] for f in sub], False, False)
+        w = len(sub)
+        if first:
+            counts[L.o_n3d:L.o_n3d + n3] = cs[Ls.o_n3d:Ls.o_n3d + n3]
+            counts[L.o_n1d:L.o_n1d + n1] = cs[Ls.o_n1d:Ls.o_n1d + n1]
+            counts[L.o_n2d:L.o_n2d + B2] = cs[Ls.o_n2d:Ls.o_n2d + B2]
+            sums[L.o_k3d:L.o_k3d + n3] = ss[Ls.o_k3d:Ls.o_k3d + n3]
+            first = False
+        views = []
+        for o_p, o_x, rows, mult in (("o_p3d", "o_x3d", n3 * 3, None), ("o_p1d", "o_x1d", n1, None), ("o_p2d", "o_x2d", B2, None)):
+            P_full = sums[getattr(L, o_p):getattr(L, o_p) + rows * F].view(rows, F)
+            X_full = sums[getattr(L, o_x):getattr(L, o_x) + rows * L.X].view(rows, L.X)
+            P_sub = ss[getattr(Ls, o_p):getattr(Ls, o_p) + rows * w].view(rows, w)
+            X_sub = ss[getattr(Ls, o_x):getattr(Ls, o_x) + rows * Ls.X].view(rows, Ls.X)
+            views.append((P_full, X_full, P_sub, X_sub))
+        for a, fa in enumerate(sub):
+            if fa not in done_f:
+                for P_full, _, P_sub, _ in views:
+                    P_full[:, fa] = P_sub[:, a]
+            for b in range(a + 1, w):
+                fb = sub[b]
+                if (fa, fb) not in done_x:
+                    for _, X_full, _, X_sub in views:
+                        X_full[:, pair(fa, fb, F)] = X_sub[:, pair(a, b, w)]
+                    done_x.add((fa, fb))
+        done_f.update(sub)
+    return L, sums, counts
+
+
 _KGRID = {}
 
 
@@ -351,13 +408,16 @@ class XPk(object):
         lib = _lib.load()
         dev = _device()
         stream = torch.cuda.current_stream(dev)
-        swap = int(axis) if (int(axis) in (0, 1) and fields <= 3 and (ALGO & 3) != _lib.BIN_GENERIC and SWAP_AXES
+        swap = int(axis) if (int(axis) in (0, 1) and (ALGO & 3) != _lib.BIN_GENERIC and SWAP_AXES
                              and not self._ALGO_FLAGS) else 2
         delta_k = [_fft_field(lib, d, dims, dev, stream, swap, pad=True) for d in delta]   # even row pitch: one aligned row table
         _say("Time FFTS = %.2f" % (time.time() - start))
         start2 = time.time()
-        L, sums, counts = bin_modes(delta_k, dims, 2 if swap != 2 else int(axis), mas_index[:fields], False, False,
-                                    algo=ALGO | self._ALGO_FLAGS)
+        if fields > 3 and not self._ALGO_FLAGS and (ALGO & 3) != _lib.BIN_GENERIC and (swap != 2 or int(axis) == 2):
+            L, sums, counts = bin_modes_by_subsets(delta_k, dims, 2, mas_index[:fields])      # three fields at a time
+        else:
+            L, sums, counts = bin_modes(delta_k, dims, 2 if swap != 2 else int(axis), mas_index[:fields], False, False,
+                                        algo=ALGO | self._ALGO_FLAGS)
         bins = _Bins(L, sums, counts, (BoxSize / dims ** 2) ** 3)
         _say("Time loop = %.2f" % (time.time() - start2))
         _finish(self, bins, dims, BoxSize, True)

@@ -513,6 +513,26 @@ def test_pk_axis_keep_deltak_fast_path_vs_generic(PKL, dims, axis):
     parity.check_pk(fast, slow)
 
 
+@pytest.mark.parametrize("fields,dims,axis", [(4, 48, 2), (5, 32, 0), (4, 32, 1)])
+def test_xpk_more_than_three_fields_by_subsets(PKL, fields, dims, axis):
+    """XPk with 4 and 5 fields (what Pk_Gadget needs for four particle types): binned three fields at a time by the ring
+    kernel and assembled on the device, against the one-thread-per-mode kernel and the oracle."""
+    import pylians_b200.Pk_library as P
+    rng = np.random.default_rng(10 * fields + axis)
+    base = rng.standard_normal((dims,) * 3).astype(np.float32)
+    deltas = [(base * (0.3 + 0.2 * f) + rng.standard_normal((dims,) * 3)).astype(np.float32) for f in range(fields)]   # correlated fields
+    mas = ["CIC", "PCS", "None", "TSC", "NGP"][:fields]
+    fast = PKL.XPk(deltas, 1000.0, axis, mas, 1)
+    old, P.ALGO = P.ALGO, 1                                      # BIN_GENERIC
+    try:
+        slow = PKL.XPk(deltas, 1000.0, axis, mas, 1)
+    finally:
+        P.ALGO = old
+    assert fast.Pk.shape == slow.Pk.shape and fast.XPk.shape == slow.XPk.shape == (slow.Pk.shape[0], 3, fields * (fields - 1) // 2)
+    parity.check_xpk(fast, slow)
+    parity.check_xpk(fast, O.XPk(deltas, 1000.0, axis, mas, 1))
+
+
 def test_pk_errors(PKL):
     with pytest.raises(ValueError):
         PKL.Pk(np.zeros((8, 8, 8), np.float64), 1.0, 2, "CIC", 1)
