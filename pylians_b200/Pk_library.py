@@ -190,7 +190,7 @@ def _field_subsets(F, width=3):
     return subsets
 
 
-def bin_modes_by_subsets(delta_k, dims, axis, mas_index, width=3):
+def bin_modes_by_subsets(delta_k, dims, axis, mas_index, width=3, ks=None):
     """The bins of F > 3 fields from the two- / three-field ring kernel: every auto and cross spectrum of F fields is an
     auto or cross spectrum of some subset of three of them, so the fields are binned three at a time (F = 4: three passes,
     F = 5: four) and the sums are copied into the F-field layout on the device.  The mode counts, sum |k| and the bin
@@ -206,7 +206,7 @@ def bin_modes_by_subsets(delta_k, dims, axis, mas_index, width=3):
     pair = lambda i, j, nf: i * nf - i * (i + 1) // 2 + (j - i - 1)
     done_f, done_x, first = set(), set(), True
     for sub in _field_subsets(F, width):
-        Ls, ss, cs = bin_modes([delta_k[f] for f in sub], dims, axis, [mas_index[f] for f in sub], False, False)
+        Ls, ss, cs = bin_modes([delta_k[f] for f in sub], dims, axis, [mas_index[f] for f in sub], False, False, ks=ks)
         w = len(sub)
         if first:
             counts[L.o_n3d:L.o_n3d + n3] = cs[Ls.o_n3d:Ls.o_n3d + n3]

@@ -120,6 +120,8 @@ class CudaOps(object):
     def bin(self, fields, dims, axis, mas_index, want_phase, y0, nyl):
         pitch = fields[0].shape[2]
         ks = _lib.KSpace(dims, 0, dims, int(y0), int(nyl), nyl * pitch, pitch)
+        if len(fields) > 3 and int(axis) == 2 and not want_phase:
+            return PKL.bin_modes_by_subsets(fields, dims, 2, mas_index, ks=ks)      # three fields at a time (ring kernel)
         return PKL.bin_modes(fields, dims, axis, mas_index, want_phase, False, ks=ks)
 
     def overdensity_mean(self, slab, mean):

@@ -47,6 +47,21 @@ def test_slab_g1_matches_single_gpu_and_oracle(dims, mas, axis):
     parity.check_pk(got, O.Pk(r, box, axis, mas, 1), rtol=1e-3 if mas != "CIC" else 1e-5)
 
 
+def test_slab_g1_four_fields_xpk():
+    """run_x with four particle sets on the slab engine (G = 1): the k-space window binned three fields at a time."""
+    import MAS_library as MASL
+    import Pk_library as PKL
+    from pylians_b200.dist import SlabPk
+    dims, box = 48, 800.0
+    sets = [_particles(dims, box, 40 + f, 1) for f in range(4)]
+    mas = ["CIC", "TSC", "NGP", "PCS"]
+    got = SlabPk(dims, box, "CIC", 2).run_x([torch.from_numpy(p).cuda() for p in sets], None, mas)
+    grids = []
+    for p, m in zip(sets, mas):
+        d = np.zeros((dims,) * 3, np.float32); MASL.MA(p, d, box, m); MASL.overdensity(d); grids.append(d)
+    parity.check_xpk(got, PKL.XPk(grids, box, 2, mas, 1), rtol=1e-3)      # slab vs monolithic cuFFT: see the test above
+
+
 @pytest.mark.parametrize("mas", ["NGP", "CIC", "TSC", "PCS"])
 @pytest.mark.parametrize("weighted", [False, True])
 def test_particle_exchange_pieces_with_logical_ranks(mas, weighted):
